@@ -1,0 +1,199 @@
+/*
+ * ptk.h -- C ABI of libptk.so, the B200 (sm_100a) stereo-reconstruction hot path.
+ *
+ * The reference (ANP-Granular/ParticleTracking, package ParticleDetection) is pure
+ * Python and has no FFI of its own, so the boundary a maintainer would
+ * bind is the body of three functions.  Each entry point below names the reference
+ * lines it replaces; paths are relative to
+ *   ParticleDetection/src/ParticleDetection/reconstruct_3D/
+ * INTEGRATION.md shows the ctypes stub for each.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no C++/torch types.  Functions whose names end in
+ *    `_host` take HOST pointers and do their own (pinned, chunked, overlapped) copies;
+ *    all others take DEVICE pointers owned by the caller, never allocate, and only
+ *    enqueue work on `stream` (a cudaStream_t passed as void*; NULL = default stream).
+ *  - return 0 on success, a negative ptk_status otherwise; never throw, never exit.
+ *  - all floating point is IEEE binary64; indices are int32; a "problem" is one
+ *    (frame, colour) matching problem; arrays are dense, row-major, padded to Nmax.
+ *  - re-entrant: no global mutable state; a ptk_ctx must not be used from two threads
+ *    at once (the reference's callers run one worker per colour -- give each its own).
+ */
+#ifndef PTK_H_
+#define PTK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTK_VERSION 100 /* 0.1.0 */
+#define PTK_MAX_RODS 256 /* largest N1, N2, N per problem (BASELINE config 5) */
+#define PTK_ROW_COLS 18  /* x1 y1 z1 x2 y2 z2 x y z l + 4 cam1 + 4 cam2 (match2D.py:963,986) */
+
+typedef enum ptk_status {
+    PTK_OK = 0,
+    PTK_ERR_INVALID_ARG = -1, /* NULL pointer, negative size, N > PTK_MAX_RODS */
+    PTK_ERR_CUDA = -2,        /* a CUDA runtime call failed; see ptk_last_cuda_error() */
+    PTK_ERR_WORKSPACE = -3,   /* workspace too small; see ptk_workspace_bytes() */
+    PTK_ERR_NO_DEVICE = -4,   /* no CUDA device / not an sm_100 device */
+    PTK_ERR_NUMERIC = -5      /* host API only: some problem had NaN/-inf costs or was infeasible
+                                 (scipy raises ValueError there); per-problem detail in `status` */
+} ptk_status;
+
+/* per-problem status written by the solver kernels (mirrors scipy's rectangular_lsap codes,
+ * which match2D.py:933 and tracking.py:122 surface as ValueError) */
+#define PTK_PROBLEM_OK 0
+#define PTK_PROBLEM_INVALID 1    /* cost matrix contains NaN or -inf */
+#define PTK_PROBLEM_INFEASIBLE 2 /* no finite assignment */
+#define PTK_PROBLEM_EMPTY 3      /* n1 == 0 or n2 == 0: match_frame returns None (match2D.py:838-840) */
+
+/*
+ * The rig: everything match_frame receives besides the rod data (match2D.py:741-757).
+ * The reference passes P1, P2, r1, r2, t1, t2 redundantly with `calibration`; they are
+ * honoured as passed, not recomputed.
+ */
+typedef struct ptk_rig {
+    double CM1[9], CM2[9];       /* calibration["CM1"], ["CM2"], row-major 3x3 */
+    double dist1[14], dist2[14]; /* calibration["dist1"], ["dist2"], zero padded (k1 k2 p1 p2 k3 k4 k5 k6 s1..s4 tx ty) */
+    double R1[9], t1[3];         /* r1, t1 given to cv2.projectPoints for camera 1 (match2D.py:898) */
+    double R2[9], t2[3];         /* r2, t2 for camera 2 (match2D.py:901) */
+    double P1[12], P2[12];       /* 3x4 projection matrices given to cv2.triangulatePoints (match2D.py:889) */
+    double Rw[9], tw[3];         /* world transform: X_w = Rw X + tw == rot.apply(X) + trans (match2D.py:913) */
+    int32_t agg_sum;             /* 0: mean over the two cameras (match2D.py:910); 1: sum (matchND.py:525) */
+    int32_t reserved;
+} ptk_rig;
+
+/* ---- library ----------------------------------------------------------------------- */
+int ptk_version(void);
+const char* ptk_strerror(int status);
+/* cudaGetErrorString of the last CUDA failure seen by the calling thread ("" if none). */
+const char* ptk_last_cuda_error(void);
+/* number of CUDA devices usable by this library (compute capability 10.x); 0 if none. */
+int ptk_device_count(void);
+
+/* ---- K0: undistortion with the reference's reshape quirk ----------------------------
+ * Replaces match2D.py:846-863 (== matchND.py:473-490): cv2.undistortImagePoints on
+ * rods.reshape(2,-1) plus the Python write-back loop.
+ * cam[P,Nmax,2(end),2(xy)], n[P] -> und[P,Nmax,2,2]; rows >= n[p] are not written. */
+int ptk_undistort_batch(const ptk_rig* rig, int P, int Nmax,
+                        const double* cam1, const double* cam2,
+                        const int32_t* n1, const int32_t* n2,
+                        double* und1, double* und2, void* stream);
+
+/* ---- K0+K1: cost matrix ---------------------------------------------------------------
+ * Replaces match2D.py:846-932/936-939 (all cam1 x cam2 rod pairs x 4 end-point combos ->
+ * cv2.triangulatePoints -> 2x cv2.projectPoints -> error -> cost, choice).
+ * cost[P,Nmax,Nmax] (row = cam1 rod); choice (uint8, optional, may be NULL) = (e0+e3 <= e1+e2).
+ * Optional per-combo outputs for matchND.create_weights (matchND.py:549-551), may be NULL:
+ *   p_world[P,Nmax,Nmax,4,3] world-transformed points, rep_errs[P,Nmax,Nmax,4,2].
+ * workspace: ptk_workspace_bytes(PTK_WS_COST, P, Nmax). */
+int ptk_cost_batch(const ptk_rig* rig, int P, int Nmax,
+                   const double* cam1, const double* cam2,
+                   const int32_t* n1, const int32_t* n2,
+                   double* cost, uint8_t* choice, double* p_world, double* rep_errs,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K2: batched rectangular linear-sum assignment ----------------------------------
+ * Replaces scipy.optimize.linear_sum_assignment at match2D.py:933 and tracking.py:122,
+ * with SciPy's scan order and tie rules so that results are identical
+ * also on tied costs.  cost[P, ld_rows, ld_cols] (only the leading nr[p] x nc[p] block is
+ * read; nr/nc may be NULL = ld_rows/ld_cols for every problem).
+ * row_ind, col_ind[P, min(ld_rows,ld_cols)]: the first n_out[p] = min(nr,nc) entries are
+ * SciPy's (row_ind sorted ascending); the rest are -1.  status[P]: PTK_PROBLEM_*. */
+int ptk_lsap_batch(int P, int ld_rows, int ld_cols, const double* cost,
+                   const int32_t* nr, const int32_t* nc,
+                   int32_t* row_ind, int32_t* col_ind, int32_t* n_out, int32_t* status,
+                   void* stream);
+
+/* ---- K0..K3: the whole match_frame body for P problems ------------------------------
+ * Replaces match2D.py:843-983 with renumber=True, per (frame, colour) problem:
+ * undistort -> pairs -> DLT -> reproject -> cost -> LSAP -> 18-column rows, including the
+ * loop-index quirk for N1 > N2 and the end-point reversal.
+ *   rows[P,Nmax,18], match_cost[P,Nmax] (== costs, match2D.py:934), row_ind/col_ind[P,Nmax],
+ *   n_out[P] = min(n1,n2), status[P].
+ * Optional (NULL to skip): cost[P,Nmax,Nmax], choice[P,Nmax,Nmax].
+ * Extension (no reference counterpart): keep_mask[P,Nmax] (uint8, may be NULL)
+ * = match_cost <= max_repr_err; pass +inf to switch the threshold off.  Nothing else depends on it.
+ * workspace: ptk_workspace_bytes(PTK_WS_MATCH, P, Nmax). */
+int ptk_match_batch(const ptk_rig* rig, int P, int Nmax,
+                    const double* cam1, const double* cam2,
+                    const int32_t* n1, const int32_t* n2,
+                    double* cost, uint8_t* choice,
+                    int32_t* row_ind, int32_t* col_ind, int32_t* n_out, int32_t* status,
+                    double* rows, double* match_cost,
+                    double max_repr_err, uint8_t* keep_mask,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K4 (+K2): tracking_global_assignment over all consecutive frame pairs ----------
+ * Replaces tracking.py:97-123,136-137 for C colours at once.
+ *   ends[C,F,N,2,3]: (x1,y1,z1),(x2,y2,z2) per rod in DataFrame row order.
+ *   cost[C,F-1,N,N] optional (NULL: kept in workspace only); col_ind[C,F-1,N];
+ *   total_cost[C,F-1]; status[C,F-1].
+ * The cost arithmetic follows numpy's operation order exactly (bit-identical costs for
+ * identical inputs; the reference's cost is massively tied, so this is what makes col_ind
+ * reproducible).  workspace: ptk_workspace_bytes(PTK_WS_TRACK, C*(F-1), N). */
+int ptk_track_batch(int C, int F, int N, const double* ends,
+                    double* cost, int32_t* col_ind, double* total_cost, int32_t* status,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K5: chain pass (extension; SURVEY.md App. D.3, no reference counterpart) --------
+ * ids[c,0] = ids_in[c] (or arange(N) if ids_in is NULL); ids[c,f+1][col_ind[c,f][a]] = ids[c,f][a].
+ * col_ind[C,F-1,N] -> track_id[C,F,N]; last_ids[C,N] (optional) = track_id[c,F-1]. */
+int ptk_chain_tracks(int C, int F, int N, const int32_t* col_ind, const int32_t* ids_in,
+                     int32_t* track_id, void* stream);
+
+/* ---- K6: matchND.create_weights ("next" row) --------------------------
+ * Replaces matchND.py:141-217.  p_3D[N1,N2,4,3], p_prev[Np,2,3], rep_errs[N1,N2,4,2] ->
+ * weights[Np,N1,N2] (= max(w) - w), choices[Np,N1,N2] (float64 0..3, as the reference).
+ * workspace: ptk_workspace_bytes(PTK_WS_WEIGHTS, Np*N1*N2, 0). */
+int ptk_create_weights(int Np, int N1, int N2, const double* p_3D, const double* p_prev,
+                       const double* rep_errs, double* weights, double* choices,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- workspace sizing ---------------------------------------------------------------- */
+#define PTK_WS_COST 1
+#define PTK_WS_MATCH 2
+#define PTK_WS_TRACK 3
+#define PTK_WS_WEIGHTS 4
+size_t ptk_workspace_bytes(int kind, long long n_problems, int Nmax);
+
+/* ---- host-buffer pipeline (what bench.py's `e2e` and match_csv_complex call) ----------
+ * A ptk_ctx owns a device, streams, pinned staging and device buffers sized on demand. */
+typedef struct ptk_ctx ptk_ctx;
+int ptk_ctx_create(int device, ptk_ctx** out);
+void ptk_ctx_destroy(ptk_ctx* ctx);
+
+/* match (+ optional track + chain) for a whole experiment held in HOST memory.
+ *   cam1, cam2 [F,C,Nmax,2,2]; n1, n2 [F,C]   (problem index = f*C + c)
+ * outputs (host; any may be NULL except rows/n_out/status):
+ *   rows[F,C,Nmax,18], match_cost[F,C,Nmax], row_ind/col_ind[F,C,Nmax], n_out[F,C], status[F,C],
+ *   keep_mask[F,C,Nmax]
+ * if do_track != 0 (requires n_out == N for every problem, as tracking.py:97 does):
+ *   track_col[C,F-1,N], track_total[C,F-1], track_id[C,F,N], track_status[C,F-1]
+ * Copies are chunked over frames and overlapped with compute on separate streams.
+ * Returns PTK_ERR_NUMERIC if any status != OK/EMPTY (outputs are still filled). */
+int ptk_reconstruct_host(ptk_ctx* ctx, const ptk_rig* rig, int F, int C, int Nmax,
+                         const double* cam1, const double* cam2,
+                         const int32_t* n1, const int32_t* n2,
+                         double* rows, double* match_cost,
+                         int32_t* row_ind, int32_t* col_ind, int32_t* n_out, int32_t* status,
+                         double max_repr_err, uint8_t* keep_mask,
+                         int do_track, int32_t* track_col, double* track_total,
+                         int32_t* track_id, int32_t* track_status);
+
+/* ---- measurement helper: FP64 FMA peak of the device (roofline denominator) ----------
+ * Runs a dependent-free DFMA loop on every SM and returns achieved FLOP/s in *flops
+ * (2 flop per DFMA), timed with CUDA events on `stream`. */
+int ptk_measure_fp64_peak(int iters, double* flops, void* stream);
+
+/* number of kernel launches enqueued by this library since the last call with reset != 0
+ * (process-wide, atomic) -- bench.py's `gpu_launches`. */
+long long ptk_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTK_H_ */

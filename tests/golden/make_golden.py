@@ -1,0 +1,144 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference from
+/root/reference (build container only; `python tests/golden/make_golden.py`).
+
+The reference's own tests hold no numeric goldens for this path, so the
+known answers are produced here: seeded synthetic inputs (particletracking_b200.synthetic,
+SURVEY.md App. F) go through the reference's match2D.match_frame / match_complex,
+tracking.tracking_global_assignment and matchND.create_weights, and inputs + outputs are
+stored.  scipy's linear_sum_assignment is wrapped (not replaced) inside the reference
+modules while they run, to also record the cost matrices and assignments the reference
+saw -- those never leave match_frame otherwise.
+
+Versions at generation time are stored in each file (`versions`).
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle import refload  # noqa: E402
+from particletracking_b200 import synthetic as syn  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def versions():
+    import cv2
+    import pandas
+    import scipy
+
+    return np.array([f"cv2={cv2.__version__}", f"scipy={scipy.__version__}",
+                     f"numpy={np.__version__}", f"pandas={pandas.__version__}"])
+
+
+class Spy:
+    """Wraps linear_sum_assignment inside a reference module and records calls."""
+
+    def __init__(self, module):
+        self.module = module
+        self.orig = module.linear_sum_assignment
+        self.calls = []
+
+    def __enter__(self):
+        def wrapped(cost, *a, **k):
+            r = self.orig(cost, *a, **k)
+            self.calls.append((np.array(cost, copy=True), np.array(r[0]), np.array(r[1])))
+            return r
+
+        self.module.linear_sum_assignment = wrapped
+        return self
+
+    def __exit__(self, *exc):
+        self.module.linear_sum_assignment = self.orig
+
+
+def rig_args():
+    from scipy.spatial.transform import Rotation
+
+    cal = syn.synthetic_calibration()
+    trf = syn.synthetic_transformation()
+    P1, P2, r1, r2, t1, t2 = syn.projection_matrices(cal)
+    return cal, trf, (cal, P1, P2, Rotation.from_matrix(trf["rotation"]), trf["translation"], r1, r2, t1, t2)
+
+
+def golden_match(name, F, C, N, seed, **kw):
+    m2d = refload.load()[0]
+    cal, trf, args = rig_args()
+    data = syn.make_stereo(F, C, N, seed=seed, **kw)
+    dfs = syn.to_dataframes(data)
+    rows = np.full((F, C, N, 18), np.nan)
+    costs = np.full((F, C, N), np.nan)
+    lengths = np.full((F, C, N), np.nan)
+    cost_mat = np.full((F, C, N, N), np.nan)
+    row_ind = np.full((F, C, N), -1, dtype=np.int32)
+    col_ind = np.full((F, C, N), -1, dtype=np.int32)
+    n_out = np.zeros((F, C), dtype=np.int32)
+    for ci, color in enumerate(data.colors):
+        for fi, f in enumerate(data.frames):
+            with Spy(m2d) as spy:
+                df, c, l = m2d.match_frame(dfs[color], "gp1", "gp2", int(f), color, *args, renumber=True)
+            n = len(df)
+            n_out[fi, ci] = n
+            rows[fi, ci, :n] = df.iloc[:, :18].to_numpy()
+            costs[fi, ci, :n] = c
+            lengths[fi, ci, :n] = l
+            cm, ri, cj = spy.calls[0]
+            cost_mat[fi, ci, : cm.shape[0], : cm.shape[1]] = cm
+            row_ind[fi, ci, :n] = ri
+            col_ind[fi, ci, :n] = cj
+            assert list(df["particle"]) == list(range(n)) and (df["frame"] == f).all()
+    np.savez_compressed(
+        os.path.join(OUT, name), cam1=data.cam1, cam2=data.cam2, n1=data.n1, n2=data.n2,
+        rows=rows, costs=costs, lengths=lengths, cost=cost_mat, row_ind=row_ind, col_ind=col_ind,
+        n_out=n_out, versions=versions(),
+        params=np.array([F, C, N, seed]), kw=np.array([f"{k}={v}" for k, v in kw.items()]))
+    print(name, "ok", n_out.min(), n_out.max())
+    return data, dfs
+
+
+def golden_tracking(name, F, N, seed):
+    m2d, _, trk, _ = refload.load()
+    cal, trf, args = rig_args()
+    data = syn.make_stereo(F, 1, N, seed=seed)
+    df = syn.to_dataframes(data)["black"]
+    matched = m2d.match_complex(df, list(data.frames), "black", cal, trf)[0]
+    with Spy(trk) as spy:
+        out, total = trk.tracking_global_assignment(matched)
+    ends = matched[["x1", "y1", "z1", "x2", "y2", "z2"]].to_numpy().reshape(F, N, 2, 3)
+    np.savez_compressed(
+        os.path.join(OUT, name), ends=ends,
+        cost=np.stack([c[0] for c in spy.calls]), col_ind=np.stack([c[2] for c in spy.calls]).astype(np.int32),
+        total_cost=total, particle_in=matched["particle"].to_numpy(), frame_in=matched["frame"].to_numpy(),
+        particle_out=out["particle"].to_numpy(), frame_out=out["frame"].to_numpy(),
+        x1_out=out["x1"].to_numpy(), versions=versions(), params=np.array([F, N, seed]))
+    print(name, "ok", total[:3])
+
+
+def golden_weights(name, seed):
+    mnd = refload.load()[1]
+    rng = np.random.default_rng(seed)
+    p3 = rng.normal(size=(6, 7, 4, 3)) * 25
+    prev = rng.normal(size=(5, 2, 3)) * 25
+    re = rng.random((6, 7, 4, 2)) * 3
+    w, ch = mnd.create_weights(p3, prev, re)
+    np.savez_compressed(os.path.join(OUT, name), p_3D=p3, p_prev=prev, rep_errs=re,
+                        weights=w, choices=ch, versions=versions())
+    print(name, "ok")
+
+
+if __name__ == "__main__":
+    assert refload.available(), "needs /root/reference"
+    # C1 of BASELINE.json: one stereo frame pair, 3 colours x 12 rods (+ one more frame)
+    golden_match("c1_3x12.npz", 2, 3, 12, seed=1)
+    # ragged: dropped detections (N1 != N2, both orientations) and dummy -1 rods
+    golden_match("ragged_2x16.npz", 5, 2, 16, seed=3, p_drop=0.2, p_dummy=0.1, sigma_px=0.5)
+    # tiny problems: the N == 1 undistortion special case and N == 2
+    golden_match("tiny_n1.npz", 3, 2, 1, seed=11)
+    golden_match("tiny_n2.npz", 3, 2, 2, seed=12)
+    golden_match("n32.npz", 1, 2, 32, seed=2)
+    golden_tracking("track_12.npz", 6, 12, seed=21)
+    golden_tracking("track_25.npz", 4, 25, seed=22)
+    golden_weights("weights.npz", seed=5)

@@ -1,0 +1,106 @@
+"""Pins oracle/port.py against the UNMODIFIED reference, live, whenever
+/root/reference is present (build container).  On the GPU box these skip and
+the committed goldens (tests/golden/) carry the pin."""
+import numpy as np
+import pandas as pd
+import pytest
+
+from conftest import rel_err
+from oracle import port, refload
+from particletracking_b200 import synthetic as syn
+
+pytestmark = [
+    pytest.mark.reference,
+    pytest.mark.skipif(not refload.available(), reason="reference tree not present"),
+]
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return refload.load()
+
+
+def _rig_args(rig):
+    return (rig["calibration"], rig["P1"], rig["P2"], rig["rot"], rig["trans"],
+            rig["r1"], rig["r2"], rig["t1"], rig["t2"])
+
+
+@pytest.mark.parametrize("n,drop,dummy", [(12, 0.0, 0.0), (1, 0.0, 0.0), (2, 0.0, 0.0),
+                                           (9, 0.3, 0.0), (16, 0.1, 0.15), (32, 0.0, 0.0)])
+def test_match_frame_matches_reference(ref, rig, n, drop, dummy):
+    m2d = ref[0]
+    data = syn.make_stereo(4, 1, n, seed=100 + n, p_drop=drop, p_dummy=dummy)
+    df = syn.to_dataframes(data)[data.colors[0]]
+    for f in data.frames:
+        r = m2d.match_frame(df, "gp1", "gp2", int(f), "black", *_rig_args(rig), renumber=True)
+        o = port.match_frame(df, "gp1", "gp2", int(f), "black", *_rig_args(rig))
+        assert (r is None) == (o is None)
+        rdf, rc, rl = r
+        odf, oc, ol = o
+        assert list(rdf.columns) == list(odf.columns)
+        assert (rdf.dtypes.values == odf.dtypes.values).all()
+        a = rdf.drop(columns=["color"]).to_numpy(dtype=float)
+        b = odf.drop(columns=["color"]).to_numpy(dtype=float)
+        assert a.shape == b.shape
+        np.testing.assert_array_equal(a[:, 10:], b[:, 10:])  # 2D columns, ids: exact
+        assert rel_err(b[:, :10], a[:, :10]) < 1e-12
+        assert rel_err(oc, rc) < 1e-12 and rel_err(ol, rl) < 1e-12
+
+
+def test_match_frame_on_reference_fixture(ref):
+    """The reference's own example data (frames 500-510 x 25 rods, real rig)."""
+    m2d, _, _, dl = ref
+    ex = refload.REFERENCE_EXAMPLES
+    cal = dl.load_camera_calibration(f"{ex}/gp34.json")
+    trf = dl.load_world_transformation(f"{ex}/transformation.json")
+    P1, P2, r1, r2, t1, t2 = syn.projection_matrices(cal)
+    from scipy.spatial.transform import Rotation
+
+    rot = Rotation.from_matrix(trf["rotation"])
+    for color in ("black", "green"):
+        df = pd.read_csv(f"{ex}/rods_df_{color}.csv", index_col=0)
+        for f in (505, 508):
+            args = (cal, P1, P2, rot, trf["translation"], r1, r2, t1, t2)
+            rdf, rc, rl = m2d.match_frame(df, "gp3", "gp4", f, color, *args, renumber=True)
+            odf, oc, ol = port.match_frame(df, "gp3", "gp4", f, color, *args)
+            a = rdf.drop(columns=["color"]).to_numpy(dtype=float)
+            b = odf.drop(columns=["color"]).to_numpy(dtype=float)
+            np.testing.assert_array_equal(a[:, 10:], b[:, 10:])
+            assert rel_err(b[:, :10], a[:, :10]) < 1e-12
+            assert rel_err(oc, rc) < 1e-12
+
+
+def test_match_complex_matches_reference(ref, rig):
+    m2d = ref[0]
+    data = syn.make_stereo(3, 1, 8, seed=7)
+    df = syn.to_dataframes(data)["black"]
+    r = m2d.match_complex(df, list(data.frames), "black", rig["calibration"], rig["transformation"])
+    o = port.match_complex(df, list(data.frames), "black", rig["calibration"], rig["transformation"])
+    pd.testing.assert_frame_equal(r[0], o[0], rtol=1e-12, atol=1e-12)
+    for x, y in zip(r[1], o[1]):
+        assert rel_err(y, x) < 1e-12
+
+
+@pytest.mark.parametrize("n", [2, 5, 12, 25])
+def test_tracking_matches_reference_bit_exact(ref, rig, n):
+    """Same 3D DataFrame in -> identical particle column, identical total_cost."""
+    trk = ref[2]
+    data = syn.make_stereo(6, 1, n, seed=40 + n)
+    df = syn.to_dataframes(data)["black"]
+    matched = port.match_complex(df, list(data.frames), "black", rig["calibration"], rig["transformation"])[0]
+    rdf, rtot = trk.tracking_global_assignment(matched)
+    odf, otot = port.tracking_global_assignment(matched)
+    pd.testing.assert_frame_equal(rdf, odf, check_exact=True)
+    np.testing.assert_array_equal(rtot, otot)
+
+
+def test_create_weights_matches_reference(ref, rig):
+    mnd = ref[1]
+    rng = np.random.default_rng(3)
+    p3 = rng.normal(size=(5, 6, 4, 3)) * 20
+    prev = rng.normal(size=(4, 2, 3)) * 20
+    re = rng.random((5, 6, 4, 2))
+    rw, rc = mnd.create_weights(p3, prev, re)
+    ow, oc = port.create_weights(p3, prev, re)
+    np.testing.assert_array_equal(rc, oc)
+    assert rel_err(ow, rw) < 1e-14
