@@ -1,0 +1,94 @@
+"""ctypes binding of ``libptk.so`` (C ABI declared in ``include/ptk.h``).
+
+There is no CPU fallback: importing this module without the built library, or calling
+it without a B200-class device, raises.  Build with ``python -c "import __graft_entry__ as
+g; g.build()"`` or ``make -C particletracking_b200/csrc``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+from .rig import PtkRig
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libptk.so")
+
+PTK_OK = 0
+PTK_ERR_NUMERIC = -5
+PROBLEM_OK, PROBLEM_INVALID, PROBLEM_INFEASIBLE, PROBLEM_EMPTY = 0, 1, 2, 3
+WS_COST, WS_MATCH, WS_TRACK, WS_WEIGHTS = 1, 2, 3, 4
+ROW_COLS = 18
+MAX_RODS = 256
+
+# every symbol include/ptk.h declares (tests/test_abi.py checks header <-> library <-> this list)
+SYMBOLS = [
+    "ptk_version", "ptk_strerror", "ptk_last_cuda_error", "ptk_device_count",
+    "ptk_undistort_batch", "ptk_cost_batch", "ptk_lsap_batch", "ptk_match_batch",
+    "ptk_track_batch", "ptk_chain_tracks", "ptk_create_weights", "ptk_workspace_bytes",
+    "ptk_ctx_create", "ptk_ctx_destroy", "ptk_reconstruct_host",
+    "ptk_measure_fp64_peak", "ptk_launch_count",
+]
+
+
+class NativeLibraryMissing(ImportError):
+    pass
+
+
+class PtkError(RuntimeError):
+    def __init__(self, status: int, where: str):
+        self.status = status
+        msg = lib().ptk_strerror(status).decode()
+        cuda = lib().ptk_last_cuda_error().decode()
+        super().__init__(f"{where}: {msg}" + (f" [{cuda}]" if cuda and status == -2 else ""))
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """The loaded library; raises NativeLibraryMissing if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeLibraryMissing(
+            f"{LIB_PATH} not found: the CUDA library has not been built "
+            "(run __graft_entry__.build() or `make -C particletracking_b200/csrc`). "
+            "particletracking_b200 has no CPU fallback."
+        )
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i32, dbl, sz, ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_size_t, ctypes.c_longlong
+    rigp = ctypes.POINTER(PtkRig)
+    L.ptk_version.restype = i32
+    L.ptk_strerror.restype = ctypes.c_char_p
+    L.ptk_strerror.argtypes = [i32]
+    L.ptk_last_cuda_error.restype = ctypes.c_char_p
+    L.ptk_device_count.restype = i32
+    L.ptk_launch_count.restype = ll
+    L.ptk_launch_count.argtypes = [i32]
+    L.ptk_workspace_bytes.restype = sz
+    L.ptk_workspace_bytes.argtypes = [i32, ll, i32]
+    L.ptk_undistort_batch.argtypes = [rigp, i32, i32] + [vp] * 6 + [vp]
+    L.ptk_cost_batch.argtypes = [rigp, i32, i32] + [vp] * 8 + [vp, sz, vp]
+    L.ptk_lsap_batch.argtypes = [i32, i32, i32] + [vp] * 7 + [vp]
+    L.ptk_match_batch.argtypes = [rigp, i32, i32] + [vp] * 12 + [dbl, vp, vp, sz, vp]
+    L.ptk_track_batch.argtypes = [i32, i32, i32] + [vp] * 5 + [vp, sz, vp]
+    L.ptk_chain_tracks.argtypes = [i32, i32, i32, vp, vp, vp, vp]
+    L.ptk_create_weights.argtypes = [i32, i32, i32] + [vp] * 5 + [vp, sz, vp]
+    L.ptk_ctx_create.argtypes = [i32, ctypes.POINTER(vp)]
+    L.ptk_ctx_destroy.argtypes = [vp]
+    L.ptk_ctx_destroy.restype = None
+    L.ptk_reconstruct_host.argtypes = [vp, rigp, i32, i32, i32] + [vp] * 10 + [dbl, vp, i32] + [vp] * 4
+    L.ptk_measure_fp64_peak.argtypes = [i32, ctypes.POINTER(dbl), vp]
+    for name in SYMBOLS:
+        f = getattr(L, name)
+        if f.restype is ctypes.c_int and name not in ("ptk_version", "ptk_device_count"):
+            pass
+    _lib = L
+    return L
+
+
+def check(status: int, where: str) -> None:
+    if status != PTK_OK:
+        raise PtkError(status, where)

@@ -1,0 +1,624 @@
+// ptk_api.cu -- C ABI of libptk.so (see include/ptk.h): argument checks, workspace carving,
+// kernel launches, and the host-buffer pipeline.  No torch, no C++ types across the boundary.
+//
+// Build (see particletracking_b200/csrc/Makefile):
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "ptk_kernels.cuh"
+
+using namespace ptk;
+
+#define PTK_API extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+thread_local char g_cuda_err[256] = "";
+std::atomic<long long> g_launches{0};
+
+inline int cuda_fail(cudaError_t e, const char* what)
+{
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", what, cudaGetErrorString(e));
+    return PTK_ERR_CUDA;
+}
+
+#define CK(call)                                              \
+    do {                                                      \
+        cudaError_t e__ = (call);                             \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+#define LAUNCHED(name)                                           \
+    do {                                                         \
+        g_launches.fetch_add(1, std::memory_order_relaxed);      \
+        cudaError_t e__ = cudaPeekAtLastError();                 \
+        if (e__ != cudaSuccess) return cuda_fail(e__, name);     \
+    } while (0)
+
+DevRig make_devrig(const ptk_rig* r)
+{
+    DevRig d;
+    memcpy(d.P1, r->P1, sizeof(d.P1));
+    memcpy(d.P2, r->P2, sizeof(d.P2));
+    memcpy(d.R1, r->R1, sizeof(d.R1));
+    memcpy(d.t1, r->t1, sizeof(d.t1));
+    memcpy(d.R2, r->R2, sizeof(d.R2));
+    memcpy(d.t2, r->t2, sizeof(d.t2));
+    d.CM1[0] = r->CM1[0]; d.CM1[1] = r->CM1[4]; d.CM1[2] = r->CM1[2]; d.CM1[3] = r->CM1[5];
+    d.CM2[0] = r->CM2[0]; d.CM2[1] = r->CM2[4]; d.CM2[2] = r->CM2[2]; d.CM2[3] = r->CM2[5];
+    memcpy(d.k1, r->dist1, sizeof(d.k1));
+    memcpy(d.k2, r->dist2, sizeof(d.k2));
+    memcpy(d.Rw, r->Rw, sizeof(d.Rw));
+    memcpy(d.tw, r->tw, sizeof(d.tw));
+    d.agg_sum = r->agg_sum;
+    return d;
+}
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// Problems per internal pass of ptk_match_batch: the cost-matrix chunk is kept around 64 MB so
+// it stays L2-resident (126 MB) between K1 writing it and K2 reading it.
+long long match_chunk(long long P, int Nmax)
+{
+    const size_t per = (size_t)Nmax * Nmax * sizeof(double);
+    long long c = (long long)((64ull << 20) / (per ? per : 1));
+    if (c < 296) c = 296;  // >= 2 CTAs per SM worth of problems even for N = 256
+    if (c > P) c = P;
+    if (c < 1) c = 1;
+    return c;
+}
+
+struct MatchWs {
+    double *und1, *und2, *cost;
+    size_t bytes;
+};
+
+MatchWs carve_match(void* ws, long long chunk, int Nmax, bool need_cost)
+{
+    MatchWs m;
+    char* b = static_cast<char*>(ws);
+    size_t o = 0;
+    const size_t und = align_up((size_t)chunk * Nmax * 4 * sizeof(double));
+    m.und1 = reinterpret_cast<double*>(b + o); o += und;
+    m.und2 = reinterpret_cast<double*>(b + o); o += und;
+    m.cost = reinterpret_cast<double*>(b + o);
+    if (need_cost) o += align_up((size_t)chunk * Nmax * Nmax * sizeof(double));
+    m.bytes = o;
+    return m;
+}
+
+int launch_undistort(const DevRig& rig, long long P, int Nmax, const double* cam1, const double* cam2,
+                     const int32_t* n1, const int32_t* n2, double* und1, double* und2, cudaStream_t st)
+{
+    // gridDim.y is limited to 65535: slice the problem axis
+    for (long long p0 = 0; p0 < P; p0 += 65535) {
+        const int np = (int)((P - p0) < 65535 ? (P - p0) : 65535);
+        dim3 grid((2 * Nmax + 127) / 128, np, 2);
+        k_undistort<<<grid, 128, 0, st>>>(rig, Nmax, cam1 + (size_t)p0 * Nmax * 4, cam2 + (size_t)p0 * Nmax * 4, n1 + p0,
+                                          n2 + p0, und1 + (size_t)p0 * Nmax * 4, und2 + (size_t)p0 * Nmax * 4);
+        LAUNCHED("k_undistort");
+    }
+    return PTK_OK;
+}
+
+int launch_cost(const DevRig& rig, long long P, int Nmax, const double* cam1, const double* cam2, const double* und1,
+                const double* und2, const int32_t* n1, const int32_t* n2, double* cost, uint8_t* choice,
+                double* p_world, double* rep_errs, cudaStream_t st)
+{
+    CostArgs a;
+    a.Nmax = Nmax;
+    a.tiles = (Nmax * Nmax + 31) / 32;
+    // 1-D grids hold 2^31-1 blocks; slice anyway to stay far below
+    const long long max_p = (long long)(1u << 30) / a.tiles;
+    for (long long p0 = 0; p0 < P; p0 += max_p) {
+        const long long np = (P - p0) < max_p ? (P - p0) : max_p;
+        const size_t o4 = (size_t)p0 * Nmax * 4, o2 = (size_t)p0 * Nmax * Nmax;
+        a.cam1 = cam1 + o4; a.cam2 = cam2 + o4; a.und1 = und1 + o4; a.und2 = und2 + o4;
+        a.n1 = n1 + p0; a.n2 = n2 + p0;
+        a.cost = cost + o2;
+        a.choice = choice ? choice + o2 : nullptr;
+        a.p_world = p_world ? p_world + o2 * 12 : nullptr;
+        a.rep_errs = rep_errs ? rep_errs + o2 * 8 : nullptr;
+        k_cost<<<(unsigned)(np * a.tiles), 128, 0, st>>>(rig, a);
+        LAUNCHED("k_cost");
+    }
+    return PTK_OK;
+}
+
+int launch_lsap(long long P, LsapArgs a, cudaStream_t st)
+{
+    const int M = a.ld_rows > a.ld_cols ? a.ld_rows : a.ld_cols;
+    const size_t smem = lsap_smem_bytes(M);
+    const long long max_p = 1ll << 30;
+    for (long long p0 = 0; p0 < P; p0 += max_p) {
+        const long long np = (P - p0) < max_p ? (P - p0) : max_p;
+        LsapArgs b = a;
+        b.cost = a.cost + (size_t)p0 * a.cost_stride;
+        if (a.nr) b.nr = a.nr + p0;
+        if (a.nc) b.nc = a.nc + p0;
+        if (a.row_ind) b.row_ind = a.row_ind + (size_t)p0 * a.out_ld;
+        b.col_ind = a.col_ind + (size_t)p0 * a.out_ld;
+        if (a.n_out) b.n_out = a.n_out + p0;
+        if (a.status) b.status = a.status + p0;
+        if (a.assigned) b.assigned = a.assigned + (size_t)p0 * a.out_ld;
+        if (a.total) b.total = a.total + p0;
+        if (a.keep) b.keep = a.keep + (size_t)p0 * a.out_ld;
+        k_lsap<<<(unsigned)np, 32, smem, st>>>(b);
+        LAUNCHED("k_lsap");
+    }
+    return PTK_OK;
+}
+
+int launch_rows(const DevRig& rig, long long P, int Nmax, const double* cam1, const double* cam2, const double* und1,
+                const double* und2, const int32_t* col_ind, const int32_t* n_out, double* rows, cudaStream_t st)
+{
+    for (long long p0 = 0; p0 < P; p0 += 65535) {
+        const int np = (int)((P - p0) < 65535 ? (P - p0) : 65535);
+        RowsArgs a;
+        a.Nmax = Nmax;
+        const size_t o4 = (size_t)p0 * Nmax * 4;
+        a.cam1 = cam1 + o4; a.cam2 = cam2 + o4; a.und1 = und1 + o4; a.und2 = und2 + o4;
+        a.col_ind = col_ind + (size_t)p0 * Nmax;
+        a.n_out = n_out + p0;
+        a.rows = rows + (size_t)p0 * Nmax * PTK_ROW_COLS;
+        dim3 grid((Nmax + 31) / 32, np);
+        k_rows<<<grid, 128, 0, st>>>(rig, a);
+        LAUNCHED("k_rows");
+    }
+    return PTK_OK;
+}
+
+bool bad_n(int Nmax) { return Nmax <= 0 || Nmax > PTK_MAX_RODS; }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------ library
+PTK_API int ptk_version(void) { return PTK_VERSION; }
+
+PTK_API const char* ptk_strerror(int status)
+{
+    switch (status) {
+        case PTK_OK: return "ok";
+        case PTK_ERR_INVALID_ARG: return "invalid argument";
+        case PTK_ERR_CUDA: return "CUDA runtime error (see ptk_last_cuda_error)";
+        case PTK_ERR_WORKSPACE: return "workspace too small (see ptk_workspace_bytes)";
+        case PTK_ERR_NO_DEVICE: return "no usable CUDA device (need compute capability 10.x)";
+        case PTK_ERR_NUMERIC: return "cost matrix contains invalid numeric entries or is infeasible";
+        default: return "unknown status";
+    }
+}
+
+PTK_API const char* ptk_last_cuda_error(void) { return g_cuda_err; }
+
+PTK_API int ptk_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int d = 0; d < n; d++) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ok++;
+    }
+    return ok;
+}
+
+PTK_API long long ptk_launch_count(int reset)
+{
+    return reset ? g_launches.exchange(0) : g_launches.load();
+}
+
+PTK_API size_t ptk_workspace_bytes(int kind, long long n_problems, int Nmax)
+{
+    if (n_problems < 0) return 0;
+    switch (kind) {
+        case PTK_WS_COST: {
+            if (bad_n(Nmax)) return 0;
+            return carve_match(nullptr, n_problems, Nmax, false).bytes + 256;
+        }
+        case PTK_WS_MATCH: {
+            if (bad_n(Nmax)) return 0;
+            return carve_match(nullptr, match_chunk(n_problems, Nmax), Nmax, true).bytes + 256;
+        }
+        case PTK_WS_TRACK: {
+            if (bad_n(Nmax)) return 0;
+            return align_up((size_t)match_chunk(n_problems, Nmax) * Nmax * Nmax * sizeof(double)) + 256;
+        }
+        case PTK_WS_WEIGHTS:
+            return align_up((size_t)((n_problems + 255) / 256) * sizeof(double)) + 256;
+        default: return 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------ K0
+PTK_API int ptk_undistort_batch(const ptk_rig* rig, int P, int Nmax, const double* cam1, const double* cam2,
+                                const int32_t* n1, const int32_t* n2, double* und1, double* und2, void* stream)
+{
+    if (!rig || P < 0 || bad_n(Nmax) || !cam1 || !cam2 || !n1 || !n2 || !und1 || !und2) return PTK_ERR_INVALID_ARG;
+    if (P == 0) return PTK_OK;
+    return launch_undistort(make_devrig(rig), P, Nmax, cam1, cam2, n1, n2, und1, und2, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------ K0+K1
+PTK_API int ptk_cost_batch(const ptk_rig* rig, int P, int Nmax, const double* cam1, const double* cam2,
+                           const int32_t* n1, const int32_t* n2, double* cost, uint8_t* choice, double* p_world,
+                           double* rep_errs, void* workspace, size_t workspace_bytes, void* stream)
+{
+    if (!rig || P < 0 || bad_n(Nmax) || !cam1 || !cam2 || !n1 || !n2 || !cost) return PTK_ERR_INVALID_ARG;
+    if (P == 0) return PTK_OK;
+    if (!workspace || workspace_bytes < ptk_workspace_bytes(PTK_WS_COST, P, Nmax)) return PTK_ERR_WORKSPACE;
+    const DevRig d = make_devrig(rig);
+    cudaStream_t st = (cudaStream_t)stream;
+    MatchWs w = carve_match((void*)align_up((size_t)workspace), P, Nmax, false);
+    int rc = launch_undistort(d, P, Nmax, cam1, cam2, n1, n2, w.und1, w.und2, st);
+    if (rc) return rc;
+    return launch_cost(d, P, Nmax, cam1, cam2, w.und1, w.und2, n1, n2, cost, choice, p_world, rep_errs, st);
+}
+
+// ------------------------------------------------------------------------------------ K2
+PTK_API int ptk_lsap_batch(int P, int ld_rows, int ld_cols, const double* cost, const int32_t* nr, const int32_t* nc,
+                           int32_t* row_ind, int32_t* col_ind, int32_t* n_out, int32_t* status, void* stream)
+{
+    if (P < 0 || bad_n(ld_rows) || bad_n(ld_cols) || !cost || !row_ind || !col_ind) return PTK_ERR_INVALID_ARG;
+    if (P == 0) return PTK_OK;
+    LsapArgs a{};
+    a.ld_rows = ld_rows; a.ld_cols = ld_cols;
+    a.cost_stride = (size_t)ld_rows * ld_cols;
+    a.cost = cost; a.nr = nr; a.nc = nc;
+    a.out_ld = ld_rows < ld_cols ? ld_rows : ld_cols;
+    a.row_ind = row_ind; a.col_ind = col_ind; a.n_out = n_out; a.status = status;
+    a.max_err = INFINITY;
+    return launch_lsap(P, a, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------ K0..K3
+PTK_API int ptk_match_batch(const ptk_rig* rig, int P, int Nmax, const double* cam1, const double* cam2,
+                            const int32_t* n1, const int32_t* n2, double* cost, uint8_t* choice, int32_t* row_ind,
+                            int32_t* col_ind, int32_t* n_out, int32_t* status, double* rows, double* match_cost,
+                            double max_repr_err, uint8_t* keep_mask, void* workspace, size_t workspace_bytes,
+                            void* stream)
+{
+    if (!rig || P < 0 || bad_n(Nmax) || !cam1 || !cam2 || !n1 || !n2 || !row_ind || !col_ind || !n_out || !status ||
+        !rows || !match_cost)
+        return PTK_ERR_INVALID_ARG;
+    if (P == 0) return PTK_OK;
+    if (!workspace || workspace_bytes < ptk_workspace_bytes(PTK_WS_MATCH, P, Nmax)) return PTK_ERR_WORKSPACE;
+    const DevRig d = make_devrig(rig);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long chunk = match_chunk(P, Nmax);
+    MatchWs w = carve_match((void*)align_up((size_t)workspace), chunk, Nmax, true);
+    const size_t NN = (size_t)Nmax * Nmax;
+    for (long long p0 = 0; p0 < P; p0 += chunk) {
+        const long long np = (P - p0) < chunk ? (P - p0) : chunk;
+        const size_t o4 = (size_t)p0 * Nmax * 4;
+        double* cchunk = cost ? cost + (size_t)p0 * NN : w.cost;
+        int rc = launch_undistort(d, np, Nmax, cam1 + o4, cam2 + o4, n1 + p0, n2 + p0, w.und1, w.und2, st);
+        if (rc) return rc;
+        rc = launch_cost(d, np, Nmax, cam1 + o4, cam2 + o4, w.und1, w.und2, n1 + p0, n2 + p0, cchunk,
+                         choice ? choice + (size_t)p0 * NN : nullptr, nullptr, nullptr, st);
+        if (rc) return rc;
+        LsapArgs a{};
+        a.ld_rows = Nmax; a.ld_cols = Nmax; a.cost_stride = NN; a.cost = cchunk;
+        a.nr = n1 + p0; a.nc = n2 + p0; a.out_ld = Nmax;
+        a.row_ind = row_ind + (size_t)p0 * Nmax; a.col_ind = col_ind + (size_t)p0 * Nmax;
+        a.n_out = n_out + p0; a.status = status + p0;
+        a.assigned = match_cost + (size_t)p0 * Nmax;
+        a.keep = keep_mask ? keep_mask + (size_t)p0 * Nmax : nullptr;
+        a.max_err = max_repr_err;
+        rc = launch_lsap(np, a, st);
+        if (rc) return rc;
+        rc = launch_rows(d, np, Nmax, cam1 + o4, cam2 + o4, w.und1, w.und2, col_ind + (size_t)p0 * Nmax, n_out + p0,
+                         rows + (size_t)p0 * Nmax * PTK_ROW_COLS, st);
+        if (rc) return rc;
+    }
+    return PTK_OK;
+}
+
+// ------------------------------------------------------------------------------------ K4 (+K2)
+PTK_API int ptk_track_batch(int C, int F, int N, const double* ends, double* cost, int32_t* col_ind,
+                            double* total_cost, int32_t* status, void* workspace, size_t workspace_bytes, void* stream)
+{
+    if (C < 0 || F < 1 || bad_n(N) || !ends || !col_ind || !total_cost) return PTK_ERR_INVALID_ARG;
+    const long long Q = (long long)C * (F - 1);
+    if (Q == 0) return PTK_OK;
+    if (!cost && (!workspace || workspace_bytes < ptk_workspace_bytes(PTK_WS_TRACK, Q, N))) return PTK_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t NN = (size_t)N * N;
+    long long chunk = cost ? Q : match_chunk(Q, N);
+    if (chunk > 65535) chunk = 65535;  // gridDim.y
+    double* wcost = cost ? cost : reinterpret_cast<double*>(align_up((size_t)workspace));
+    for (long long q0 = 0; q0 < Q; q0 += chunk) {
+        const long long nq = (Q - q0) < chunk ? (Q - q0) : chunk;
+        double* cchunk = cost ? cost + (size_t)q0 * NN : wcost;
+        dim3 grid((unsigned)((NN + 255) / 256), (unsigned)nq);
+        k_track_cost<<<grid, 256, 0, st>>>(N, F, q0, ends, cchunk);
+        LAUNCHED("k_track_cost");
+        LsapArgs a{};
+        a.ld_rows = N; a.ld_cols = N; a.cost_stride = NN; a.cost = cchunk;
+        a.out_ld = N;
+        a.col_ind = col_ind + (size_t)q0 * N;
+        a.status = status ? status + q0 : nullptr;
+        a.total = total_cost + q0;
+        a.max_err = INFINITY;
+        int rc = launch_lsap(nq, a, st);
+        if (rc) return rc;
+    }
+    return PTK_OK;
+}
+
+// ------------------------------------------------------------------------------------ K5
+namespace {
+int chain_impl(int C, int F, int N, const int32_t* col_ind, const int32_t* ids_in, int32_t* track_id, int32_t* scratch,
+               cudaStream_t st)
+{
+    const int nseg = (F + kChainSeg - 1) / kChainSeg;
+    int32_t* seg_map = scratch;
+    int32_t* seg_start = scratch + (size_t)C * nseg * N;
+    const int threads = N < 32 ? 32 : ((N + 31) / 32 * 32);
+    const size_t smem = 2 * (size_t)N * sizeof(int32_t);
+    k_chain_local<<<dim3(nseg, C), threads, smem, st>>>(F, N, nseg, col_ind, track_id, seg_map);
+    LAUNCHED("k_chain_local");
+    k_chain_scan<<<C, threads, smem, st>>>(N, nseg, ids_in, seg_map, seg_start);
+    LAUNCHED("k_chain_scan");
+    const long long total = (long long)C * F * N;
+    k_chain_apply<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(F, N, nseg, seg_start, track_id, total);
+    LAUNCHED("k_chain_apply");
+    return PTK_OK;
+}
+size_t chain_scratch_ints(int C, int F, int N)
+{
+    const int nseg = (F + kChainSeg - 1) / kChainSeg;
+    return 2 * (size_t)C * nseg * N;
+}
+}  // namespace
+
+PTK_API int ptk_chain_tracks(int C, int F, int N, const int32_t* col_ind, const int32_t* ids_in, int32_t* track_id,
+                             void* stream)
+{
+    if (C < 0 || F < 1 || bad_n(N) || !track_id || (F > 1 && !col_ind)) return PTK_ERR_INVALID_ARG;
+    if (C == 0) return PTK_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    // segment maps are tiny (2*C*ceil(F/32)*N ints); stream-ordered allocation keeps the ABI simple
+    int32_t* scratch = nullptr;
+    CK(cudaMallocAsync((void**)&scratch, chain_scratch_ints(C, F, N) * sizeof(int32_t) + 16, st));
+    int rc = chain_impl(C, F, N, col_ind, ids_in, track_id, scratch, st);
+    cudaFreeAsync(scratch, st);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------ K6
+PTK_API int ptk_create_weights(int Np, int N1, int N2, const double* p_3D, const double* p_prev, const double* rep_errs,
+                               double* weights, double* choices, void* workspace, size_t workspace_bytes, void* stream)
+{
+    if (Np < 0 || N1 < 0 || N2 < 0 || !p_3D || !p_prev || !rep_errs || !weights || !choices) return PTK_ERR_INVALID_ARG;
+    const long long tot = (long long)Np * N1 * N2;
+    if (tot == 0) return PTK_OK;
+    if (!workspace || workspace_bytes < ptk_workspace_bytes(PTK_WS_WEIGHTS, tot, 0)) return PTK_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    double* bm = reinterpret_cast<double*>(align_up((size_t)workspace));
+    const int nb = (int)((tot + 255) / 256);
+    k_weights_raw<<<nb, 256, 0, st>>>(Np, N1, N2, p_3D, p_prev, rep_errs, weights, choices, bm);
+    LAUNCHED("k_weights_raw");
+    k_weights_finish<<<nb, 256, 0, st>>>(tot, nb, bm, weights);
+    LAUNCHED("k_weights_finish");
+    return PTK_OK;
+}
+
+// ------------------------------------------------------------------------------------ FP64 peak
+PTK_API int ptk_measure_fp64_peak(int iters, double* flops, void* stream)
+{
+    if (iters <= 0 || !flops) return PTK_ERR_INVALID_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0, sms = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    double* out = nullptr;
+    CK(cudaMalloc((void**)&out, sizeof(double)));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    const int blocks = sms * 8, threads = 256;
+    k_dfma_peak<<<blocks, threads, 0, st>>>(iters / 8 + 1, out);  // warm-up
+    LAUNCHED("k_dfma_peak");
+    CK(cudaEventRecord(e0, st));
+    k_dfma_peak<<<blocks, threads, 0, st>>>(iters, out);
+    LAUNCHED("k_dfma_peak");
+    CK(cudaEventRecord(e1, st));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    *flops = 2.0 * 64.0 * (double)iters * blocks * threads / (ms * 1e-3);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    return PTK_OK;
+}
+
+// ------------------------------------------------------------------------------------ host pipeline
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return PTK_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        CK(cudaMalloc(&p, bytes));
+        cap = bytes;
+        return PTK_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct ptk_ctx {
+    int device = 0;
+    cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
+    std::vector<cudaEvent_t> ev_in, ev_comp;
+    cudaEvent_t ev_track = nullptr;
+    DevBuf cam1, cam2, n1, n2, rows, mc, row, col, nout, status, keep, ws;
+    DevBuf ends, tcol, ttot, tid, tstatus, tws, tscratch;
+};
+
+PTK_API int ptk_ctx_create(int device, ptk_ctx** out)
+{
+    if (!out) return PTK_ERR_INVALID_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return PTK_ERR_NO_DEVICE; }
+    if (device < 0 || device >= n) return PTK_ERR_INVALID_ARG;
+    int major = 0;
+    CK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    if (major != 10) return PTK_ERR_NO_DEVICE;
+    CK(cudaSetDevice(device));
+    ptk_ctx* c = new (std::nothrow) ptk_ctx();
+    if (!c) return PTK_ERR_INVALID_ARG;
+    c->device = device;
+    CK(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->ev_track, cudaEventDisableTiming));
+    *out = c;
+    return PTK_OK;
+}
+
+PTK_API void ptk_ctx_destroy(ptk_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    DevBuf* bufs[] = {&c->cam1, &c->cam2, &c->n1, &c->n2, &c->rows, &c->mc, &c->row, &c->col, &c->nout, &c->status,
+                      &c->keep, &c->ws, &c->ends, &c->tcol, &c->ttot, &c->tid, &c->tstatus, &c->tws, &c->tscratch};
+    for (DevBuf* b : bufs) b->release();
+    for (cudaEvent_t e : c->ev_in) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->ev_comp) cudaEventDestroy(e);
+    if (c->ev_track) cudaEventDestroy(c->ev_track);
+    if (c->s_in) cudaStreamDestroy(c->s_in);
+    if (c->s_comp) cudaStreamDestroy(c->s_comp);
+    if (c->s_out) cudaStreamDestroy(c->s_out);
+    delete c;
+}
+
+PTK_API int ptk_reconstruct_host(ptk_ctx* c, const ptk_rig* rig, int F, int C, int Nmax, const double* cam1,
+                                 const double* cam2, const int32_t* n1, const int32_t* n2, double* rows,
+                                 double* match_cost, int32_t* row_ind, int32_t* col_ind, int32_t* n_out,
+                                 int32_t* status, double max_repr_err, uint8_t* keep_mask, int do_track,
+                                 int32_t* track_col, double* track_total, int32_t* track_id, int32_t* track_status)
+{
+    if (!c || !rig || F < 0 || C < 0 || bad_n(Nmax) || !cam1 || !cam2 || !n1 || !n2 || !rows || !n_out || !status)
+        return PTK_ERR_INVALID_ARG;
+    if (do_track && (!track_col || !track_total || F < 1)) return PTK_ERR_INVALID_ARG;
+    const long long P = (long long)F * C;
+    if (P == 0) return PTK_OK;
+    CK(cudaSetDevice(c->device));
+    const DevRig d = make_devrig(rig);
+    const size_t n4 = (size_t)Nmax * 4 * sizeof(double), n18 = (size_t)Nmax * PTK_ROW_COLS * sizeof(double);
+    const size_t nd = (size_t)Nmax * sizeof(double), ni = (size_t)Nmax * sizeof(int32_t);
+
+    // frames per chunk: ~2048 problems, at most 32 chunks
+    int fchunk = (2048 + C - 1) / C;
+    if ((F + fchunk - 1) / fchunk > 32) fchunk = (F + 31) / 32;
+    const int nchunks = (F + fchunk - 1) / fchunk;
+    const long long pchunk = (long long)fchunk * C;
+
+    int rc;
+    if ((rc = c->cam1.ensure(P * n4))) return rc;
+    if ((rc = c->cam2.ensure(P * n4))) return rc;
+    if ((rc = c->n1.ensure(P * sizeof(int32_t)))) return rc;
+    if ((rc = c->n2.ensure(P * sizeof(int32_t)))) return rc;
+    if ((rc = c->rows.ensure(P * n18))) return rc;
+    if ((rc = c->mc.ensure(P * nd))) return rc;
+    if ((rc = c->row.ensure(P * ni))) return rc;
+    if ((rc = c->col.ensure(P * ni))) return rc;
+    if ((rc = c->nout.ensure(P * sizeof(int32_t)))) return rc;
+    if ((rc = c->status.ensure(P * sizeof(int32_t)))) return rc;
+    if (keep_mask && (rc = c->keep.ensure(P * Nmax))) return rc;
+    const size_t wsb = ptk_workspace_bytes(PTK_WS_MATCH, pchunk, Nmax);
+    if ((rc = c->ws.ensure(wsb))) return rc;
+    while ((int)c->ev_in.size() < nchunks) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->ev_in.push_back(e);
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->ev_comp.push_back(e);
+    }
+    const int N = Nmax;
+    const long long Q = (long long)C * (F - 1);
+    if (do_track) {
+        if ((rc = c->ends.ensure((size_t)C * F * N * 6 * sizeof(double)))) return rc;
+        if ((rc = c->tcol.ensure((size_t)(Q > 0 ? Q : 1) * N * sizeof(int32_t)))) return rc;
+        if ((rc = c->ttot.ensure((size_t)(Q > 0 ? Q : 1) * sizeof(double)))) return rc;
+        if ((rc = c->tstatus.ensure((size_t)(Q > 0 ? Q : 1) * sizeof(int32_t)))) return rc;
+        if ((rc = c->tws.ensure(ptk_workspace_bytes(PTK_WS_TRACK, Q > 0 ? Q : 1, N)))) return rc;
+        if (track_id) {
+            if ((rc = c->tid.ensure((size_t)C * F * N * sizeof(int32_t)))) return rc;
+            if ((rc = c->tscratch.ensure(chain_scratch_ints(C, F, N) * sizeof(int32_t) + 16))) return rc;
+        }
+    }
+
+    for (int k = 0; k < nchunks; k++) {
+        const int f0 = k * fchunk;
+        const int fn = (F - f0) < fchunk ? (F - f0) : fchunk;
+        const long long p0 = (long long)f0 * C, np = (long long)fn * C;
+        // H2D
+        CK(cudaMemcpyAsync(c->cam1.as<char>() + p0 * n4, (const char*)cam1 + p0 * n4, np * n4, cudaMemcpyHostToDevice, c->s_in));
+        CK(cudaMemcpyAsync(c->cam2.as<char>() + p0 * n4, (const char*)cam2 + p0 * n4, np * n4, cudaMemcpyHostToDevice, c->s_in));
+        CK(cudaMemcpyAsync(c->n1.as<int32_t>() + p0, n1 + p0, np * sizeof(int32_t), cudaMemcpyHostToDevice, c->s_in));
+        CK(cudaMemcpyAsync(c->n2.as<int32_t>() + p0, n2 + p0, np * sizeof(int32_t), cudaMemcpyHostToDevice, c->s_in));
+        CK(cudaEventRecord(c->ev_in[k], c->s_in));
+        // compute
+        CK(cudaStreamWaitEvent(c->s_comp, c->ev_in[k], 0));
+        rc = ptk_match_batch(rig, (int)np, Nmax, c->cam1.as<double>() + p0 * Nmax * 4, c->cam2.as<double>() + p0 * Nmax * 4,
+                             c->n1.as<int32_t>() + p0, c->n2.as<int32_t>() + p0, nullptr, nullptr,
+                             c->row.as<int32_t>() + p0 * Nmax, c->col.as<int32_t>() + p0 * Nmax,
+                             c->nout.as<int32_t>() + p0, c->status.as<int32_t>() + p0,
+                             c->rows.as<double>() + p0 * Nmax * PTK_ROW_COLS, c->mc.as<double>() + p0 * Nmax, max_repr_err,
+                             keep_mask ? c->keep.as<uint8_t>() + p0 * Nmax : nullptr, c->ws.p, c->ws.cap, c->s_comp);
+        if (rc) return rc;
+        if (do_track) {
+            const long long tot = np * N * 6;
+            k_rows_to_ends<<<(unsigned)((tot + 255) / 256), 256, 0, c->s_comp>>>(
+                f0, fn, F, C, N, Nmax, c->rows.as<double>() + p0 * Nmax * PTK_ROW_COLS, c->ends.as<double>());
+            LAUNCHED("k_rows_to_ends");
+        }
+        CK(cudaEventRecord(c->ev_comp[k], c->s_comp));
+        // D2H
+        CK(cudaStreamWaitEvent(c->s_out, c->ev_comp[k], 0));
+        CK(cudaMemcpyAsync((char*)rows + p0 * n18, c->rows.as<char>() + p0 * n18, np * n18, cudaMemcpyDeviceToHost, c->s_out));
+        if (match_cost) CK(cudaMemcpyAsync((char*)match_cost + p0 * nd, c->mc.as<char>() + p0 * nd, np * nd, cudaMemcpyDeviceToHost, c->s_out));
+        if (row_ind) CK(cudaMemcpyAsync((char*)row_ind + p0 * ni, c->row.as<char>() + p0 * ni, np * ni, cudaMemcpyDeviceToHost, c->s_out));
+        if (col_ind) CK(cudaMemcpyAsync((char*)col_ind + p0 * ni, c->col.as<char>() + p0 * ni, np * ni, cudaMemcpyDeviceToHost, c->s_out));
+        CK(cudaMemcpyAsync(n_out + p0, c->nout.as<int32_t>() + p0, np * sizeof(int32_t), cudaMemcpyDeviceToHost, c->s_out));
+        CK(cudaMemcpyAsync(status + p0, c->status.as<int32_t>() + p0, np * sizeof(int32_t), cudaMemcpyDeviceToHost, c->s_out));
+        if (keep_mask) CK(cudaMemcpyAsync(keep_mask + p0 * Nmax, c->keep.as<uint8_t>() + p0 * Nmax, np * Nmax, cudaMemcpyDeviceToHost, c->s_out));
+    }
+    if (do_track && Q > 0) {
+        rc = ptk_track_batch(C, F, N, c->ends.as<double>(), nullptr, c->tcol.as<int32_t>(), c->ttot.as<double>(),
+                             c->tstatus.as<int32_t>(), c->tws.p, c->tws.cap, c->s_comp);
+        if (rc) return rc;
+        if (track_id) {
+            rc = chain_impl(C, F, N, c->tcol.as<int32_t>(), nullptr, c->tid.as<int32_t>(), c->tscratch.as<int32_t>(), c->s_comp);
+            if (rc) return rc;
+        }
+        CK(cudaEventRecord(c->ev_track, c->s_comp));
+        CK(cudaStreamWaitEvent(c->s_out, c->ev_track, 0));
+        CK(cudaMemcpyAsync(track_col, c->tcol.p, (size_t)Q * N * sizeof(int32_t), cudaMemcpyDeviceToHost, c->s_out));
+        CK(cudaMemcpyAsync(track_total, c->ttot.p, (size_t)Q * sizeof(double), cudaMemcpyDeviceToHost, c->s_out));
+        if (track_status) CK(cudaMemcpyAsync(track_status, c->tstatus.p, (size_t)Q * sizeof(int32_t), cudaMemcpyDeviceToHost, c->s_out));
+        if (track_id) CK(cudaMemcpyAsync(track_id, c->tid.p, (size_t)C * F * N * sizeof(int32_t), cudaMemcpyDeviceToHost, c->s_out));
+    } else if (do_track && track_id && F == 1) {
+        for (int cc = 0; cc < C; cc++)
+            for (int a = 0; a < N; a++) track_id[(size_t)cc * N + a] = a;
+    }
+    CK(cudaStreamSynchronize(c->s_out));
+    CK(cudaStreamSynchronize(c->s_comp));
+    for (long long p = 0; p < P; p++)
+        if (status[p] != PTK_PROBLEM_OK && status[p] != PTK_PROBLEM_EMPTY) return PTK_ERR_NUMERIC;
+    if (do_track && track_status)
+        for (long long q = 0; q < Q; q++)
+            if (track_status[q] != PTK_PROBLEM_OK) return PTK_ERR_NUMERIC;
+    return PTK_OK;
+}

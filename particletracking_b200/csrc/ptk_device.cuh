@@ -1,0 +1,213 @@
+// ptk_device.cuh -- FP64 device math of the stereo hot path (sm_100a).
+//
+// Everything here is plain CUDA-core FP64: the path is ~1300 flop/B, has no
+// dense contraction, so neither tensor cores nor TMA have anything to do; the design rules
+// that matter are (i) keep the 4x4 Jacobi state in registers, (ii) spend FP64-pipe issue
+// slots on FMAs, (iii) keep div/sqrt sequences off the critical loop.
+//
+// The translation unit is compiled with -fmad=false: the compiler never contracts on its
+// own, every fused multiply-add below is an explicit fma().  That makes the arithmetic a
+// pure function of the inputs -- K1 (cost matrix) and K3 (row gather) re-evaluate the same
+// rod pair and must get the same bits -- and lets K0/K4 follow OpenCV's / numpy's unfused
+// operation order exactly where bit-identity with the CPU path is wanted.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/ptk.h"
+
+namespace ptk {
+
+// Device-side copy of the rig, pre-digested (reciprocal focal lengths etc.).
+struct DevRig {
+    double P1[12], P2[12];
+    double R1[9], t1[3], R2[9], t2[3];
+    double CM1[4], CM2[4];  // fx, fy, cx, cy
+    double k1[12], k2[12];  // k1 k2 p1 p2 k3 k4 k5 k6 s1 s2 s3 s4
+    double Rw[9], tw[3];
+    int agg_sum;
+};
+
+// ---------------------------------------------------------------------------------------
+// cv2.undistortImagePoints for one point (reference call sites match2D.py:847,856; SURVEY
+// App. B.1): 5 fixed-point iterations, then re-projection with P = CM.  Unfused arithmetic
+// in OpenCV's operation order: bit-identical to cv2 4.13 on the CPU (tests/test_gpu_*).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void undistort_point(const double* __restrict__ cm, const double* __restrict__ k,
+                                                double u, double v, double& ou, double& ov)
+{
+    const double fx = cm[0], fy = cm[1], cx = cm[2], cy = cm[3];
+    const double ifx = 1.0 / fx, ify = 1.0 / fy;
+    double x = (u - cx) * ifx, y = (v - cy) * ify;
+    const double x0 = x, y0 = y;
+#pragma unroll 1
+    for (int j = 0; j < 5; j++) {
+        double r2 = x * x + y * y;
+        double icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+        if (icdist < 0) {
+            x = (u - cx) * ifx;
+            y = (v - cy) * ify;
+            break;
+        }
+        double dx = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2;
+        double dy = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2;
+        x = (x0 - dx) * icdist;
+        y = (y0 - dy) * icdist;
+    }
+    double xx = fx * x + 0.0 * y + cx;
+    double yy = 0.0 * x + fy * y + cy;
+    double ww = 1.0 / (0.0 * x + 0.0 * y + 1.0);
+    ou = xx * ww;
+    ov = yy * ww;
+}
+
+// ---------------------------------------------------------------------------------------
+// One Jacobi rotation of rows i, j of At (columns of A) and of Vt, as OpenCV's
+// JacobiSVDImpl_<double> does it, restructured for the FP64 pipe:
+//  - the skip test |p| <= eps*sqrt(a*b) is evaluated squared (no sqrt);
+//  - (c, s) come from two rsqrt() instead of hypot + 2 sqrt + 2 div:
+//        g = 1/hypot(2p, beta),  t = (1 + |beta| g)/2,  big = sqrt(t) = t*rsqrt(t),
+//        small = p g rsqrt(t)        (p here is the un-doubled dot product)
+//    which is the same rotation to a few ulp; Jacobi is self-correcting, the column norms
+//    are recomputed from the rotated data exactly as OpenCV does.
+// ---------------------------------------------------------------------------------------
+#define PTK_JACOBI_EPS2 (4.930380657631324e-30) /* (10*DBL_EPSILON)^2 */
+
+__device__ __forceinline__ bool jacobi_pair(double (&Ai)[4], double (&Aj)[4], double (&Vi)[4], double (&Vj)[4],
+                                            double& Wi, double& Wj)
+{
+    double p = Ai[0] * Aj[0];
+    p = fma(Ai[1], Aj[1], p);
+    p = fma(Ai[2], Aj[2], p);
+    p = fma(Ai[3], Aj[3], p);
+    const double a = Wi, b = Wj;
+    if (!(p * p > PTK_JACOBI_EPS2 * (a * b))) return false;  // also false for p == 0
+    const double beta = a - b;
+    const double p2 = p + p;
+    const double g = rsqrt(fma(p2, p2, beta * beta));
+    const double t = fma(fabs(beta), 0.5 * g, 0.5);
+    const double rt = rsqrt(t);
+    const double big = t * rt;
+    const double small_ = p * g * rt;
+    const double c = beta < 0 ? small_ : big;
+    const double s = beta < 0 ? big : small_;
+    double na = 0, nb = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const double x = Ai[k], y = Aj[k];
+        const double t0 = fma(c, x, s * y);
+        const double t1 = fma(c, y, -(s * x));
+        Ai[k] = t0;
+        Aj[k] = t1;
+        na = fma(t0, t0, na);
+        nb = fma(t1, t1, nb);
+    }
+    Wi = na;
+    Wj = nb;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const double x = Vi[k], y = Vj[k];
+        Vi[k] = fma(c, x, s * y);
+        Vj[k] = fma(c, y, -(s * x));
+    }
+    return true;
+}
+
+// cv2.triangulatePoints for one point (match2D.py:889) + the reference's p[0:3]/p[3]
+// (match2D.py:895).  Returns the point in camera-1 coordinates.
+__device__ __forceinline__ void dlt_triangulate(const double* __restrict__ P1, const double* __restrict__ P2,
+                                                double x1, double y1, double x2, double y2,
+                                                double& X, double& Y, double& Z, int* n_rot = nullptr)
+{
+    double A0[4], A1[4], A2[4], A3[4];  // rows of At = columns of the DLT matrix
+    double V0[4] = {1, 0, 0, 0}, V1[4] = {0, 1, 0, 0}, V2[4] = {0, 0, 1, 0}, V3[4] = {0, 0, 0, 1};
+    // At[k][r]: r = 0: x1*P1[2,k]-P1[0,k]; 1: y1*P1[2,k]-P1[1,k]; 2,3: same for view 2
+#define PTK_COL(Ak, k)                       \
+    Ak[0] = fma(x1, P1[8 + k], -P1[0 + k]);  \
+    Ak[1] = fma(y1, P1[8 + k], -P1[4 + k]);  \
+    Ak[2] = fma(x2, P2[8 + k], -P2[0 + k]);  \
+    Ak[3] = fma(y2, P2[8 + k], -P2[4 + k]);
+    PTK_COL(A0, 0) PTK_COL(A1, 1) PTK_COL(A2, 2) PTK_COL(A3, 3)
+#undef PTK_COL
+    double W0, W1, W2, W3;
+#define PTK_NRM(Ak) fma(Ak[3], Ak[3], fma(Ak[2], Ak[2], fma(Ak[1], Ak[1], Ak[0] * Ak[0])))
+    W0 = PTK_NRM(A0); W1 = PTK_NRM(A1); W2 = PTK_NRM(A2); W3 = PTK_NRM(A3);
+    int rot = 0;
+#pragma unroll 1
+    for (int iter = 0; iter < 30; iter++) {
+        bool ch = false;
+        bool r;
+        r = jacobi_pair(A0, A1, V0, V1, W0, W1); ch |= r; rot += r;
+        r = jacobi_pair(A0, A2, V0, V2, W0, W2); ch |= r; rot += r;
+        r = jacobi_pair(A0, A3, V0, V3, W0, W3); ch |= r; rot += r;
+        r = jacobi_pair(A1, A2, V1, V2, W1, W2); ch |= r; rot += r;
+        r = jacobi_pair(A1, A3, V1, V3, W1, W3); ch |= r; rot += r;
+        r = jacobi_pair(A2, A3, V2, V3, W2, W3); ch |= r; rot += r;
+        if (!ch) break;
+    }
+    if (n_rot) *n_rot = rot;
+    // W already holds the squared column norms of the final A V (recomputed by every rotation,
+    // exactly what OpenCV's closing pass computes before its sqrt); smallest wins, ties -> later
+    // row, matching OpenCV's descending selection sort for the generic case.
+    double wm = W0, vx = V0[0], vy = V0[1], vz = V0[2], vw = V0[3];
+    if (W1 <= wm) { wm = W1; vx = V1[0]; vy = V1[1]; vz = V1[2]; vw = V1[3]; }
+    if (W2 <= wm) { wm = W2; vx = V2[0]; vy = V2[1]; vz = V2[2]; vw = V2[3]; }
+    if (W3 <= wm) { wm = W3; vx = V3[0]; vy = V3[1]; vz = V3[2]; vw = V3[3]; }
+#undef PTK_NRM
+    X = vx / vw;
+    Y = vy / vw;
+    Z = vz / vw;
+}
+
+// cv2.projectPoints for one point (match2D.py:898-903) and the distance to
+// the original (distorted) detection (match2D.py:905-910).
+__device__ __forceinline__ double reproject_dist(const double* __restrict__ R, const double* __restrict__ t,
+                                                 const double* __restrict__ cm, const double* __restrict__ k,
+                                                 double X, double Y, double Z, double ou, double ov)
+{
+    double x = fma(R[2], Z, fma(R[1], Y, R[0] * X)) + t[0];
+    double y = fma(R[5], Z, fma(R[4], Y, R[3] * X)) + t[1];
+    double z = fma(R[8], Z, fma(R[7], Y, R[6] * X)) + t[2];
+    z = (z != 0.0) ? 1.0 / z : 1.0;
+    x *= z;
+    y *= z;
+    const double r2 = fma(x, x, y * y), r4 = r2 * r2, r6 = r4 * r2;
+    const double a1 = 2 * x * y, a2 = fma(2 * x, x, r2), a3 = fma(2 * y, y, r2);
+    const double cdist = fma(k[4], r6, fma(k[1], r4, fma(k[0], r2, 1.0)));
+    const double icdist2 = 1.0 / fma(k[7], r6, fma(k[6], r4, fma(k[5], r2, 1.0)));
+    const double rad = cdist * icdist2;
+    const double xd = fma(k[9], r4, fma(k[8], r2, fma(k[3], a2, fma(k[2], a1, x * rad))));
+    const double yd = fma(k[11], r4, fma(k[10], r2, fma(k[3], a1, fma(k[2], a3, y * rad))));
+    const double ex = ou - fma(xd, cm[0], cm[2]);
+    const double ey = ov - fma(yd, cm[1], cm[3]);
+    return sqrt(fma(ex, ex, ey * ey));
+}
+
+// One end-point combination (match2D.py:889-913): triangulate the undistorted pair, reproject
+// into both cameras, per-camera distances d1, d2, and the point in camera-1 coordinates.
+__device__ __forceinline__ void eval_combo(const DevRig& rig, double u1x, double u1y, double u2x, double u2y,
+                                           double o1x, double o1y, double o2x, double o2y,
+                                           double& d1, double& d2, double& X, double& Y, double& Z)
+{
+    dlt_triangulate(rig.P1, rig.P2, u1x, u1y, u2x, u2y, X, Y, Z);
+    d1 = reproject_dist(rig.R1, rig.t1, rig.CM1, rig.k1, X, Y, Z, o1x, o1y);
+    d2 = reproject_dist(rig.R2, rig.t2, rig.CM2, rig.k2, X, Y, Z, o2x, o2y);
+}
+
+// match2D.py:913: X_w = rot.apply(X) + trans
+__device__ __forceinline__ void to_world(const DevRig& rig, double X, double Y, double Z,
+                                         double& wx, double& wy, double& wz)
+{
+    wx = fma(rig.Rw[2], Z, fma(rig.Rw[1], Y, rig.Rw[0] * X)) + rig.tw[0];
+    wy = fma(rig.Rw[5], Z, fma(rig.Rw[4], Y, rig.Rw[3] * X)) + rig.tw[1];
+    wz = fma(rig.Rw[8], Z, fma(rig.Rw[7], Y, rig.Rw[6] * X)) + rig.tw[2];
+}
+
+// np.min([a, b]) -- propagates NaN (match2D.py:923-930, tracking.py:118)
+__device__ __forceinline__ double np_min(double a, double b)
+{
+    return (a != a) ? a : ((b != b) ? b : (b < a ? b : a));
+}
+
+}  // namespace ptk

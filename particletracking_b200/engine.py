@@ -1,0 +1,299 @@
+"""Tensor-level API of the CUDA hot path: PyTorch owns device memory and streams,
+``libptk.so`` does the work (``include/ptk.h``).  Everything the reference-shaped
+functions in ``reconstruct_3D/`` do goes through here.
+
+No CPU fallback: every function raises if the tensors are not CUDA tensors / the
+library is missing.
+"""
+from __future__ import annotations
+
+import ctypes
+import dataclasses
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from .rig import PtkRig
+
+_f64, _i32, _u8 = torch.float64, torch.int32, torch.uint8
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("particletracking_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor")
+    if t.dtype != dtype:
+        raise ValueError(f"{name} must be {dtype}, got {t.dtype}")
+    return t.contiguous()
+
+
+class _Workspace:
+    """Per-thread, per-device scratch (the callers run one worker per colour)."""
+
+    def __init__(self):
+        import threading
+
+        self._tls = threading.local()
+
+    def get(self, nbytes: int, device) -> torch.Tensor:
+        key = f"ws_{device}"
+        buf = getattr(self._tls, key, None)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+            setattr(self._tls, key, buf)
+        return buf
+
+
+_ws = _Workspace()
+
+
+@dataclasses.dataclass
+class MatchResult:
+    rows: torch.Tensor        # [P,Nmax,18] float64, NaN beyond n_out
+    match_cost: torch.Tensor  # [P,Nmax]
+    row_ind: torch.Tensor     # [P,Nmax] int32, -1 beyond n_out
+    col_ind: torch.Tensor
+    n_out: torch.Tensor       # [P] int32
+    status: torch.Tensor      # [P] int32 (PTK_PROBLEM_*)
+    cost: Optional[torch.Tensor] = None    # [P,Nmax,Nmax] if requested
+    choice: Optional[torch.Tensor] = None  # [P,Nmax,Nmax] uint8 if requested
+    keep: Optional[torch.Tensor] = None    # [P,Nmax] uint8 if max_repr_err given
+
+
+def undistort_batch(rig: PtkRig, cam1, cam2, n1, n2):
+    """K0: quirk-exact undistortion (reference match2D.py:846-863)."""
+    _require_cuda()
+    cam1, cam2 = _chk(cam1, _f64, "cam1"), _chk(cam2, _f64, "cam2")
+    n1, n2 = _chk(n1, _i32, "n1"), _chk(n2, _i32, "n2")
+    P, Nmax = cam1.shape[:2]
+    u1 = torch.full_like(cam1, float("nan"))
+    u2 = torch.full_like(cam2, float("nan"))
+    with torch.cuda.device(cam1.device):
+        nat.check(nat.lib().ptk_undistort_batch(ctypes.byref(rig), P, Nmax, _ptr(cam1), _ptr(cam2), _ptr(n1), _ptr(n2),
+                                                _ptr(u1), _ptr(u2), _stream()), "ptk_undistort_batch")
+    return u1, u2
+
+
+def cost_batch(rig: PtkRig, cam1, cam2, n1, n2, want_choice=True, want_combos=False):
+    """K0+K1: cost[P,Nmax,Nmax] (+choice, +per-combo world points / reprojection errors)."""
+    _require_cuda()
+    cam1, cam2 = _chk(cam1, _f64, "cam1"), _chk(cam2, _f64, "cam2")
+    n1, n2 = _chk(n1, _i32, "n1"), _chk(n2, _i32, "n2")
+    P, Nmax = cam1.shape[:2]
+    dev = cam1.device
+    cost = torch.full((P, Nmax, Nmax), float("nan"), dtype=_f64, device=dev)
+    choice = torch.zeros((P, Nmax, Nmax), dtype=_u8, device=dev) if want_choice else None
+    pw = torch.full((P, Nmax, Nmax, 4, 3), float("nan"), dtype=_f64, device=dev) if want_combos else None
+    re = torch.full((P, Nmax, Nmax, 4, 2), float("nan"), dtype=_f64, device=dev) if want_combos else None
+    nb = nat.lib().ptk_workspace_bytes(nat.WS_COST, P, Nmax)
+    ws = _ws.get(nb, dev)
+    with torch.cuda.device(dev):
+        nat.check(nat.lib().ptk_cost_batch(ctypes.byref(rig), P, Nmax, _ptr(cam1), _ptr(cam2), _ptr(n1), _ptr(n2),
+                                           _ptr(cost), _ptr(choice), _ptr(pw), _ptr(re), _ptr(ws), ws.numel(), _stream()),
+                  "ptk_cost_batch")
+    return cost, choice, pw, re
+
+
+def lsap_batch(cost: torch.Tensor, nr: Optional[torch.Tensor] = None, nc: Optional[torch.Tensor] = None):
+    """K2: batched scipy-exact linear_sum_assignment.  cost[P,R,C] -> row_ind, col_ind, n_out, status."""
+    _require_cuda()
+    cost = _chk(cost, _f64, "cost")
+    P, R, C = cost.shape
+    dev = cost.device
+    k = min(R, C)
+    row = torch.empty((P, k), dtype=_i32, device=dev)
+    col = torch.empty((P, k), dtype=_i32, device=dev)
+    n_out = torch.empty((P,), dtype=_i32, device=dev)
+    status = torch.empty((P,), dtype=_i32, device=dev)
+    if nr is not None:
+        nr = _chk(nr, _i32, "nr")
+    if nc is not None:
+        nc = _chk(nc, _i32, "nc")
+    with torch.cuda.device(dev):
+        nat.check(nat.lib().ptk_lsap_batch(P, R, C, _ptr(cost), _ptr(nr), _ptr(nc), _ptr(row), _ptr(col), _ptr(n_out),
+                                           _ptr(status), _stream()), "ptk_lsap_batch")
+    return row, col, n_out, status
+
+
+def match_batch(rig: PtkRig, cam1, cam2, n1, n2, want_cost=False, max_repr_err: Optional[float] = None) -> MatchResult:
+    """K0..K3: the whole ``match_frame`` body (match2D.py:843-983) for P problems."""
+    _require_cuda()
+    cam1, cam2 = _chk(cam1, _f64, "cam1"), _chk(cam2, _f64, "cam2")
+    n1, n2 = _chk(n1, _i32, "n1"), _chk(n2, _i32, "n2")
+    P, Nmax = cam1.shape[:2]
+    if cam2.shape[:2] != (P, Nmax) or n1.numel() != P or n2.numel() != P:
+        raise ValueError("cam1/cam2 must be [P,Nmax,2,2] with n1/n2 [P]")
+    dev = cam1.device
+    rows = torch.empty((P, Nmax, nat.ROW_COLS), dtype=_f64, device=dev)
+    mc = torch.empty((P, Nmax), dtype=_f64, device=dev)
+    row = torch.empty((P, Nmax), dtype=_i32, device=dev)
+    col = torch.empty((P, Nmax), dtype=_i32, device=dev)
+    n_out = torch.empty((P,), dtype=_i32, device=dev)
+    status = torch.empty((P,), dtype=_i32, device=dev)
+    cost = torch.full((P, Nmax, Nmax), float("nan"), dtype=_f64, device=dev) if want_cost else None
+    choice = torch.zeros((P, Nmax, Nmax), dtype=_u8, device=dev) if want_cost else None
+    keep = torch.empty((P, Nmax), dtype=_u8, device=dev) if max_repr_err is not None else None
+    nb = nat.lib().ptk_workspace_bytes(nat.WS_MATCH, P, Nmax)
+    ws = _ws.get(nb, dev)
+    thr = float("inf") if max_repr_err is None else float(max_repr_err)
+    with torch.cuda.device(dev):
+        nat.check(nat.lib().ptk_match_batch(ctypes.byref(rig), P, Nmax, _ptr(cam1), _ptr(cam2), _ptr(n1), _ptr(n2),
+                                            _ptr(cost), _ptr(choice), _ptr(row), _ptr(col), _ptr(n_out), _ptr(status),
+                                            _ptr(rows), _ptr(mc), thr, _ptr(keep), _ptr(ws), ws.numel(), _stream()),
+                  "ptk_match_batch")
+    return MatchResult(rows, mc, row, col, n_out, status, cost, choice, keep)
+
+
+def track_batch(ends: torch.Tensor, want_cost=False):
+    """K4+K2: ``tracking_global_assignment`` (tracking.py:97-123,136-137) for C colours.
+    ends[C,F,N,2,3] -> col_ind[C,F-1,N], total_cost[C,F-1], status[C,F-1] (, cost[C,F-1,N,N])."""
+    _require_cuda()
+    ends = _chk(ends, _f64, "ends")
+    C, F, N = ends.shape[:3]
+    dev = ends.device
+    col = torch.empty((C, max(F - 1, 0), N), dtype=_i32, device=dev)
+    tot = torch.empty((C, max(F - 1, 0)), dtype=_f64, device=dev)
+    status = torch.empty((C, max(F - 1, 0)), dtype=_i32, device=dev)
+    cost = torch.empty((C, max(F - 1, 0), N, N), dtype=_f64, device=dev) if want_cost else None
+    nb = nat.lib().ptk_workspace_bytes(nat.WS_TRACK, max(C * (F - 1), 1), N)
+    ws = _ws.get(nb, dev)
+    with torch.cuda.device(dev):
+        nat.check(nat.lib().ptk_track_batch(C, F, N, _ptr(ends), _ptr(cost), _ptr(col), _ptr(tot), _ptr(status),
+                                            _ptr(ws), ws.numel(), _stream()), "ptk_track_batch")
+    return col, tot, status, cost
+
+
+def chain_tracks(col_ind: torch.Tensor, ids_in: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """K5 (extension): col_ind[C,F-1,N] -> track_id[C,F,N]."""
+    _require_cuda()
+    col_ind = _chk(col_ind, _i32, "col_ind")
+    C, Fm1, N = col_ind.shape
+    out = torch.empty((C, Fm1 + 1, N), dtype=_i32, device=col_ind.device)
+    if ids_in is not None:
+        ids_in = _chk(ids_in, _i32, "ids_in")
+    with torch.cuda.device(col_ind.device):
+        nat.check(nat.lib().ptk_chain_tracks(C, Fm1 + 1, N, _ptr(col_ind), _ptr(ids_in), _ptr(out), _stream()),
+                  "ptk_chain_tracks")
+    return out
+
+
+def create_weights(p_3D: torch.Tensor, p_prev: torch.Tensor, rep_errs: torch.Tensor):
+    """K6: ``matchND.create_weights`` (matchND.py:141-217)."""
+    _require_cuda()
+    p_3D, p_prev, rep_errs = _chk(p_3D, _f64, "p_3D"), _chk(p_prev, _f64, "p_prev"), _chk(rep_errs, _f64, "rep_errs")
+    N1, N2 = p_3D.shape[:2]
+    Np = p_prev.shape[0]
+    dev = p_3D.device
+    w = torch.empty((Np, N1, N2), dtype=_f64, device=dev)
+    ch = torch.empty((Np, N1, N2), dtype=_f64, device=dev)
+    nb = nat.lib().ptk_workspace_bytes(nat.WS_WEIGHTS, Np * N1 * N2, 0)
+    ws = _ws.get(nb, dev)
+    with torch.cuda.device(dev):
+        nat.check(nat.lib().ptk_create_weights(Np, N1, N2, _ptr(p_3D), _ptr(p_prev), _ptr(rep_errs), _ptr(w), _ptr(ch),
+                                               _ptr(ws), ws.numel(), _stream()), "ptk_create_weights")
+    return w, ch
+
+
+def measure_fp64_peak(iters: int = 20000) -> float:
+    """FLOP/s of a dependency-free DFMA loop on the current device (roofline denominator)."""
+    _require_cuda()
+    out = ctypes.c_double(0.0)
+    nat.check(nat.lib().ptk_measure_fp64_peak(int(iters), ctypes.byref(out), _stream()), "ptk_measure_fp64_peak")
+    return out.value
+
+
+def launch_count(reset: bool = False) -> int:
+    return int(nat.lib().ptk_launch_count(1 if reset else 0))
+
+
+# ----------------------------------------------------------------------------------------
+class HostPipeline:
+    """Host-buffer entry point (``ptk_reconstruct_host``): numpy / pinned-torch arrays in,
+    arrays out, copies chunked over frames and overlapped with compute inside the library.
+    This is what ``match_csv_complex`` and bench.py's ``e2e`` use."""
+
+    def __init__(self, device: int = 0):
+        _require_cuda()
+        self._ctx = ctypes.c_void_p()
+        nat.check(nat.lib().ptk_ctx_create(int(device), ctypes.byref(self._ctx)), "ptk_ctx_create")
+        self.device = device
+        self._out = {}
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            nat.lib().ptk_ctx_destroy(self._ctx)
+            self._ctx = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _buf(self, name, shape, dtype):
+        """Pinned output buffers, reused across calls of the same shape."""
+        t = self._out.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.empty(shape, dtype=dtype, pin_memory=True)
+            self._out[name] = t
+        return t
+
+    def reconstruct(self, rig: PtkRig, cam1, cam2, n1, n2, track: bool = False, max_repr_err: Optional[float] = None,
+                    raise_on_invalid: bool = True):
+        """cam1, cam2: [F,C,Nmax,2,2] float64 host (numpy or CPU torch, ideally pinned);
+        n1, n2: [F,C] int32.  Returns a dict of pinned CPU torch tensors (views reused by the
+        next call -- copy what you keep)."""
+        c1, c2 = _as_host(cam1, _f64), _as_host(cam2, _f64)
+        m1, m2 = _as_host(n1, _i32), _as_host(n2, _i32)
+        F, C, Nmax = c1.shape[:3]
+        rows = self._buf("rows", (F, C, Nmax, nat.ROW_COLS), _f64)
+        mc = self._buf("mc", (F, C, Nmax), _f64)
+        row = self._buf("row", (F, C, Nmax), _i32)
+        col = self._buf("col", (F, C, Nmax), _i32)
+        n_out = self._buf("n_out", (F, C), _i32)
+        status = self._buf("status", (F, C), _i32)
+        keep = self._buf("keep", (F, C, Nmax), _u8) if max_repr_err is not None else None
+        tcol = ttot = tid = tst = None
+        if track:
+            tcol = self._buf("tcol", (C, max(F - 1, 0), Nmax), _i32)
+            ttot = self._buf("ttot", (C, max(F - 1, 0)), _f64)
+            tid = self._buf("tid", (C, F, Nmax), _i32)
+            tst = self._buf("tst", (C, max(F - 1, 0)), _i32)
+        thr = float("inf") if max_repr_err is None else float(max_repr_err)
+        rc = nat.lib().ptk_reconstruct_host(self._ctx, ctypes.byref(rig), F, C, Nmax, _ptr(c1), _ptr(c2), _ptr(m1), _ptr(m2),
+                                            _ptr(rows), _ptr(mc), _ptr(row), _ptr(col), _ptr(n_out), _ptr(status), thr,
+                                            _ptr(keep), 1 if track else 0, _ptr(tcol), _ptr(ttot), _ptr(tid), _ptr(tst))
+        if rc == nat.PTK_ERR_NUMERIC:
+            if raise_on_invalid:
+                # scipy raises ValueError from linear_sum_assignment (match2D.py:933, tracking.py:122)
+                raise ValueError("matrix contains invalid numeric entries")
+        else:
+            nat.check(rc, "ptk_reconstruct_host")
+        return dict(rows=rows, match_cost=mc, row_ind=row, col_ind=col, n_out=n_out, status=status, keep=keep,
+                    track_col=tcol, track_total=ttot, track_id=tid, track_status=tst)
+
+
+def _as_host(a, dtype) -> torch.Tensor:
+    if isinstance(a, np.ndarray):
+        t = torch.from_numpy(np.ascontiguousarray(a))
+    else:
+        t = a
+    if t.is_cuda:
+        raise ValueError("HostPipeline takes host buffers")
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()

@@ -1,0 +1,364 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI
+(particletracking_b200.engine -> libptk.so), against the oracle on the same seeded inputs
+and against the committed goldens made by the unmodified reference.
+
+Bars (BASELINE.json north_star): assignments / track ids bit-exact; coordinates and
+reprojection errors within TOL = 1e-9 norm-relative (max|a-b| / max(max|b|, 1))."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device")
+    from particletracking_b200 import engine
+
+    return engine
+
+
+@pytest.fixture(scope="module")
+def crig(rig):
+    from particletracking_b200 import rig as rigmod
+
+    return rigmod.rig_from_dicts(rig["calibration"], rig["transformation"])
+
+
+def dev(a, dtype=None):
+    import torch
+
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def run_match(eng, crig, cam1, cam2, n1, n2, **kw):
+    import torch
+
+    r = eng.match_batch(crig, dev(cam1), dev(cam2), dev(n1, torch.int32), dev(n2, torch.int32), **kw)
+    torch.cuda.synchronize()
+    return r
+
+
+# ------------------------------------------------------------------ K0
+def test_undistort_bit_exact(eng, crig, rig):
+    """K0 follows OpenCV's unfused operation order: identical bits to cv2 (via the C oracle,
+    itself bit-exact vs cv2 in tests/test_oracle_cpu.py), including N == 1 and ragged n."""
+    import torch
+    from oracle import c_oracle as co
+
+    rng = np.random.default_rng(0)
+    P, Nmax = 40, 33
+    cam1 = rng.uniform(50, 1250, size=(P, Nmax, 2, 2))
+    cam2 = rng.uniform(50, 1250, size=(P, Nmax, 2, 2))
+    n1 = rng.integers(0, Nmax + 1, size=P).astype(np.int32)
+    n2 = rng.integers(0, Nmax + 1, size=P).astype(np.int32)
+    n1[:3] = [1, 2, Nmax]
+    n2[:3] = [1, 1, Nmax]
+    cam1[5, 0] = -1.0  # dummy rod
+    u1, u2 = eng.undistort_batch(crig, dev(cam1), dev(cam2), dev(n1), dev(n2))
+    u1, u2 = u1.cpu().numpy(), u2.cpu().numpy()
+    cal = rig["calibration"]
+    for p in range(P):
+        np.testing.assert_array_equal(u1[p, : n1[p]], co.undistort_rods(cal["CM1"], cal["dist1"], cam1[p, : n1[p]]))
+        np.testing.assert_array_equal(u2[p, : n2[p]], co.undistort_rods(cal["CM2"], cal["dist2"], cam2[p, : n2[p]]))
+
+
+# ------------------------------------------------------------------ K1
+@pytest.mark.parametrize("agg_sum", [False, True])
+def test_cost_matrix_and_combos_vs_oracle(eng, rig, agg_sum):
+    import torch
+    from oracle import c_oracle as co
+    from particletracking_b200 import rig as rigmod
+    from particletracking_b200 import synthetic as syn
+
+    r = rigmod.rig_from_dicts(rig["calibration"], rig["transformation"], agg_sum=agg_sum)
+    data = syn.make_stereo(2, 2, 20, seed=31, p_drop=0.15, p_dummy=0.05)
+    c1, c2, n1, n2 = data.problems()
+    cost, choice, pw, re = eng.cost_batch(r, dev(c1), dev(c2), dev(n1), dev(n2), want_combos=True)
+    cost, choice, pw, re = (x.cpu().numpy() for x in (cost, choice, pw, re))
+    for p in range(len(n1)):
+        o = co.cost_problem(r, c1[p, : n1[p]], c2[p, : n2[p]], want_combos=True)
+        a, b = n1[p], n2[p]
+        assert rel_err(cost[p, :a, :b], o["cost"]) < TOL
+        np.testing.assert_array_equal(choice[p, :a, :b].astype(bool), o["choice"])
+        assert rel_err(re[p, :a, :b], o["rep_errs"]) < TOL
+        # 3D: norm-relative per point
+        d = np.abs(pw[p, :a, :b] - o["p_world"]).max(axis=-1)
+        s = np.maximum(np.abs(o["p_world"]).max(axis=-1), 1.0)
+        assert (d / s).max() < TOL
+
+
+# ------------------------------------------------------------------ K2
+def test_lsap_identical_to_scipy(eng):
+    import torch
+    from scipy.optimize import linear_sum_assignment
+    from test_oracle_cpu import _lsap_cases
+
+    cases = _lsap_cases()
+    R = max(c.shape[0] for c in cases)
+    Cc = max(c.shape[1] for c in cases)
+    P = len(cases)
+    cost = np.full((P, R, Cc), np.nan)
+    nr = np.zeros(P, dtype=np.int32)
+    nc = np.zeros(P, dtype=np.int32)
+    for p, c in enumerate(cases):
+        cost[p, : c.shape[0], : c.shape[1]] = c
+        nr[p], nc[p] = c.shape
+    row, col, n_out, status = eng.lsap_batch(dev(cost), dev(nr), dev(nc))
+    row, col, n_out, status = (x.cpu().numpy() for x in (row, col, n_out, status))
+    assert (status == 0).all()
+    for p, c in enumerate(cases):
+        er, ec = linear_sum_assignment(c)
+        k = len(er)
+        assert n_out[p] == k
+        np.testing.assert_array_equal(row[p, :k], er)
+        np.testing.assert_array_equal(col[p, :k], ec)
+        assert (row[p, k:] == -1).all() and (col[p, k:] == -1).all()
+
+
+def test_lsap_large_and_status_codes(eng):
+    import torch
+    from scipy.optimize import linear_sum_assignment
+
+    rng = np.random.default_rng(5)
+    # N = 256 (BASELINE config 5 upper end), random + tied + separable
+    mats = [rng.random((256, 256)), rng.integers(0, 8, size=(256, 256)).astype(float),
+            rng.random(256)[:, None] + rng.random(256)[None, :], rng.random((200, 256)), rng.random((256, 190))]
+    cost = np.full((len(mats) + 3, 256, 256), 0.5)
+    nr = np.full(len(cost), 4, dtype=np.int32)
+    nc = np.full(len(cost), 4, dtype=np.int32)
+    for p, m in enumerate(mats):
+        cost[p, : m.shape[0], : m.shape[1]] = m
+        nr[p], nc[p] = m.shape
+    k = len(mats)
+    cost[k, 1, 2] = np.nan            # -> INVALID (scipy: ValueError)
+    cost[k + 1, :4, :4] = np.inf      # -> INFEASIBLE
+    nr[k + 2] = 0                     # -> EMPTY
+    row, col, n_out, status = (x.cpu().numpy() for x in eng.lsap_batch(dev(cost), dev(nr), dev(nc)))
+    np.testing.assert_array_equal(status[k:], [1, 2, 3])
+    assert (n_out[k:] == 0).all() and (col[k:] == -1).all()
+    for p, m in enumerate(mats):
+        er, ec = linear_sum_assignment(m)
+        np.testing.assert_array_equal(row[p, : len(er)], er)
+        np.testing.assert_array_equal(col[p, : len(ec)], ec)
+
+
+# ------------------------------------------------------------------ K0..K3 vs goldens (reference outputs)
+@pytest.mark.parametrize("name", ["c1_3x12.npz", "ragged_2x16.npz", "tiny_n1.npz", "tiny_n2.npz", "n32.npz"])
+def test_match_batch_vs_reference_goldens(eng, crig, name):
+    g = np.load(os.path.join(GOLDEN, name))
+    F, C, Nm = g["cam1"].shape[:3]
+    r = run_match(eng, crig, g["cam1"].reshape(F * C, Nm, 2, 2), g["cam2"].reshape(F * C, Nm, 2, 2),
+                  g["n1"].ravel(), g["n2"].ravel(), want_cost=True)
+    rows, mc, row, col, n_out, status, cost = (x.cpu().numpy() for x in
+                                               (r.rows, r.match_cost, r.row_ind, r.col_ind, r.n_out, r.status, r.cost))
+    assert (status == 0).all()
+    np.testing.assert_array_equal(n_out, g["n_out"].ravel())
+    np.testing.assert_array_equal(row, g["row_ind"].reshape(F * C, Nm))   # bit-exact assignments
+    np.testing.assert_array_equal(col, g["col_ind"].reshape(F * C, Nm))
+    for p in range(F * C):
+        f, c = divmod(p, C)
+        a, b, n = g["n1"][f, c], g["n2"][f, c], g["n_out"][f, c]
+        np.testing.assert_array_equal(rows[p, :n, 10:], g["rows"][f, c, :n, 10:])  # 2D columns exact
+        assert np.isnan(rows[p, n:]).all() and np.isnan(mc[p, n:]).all()
+        for k in range(n):  # 3D end points / centre: norm-relative per point
+            for s in (slice(0, 3), slice(3, 6), slice(6, 9)):
+                assert rel_err(rows[p, k, s], g["rows"][f, c, k, s]) < TOL
+        assert rel_err(rows[p, :n, 9], g["lengths"][f, c, :n]) < TOL
+        assert rel_err(cost[p, :a, :b], g["cost"][f, c, :a, :b]) < TOL
+        assert rel_err(mc[p, :n], g["costs"][f, c, :n]) < TOL
+
+
+@pytest.mark.parametrize("n,drop,dummy,seed", [(12, 0.0, 0.0, 1), (32, 0.0, 0.0, 2), (24, 0.2, 0.1, 3),
+                                               (64, 0.03, 0.02, 4), (7, 0.5, 0.0, 5)])
+def test_match_batch_vs_c_oracle(eng, crig, n, drop, dummy, seed):
+    from oracle import c_oracle as co
+    from particletracking_b200 import synthetic as syn
+
+    data = syn.make_stereo(6, 3, n, seed=seed, p_drop=drop, p_dummy=dummy, sigma_px=0.5)
+    c1, c2, n1, n2 = data.problems()
+    o = co.match_batch(crig, c1, c2, n1, n2, want_cost=True)
+    r = run_match(eng, crig, c1, c2, n1, n2, want_cost=True, max_repr_err=5.0)
+    np.testing.assert_array_equal(r.status.cpu().numpy(), o["status"])
+    np.testing.assert_array_equal(r.n_out.cpu().numpy(), o["n_out"])
+    np.testing.assert_array_equal(r.row_ind.cpu().numpy(), o["row_ind"])
+    np.testing.assert_array_equal(r.col_ind.cpu().numpy(), o["col_ind"])
+    rows, mc, keep = r.rows.cpu().numpy(), r.match_cost.cpu().numpy(), r.keep.cpu().numpy()
+    for p in range(len(n1)):
+        k = o["n_out"][p]
+        np.testing.assert_array_equal(rows[p, :k, 10:], o["rows"][p, :k, 10:])
+        assert rel_err(rows[p, :k, :10], o["rows"][p, :k, :10]) < TOL
+        assert rel_err(mc[p, :k], o["match_cost"][p, :k]) < TOL
+        # threshold extension: mask over the returned costs, nothing else changes
+        np.testing.assert_array_equal(keep[p, :k].astype(bool), mc[p, :k] <= 5.0)
+        assert (keep[p, k:] == 0).all()
+
+
+def test_match_loop_index_quirk_n1_gt_n2(eng, crig, rig):
+    """N1 > N2: output row m pairs cam1 rod m (not row_ind[m]) with cam2 rod col_ind[m], while
+    costs[m] = cost[row_ind[m], col_ind[m]] -- checked against the numpy port,
+    which was checked against the reference."""
+    from oracle import port
+    from particletracking_b200 import synthetic as syn
+
+    data = syn.make_stereo(1, 1, 14, seed=77)
+    c1, c2 = data.cam1[0, 0], data.cam2[0, 0, :9]
+    n1, n2 = np.array([14], dtype=np.int32), np.array([9], dtype=np.int32)
+    cam2 = np.full((1, 14, 2, 2), np.nan)
+    cam2[0, :9] = c2
+    r = run_match(eng, crig, c1[None], cam2, n1, n2)
+    ref = port.match_arrays(c1, c2, rig["calibration"], rig["P1"], rig["P2"], rig["rot"], rig["trans"],
+                            rig["r1"], rig["r2"], rig["t1"], rig["t2"])
+    assert not np.array_equal(ref["row_ind"], np.arange(9))  # the quirk is actually exercised
+    np.testing.assert_array_equal(r.row_ind.cpu().numpy()[0, :9], ref["row_ind"])
+    np.testing.assert_array_equal(r.col_ind.cpu().numpy()[0, :9], ref["col_ind"])
+    rows = r.rows.cpu().numpy()[0, :9]
+    np.testing.assert_array_equal(rows[:, 10:], ref["rows"][:, 10:])
+    assert rel_err(rows[:, :10], ref["rows"][:, :10]) < TOL
+    assert rel_err(r.match_cost.cpu().numpy()[0, :9], ref["costs"]) < TOL
+
+
+def test_match_nan_rod_reports_invalid(eng, crig):
+    """A partially-NaN rod survives the reference's filter and makes scipy raise ValueError
+    (SURVEY App. A.1); the batch reports it per problem and leaves the others intact."""
+    from particletracking_b200 import synthetic as syn
+
+    data = syn.make_stereo(1, 3, 8, seed=9)
+    c1, c2, n1, n2 = data.problems()
+    c1 = c1.copy()
+    c1[1, 2, 0, 0] = np.nan
+    n1 = n1.copy()
+    n1[2] = 0
+    r = run_match(eng, crig, c1, c2, n1, n2)
+    np.testing.assert_array_equal(r.status.cpu().numpy(), [0, 1, 3])
+    np.testing.assert_array_equal(r.n_out.cpu().numpy(), [8, 0, 0])
+    assert np.isnan(r.rows.cpu().numpy()[1:]).all()
+
+
+# ------------------------------------------------------------------ K4 / K5
+@pytest.mark.parametrize("name", ["track_12.npz", "track_25.npz"])
+def test_tracking_vs_reference_goldens_bit_exact(eng, name):
+    g = np.load(os.path.join(GOLDEN, name))
+    col, tot, status, cost = eng.track_batch(dev(g["ends"][None]), want_cost=True)
+    assert (status.cpu().numpy() == 0).all()
+    np.testing.assert_array_equal(cost.cpu().numpy()[0], g["cost"])        # numpy-order arithmetic: identical bits
+    np.testing.assert_array_equal(col.cpu().numpy()[0], g["col_ind"])      # bit-exact assignments
+    assert rel_err(tot.cpu().numpy()[0], g["total_cost"]) < 1e-13
+
+
+@pytest.mark.parametrize("C,F,N", [(2, 9, 16), (8, 40, 32), (1, 70, 64), (3, 2, 5), (2, 33, 7), (2, 65, 3)])
+def test_tracking_and_chain_vs_c_oracle(eng, C, F, N):
+    import torch
+    from oracle import c_oracle as co
+
+    rng = np.random.default_rng(C * 1000 + F)
+    base = rng.normal(size=(C, 1, N, 2, 3)) * 30
+    ends = base + np.cumsum(rng.normal(size=(C, F, N, 2, 3)) * 0.2, axis=1)
+    o = co.track_batch(ends, want_cost=True)
+    col, tot, status, cost = eng.track_batch(dev(ends), want_cost=True)
+    np.testing.assert_array_equal(cost.cpu().numpy(), o["cost"])
+    np.testing.assert_array_equal(col.cpu().numpy(), o["col_ind"])
+    assert rel_err(tot.cpu().numpy(), o["total_cost"]) < 1e-13
+    # same without the optional cost output (workspace path)
+    col2, tot2, _, _ = eng.track_batch(dev(ends))
+    np.testing.assert_array_equal(col2.cpu().numpy(), o["col_ind"])
+    # chain pass
+    tid = eng.chain_tracks(col).cpu().numpy()
+    np.testing.assert_array_equal(tid, co.chain_tracks(o["col_ind"]))
+    ids0 = np.stack([rng.permutation(N) for _ in range(C)]).astype(np.int32)
+    tid2 = eng.chain_tracks(col, dev(ids0)).cpu().numpy()
+    np.testing.assert_array_equal(tid2, co.chain_tracks(o["col_ind"], ids0))
+
+
+def test_chain_long_sequence_properties(eng):
+    """Size-independent property at a length the oracle loop would be slow for: ids are a
+    permutation in every frame and following col_ind forward preserves the id."""
+    import torch
+
+    rng = np.random.default_rng(3)
+    C, F, N = 4, 5000, 64
+    col = np.stack([np.stack([rng.permutation(N) for _ in range(F - 1)]) for _ in range(C)]).astype(np.int32)
+    tid = eng.chain_tracks(dev(col)).cpu().numpy()
+    assert (np.sort(tid, axis=-1) == np.arange(N)).all()
+    nxt = np.take_along_axis(tid[:, 1:], col, axis=2)  # ids[f+1][col[f][a]]
+    np.testing.assert_array_equal(nxt, tid[:, :-1])
+
+
+# ------------------------------------------------------------------ K6
+def test_create_weights_vs_golden_and_oracle(eng):
+    from oracle import c_oracle as co
+
+    g = np.load(os.path.join(GOLDEN, "weights.npz"))
+    w, ch = eng.create_weights(dev(g["p_3D"]), dev(g["p_prev"]), dev(g["rep_errs"]))
+    np.testing.assert_array_equal(ch.cpu().numpy(), g["choices"])
+    assert rel_err(w.cpu().numpy(), g["weights"]) < 1e-12
+    rng = np.random.default_rng(8)
+    p3, prev, re = rng.normal(size=(33, 31, 4, 3)) * 20, rng.normal(size=(29, 2, 3)) * 20, rng.random((33, 31, 4, 2))
+    w, ch = eng.create_weights(dev(p3), dev(prev), dev(re))
+    ow, och = co.create_weights(p3, prev, re)
+    np.testing.assert_array_equal(ch.cpu().numpy(), och)
+    assert rel_err(w.cpu().numpy(), ow) < 1e-12
+
+
+# ------------------------------------------------------------------ host pipeline (e2e entry point)
+def test_host_pipeline_matches_device_api(eng, crig):
+    import torch
+    from oracle import c_oracle as co
+    from particletracking_b200 import synthetic as syn
+
+    data = syn.make_stereo(300, 4, 16, seed=12)   # > 1 chunk (2048 problems per chunk) would need more; force via frames
+    pipe = eng.HostPipeline(0)
+    out = pipe.reconstruct(crig, data.cam1, data.cam2, data.n1, data.n2, track=True, max_repr_err=5.0)
+    c1, c2, n1, n2 = data.problems()
+    r = run_match(eng, crig, c1, c2, n1, n2)
+    F, C, N = 300, 4, 16
+    np.testing.assert_array_equal(out["col_ind"].numpy().reshape(F * C, N), r.col_ind.cpu().numpy())
+    np.testing.assert_array_equal(out["rows"].numpy().reshape(F * C, N, 18), r.rows.cpu().numpy())  # same kernels, same bits
+    assert (out["status"].numpy() == 0).all()
+    # tracking on the pipeline's own rows == device API on the same ends
+    ends = out["rows"].numpy()[..., :6].reshape(F, C, N, 2, 3).transpose(1, 0, 2, 3, 4).copy()
+    o = co.track_batch(ends)
+    np.testing.assert_array_equal(out["track_col"].numpy(), o["col_ind"])
+    np.testing.assert_array_equal(out["track_id"].numpy(), co.chain_tracks(o["col_ind"]))
+    assert rel_err(out["track_total"].numpy(), o["total_cost"]) < 1e-13
+    pipe.close()
+
+
+# ------------------------------------------------------------------ full-size properties (BASELINE config 2)
+def test_full_size_c2_properties(eng, crig):
+    """1000 frames x 8 colours x 32 rods: sampled problems vs the C oracle, and
+    size-independent properties on all 8000 (col_ind is a permutation; rows are self-consistent:
+    centre = mean of ends, length = |end2-end1|; planted correspondence recovered)."""
+    import torch
+    from oracle import c_oracle as co
+    from particletracking_b200 import synthetic as syn
+
+    data = syn.make_stereo(1000, 8, 32, seed=2)
+    c1, c2, n1, n2 = data.problems()
+    r = run_match(eng, crig, c1, c2, n1, n2)
+    col = r.col_ind.cpu().numpy()
+    rows = r.rows.cpu().numpy()
+    assert (r.status.cpu().numpy() == 0).all() and (r.n_out.cpu().numpy() == 32).all()
+    assert (np.sort(col, axis=1) == np.arange(32)).all()
+    np.testing.assert_allclose(rows[..., 6:9], (rows[..., 0:3] + rows[..., 3:6]) / 2, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(rows[..., 9], np.linalg.norm(rows[..., 3:6] - rows[..., 0:3], axis=-1), rtol=1e-14)
+    truth = data.truth_perm.reshape(-1, 32)
+    hit = (np.take_along_axis(truth, col, axis=1) == np.arange(32)).mean()
+    assert hit > 0.99
+    sel = np.arange(0, 8000, 37)
+    o = co.match_batch(crig, c1[sel], c2[sel], n1[sel], n2[sel], nthreads=0)
+    np.testing.assert_array_equal(col[sel], o["col_ind"])
+    assert rel_err(rows[sel][..., :10], o["rows"][..., :10]) < TOL
+    np.testing.assert_array_equal(rows[sel][..., 10:], o["rows"][..., 10:])
