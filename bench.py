@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py -- stereo frames/s (match + triangulate + track) on N B200s vs the host CPU.
+
+Metric (BASELINE.json): stereo frames/sec for the hot path match -> DLT triangulate ->
+reproject -> LSAP -> rows -> frame-to-frame tracking assignment (+ chain pass).
+
+Workload at N=1: BASELINE.json configs[1] -- 1,000 synthetic frames x 8 colours x 32 rods
+(P = 8,000 matching problems, 7,992 tracking problems per step).  N>1: every rank runs that
+workload on its own contiguous frame range (weak scaling); per step the ranks exchange the
+1-frame tracking halo, all-gather the chain-pass boundary maps and gather rows + track ids to
+rank 0 over NCCL.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Prints ONE JSON line on rank 0 (see the contract in the task description):
+  value    whole-job frames/s, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e      same metric through the host-buffer C-ABI entry point (ptk_reconstruct_host) with
+           pinned host inputs/outputs, H2D + D2H inside the timed region
+  roofline dominant kernel (K1 k_cost): algorithmic FP64 flop / event-timed duration vs the
+           FP64 FMA peak measured in this run (MEASURED_PEAKS.json has no FP64 figure), plus
+           its algorithmic HBM GB/s vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the oracle port (cv2 + scipy, what the reference calls) on one host core on a
+           bounded sample of the same workload
+`--impl reference` times the reference's CPU path (oracle port: cv2.triangulatePoints +
+scipy.linear_sum_assignment per (frame, colour), then the tracking assignment) on all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+FRAMES, COLORS, RODS = 1000, 8, 32
+WORKLOAD = "match_csv_complex+tracking_global_assignment: 1000 frames x 8 colours x 32 rods (BASELINE configs[1])"
+METRIC = "stereo frames/sec (match+triangulate+track)"
+# 245 + 80*R + 66*S flop per end-point combination with R = 20.5 Jacobi
+# rotations and S = 4.9 sweeps -> 2210 per combo, 8840 per rod pair.
+FLOP_PER_PAIR = 8840.0
+N_BATCHES = 4  # distinct synthetic input batches the timed steps rotate over
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=FRAMES, help=argparse.SUPPRESS)
+    ap.add_argument("--rods", type=int, default=RODS, help=argparse.SUPPRESS)
+    ap.add_argument("--colors", type=int, default=COLORS, help=argparse.SUPPRESS)
+    ap.add_argument("--no-cpu-baseline", action="store_true", help=argparse.SUPPRESS)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------
+# CPU side (oracle port) -- the only place bench.py executes oracle/
+# ------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    """Reference CPU path on a frame range: per colour, per frame match (cv2 + scipy), then the
+    tracking assignment per colour.  Returns frames processed."""
+    import cv2
+
+    cv2.setNumThreads(1)
+    from scipy.spatial.transform import Rotation
+
+    from oracle import port
+    from particletracking_b200 import synthetic as syn
+
+    cam1, cam2, seed = args
+    F, C, N = cam1.shape[:3]
+    cal, trf = syn.synthetic_calibration(), syn.synthetic_transformation()
+    P1, P2, r1, r2, t1, t2 = syn.projection_matrices(cal)
+    rot = Rotation.from_matrix(trf["rotation"])
+    for c in range(C):
+        ends = np.zeros((F, N, 2, 3))
+        for f in range(F):
+            r = port.match_arrays(cam1[f, c], cam2[f, c], cal, P1, P2, rot, trf["translation"], r1, r2, t1, t2)
+            ends[f] = r["rows"][:, :6].reshape(N, 2, 3)
+        if F > 1:
+            port.tracking_arrays(ends[:, :, 0], ends[:, :, 1])
+    return F
+
+
+def cpu_port_fps(n_frames: int, rods: int, colors: int, cores: int, pool=None):
+    """frames/s of the oracle port on `cores` processes, `n_frames` frames of the workload."""
+    from particletracking_b200 import synthetic as syn
+
+    data = syn.make_stereo(n_frames, colors, rods, seed=99)
+    if cores <= 1:
+        t0 = time.perf_counter()
+        _cpu_worker((data.cam1, data.cam2, 0))
+        return n_frames / (time.perf_counter() - t0)
+    per = [np.array_split(np.arange(n_frames), cores)[i] for i in range(cores)]
+    jobs = []
+    for idx in per:
+        if len(idx) == 0:
+            continue
+        lo, hi = idx[0], min(idx[-1] + 2, n_frames)  # 1-frame overlap so every pair is tracked once
+        jobs.append((data.cam1[lo:hi], data.cam2[lo:hi], 0))
+    t0 = time.perf_counter()
+    pool.map(_cpu_worker, jobs)
+    return n_frames / (time.perf_counter() - t0)
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's CPU path on all host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+
+    cores = len(os.sched_getaffinity(0))
+    frames_per_step = max(cores, 8) * 2
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        for _ in range(args.warmup):
+            cpu_port_fps(frames_per_step, args.rods, args.colors, cores, pool)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            cpu_port_fps(frames_per_step, args.rods, args.colors, cores, pool)
+        dt = time.perf_counter() - t0
+    fps = frames_per_step * args.steps / dt
+    sample = f"{frames_per_step} frames x {args.colors} colours x {args.rods} rods per step, frame ranges over {cores} processes"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append((time.perf_counter(), ln.strip()))
+
+    def stop(self, t0=None, t1=None):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ts, ln in self.lines:
+            if t0 is not None and not (t0 - 0.05 <= ts <= t1 + 0.15):
+                continue
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# GPU side
+# ------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from particletracking_b200 import distributed as pdist
+    from particletracking_b200 import engine, rig as rigmod, synthetic as syn
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    F, C, N = args.frames, args.colors, args.rods
+    K, W = args.steps, max(args.warmup, 3)
+
+    # ---- synthetic inputs: N_BATCHES distinct experiments per rank, resident in HBM
+    rig = None
+    batches, host_batches = [], []
+    for b in range(N_BATCHES):
+        data = syn.make_stereo(F, C, N, seed=1000 * (rank + 1) + b)
+        if rig is None:
+            rig = rigmod.rig_from_dicts(data.calibration, data.transformation)
+        c1, c2, n1, n2 = data.problems()
+        batches.append(tuple(torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (c1, c2, n1, n2)))
+        if b < 2:
+            host_batches.append(tuple(torch.from_numpy(np.ascontiguousarray(x)).pin_memory()
+                                      for x in (data.cam1, data.cam2, data.n1, data.n2)))
+    sharded = pdist.ShardedReconstructor(rig, F, C, N, dev) if world > 1 else None
+
+    def step(i):
+        c1, c2, n1, n2 = batches[i % N_BATCHES]
+        if sharded is not None:
+            return sharded.step(c1, c2, n1, n2)
+        return engine.reconstruct_device(rig, c1, c2, n1, n2, F, C, track=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    fp64_peak = engine.measure_fp64_peak(20000)  # also warms the clocks
+    for i in range(W):
+        out = step(i)
+    barrier()
+    st = out[0].status if sharded is None else out["status"]
+    assert int((st != 0).sum().item()) == 0, "matching reported invalid problems"
+
+    clocks = ClockSampler(local)
+    clocks.start()
+    time.sleep(0.3)
+    engine.kernel_timing(True)
+    engine.kernel_timing_read(reset=True)
+    engine.launch_count(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.perf_counter()
+    e0.record()
+    for i in range(K):
+        step(W + i)
+    e1.record()
+    barrier()
+    t_wall1 = time.perf_counter()
+    ms = e0.elapsed_time(e1)
+    launches = engine.launch_count()
+    k1_ms, k1_n = engine.kernel_timing_read(reset=True)
+    engine.kernel_timing(False)
+    clk = clocks.stop(t_wall0, t_wall1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * F * K / (ms * 1e-3)
+
+    # ---- e2e: host buffers through ptk_reconstruct_host (H2D + D2H inside), every rank its own shard
+    pipe = engine.HostPipeline(local)
+    for i in range(2):
+        pipe.reconstruct(rig, *host_batches[i % 2], track=True)
+    barrier()
+    Ke = max(3, min(K, 10))
+    t0 = time.perf_counter()
+    for i in range(Ke):
+        pipe.reconstruct(rig, *host_batches[i % 2], track=True)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_fps = world * F * Ke / e2e_s
+    P = F * C
+    h2d = P * N * 4 * 8 * 2 + P * 4 * 2
+    d2h = P * N * 18 * 8 + P * N * 8 + 2 * P * N * 4 + 2 * P * 4 + C * (F - 1) * (N * 4 + 8 + 4) + C * F * N * 4
+    pipe.close()
+
+    # ---- roofline of the dominant kernel (K1)
+    pairs_per_launch = P * N * N / max(k1_n / K, 1) if k1_n else P * N * N
+    k1_avg_ms = k1_ms / k1_n if k1_n else float("nan")
+    flops_per_launch = FLOP_PER_PAIR * pairs_per_launch
+    achieved_tf = flops_per_launch / (k1_avg_ms * 1e-3) / 1e12
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    bytes_per_launch = pairs_per_launch * (8 + 1) + (pairs_per_launch / N) * 2 * 4 * 8 * 2  # cost+choice out, und+orig rods in
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "k_cost_traffic.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {
+        "kernel": "k_cost (K1: DLT Jacobi-SVD + reprojection, 1 thread per end-point combination)",
+        "bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
+        "frac": achieved_tf / (fp64_peak / 1e12),
+        "peak_source": "measured in this run: dependency-free DFMA loop on all SMs (ptk_measure_fp64_peak); "
+                       "MEASURED_PEAKS.json has no FP64 figure",
+        "algorithmic_flop_per_pair": FLOP_PER_PAIR, "pairs_per_launch": pairs_per_launch,
+        "kernel_ms": k1_avg_ms, "kernel_share_of_step": (k1_ms / K) / (ms / K),
+        "hbm": {"achieved": bytes_per_launch / (k1_avg_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": bytes_per_launch / (k1_avg_ms * 1e-3) / 1e9 / hbm_peak,
+                "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
+        "traffic": traffic,
+    }
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_gpu": F, "colours": C, "rods": N, "problems_per_step": P,
+                   "l2": f"inputs rotate over {N_BATCHES} distinct batches; per-step working set "
+                         f"{(P * N * N * 8 * 2 + P * N * 18 * 8) / 1e6:.0f} MB > 126 MB L2",
+                   "parallelism": f"frames sharded over {world} GPU(s)" + ("; halo + chain maps + final gather over NCCL" if world > 1 else "")},
+        "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": Ke, "api": "ptk_reconstruct_host (HostPipeline.reconstruct), pinned host buffers"},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "clocks": clk,
+        "wall_s": t_wall1 - t_wall0,
+    }
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sample_frames = 24
+        fps1 = cpu_port_fps(sample_frames, N, C, 1)
+        line["cpu_baseline"] = {"value": fps1, "unit": "frames/s", "cores": 1, "kind": "port",
+                                "sample": f"{sample_frames} frames x {C} colours x {N} rods (oracle/port.py: cv2.triangulatePoints "
+                                          f"+ projectPoints + scipy LSAP per (frame, colour), then tracking), one process, cv2 threads = 1"}
+        try:
+            from oracle import c_oracle as co
+
+            data = syn.make_stereo(200, C, N, seed=7)
+            c1, c2, n1, n2 = data.problems()
+            nt = co.num_threads()
+            t0 = time.perf_counter()
+            o = co.match_batch(rig, c1, c2, n1, n2, nthreads=nt)
+            ends = o["rows"][..., :6].reshape(200, C, N, 2, 3).transpose(1, 0, 2, 3, 4).copy()
+            co.track_batch(ends, nthreads=nt)
+            line["cpu_c_oracle"] = {"value": 200 / (time.perf_counter() - t0), "unit": "frames/s", "cores": nt,
+                                    "kind": "port", "sample": "200 frames, oracle/ptk_oracle.c (plain C, OpenMP)"}
+        except Exception as e:  # the C oracle is optional for the bench
+            line["cpu_c_oracle"] = {"error": str(e)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -127,6 +127,11 @@ int ptk_match_batch(const ptk_rig* rig, int P, int Nmax,
                     double max_repr_err, uint8_t* keep_mask,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- glue: matched rows -> tracking layout ----------------------------------------------
+ * Replaces tracking.py:97-98 (data[["x1","y1","z1"]] / [["x2","y2","z2"]] .reshape(F,-1,3)) for C
+ * colours: rows[F,C,Nmax,18] (problem index f*C+c) -> ends[C,F,N,2,3], first N rows of each problem. */
+int ptk_rows_to_ends(int F, int C, int N, int Nmax, const double* rows, double* ends, void* stream);
+
 /* ---- K4 (+K2): tracking_global_assignment over all consecutive frame pairs ----------
  * Replaces tracking.py:97-123,136-137 for C colours at once.
  *   ends[C,F,N,2,3]: (x1,y1,z1),(x2,y2,z2) per rod in DataFrame row order.
@@ -188,6 +193,12 @@ int ptk_reconstruct_host(ptk_ctx* ctx, const ptk_rig* rig, int F, int C, int Nma
  * Runs a dependent-free DFMA loop on every SM and returns achieved FLOP/s in *flops
  * (2 flop per DFMA), timed with CUDA events on `stream`. */
 int ptk_measure_fp64_peak(int iters, double* flops, void* stream);
+
+/* Per-kernel timing for bench.py's roofline: when enabled, CUDA event pairs are recorded on the
+ * launching stream around every launch of the dominant kernel (K1, k_cost).  ptk_timing_read
+ * sums their durations (call after synchronising); off by default. */
+void ptk_timing_enable(int on);
+int ptk_timing_read(double* cost_kernel_ms, long long* cost_kernel_launches, int reset);
 
 /* number of kernel launches enqueued by this library since the last call with reset != 0
  * (process-wide, atomic) -- bench.py's `gpu_launches`. */

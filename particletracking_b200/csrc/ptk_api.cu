@@ -6,7 +6,9 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
+#include <utility>
 #include <vector>
 
 #include "ptk_kernels.cuh"
@@ -19,6 +21,26 @@ namespace {
 
 thread_local char g_cuda_err[256] = "";
 std::atomic<long long> g_launches{0};
+
+// Optional per-kernel timing (ptk_timing_enable): CUDA event pairs recorded on the launching
+// stream around every k_cost launch, so bench.py can report the dominant kernel's duration
+// measured inside the timed region.  Off by default (no events are recorded).
+std::atomic<int> g_timing{0};
+std::mutex g_timing_mu;
+std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_cost_events;
+std::vector<cudaEvent_t> g_event_pool;
+
+cudaEvent_t timing_event()
+{
+    if (!g_event_pool.empty()) {
+        cudaEvent_t e = g_event_pool.back();
+        g_event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
 
 inline int cuda_fail(cudaError_t e, const char* what)
 {
@@ -123,7 +145,19 @@ int launch_cost(const DevRig& rig, long long P, int Nmax, const double* cam1, co
         a.choice = choice ? choice + o2 : nullptr;
         a.p_world = p_world ? p_world + o2 * 12 : nullptr;
         a.rep_errs = rep_errs ? rep_errs + o2 * 8 : nullptr;
+        cudaEvent_t t0 = nullptr, t1 = nullptr;
+        if (g_timing.load(std::memory_order_relaxed)) {
+            std::lock_guard<std::mutex> lk(g_timing_mu);
+            t0 = timing_event();
+            t1 = timing_event();
+        }
+        if (t0) cudaEventRecord(t0, st);
         k_cost<<<(unsigned)(np * a.tiles), 128, 0, st>>>(rig, a);
+        if (t1) {
+            cudaEventRecord(t1, st);
+            std::lock_guard<std::mutex> lk(g_timing_mu);
+            g_cost_events.emplace_back(t0, t1);
+        }
         LAUNCHED("k_cost");
     }
     return PTK_OK;
@@ -209,6 +243,27 @@ PTK_API int ptk_device_count(void)
 PTK_API long long ptk_launch_count(int reset)
 {
     return reset ? g_launches.exchange(0) : g_launches.load();
+}
+
+PTK_API void ptk_timing_enable(int on) { g_timing.store(on ? 1 : 0); }
+
+PTK_API int ptk_timing_read(double* cost_kernel_ms, long long* cost_kernel_launches, int reset)
+{
+    // caller must have synchronised the streams the work ran on
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    double ms = 0;
+    for (auto& pr : g_cost_events) {
+        float t = 0;
+        CK(cudaEventElapsedTime(&t, pr.first, pr.second));
+        ms += t;
+    }
+    if (cost_kernel_ms) *cost_kernel_ms = ms;
+    if (cost_kernel_launches) *cost_kernel_launches = (long long)g_cost_events.size();
+    if (reset) {
+        for (auto& pr : g_cost_events) { g_event_pool.push_back(pr.first); g_event_pool.push_back(pr.second); }
+        g_cost_events.clear();
+    }
+    return PTK_OK;
 }
 
 PTK_API size_t ptk_workspace_bytes(int kind, long long n_problems, int Nmax)
@@ -314,6 +369,17 @@ PTK_API int ptk_match_batch(const ptk_rig* rig, int P, int Nmax, const double* c
                          rows + (size_t)p0 * Nmax * PTK_ROW_COLS, st);
         if (rc) return rc;
     }
+    return PTK_OK;
+}
+
+// rows[F,C,Nmax,18] -> ends[C,F,N,2,3] (tracking.py:97-98 extracts the same six columns)
+PTK_API int ptk_rows_to_ends(int F, int C, int N, int Nmax, const double* rows, double* ends, void* stream)
+{
+    if (F < 0 || C < 0 || bad_n(Nmax) || N < 0 || N > Nmax || !rows || !ends) return PTK_ERR_INVALID_ARG;
+    const long long tot = (long long)F * C * N * 6;
+    if (tot == 0) return PTK_OK;
+    k_rows_to_ends<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(0, F, F, C, N, Nmax, rows, ends);
+    LAUNCHED("k_rows_to_ends");
     return PTK_OK;
 }
 

@@ -1,0 +1,163 @@
+"""Frame sharding across the GPUs of one box.
+
+One process per GPU (``torch.distributed``, backend ``nccl``; ``gloo`` in the CPU tests).
+The path shards naturally:
+
+* matching: every (frame, colour) problem is independent -> contiguous frame ranges per
+  rank, no exchange;
+* tracking: the pair (f, f+1) needs only those two frames' rows -> same partition plus a
+  1-frame halo: rank r receives the first frame's end points of rank r+1 (``[C,N,2,3]``,
+  a few KB) and solves the boundary pair itself;
+* chain pass: permutation composition is associative -> every rank chains locally from the
+  identity, the per-rank boundary maps (``[C,N]`` int32) are all-gathered, composed
+  (``compose_rank_maps``), and the local ids are re-based with the rank's start ids;
+* final collective: gather of the 18-column rows and track ids to rank 0.
+
+There is no data-path collective inside matching or the per-pair assignment; NCCL carries
+only the halo, the boundary maps and the final gather.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_frames(n_frames: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous frame range [f0, f1) of ``rank``; sizes differ by at most one."""
+    base, rem = divmod(n_frames, world)
+    f0 = rank * base + min(rank, rem)
+    return f0, f0 + base + (1 if rank < rem else 0)
+
+
+def compose_rank_maps(maps: torch.Tensor) -> torch.Tensor:
+    """maps[W,C,N]: for rank r, position x in rank r+1's first frame -> local id (position in
+    rank r's first frame).  Returns starts[W,C,N]: global track id of local id x on rank r:
+    starts[0] = arange(N), starts[r+1][c][x] = starts[r][c][maps[r][c][x]]."""
+    W, C, N = maps.shape
+    starts = torch.empty_like(maps)
+    cur = torch.arange(N, dtype=maps.dtype, device=maps.device).expand(C, N).contiguous()
+    for r in range(W):
+        starts[r] = cur
+        if r + 1 < W:
+            cur = torch.gather(cur, 1, maps[r].long())
+    return starts
+
+
+class _CudaOps:
+    """The product's compute: libptk.so kernels through particletracking_b200.engine."""
+
+    def __init__(self, rig):
+        from . import engine
+
+        self.e = engine
+        self.rig = rig
+
+    def match(self, cam1, cam2, n1, n2):
+        m = self.e.match_batch(self.rig, cam1, cam2, n1, n2)
+        return m.rows, m.col_ind, m.status
+
+    def rows_to_ends(self, rows, F, C):
+        return self.e.rows_to_ends(rows, F, C)
+
+    def track(self, ends):
+        col, tot, st, _ = self.e.track_batch(ends)
+        return col, tot, st
+
+    def chain(self, col, ids_in=None):
+        return self.e.chain_tracks(col, ids_in)
+
+
+class ShardedReconstructor:
+    """match -> track -> chain for one rank's frame range, with the halo / boundary-map /
+    gather exchanges described in the module docstring.
+
+    ``ops`` is the compute back end (default: the CUDA kernels).  The CPU tests inject an
+    oracle-backed one to exercise the exchange logic under ``gloo`` -- test infrastructure,
+    not a fallback: the default never touches it.
+    """
+
+    def __init__(self, rig, n_frames_local: int, n_colors: int, n_rods: int, device, ops=None,
+                 gather_to_root: bool = True, group=None, n_frames_total: Optional[int] = None):
+        self.F, self.C, self.N = n_frames_local, n_colors, n_rods
+        self.device = device
+        self.ops = ops if ops is not None else _CudaOps(rig)
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.gather_to_root = gather_to_root
+        # frames held by every rank (shards may differ by one frame; gathers are padded to the max)
+        total = n_frames_total if n_frames_total is not None else n_frames_local * self.world
+        self.shard_sizes = [b - a for a, b in (shard_frames(total, self.world, r) for r in range(self.world))]
+        if self.shard_sizes[self.rank] != n_frames_local:
+            raise ValueError("n_frames_local does not match shard_frames(n_frames_total, world, rank)")
+        self._rows_all = None
+        self._tid_all = None
+
+    # -- exchanges ------------------------------------------------------------------------
+    def _halo(self, first_frame_ends: torch.Tensor) -> Optional[torch.Tensor]:
+        """Send my first frame's ends to rank-1, receive rank+1's.  Returns None on the last rank."""
+        if self.world == 1:
+            return None
+        ops = []
+        recv = None
+        if self.rank > 0:
+            ops.append(dist.P2POp(dist.isend, first_frame_ends, self.rank - 1, self.group))
+        if self.rank < self.world - 1:
+            recv = torch.empty_like(first_frame_ends)
+            ops.append(dist.P2POp(dist.irecv, recv, self.rank + 1, self.group))
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        return recv
+
+    def _gather(self, t: torch.Tensor, cache_name: str, frame_dim: int):
+        """Gather ``t`` (frames along ``frame_dim``) to rank 0; returns the list of per-rank
+        shards there, None elsewhere.  Shards of unequal length are padded for the collective."""
+        if self.world == 1:
+            return [t]
+        fmax = max(self.shard_sizes)
+        if t.shape[frame_dim] < fmax:
+            pad_shape = list(t.shape)
+            pad_shape[frame_dim] = fmax - t.shape[frame_dim]
+            t = torch.cat([t, t.new_zeros(pad_shape)], dim=frame_dim)
+        t = t.contiguous()
+        if self.rank == 0:
+            buf = getattr(self, cache_name)
+            if buf is None or buf[0].shape != t.shape:
+                buf = [torch.empty_like(t) for _ in range(self.world)]
+                setattr(self, cache_name, buf)
+            dist.gather(t, buf, dst=0, group=self.group)
+            return [b.narrow(frame_dim, 0, n) for b, n in zip(buf, self.shard_sizes)]
+        dist.gather(t, None, dst=0, group=self.group)
+        return None
+
+    # -- one pass over this rank's frames ----------------------------------------------------
+    def step(self, cam1, cam2, n1, n2):
+        """cam1/cam2 [F*C,Nmax,2,2] (problem = f*C+c), n1/n2 [F*C] for this rank's frames.
+        Returns a dict; on rank 0 ``rows_all`` / ``track_id_all`` hold every rank's shard."""
+        F, C, N = self.F, self.C, self.N
+        rows, col_m, status = self.ops.match(cam1, cam2, n1, n2)
+        ends = self.ops.rows_to_ends(rows, F, C)  # [C,F,N,2,3]
+        halo = self._halo(ends[:, 0].contiguous())
+        if halo is not None:
+            ends = torch.cat([ends, halo[:, None]], dim=1)  # boundary pair solved here
+        col, total, tstatus = self.ops.track(ends)
+        local = self.ops.chain(col)  # ids relative to this rank's first frame
+        if self.world > 1:
+            if halo is not None:
+                my_map = local[:, -1].contiguous()
+            else:
+                my_map = torch.arange(N, dtype=local.dtype, device=local.device).expand(C, N).contiguous()
+            maps = torch.empty((self.world * C, N), dtype=local.dtype, device=local.device)
+            dist.all_gather_into_tensor(maps, my_map, group=self.group)
+            start = compose_rank_maps(maps.view(self.world, C, N))[self.rank].contiguous()
+            track_id = self.ops.chain(col, start)[:, :F].contiguous()
+        else:
+            track_id = local
+        out = dict(rows=rows, col_ind=col_m, status=status, track_col=col, track_total=total,
+                   track_status=tstatus, track_id=track_id)
+        if self.gather_to_root:
+            out["rows_all"] = self._gather(rows.view(F, C, -1, rows.shape[-1]), "_rows_all", 0)  # [F,C,Nmax,18] per rank
+            out["track_id_all"] = self._gather(track_id, "_tid_all", 1)                         # [C,F,N] per rank
+        return out

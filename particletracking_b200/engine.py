@@ -158,6 +158,33 @@ def match_batch(rig: PtkRig, cam1, cam2, n1, n2, want_cost=False, max_repr_err: 
     return MatchResult(rows, mc, row, col, n_out, status, cost, choice, keep)
 
 
+def rows_to_ends(rows: torch.Tensor, F: int, C: int, N: Optional[int] = None) -> torch.Tensor:
+    """rows[F*C,Nmax,18] (problem = f*C+c) -> ends[C,F,N,2,3]: the six columns
+    tracking_global_assignment reads (tracking.py:97-98)."""
+    _require_cuda()
+    rows = _chk(rows, _f64, "rows")
+    Nmax = rows.shape[-2]
+    N = Nmax if N is None else N
+    ends = torch.empty((C, F, N, 2, 3), dtype=_f64, device=rows.device)
+    with torch.cuda.device(rows.device):
+        nat.check(nat.lib().ptk_rows_to_ends(F, C, N, Nmax, _ptr(rows), _ptr(ends), _stream()), "ptk_rows_to_ends")
+    return ends
+
+
+def reconstruct_device(rig: PtkRig, cam1, cam2, n1, n2, F: int, C: int, track: bool = True,
+                       max_repr_err: Optional[float] = None):
+    """The whole hot path on device-resident tensors: match (K0-K3) -> ends -> track (K4+K2) ->
+    chain (K5).  cam1/cam2 [F*C,Nmax,2,2] with problem index f*C+c.  Returns
+    (MatchResult, col_ind[C,F-1,N], total_cost[C,F-1], track_id[C,F,N], track_status)."""
+    m = match_batch(rig, cam1, cam2, n1, n2, max_repr_err=max_repr_err)
+    if not track:
+        return m, None, None, None, None
+    ends = rows_to_ends(m.rows, F, C)
+    col, tot, st, _ = track_batch(ends)
+    tid = chain_tracks(col)
+    return m, col, tot, tid, st
+
+
 def track_batch(ends: torch.Tensor, want_cost=False):
     """K4+K2: ``tracking_global_assignment`` (tracking.py:97-123,136-137) for C colours.
     ends[C,F,N,2,3] -> col_ind[C,F-1,N], total_cost[C,F-1], status[C,F-1] (, cost[C,F-1,N,N])."""
@@ -214,6 +241,19 @@ def measure_fp64_peak(iters: int = 20000) -> float:
     out = ctypes.c_double(0.0)
     nat.check(nat.lib().ptk_measure_fp64_peak(int(iters), ctypes.byref(out), _stream()), "ptk_measure_fp64_peak")
     return out.value
+
+
+def kernel_timing(enable: bool) -> None:
+    """Switch CUDA-event timing of the dominant kernel (K1) on or off."""
+    nat.lib().ptk_timing_enable(1 if enable else 0)
+
+
+def kernel_timing_read(reset: bool = True):
+    """(total ms, launches) of K1 since the last reset; synchronise first."""
+    ms = ctypes.c_double(0.0)
+    n = ctypes.c_longlong(0)
+    nat.check(nat.lib().ptk_timing_read(ctypes.byref(ms), ctypes.byref(n), 1 if reset else 0), "ptk_timing_read")
+    return ms.value, n.value
 
 
 def launch_count(reset: bool = False) -> int:

@@ -143,7 +143,9 @@ def make_stereo(
     d /= np.linalg.norm(d, axis=-1, keepdims=True)
     vel = rng.normal(0.0, 0.2, size=(C, N, 3))
     t = np.arange(F, dtype=np.float64)[:, None, None, None]
-    centre = centre0[None] + vel[None] * t  # [F,C,N,3]
+    # ballistic flight with elastic reflection at the box walls (triangle-wave folding), so
+    # that arbitrarily long sequences stay inside both cameras' fields of view
+    centre = _fold(centre0[None] + vel[None] * t, box)  # [F,C,N,3]
     half = 0.5 * rod_length * d[None]
     ends_w = np.stack([centre - half, centre + half], axis=3)  # [F,C,N,2,3]
 
@@ -190,6 +192,13 @@ def make_stereo(
         calibration=cal,
         transformation=trf,
     )
+
+
+def _fold(x: np.ndarray, half: np.ndarray) -> np.ndarray:
+    """Reflect coordinates into [-half, half] (period 4*half triangle wave)."""
+    y = np.mod(x + half, 4.0 * half)
+    y = np.where(y > 2.0 * half, 4.0 * half - y, y)
+    return y - half
 
 
 def _compact(uv: np.ndarray, keep: np.ndarray):
