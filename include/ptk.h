@@ -127,6 +127,20 @@ int ptk_match_batch(const ptk_rig* rig, int P, int Nmax,
                     double max_repr_err, uint8_t* keep_mask,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- K0+K3: rows for GIVEN assignments ------------------------------------------------
+ * Replaces match2D.py:876-884,941-983 with renumber=False: the rod pairing is kept
+ * (col_ind[p,m] = cam2 rod paired with cam1 rod m; the reference uses m itself after dropping
+ * rows not present in both cameras, match2D.py:831-837) and only the end-point combination is
+ * (re-)evaluated.  rows[P,Nmax,18]; pair_cost[P,Nmax] (optional) = min(e0+e3, e1+e2) of each
+ * pair == the reference's `costs` for renumber=False (match2D.py:941-947).
+ * workspace: ptk_workspace_bytes(PTK_WS_COST, P, Nmax). */
+int ptk_rows_batch(const ptk_rig* rig, int P, int Nmax,
+                   const double* cam1, const double* cam2,
+                   const int32_t* n1, const int32_t* n2,
+                   const int32_t* col_ind, const int32_t* n_out,
+                   double* rows, double* pair_cost,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- glue: matched rows -> tracking layout ----------------------------------------------
  * Replaces tracking.py:97-98 (data[["x1","y1","z1"]] / [["x2","y2","z2"]] .reshape(F,-1,3)) for C
  * colours: rows[F,C,Nmax,18] (problem index f*C+c) -> ends[C,F,N,2,3], first N rows of each problem. */

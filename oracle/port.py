@@ -176,10 +176,67 @@ def select_rods(data, cam_name: str, frame: int) -> np.ndarray:
     return v.reshape(-1, 2, 2)
 
 
-def match_frame(data, cam1_name, cam2_name, frame, color, calibration, P1, P2, rot, trans, r1, r2, t1, t2):
-    """match2D.py:741-998 with ``renumber=True``."""
+def match_arrays_keep_pairs(rods1, rods2, calibration, P1, P2, rot, trans, r1, r2, t1, t2):
+    """match2D.py:876-884,941-983 (``renumber=False``): rod i of camera 1 stays paired with
+    rod i of camera 2; only the end-point combination is chosen.  ``costs`` is the per-pair
+    minimum."""
+    n = len(rods1)
+    import cv2
+
+    u1 = undistort_quirk(rods1, calibration["CM1"], calibration["dist1"])
+    u2 = undistort_quirk(rods2, calibration["CM2"], calibration["dist2"])
+    e1 = np.array([0, 0, 1, 1])
+    e2 = np.array([0, 1, 0, 1])
+    pu1, pu2 = u1[:, e1, :].reshape(-1, 2), u2[:, e2, :].reshape(-1, 2)
+    po1, po2 = rods1[:, e1, :].reshape(-1, 2), rods2[:, e2, :].reshape(-1, 2)
+    ph = cv2.triangulatePoints(P1, P2, pu1.T.copy(), pu2.T.copy())
+    p = (ph[0:3] / ph[3]).T.copy()
+    q1 = cv2.projectPoints(p, r1, t1, calibration["CM1"], calibration["dist1"])[0].reshape(-1, 2)
+    q2 = cv2.projectPoints(p, r2, t2, calibration["CM2"], calibration["dist2"])[0].reshape(-1, 2)
+    err = np.stack([np.linalg.norm(po1 - q1, axis=1), np.linalg.norm(po2 - q2, axis=1)], axis=1).mean(axis=1)
+    pw = world_transform(p, rot, trans).reshape(n, 4, 3)
+    e = err.reshape(-1, 4)
+    s03, s12 = e[:, 0] + e[:, 3], e[:, 1] + e[:, 2]
+    costs = np.minimum(s03, s12)
+    rows = np.zeros((n, 18))
+    for m in range(n):
+        if s03[m] <= s12[m]:
+            ends, c1, c2 = pw[m, 0::3], rods1[m], rods2[m]
+        else:
+            ends, c1, c2 = pw[m, 1:3], rods1[m, ::-1], rods2[m, ::-1]
+        rows[m, 0:6] = ends.ravel()
+        rows[m, 6:9] = ends.sum(axis=0) / 2
+        rows[m, 9] = np.linalg.norm(np.diff(ends, axis=0))
+        rows[m, 10:14] = c1.ravel()
+        rows[m, 14:18] = c2.ravel()
+    return {"rows": rows, "costs": costs}
+
+
+def match_frame(data, cam1_name, cam2_name, frame, color, calibration, P1, P2, rot, trans, r1, r2, t1, t2,
+                renumber=True):
+    """match2D.py:741-998."""
     import pandas as pd
 
+    if not renumber:
+        # match2D.py:831-837,990-993: rows valid in both cameras, particle ids kept
+        cols1 = [f"{k}_{cam1_name}" for k in ("x1", "y1", "x2", "y2")]
+        cols2 = [f"{k}_{cam2_name}" for k in ("x1", "y1", "x2", "y2")]
+        sel = data.loc[data.frame == frame]
+        v1, v2 = sel[cols1].to_numpy(dtype=np.float64), sel[cols2].to_numpy(dtype=np.float64)
+        ok = lambda v: ~np.isnan(v).all(axis=1) & (v != 0).any(axis=1)
+        both = ok(v1) & ok(v2)
+        if not both.any():
+            return None
+        res = match_arrays_keep_pairs(v1[both].reshape(-1, 2, 2), v2[both].reshape(-1, 2, 2),
+                                      calibration, P1, P2, rot, trans, r1, r2, t1, t2)
+        cols = ["x1", "y1", "z1", "x2", "y2", "z2", "x", "y", "z", "l", *cols1, *cols2]
+        df = pd.DataFrame(res["rows"], columns=cols)
+        df["frame"] = frame
+        df["color"] = color
+        df["particle"] = sel["particle"].to_numpy()[both] if "particle" in data.columns else list(range(len(df)))
+        seen = [c for c in data.columns if "seen" in c]
+        df[seen] = 1
+        return df, res["costs"], res["rows"][:, 9]
     rods1 = select_rods(data, cam1_name, frame)
     rods2 = select_rods(data, cam2_name, frame)
     if len(rods1) == 0 or len(rods2) == 0:

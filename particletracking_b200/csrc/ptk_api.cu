@@ -188,7 +188,8 @@ int launch_lsap(long long P, LsapArgs a, cudaStream_t st)
 }
 
 int launch_rows(const DevRig& rig, long long P, int Nmax, const double* cam1, const double* cam2, const double* und1,
-                const double* und2, const int32_t* col_ind, const int32_t* n_out, double* rows, cudaStream_t st)
+                const double* und2, const int32_t* col_ind, const int32_t* n_out, double* rows, cudaStream_t st,
+                double* pair_cost = nullptr)
 {
     for (long long p0 = 0; p0 < P; p0 += 65535) {
         const int np = (int)((P - p0) < 65535 ? (P - p0) : 65535);
@@ -199,6 +200,7 @@ int launch_rows(const DevRig& rig, long long P, int Nmax, const double* cam1, co
         a.col_ind = col_ind + (size_t)p0 * Nmax;
         a.n_out = n_out + p0;
         a.rows = rows + (size_t)p0 * Nmax * PTK_ROW_COLS;
+        a.pair_cost = pair_cost ? pair_cost + (size_t)p0 * Nmax : nullptr;
         dim3 grid((Nmax + 31) / 32, np);
         k_rows<<<grid, 128, 0, st>>>(rig, a);
         LAUNCHED("k_rows");
@@ -370,6 +372,23 @@ PTK_API int ptk_match_batch(const ptk_rig* rig, int P, int Nmax, const double* c
         if (rc) return rc;
     }
     return PTK_OK;
+}
+
+// ------------------------------------------------------------------------------------ K0+K3
+PTK_API int ptk_rows_batch(const ptk_rig* rig, int P, int Nmax, const double* cam1, const double* cam2,
+                           const int32_t* n1, const int32_t* n2, const int32_t* col_ind, const int32_t* n_out,
+                           double* rows, double* pair_cost, void* workspace, size_t workspace_bytes, void* stream)
+{
+    if (!rig || P < 0 || bad_n(Nmax) || !cam1 || !cam2 || !n1 || !n2 || !col_ind || !n_out || !rows)
+        return PTK_ERR_INVALID_ARG;
+    if (P == 0) return PTK_OK;
+    if (!workspace || workspace_bytes < ptk_workspace_bytes(PTK_WS_COST, P, Nmax)) return PTK_ERR_WORKSPACE;
+    const DevRig d = make_devrig(rig);
+    cudaStream_t st = (cudaStream_t)stream;
+    MatchWs w = carve_match((void*)align_up((size_t)workspace), P, Nmax, false);
+    int rc = launch_undistort(d, P, Nmax, cam1, cam2, n1, n2, w.und1, w.und2, st);
+    if (rc) return rc;
+    return launch_rows(d, P, Nmax, cam1, cam2, w.und1, w.und2, col_ind, n_out, rows, st, pair_cost);
 }
 
 // rows[F,C,Nmax,18] -> ends[C,F,N,2,3] (tracking.py:97-98 extracts the same six columns)

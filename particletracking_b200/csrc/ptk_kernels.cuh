@@ -348,6 +348,7 @@ struct RowsArgs {
     const int32_t* col_ind;  // [P,Nmax]
     const int32_t* n_out;    // [P]
     double* rows;            // [P,Nmax,18]
+    double* pair_cost;       // optional [P,Nmax]: min(e0+e3, e1+e2) of the evaluated pair (m, col_ind[m])
 };
 
 __global__ void __launch_bounds__(128) k_rows(const __grid_constant__ DevRig rig, const __grid_constant__ RowsArgs a)
@@ -362,6 +363,7 @@ __global__ void __launch_bounds__(128) k_rows(const __grid_constant__ DevRig rig
         if (m < a.Nmax) {
             double* o = a.rows + (base + m) * PTK_ROW_COLS;
             for (int k = c; k < PTK_ROW_COLS; k += 4) o[k] = qnan;
+            if (a.pair_cost && c == 0) a.pair_cost[base + m] = qnan;
         }
         return;
     }
@@ -389,6 +391,7 @@ __global__ void __launch_bounds__(128) k_rows(const __grid_constant__ DevRig rig
     const double ax = __shfl_sync(kFull, wx, s1), ay = __shfl_sync(kFull, wy, s1), az = __shfl_sync(kFull, wz, s1);
     const double bx = __shfl_sync(kFull, wx, s2), by = __shfl_sync(kFull, wy, s2), bz = __shfl_sync(kFull, wz, s2);
     if (c == 0) {
+        if (a.pair_cost && m < a.Nmax) a.pair_cost[base + m] = active ? np_min(s_mine, s_other) : qnan;
         if (active) {
             double* o = a.rows + (base + m) * PTK_ROW_COLS;
             o[0] = ax; o[1] = ay; o[2] = az;

@@ -158,6 +158,26 @@ def match_batch(rig: PtkRig, cam1, cam2, n1, n2, want_cost=False, max_repr_err: 
     return MatchResult(rows, mc, row, col, n_out, status, cost, choice, keep)
 
 
+def rows_batch(rig: PtkRig, cam1, cam2, n1, n2, col_ind, n_out):
+    """K0+K3 for given assignments (``renumber=False``, match2D.py:876-884,941-983):
+    rows[P,Nmax,18] and pair_cost[P,Nmax] for the pairs (m, col_ind[p,m]), m < n_out[p]."""
+    _require_cuda()
+    cam1, cam2 = _chk(cam1, _f64, "cam1"), _chk(cam2, _f64, "cam2")
+    n1, n2 = _chk(n1, _i32, "n1"), _chk(n2, _i32, "n2")
+    col_ind, n_out = _chk(col_ind, _i32, "col_ind"), _chk(n_out, _i32, "n_out")
+    P, Nmax = cam1.shape[:2]
+    dev = cam1.device
+    rows = torch.empty((P, Nmax, nat.ROW_COLS), dtype=_f64, device=dev)
+    pc = torch.empty((P, Nmax), dtype=_f64, device=dev)
+    nb = nat.lib().ptk_workspace_bytes(nat.WS_COST, P, Nmax)
+    ws = _ws.get(nb, dev)
+    with torch.cuda.device(dev):
+        nat.check(nat.lib().ptk_rows_batch(ctypes.byref(rig), P, Nmax, _ptr(cam1), _ptr(cam2), _ptr(n1), _ptr(n2),
+                                           _ptr(col_ind), _ptr(n_out), _ptr(rows), _ptr(pc), _ptr(ws), ws.numel(),
+                                           _stream()), "ptk_rows_batch")
+    return rows, pc
+
+
 def rows_to_ends(rows: torch.Tensor, F: int, C: int, N: Optional[int] = None) -> torch.Tensor:
     """rows[F*C,Nmax,18] (problem = f*C+c) -> ends[C,F,N,2,3]: the six columns
     tracking_global_assignment reads (tracking.py:97-98)."""

@@ -1,0 +1,247 @@
+"""``match2D`` of the reference (``reconstruct_3D/match2D.py``) on the B200.
+
+Same signatures, return types and error behaviour as the reference's ``match_frame``
+(:741-998), ``match_complex`` (:634-738) and ``match_csv_complex`` (:513-631).  The numeric
+body (undistort -> pairs -> DLT -> reproject -> cost -> LSAP -> rows) runs in ``libptk.so``;
+what stays here is the DataFrame/CSV glue, batched over frames (and colours) so that one
+call to the library covers the whole request.
+
+Keyword-only extras (default off): ``max_repr_err`` adds a ``keep`` mask over
+the returned costs (north-star "threshold it"); nothing else changes.
+"""
+from __future__ import annotations
+
+import logging
+import os
+import pathlib
+from typing import Iterable, List, Optional, Sequence
+
+import numpy as np
+import pandas as pd
+import torch
+
+from .. import engine
+from ..rig import make_rig
+from ..utils import data_loading as dl
+
+_logger = logging.getLogger(__name__)
+
+COLS_3D = ["x1", "y1", "z1", "x2", "y2", "z2", "x", "y", "z", "l"]
+
+
+def _cam_cols(name: str) -> List[str]:
+    return [f"x1_{name}", f"y1_{name}", f"x2_{name}", f"y2_{name}"]
+
+
+class _FrameIndex:
+    """Row positions of every frame, in DataFrame order (``data.loc[data.frame == f]``)."""
+
+    def __init__(self, data: pd.DataFrame):
+        fr = data["frame"].to_numpy()
+        self.order = np.argsort(fr, kind="stable")
+        self.sorted = fr[self.order]
+
+    def rows(self, frame) -> np.ndarray:
+        lo = np.searchsorted(self.sorted, frame, side="left")
+        hi = np.searchsorted(self.sorted, frame, side="right")
+        return self.order[lo:hi]
+
+
+def _valid(v: np.ndarray) -> np.ndarray:
+    """match2D.py:826-830: drop rows that are all NaN, then rows that are all zero
+    (partially-NaN rows and the detector's -1 dummies survive)."""
+    return ~np.isnan(v).all(axis=1) & (v != 0).any(axis=1)
+
+
+def _pack(problems: Sequence[tuple]):
+    """[(rods1[n1,4], rods2[n2,4]), ...] -> padded host tensors for the library."""
+    P = len(problems)
+    nmax = max(1, max(max(len(a), len(b)) for a, b in problems))
+    if nmax > 256:
+        raise ValueError("more than 256 rods in one (frame, colour) problem")
+    c1 = np.full((P, nmax, 4), np.nan)
+    c2 = np.full((P, nmax, 4), np.nan)
+    n1 = np.zeros(P, dtype=np.int32)
+    n2 = np.zeros(P, dtype=np.int32)
+    for p, (a, b) in enumerate(problems):
+        n1[p], n2[p] = len(a), len(b)
+        c1[p, : len(a)] = a
+        c2[p, : len(b)] = b
+    dev = torch.device("cuda", torch.cuda.current_device())
+    t = lambda x: torch.from_numpy(x).to(dev)
+    return t(c1.reshape(P, nmax, 2, 2)), t(c2.reshape(P, nmax, 2, 2)), t(n1), t(n2)
+
+
+def _raise_for_status(status: np.ndarray):
+    # scipy.optimize.linear_sum_assignment raises these from match2D.py:933
+    if (status == 1).any():
+        raise ValueError("matrix contains invalid numeric entries")
+    if (status == 2).any():
+        raise ValueError("cost matrix is infeasible")
+
+
+def _solve(problems, rig, renumber: bool, max_repr_err: Optional[float]):
+    """Run the library on a list of (rods_cam1, rods_cam2) problems.  Returns per problem
+    (rows[n,18], costs[n], keep[n] | None)."""
+    engine._require_cuda()
+    c1, c2, n1, n2 = _pack(problems)
+    if renumber:
+        r = engine.match_batch(rig, c1, c2, n1, n2, max_repr_err=max_repr_err)
+        status = r.status.cpu().numpy()
+        _raise_for_status(status)
+        rows, costs, n_out = r.rows.cpu().numpy(), r.match_cost.cpu().numpy(), r.n_out.cpu().numpy()
+        keep = r.keep.cpu().numpy().astype(bool) if r.keep is not None else None
+    else:
+        # match2D.py:876-884, 941-955: pairs are kept (zip), only end-point combos are evaluated
+        P, nmax = c1.shape[:2]
+        col = torch.arange(nmax, dtype=torch.int32, device=c1.device).expand(P, nmax).contiguous()
+        rows_t, pc = engine.rows_batch(rig, c1, c2, n1, n2, col, n1)
+        rows, costs, n_out = rows_t.cpu().numpy(), pc.cpu().numpy(), n1.cpu().numpy()
+        keep = (costs <= max_repr_err) if max_repr_err is not None else None
+    out = []
+    for p in range(len(problems)):
+        n = int(n_out[p])
+        out.append((rows[p, :n], costs[p, :n], None if keep is None else keep[p, :n]))
+    return out
+
+
+def _select(data: pd.DataFrame, fidx: _FrameIndex, v1: np.ndarray, v2: np.ndarray, frame, renumber: bool):
+    """match2D.py:824-844 for one frame -> (rods1[n1,4], rods2[n2,4], positions kept for
+    renumber=False)."""
+    pos = fidx.rows(frame)
+    a, b = v1[pos], v2[pos]
+    k1, k2 = _valid(a), _valid(b)
+    if not renumber:
+        # match2D.py:831-837: keep index labels present in both cameras.  Labels, not positions:
+        # with a non-unique index a label survives if ANY of its rows is valid in both.
+        both = k1 & k2
+        lab = data.index.to_numpy()[pos]
+        if len(np.unique(lab)) != len(lab):
+            drop = set(lab[k1 ^ k2])
+            both = np.array([(l not in drop) for l in lab]) & k1 & k2
+        return a[both], b[both], pos[both]
+    return a[k1], b[k2], None
+
+
+def _frame_df(rows, frame, color, particle, cols, seen_cols):
+    df = pd.DataFrame(rows, columns=cols)
+    df["frame"] = frame
+    df["color"] = color
+    df["particle"] = particle
+    if seen_cols:
+        df[seen_cols] = 1
+    return df
+
+
+def match_frame(data: pd.DataFrame, cam1_name: str, cam2_name: str, frame: int, color: str, calibration: dict,
+                P1: np.ndarray, P2: np.ndarray, rot, trans: np.ndarray, r1: np.ndarray, r2: np.ndarray,
+                t1: np.ndarray, t2: np.ndarray, renumber: bool = True, *, max_repr_err: Optional[float] = None):
+    """Matches and triangulates the rods of one frame (reference match2D.py:741-998).
+
+    Returns ``(DataFrame, costs, lengths)`` -- or ``None`` when a camera has no rods in this
+    frame (:838-840).  With ``max_repr_err`` a 4th element ``keep`` (bool per row) is appended."""
+    cols = [*COLS_3D, *_cam_cols(cam1_name), *_cam_cols(cam2_name)]
+    fidx = _FrameIndex(data)
+    v1 = data[_cam_cols(cam1_name)].to_numpy(dtype=np.float64)
+    v2 = data[_cam_cols(cam2_name)].to_numpy(dtype=np.float64)
+    rods1, rods2, kept = _select(data, fidx, v1, v2, frame, renumber)
+    if len(rods1) == 0 or len(rods2) == 0:
+        return None
+    rig = make_rig(calibration, P1, P2, rot, trans, r1, r2, t1, t2)
+    rows, costs, keep = _solve([(rods1, rods2)], rig, renumber, max_repr_err)[0]
+    if (not renumber) and ("particle" in data.columns):
+        particle = data["particle"].to_numpy()[kept]  # match2D.py:990-993
+    else:
+        particle = list(range(len(rows)))
+    seen_cols = [c for c in data.columns if "seen" in c]
+    df = _frame_df(rows, frame, color, particle, cols, seen_cols)
+    if max_repr_err is not None:
+        return df, costs, rows[:, 9].copy(), keep
+    return df, costs, rows[:, 9].copy()
+
+
+def _derive_rig(calibration: dict, transform: dict):
+    """match2D.py:584-596 / 689-710: P1, P2, r, t from the calibration; world rotation and
+    translation from either transform format."""
+    from ..rig import rig_from_dicts
+
+    return rig_from_dicts(calibration, transform)
+
+
+def _match_many(data: pd.DataFrame, frame_numbers: Iterable[int], color: str, rig, cam1_name, cam2_name,
+                renumber: bool, max_repr_err=None):
+    cols = [*COLS_3D, *_cam_cols(cam1_name), *_cam_cols(cam2_name)]
+    fidx = _FrameIndex(data)
+    v1 = data[_cam_cols(cam1_name)].to_numpy(dtype=np.float64)
+    v2 = data[_cam_cols(cam2_name)].to_numpy(dtype=np.float64)
+    frames = list(frame_numbers)
+    problems, kepts = [], []
+    for f in frames:
+        a, b, kept = _select(data, fidx, v1, v2, f, renumber)
+        if len(a) == 0 or len(b) == 0:
+            # the reference's drivers unpack match_frame's None here (match2D.py:622, 733)
+            raise TypeError("cannot unpack non-iterable NoneType object")
+        problems.append((a, b))
+        kepts.append(kept)
+    if not problems:
+        return pd.DataFrame(), [], [], []
+    res = _solve(problems, rig, renumber, max_repr_err)
+    seen_cols = [c for c in data.columns if "seen" in c]
+    n_rows = [len(r[0]) for r in res]
+    allrows = np.concatenate([r[0] for r in res], axis=0)
+    df = pd.DataFrame(allrows, columns=cols)
+    df["frame"] = np.repeat(np.asarray(frames), n_rows)
+    df["color"] = color
+    if (not renumber) and ("particle" in data.columns):
+        pcol = data["particle"].to_numpy()
+        df["particle"] = np.concatenate([pcol[k] for k in kepts])
+    else:
+        df["particle"] = np.concatenate([np.arange(n) for n in n_rows]) if n_rows else []
+    if seen_cols:
+        df[seen_cols] = 1
+    costs = [r[1] for r in res]
+    lens = [r[0][:, 9].copy() for r in res]
+    keeps = [r[2] for r in res]
+    return df, costs, lens, keeps
+
+
+def match_complex(data: pd.DataFrame, frame_numbers: Iterable[int], color: str, calibration: dict, transform: dict,
+                  cam1_name="gp1", cam2_name="gp2", renumber: bool = True, *, max_repr_err: Optional[float] = None):
+    """Matches and triangulates rods from a DataFrame (reference match2D.py:634-738): all
+    requested frames go to the GPU in one batch.  Returns ``(DataFrame, costs, lengths)`` with
+    per-frame lists, as the reference does."""
+    rig = _derive_rig(calibration, transform)
+    df, costs, lens, keeps = _match_many(data, frame_numbers, color, rig, cam1_name, cam2_name, renumber, max_repr_err)
+    if max_repr_err is not None:
+        return df, costs, lens, keeps
+    return df, costs, lens
+
+
+def match_csv_complex(input_folder, output_folder, colors, cam1_name="gp1", cam2_name="gp2", frame_numbers=None,
+                      calibration_file=None, transformation_file=None, rematching=True):
+    """Matches and triangulates rods from ``rods_df_{color}.csv`` files and writes files of
+    the same layout (reference match2D.py:513-631).  Returns ``(reprojection errors, rod
+    lengths)`` as ndarrays (``np.array`` of the per-frame lists, like the reference)."""
+    if calibration_file is None:
+        raise FileNotFoundError(
+            "calibration_file: the reference's default (example_calibration/Matlab/gp12.json) is not part of this "
+            "package; pass the calibration explicitly")
+    if transformation_file is None:
+        raise FileNotFoundError(
+            "transformation_file: the reference's default (example_calibration/Matlab/world_transformation.json) "
+            "does not exist in the reference tree either; pass the transformation explicitly")
+    if not os.path.exists(output_folder):
+        os.mkdir(output_folder)
+    calibration = dl.load_camera_calibration(str(pathlib.Path(calibration_file)))
+    transforms = dl.load_world_transformation(str(pathlib.Path(transformation_file)))
+    rig = _derive_rig(calibration, transforms)
+    all_repr_errs, all_rod_lengths = [], []
+    for color in colors:
+        f_in = input_folder + f"/rods_df_{color}.csv"
+        data = pd.read_csv(f_in, sep=",", index_col=0)
+        df_out, costs, lens, _ = _match_many(data, frame_numbers, color, rig, cam1_name, cam2_name, rematching)
+        all_repr_errs.extend(costs)
+        all_rod_lengths.extend(lens)
+        df_out.reset_index(drop=True, inplace=True)
+        df_out.to_csv(os.path.join(output_folder, f"rods_df_{color}.csv"), sep=",")
+    return np.array(all_repr_errs), np.array(all_rod_lengths)

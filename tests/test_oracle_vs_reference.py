@@ -47,6 +47,30 @@ def test_match_frame_matches_reference(ref, rig, n, drop, dummy):
         assert rel_err(oc, rc) < 1e-12 and rel_err(ol, rl) < 1e-12
 
 
+@pytest.mark.parametrize("n,seed", [(10, 1), (25, 2), (1, 3)])
+def test_match_frame_keep_pairs_matches_reference(ref, rig, n, seed):
+    """renumber=False (match2D.py:876-884, 941-955): pairs kept, end-point combos re-evaluated."""
+    m2d = ref[0]
+    data = syn.make_stereo(3, 1, n, seed=seed)
+    # un-scramble camera 2 so that row i of both cameras shows the same rod (what a previous
+    # matching pass leaves behind), keep the random end-point swaps
+    inv = np.argsort(data.truth_perm, axis=-1)
+    data.cam2 = np.take_along_axis(data.cam2, inv[..., None, None], axis=2)
+    df = syn.to_dataframes(data)[data.colors[0]]
+    df["particle"] = df["particle"] + 100
+    if n > 3:
+        df.loc[df.index[2], ["x1_gp1", "y1_gp1", "x2_gp1", "y2_gp1"]] = np.nan  # seen by camera 2 only
+    for f in data.frames:
+        r = m2d.match_frame(df, "gp1", "gp2", int(f), "black", *_rig_args(rig), renumber=False)
+        o = port.match_frame(df, "gp1", "gp2", int(f), "black", *_rig_args(rig), renumber=False)
+        a = r[0].drop(columns=["color"]).to_numpy(dtype=float)
+        b = o[0].drop(columns=["color"]).to_numpy(dtype=float)
+        assert list(r[0].columns) == list(o[0].columns) and a.shape == b.shape
+        np.testing.assert_array_equal(a[:, 10:], b[:, 10:])
+        assert rel_err(b[:, :10], a[:, :10]) < 1e-12
+        assert rel_err(o[1], r[1]) < 1e-12 and rel_err(o[2], r[2]) < 1e-12
+
+
 def test_match_frame_on_reference_fixture(ref):
     """The reference's own example data (frames 500-510 x 25 rods, real rig)."""
     m2d, _, _, dl = ref
