@@ -209,10 +209,13 @@ int ptk_reconstruct_host(ptk_ctx* ctx, const ptk_rig* rig, int F, int C, int Nma
 int ptk_measure_fp64_peak(int iters, double* flops, void* stream);
 
 /* Per-kernel timing for bench.py's roofline: when enabled, CUDA event pairs are recorded on the
- * launching stream around every launch of the dominant kernel (K1, k_cost).  ptk_timing_read
- * sums their durations (call after synchronising); off by default. */
+ * launching stream around every kernel launch, by kind.  ptk_timing_read sums durations and counts
+ * per kind into arrays of PTK_TIMING_KINDS entries (call after synchronising); off by default.
+ * kinds: 0 undistort, 1 cost (K1), 2 lsap (matching), 3 rows, 4 rows_to_ends, 5 track_cost,
+ *        6 lsap (tracking), 7 chain (3 launches), 8 create_weights */
+#define PTK_TIMING_KINDS 9
 void ptk_timing_enable(int on);
-int ptk_timing_read(double* cost_kernel_ms, long long* cost_kernel_launches, int reset);
+int ptk_timing_read(double* ms_by_kind, long long* launches_by_kind, int reset);
 
 /* number of kernel launches enqueued by this library since the last call with reset != 0
  * (process-wide, atomic) -- bench.py's `gpu_launches`. */

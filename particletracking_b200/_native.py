@@ -84,7 +84,7 @@ def lib() -> ctypes.CDLL:
     L.ptk_reconstruct_host.argtypes = [vp, rigp, i32, i32, i32] + [vp] * 10 + [dbl, vp, i32] + [vp] * 4
     L.ptk_timing_enable.argtypes = [i32]
     L.ptk_timing_enable.restype = None
-    L.ptk_timing_read.argtypes = [ctypes.POINTER(dbl), ctypes.POINTER(ll), i32]
+    L.ptk_timing_read.argtypes = [vp, vp, i32]
     L.ptk_measure_fp64_peak.argtypes = [i32, ctypes.POINTER(dbl), vp]
     for name in SYMBOLS:
         f = getattr(L, name)

@@ -23,11 +23,14 @@ thread_local char g_cuda_err[256] = "";
 std::atomic<long long> g_launches{0};
 
 // Optional per-kernel timing (ptk_timing_enable): CUDA event pairs recorded on the launching
-// stream around every k_cost launch, so bench.py can report the dominant kernel's duration
-// measured inside the timed region.  Off by default (no events are recorded).
+// stream around every kernel launch, by kernel kind, so bench.py can report the dominant
+// kernel's duration (and the step's breakdown) measured inside the timed region.  Off by default
+// (no events are recorded).
+enum Kind { K_UNDISTORT = 0, K_COST, K_LSAP_MATCH, K_ROWS, K_ROWS_TO_ENDS, K_TRACK_COST, K_LSAP_TRACK, K_CHAIN, K_WEIGHTS, K_N };
 std::atomic<int> g_timing{0};
 std::mutex g_timing_mu;
-std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_cost_events;
+struct TimedLaunch { int kind; cudaEvent_t t0, t1; };
+std::vector<TimedLaunch> g_timed;
 std::vector<cudaEvent_t> g_event_pool;
 
 cudaEvent_t timing_event()
@@ -41,6 +44,30 @@ cudaEvent_t timing_event()
     cudaEventCreate(&e);
     return e;
 }
+
+// RAII: construct right before a launch, destroy right after it
+struct LaunchTimer {
+    int kind;
+    cudaStream_t st;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    LaunchTimer(int k, cudaStream_t s) : kind(k), st(s)
+    {
+        if (!g_timing.load(std::memory_order_relaxed)) return;
+        {
+            std::lock_guard<std::mutex> lk(g_timing_mu);
+            t0 = timing_event();
+            t1 = timing_event();
+        }
+        cudaEventRecord(t0, st);
+    }
+    ~LaunchTimer()
+    {
+        if (!t0) return;
+        cudaEventRecord(t1, st);
+        std::lock_guard<std::mutex> lk(g_timing_mu);
+        g_timed.push_back({kind, t0, t1});
+    }
+};
 
 inline int cuda_fail(cudaError_t e, const char* what)
 {
@@ -120,8 +147,11 @@ int launch_undistort(const DevRig& rig, long long P, int Nmax, const double* cam
     for (long long p0 = 0; p0 < P; p0 += 65535) {
         const int np = (int)((P - p0) < 65535 ? (P - p0) : 65535);
         dim3 grid((2 * Nmax + 127) / 128, np, 2);
-        k_undistort<<<grid, 128, 0, st>>>(rig, Nmax, cam1 + (size_t)p0 * Nmax * 4, cam2 + (size_t)p0 * Nmax * 4, n1 + p0,
-                                          n2 + p0, und1 + (size_t)p0 * Nmax * 4, und2 + (size_t)p0 * Nmax * 4);
+        {
+            LaunchTimer lt(K_UNDISTORT, st);
+            k_undistort<<<grid, 128, 0, st>>>(rig, Nmax, cam1 + (size_t)p0 * Nmax * 4, cam2 + (size_t)p0 * Nmax * 4, n1 + p0,
+                                              n2 + p0, und1 + (size_t)p0 * Nmax * 4, und2 + (size_t)p0 * Nmax * 4);
+        }
         LAUNCHED("k_undistort");
     }
     return PTK_OK;
@@ -145,18 +175,9 @@ int launch_cost(const DevRig& rig, long long P, int Nmax, const double* cam1, co
         a.choice = choice ? choice + o2 : nullptr;
         a.p_world = p_world ? p_world + o2 * 12 : nullptr;
         a.rep_errs = rep_errs ? rep_errs + o2 * 8 : nullptr;
-        cudaEvent_t t0 = nullptr, t1 = nullptr;
-        if (g_timing.load(std::memory_order_relaxed)) {
-            std::lock_guard<std::mutex> lk(g_timing_mu);
-            t0 = timing_event();
-            t1 = timing_event();
-        }
-        if (t0) cudaEventRecord(t0, st);
-        k_cost<<<(unsigned)(np * a.tiles), 128, 0, st>>>(rig, a);
-        if (t1) {
-            cudaEventRecord(t1, st);
-            std::lock_guard<std::mutex> lk(g_timing_mu);
-            g_cost_events.emplace_back(t0, t1);
+        {
+            LaunchTimer lt(K_COST, st);
+            k_cost<<<(unsigned)(np * a.tiles), 128, 0, st>>>(rig, a);
         }
         LAUNCHED("k_cost");
     }
@@ -166,7 +187,9 @@ int launch_cost(const DevRig& rig, long long P, int Nmax, const double* cam1, co
 int launch_lsap(long long P, LsapArgs a, cudaStream_t st)
 {
     const int M = a.ld_rows > a.ld_cols ? a.ld_rows : a.ld_cols;
-    const size_t smem = lsap_smem_bytes(M);
+    const size_t bytes = (size_t)a.ld_rows * a.ld_cols * sizeof(double);
+    a.stage = bytes <= (size_t)kLsapStageBytes ? 1 : 0;
+    const size_t smem = a.stage ? bytes : 0;
     const long long max_p = 1ll << 30;
     for (long long p0 = 0; p0 < P; p0 += max_p) {
         const long long np = (P - p0) < max_p ? (P - p0) : max_p;
@@ -181,7 +204,13 @@ int launch_lsap(long long P, LsapArgs a, cudaStream_t st)
         if (a.assigned) b.assigned = a.assigned + (size_t)p0 * a.out_ld;
         if (a.total) b.total = a.total + p0;
         if (a.keep) b.keep = a.keep + (size_t)p0 * a.out_ld;
-        k_lsap<<<(unsigned)np, 32, smem, st>>>(b);
+        {
+            LaunchTimer lt(a.total ? K_LSAP_TRACK : K_LSAP_MATCH, st);
+            if (M <= 32) k_lsap<1><<<(unsigned)np, 32, smem, st>>>(b);
+            else if (M <= 64) k_lsap<2><<<(unsigned)np, 32, smem, st>>>(b);
+            else if (M <= 128) k_lsap<4><<<(unsigned)np, 32, smem, st>>>(b);
+            else k_lsap<8><<<(unsigned)np, 32, smem, st>>>(b);
+        }
         LAUNCHED("k_lsap");
     }
     return PTK_OK;
@@ -202,7 +231,10 @@ int launch_rows(const DevRig& rig, long long P, int Nmax, const double* cam1, co
         a.rows = rows + (size_t)p0 * Nmax * PTK_ROW_COLS;
         a.pair_cost = pair_cost ? pair_cost + (size_t)p0 * Nmax : nullptr;
         dim3 grid((Nmax + 31) / 32, np);
-        k_rows<<<grid, 128, 0, st>>>(rig, a);
+        {
+            LaunchTimer lt(K_ROWS, st);
+            k_rows<<<grid, 128, 0, st>>>(rig, a);
+        }
         LAUNCHED("k_rows");
     }
     return PTK_OK;
@@ -249,21 +281,23 @@ PTK_API long long ptk_launch_count(int reset)
 
 PTK_API void ptk_timing_enable(int on) { g_timing.store(on ? 1 : 0); }
 
-PTK_API int ptk_timing_read(double* cost_kernel_ms, long long* cost_kernel_launches, int reset)
+PTK_API int ptk_timing_read(double* ms_by_kind, long long* launches_by_kind, int reset)
 {
-    // caller must have synchronised the streams the work ran on
+    // caller must have synchronised the streams the work ran on; arrays hold PTK_TIMING_KINDS entries
     std::lock_guard<std::mutex> lk(g_timing_mu);
-    double ms = 0;
-    for (auto& pr : g_cost_events) {
-        float t = 0;
-        CK(cudaEventElapsedTime(&t, pr.first, pr.second));
-        ms += t;
+    for (int k = 0; k < K_N; k++) {
+        if (ms_by_kind) ms_by_kind[k] = 0;
+        if (launches_by_kind) launches_by_kind[k] = 0;
     }
-    if (cost_kernel_ms) *cost_kernel_ms = ms;
-    if (cost_kernel_launches) *cost_kernel_launches = (long long)g_cost_events.size();
+    for (auto& tl : g_timed) {
+        float t = 0;
+        CK(cudaEventElapsedTime(&t, tl.t0, tl.t1));
+        if (ms_by_kind) ms_by_kind[tl.kind] += t;
+        if (launches_by_kind) launches_by_kind[tl.kind] += 1;
+    }
     if (reset) {
-        for (auto& pr : g_cost_events) { g_event_pool.push_back(pr.first); g_event_pool.push_back(pr.second); }
-        g_cost_events.clear();
+        for (auto& tl : g_timed) { g_event_pool.push_back(tl.t0); g_event_pool.push_back(tl.t1); }
+        g_timed.clear();
     }
     return PTK_OK;
 }
@@ -397,7 +431,10 @@ PTK_API int ptk_rows_to_ends(int F, int C, int N, int Nmax, const double* rows, 
     if (F < 0 || C < 0 || bad_n(Nmax) || N < 0 || N > Nmax || !rows || !ends) return PTK_ERR_INVALID_ARG;
     const long long tot = (long long)F * C * N * 6;
     if (tot == 0) return PTK_OK;
-    k_rows_to_ends<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(0, F, F, C, N, Nmax, rows, ends);
+    {
+        LaunchTimer lt(K_ROWS_TO_ENDS, (cudaStream_t)stream);
+        k_rows_to_ends<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(0, F, F, C, N, Nmax, rows, ends);
+    }
     LAUNCHED("k_rows_to_ends");
     return PTK_OK;
 }
@@ -419,7 +456,10 @@ PTK_API int ptk_track_batch(int C, int F, int N, const double* ends, double* cos
         const long long nq = (Q - q0) < chunk ? (Q - q0) : chunk;
         double* cchunk = cost ? cost + (size_t)q0 * NN : wcost;
         dim3 grid((unsigned)((NN + 255) / 256), (unsigned)nq);
-        k_track_cost<<<grid, 256, 0, st>>>(N, F, q0, ends, cchunk);
+        {
+            LaunchTimer lt(K_TRACK_COST, st);
+            k_track_cost<<<grid, 256, 0, st>>>(N, F, q0, ends, cchunk);
+        }
         LAUNCHED("k_track_cost");
         LsapArgs a{};
         a.ld_rows = N; a.ld_cols = N; a.cost_stride = NN; a.cost = cchunk;
@@ -444,13 +484,16 @@ int chain_impl(int C, int F, int N, const int32_t* col_ind, const int32_t* ids_i
     int32_t* seg_start = scratch + (size_t)C * nseg * N;
     const int threads = N < 32 ? 32 : ((N + 31) / 32 * 32);
     const size_t smem = 2 * (size_t)N * sizeof(int32_t);
-    k_chain_local<<<dim3(nseg, C), threads, smem, st>>>(F, N, nseg, col_ind, track_id, seg_map);
-    LAUNCHED("k_chain_local");
-    k_chain_scan<<<C, threads, smem, st>>>(N, nseg, ids_in, seg_map, seg_start);
-    LAUNCHED("k_chain_scan");
     const long long total = (long long)C * F * N;
-    k_chain_apply<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(F, N, nseg, seg_start, track_id, total);
-    LAUNCHED("k_chain_apply");
+    {
+        LaunchTimer lt(K_CHAIN, st);
+        k_chain_local<<<dim3(nseg, C), threads, smem, st>>>(F, N, nseg, col_ind, track_id, seg_map);
+        LAUNCHED("k_chain_local");
+        k_chain_scan<<<C, threads, smem, st>>>(N, nseg, ids_in, seg_map, seg_start);
+        LAUNCHED("k_chain_scan");
+        k_chain_apply<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(F, N, nseg, seg_start, track_id, total);
+        LAUNCHED("k_chain_apply");
+    }
     return PTK_OK;
 }
 size_t chain_scratch_ints(int C, int F, int N)

@@ -133,6 +133,30 @@ __device__ __forceinline__ void dlt_triangulate(const double* __restrict__ P1, c
     double W0, W1, W2, W3;
 #define PTK_NRM(Ak) fma(Ak[3], Ak[3], fma(Ak[2], Ak[2], fma(Ak[1], Ak[1], Ak[0] * Ak[0])))
     W0 = PTK_NRM(A0); W1 = PTK_NRM(A1); W2 = PTK_NRM(A2); W3 = PTK_NRM(A3);
+    // de Rijk ordering: sort the columns by decreasing norm before the first sweep.  OpenCV does
+    // not, but the singular vectors do not depend on the column order, and on DLT matrices (one
+    // column ~ f*T dominates) it cuts the rotations from 19.6 to 13.9 and the sweeps from 4.8 to
+    // 3.9 per point at the same 1e-15 accuracy (profiles/experiments/jacobi_variants.c).  Branch
+    // free 5-comparator network on registers; V starts as the identity in the permuted basis and
+    // the selected vector is un-permuted at the end.
+    int q0 = 0, q1 = 1, q2 = 2, q3 = 3;
+#define PTK_CSWAP(a, b)                                                      \
+    {                                                                        \
+        const bool sw = W##b > W##a;                                         \
+        _Pragma("unroll") for (int k = 0; k < 4; k++) {                      \
+            const double lo = sw ? A##a[k] : A##b[k];                        \
+            A##a[k] = sw ? A##b[k] : A##a[k];                                \
+            A##b[k] = lo;                                                    \
+        }                                                                    \
+        const double wl = sw ? W##a : W##b;                                  \
+        W##a = sw ? W##b : W##a;                                             \
+        W##b = wl;                                                           \
+        const int ql = sw ? q##a : q##b;                                     \
+        q##a = sw ? q##b : q##a;                                             \
+        q##b = ql;                                                           \
+    }
+    PTK_CSWAP(0, 1) PTK_CSWAP(2, 3) PTK_CSWAP(0, 2) PTK_CSWAP(1, 3) PTK_CSWAP(1, 2)
+#undef PTK_CSWAP
     int rot = 0;
 #pragma unroll 1
     for (int iter = 0; iter < 30; iter++) {
@@ -150,11 +174,15 @@ __device__ __forceinline__ void dlt_triangulate(const double* __restrict__ P1, c
     // W already holds the squared column norms of the final A V (recomputed by every rotation,
     // exactly what OpenCV's closing pass computes before its sqrt); smallest wins, ties -> later
     // row, matching OpenCV's descending selection sort for the generic case.
-    double wm = W0, vx = V0[0], vy = V0[1], vz = V0[2], vw = V0[3];
-    if (W1 <= wm) { wm = W1; vx = V1[0]; vy = V1[1]; vz = V1[2]; vw = V1[3]; }
-    if (W2 <= wm) { wm = W2; vx = V2[0]; vy = V2[1]; vz = V2[2]; vw = V2[3]; }
-    if (W3 <= wm) { wm = W3; vx = V3[0]; vy = V3[1]; vz = V3[2]; vw = V3[3]; }
+    double wm = W0, v0 = V0[0], v1 = V0[1], v2 = V0[2], v3 = V0[3];
+    if (W1 <= wm) { wm = W1; v0 = V1[0]; v1 = V1[1]; v2 = V1[2]; v3 = V1[3]; }
+    if (W2 <= wm) { wm = W2; v0 = V2[0]; v1 = V2[1]; v2 = V2[2]; v3 = V2[3]; }
+    if (W3 <= wm) { wm = W3; v0 = V3[0]; v1 = V3[1]; v2 = V3[2]; v3 = V3[3]; }
 #undef PTK_NRM
+    // component k of the permuted basis is original coordinate q_k
+#define PTK_UNPERM(j) (q0 == j ? v0 : (q1 == j ? v1 : (q2 == j ? v2 : v3)))
+    const double vx = PTK_UNPERM(0), vy = PTK_UNPERM(1), vz = PTK_UNPERM(2), vw = PTK_UNPERM(3);
+#undef PTK_UNPERM
     X = vx / vw;
     Y = vy / vw;
     Z = vz / vw;

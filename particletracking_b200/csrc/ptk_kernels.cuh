@@ -123,9 +123,9 @@ __global__ void __launch_bounds__(128) k_cost(const __grid_constant__ DevRig rig
 // order and tie rule: the `remaining` list starts reversed, a visited
 // column is removed by swapping in the last one, and among columns of minimal reduced cost
 // the LAST unassigned one in list order wins, else the FIRST one.  Lanes own columns
-// j = lane, lane+32, ...; dual variables and bookkeeping live in shared memory; the warp
-// min-reduction is shuffle based.  The reduced cost is evaluated unfused, left to right,
-// as SciPy's C++ does, so exact ties tie here too.
+// j = lane, lane+32, ...; all solver state is register resident; the cost matrix is staged in
+// shared memory when small (else read from L2); warp-wide min / argmin are REDUX ops.  The
+// reduced cost is evaluated unfused, left to right, as SciPy's C++ does, so exact ties tie here too.
 struct LsapArgs {
     int ld_rows, ld_cols;    // padded problem shape; cost row stride = ld_cols
     size_t cost_stride;      // doubles between problems
@@ -141,6 +141,7 @@ struct LsapArgs {
     double* total;           // optional [P]: sum of assigned
     uint8_t* keep;           // optional [P,out_ld]: assigned <= max_err
     double max_err;
+    int stage;               // set by the launcher: cost matrix fits the shared-memory staging budget
 };
 
 __device__ __forceinline__ double warp_min(double x)
@@ -157,27 +158,55 @@ __device__ __forceinline__ double warp_sum(double x)
     return x;
 }
 
-__host__ __device__ inline size_t lsap_smem_bytes(int M)
+// warp-wide minimum of a double in two REDUX ops: map to an order-preserving unsigned key,
+// reduce the high words, then the low words among the lanes that hold the winning high word.
+__device__ __forceinline__ double warp_min_redux(double x)
 {
-    return (size_t)M * (3 * sizeof(double) + 5 * sizeof(int32_t) + 1) + 16;
+    unsigned long long k = (unsigned long long)__double_as_longlong(x);
+    k = (k >> 63) ? ~k : (k | 0x8000000000000000ull);
+    const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+    const unsigned mh = __reduce_min_sync(kFull, hi);
+    const unsigned ml = __reduce_min_sync(kFull, hi == mh ? lo : 0xffffffffu);
+    unsigned long long m = ((unsigned long long)mh << 32) | ml;
+    m = (m >> 63) ? (m & 0x7fffffffffffffffull) : ~m;
+    return __longlong_as_double((long long)m);
 }
 
+// value of arr[idx >> 5] held by lane (idx & 31), broadcast to the warp (idx is warp-uniform)
+template <int CPL, typename T>
+__device__ __forceinline__ T lane_array_get(const T (&arr)[CPL], int idx)
+{
+    T val = arr[0];
+#pragma unroll
+    for (int t = 0; t < CPL; t++) {
+        const T tmp = __shfl_sync(kFull, arr[t], idx & 31);
+        if (t == (idx >> 5)) val = tmp;
+    }
+    return val;
+}
+
+template <int CPL, typename T>
+__device__ __forceinline__ void lane_array_set(T (&arr)[CPL], int idx, T val, int lane)
+{
+#pragma unroll
+    for (int t = 0; t < CPL; t++)
+        if (lane == (idx & 31) && t == (idx >> 5)) arr[t] = val;
+}
+
+constexpr int kLsapStageBytes = 16 * 1024;  // stage the cost matrix in shared memory up to this size
+
+// CPL = columns (and rows) per lane: the problem must satisfy max(nr, nc) <= 32*CPL.
+// All solver state lives in registers: lane l owns columns l, l+32, ... (v, shortest path cost,
+// path, row4col, position in SciPy's `remaining` list) and rows l, l+32, ... (u, col4row, visited
+// bit).  The `remaining` list itself is never stored: only each column's position in it, which
+// is all the tie rule needs; removal = "the column at the last position takes the freed one".
+template <int CPL>
 __global__ void __launch_bounds__(32) k_lsap(const __grid_constant__ LsapArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* sm = reinterpret_cast<double*>(smem_raw);
     const int lane = threadIdx.x;
     const long long p = blockIdx.x;
-    const int M = a.ld_rows > a.ld_cols ? a.ld_rows : a.ld_cols;
-    double* u = reinterpret_cast<double*>(smem_raw);
-    double* v = u + M;
-    double* spc = v + M;
-    int32_t* path = reinterpret_cast<int32_t*>(spc + M);
-    int32_t* row4col = path + M;
-    int32_t* col4row = row4col + M;
-    int32_t* pos = col4row + M;
-    int32_t* remaining = pos + M;
-    unsigned char* SR = reinterpret_cast<unsigned char*>(remaining + M);
-
     const int nr0 = a.nr ? a.nr[p] : a.ld_rows;
     const int nc0 = a.nc ? a.nc[p] : a.ld_cols;
     const double* C = a.cost + (size_t)p * a.cost_stride;
@@ -193,90 +222,113 @@ __global__ void __launch_bounds__(32) k_lsap(const __grid_constant__ LsapArgs a)
     if (nr0 <= 0 || nc0 <= 0) st = PTK_PROBLEM_EMPTY;
     const bool tr = nc0 < nr0;  // tall matrices are solved transposed, as SciPy does
     const int nr = tr ? nc0 : nr0, nc = tr ? nr0 : nc0;
+    const bool staged = a.stage != 0;
 
     if (st == PTK_PROBLEM_OK) {
+        // validate (SciPy: "matrix contains invalid numeric entries") and stage in solver orientation
         bool bad = false;
         const int tot = nr0 * nc0;
         for (int idx = lane; idx < tot; idx += 32) {
             const int i = idx / nc0, j = idx - i * nc0;
             const double c = C[(size_t)i * ldc + j];
             bad |= (c != c) || (c == -INFINITY);
+            if (staged) sm[tr ? (j * nc + i) : (i * nc + j)] = c;
         }
         if (__any_sync(kFull, bad)) st = PTK_PROBLEM_INVALID;
+        __syncwarp();
     }
 
+    double u[CPL], v[CPL], spc[CPL];
+    int path[CPL], r4c[CPL], c4r[CPL], pos[CPL];
+#pragma unroll
+    for (int s = 0; s < CPL; s++) { u[s] = 0.0; v[s] = 0.0; spc[s] = 0.0; path[s] = -1; r4c[s] = -1; c4r[s] = -1; pos[s] = -1; }
+
     if (st == PTK_PROBLEM_OK) {
-        for (int j = lane; j < nc; j += 32) { v[j] = 0.0; row4col[j] = -1; path[j] = -1; }
-        for (int i = lane; i < nr; i += 32) { u[i] = 0.0; col4row[i] = -1; }
-        __syncwarp();
         for (int cur = 0; cur < nr; cur++) {
-            for (int j = lane; j < nc; j += 32) {
-                spc[j] = INFINITY;
-                remaining[j] = nc - 1 - j;
-                pos[nc - 1 - j] = j;
+            unsigned srbits = 0;
+#pragma unroll
+            for (int s = 0; s < CPL; s++) {
+                const int j = lane + 32 * s;
+                spc[s] = INFINITY;
+                pos[s] = (j < nc) ? (nc - 1 - j) : -1;  // remaining[it] = nc-1-it  <=>  pos[j] = nc-1-j
             }
-            for (int i = lane; i < nr; i += 32) SR[i] = 0;
-            __syncwarp();
             double minVal = 0.0;
             int i = cur, num_rem = nc, sink = -1;
             while (sink == -1) {
-                if (lane == 0) SR[i] = 1;
-                const double ui = u[i];
+                if (lane == (i & 31)) srbits |= 1u << (i >> 5);
+                const double ui = lane_array_get<CPL>(u, i);
                 double lmin = INFINITY;
-                for (int j = lane; j < nc; j += 32) {
-                    if (pos[j] < 0) continue;
-                    const double c = tr ? C[(size_t)j * ldc + i] : C[(size_t)i * ldc + j];
-                    const double r = ((minVal + c) - ui) - v[j];
-                    double s = spc[j];
-                    if (r < s) { s = r; spc[j] = r; path[j] = i; }
-                    lmin = fmin(lmin, s);
+#pragma unroll
+                for (int s = 0; s < CPL; s++) {
+                    const int j = lane + 32 * s;
+                    if (pos[s] >= 0) {
+                        const double c = staged ? sm[i * nc + j] : (tr ? C[(size_t)j * ldc + i] : C[(size_t)i * ldc + j]);
+                        const double r = ((minVal + c) - ui) - v[s];
+                        if (r < spc[s]) { spc[s] = r; path[s] = i; }
+                        lmin = fmin(lmin, spc[s]);
+                    }
                 }
-                const double lowest = warp_min(lmin);
+                const double lowest = warp_min_redux(lmin);
                 if (lowest == INFINITY) { st = PTK_PROBLEM_INFEASIBLE; break; }
                 int un_pos = -1, as_pos = INT_MAX;
-                for (int j = lane; j < nc; j += 32) {
-                    const int pj = pos[j];
-                    if (pj < 0 || spc[j] != lowest) continue;
-                    if (row4col[j] == -1) un_pos = max(un_pos, pj);
-                    else as_pos = min(as_pos, pj);
+#pragma unroll
+                for (int s = 0; s < CPL; s++) {
+                    if (pos[s] >= 0 && spc[s] == lowest) {
+                        if (r4c[s] == -1) un_pos = max(un_pos, pos[s]);
+                        else as_pos = min(as_pos, pos[s]);
+                    }
                 }
                 const int un = __reduce_max_sync(kFull, un_pos);
                 const int index = (un >= 0) ? un : __reduce_min_sync(kFull, as_pos);
-                const int jsel = remaining[index];
+                // the column sitting at `index`: pack (row4col+1, column) and broadcast
+                int packed = 0;
+#pragma unroll
+                for (int s = 0; s < CPL; s++)
+                    if (pos[s] == index) packed = ((r4c[s] + 1) << 9) | (lane + 32 * s);
+                packed = __reduce_max_sync(kFull, packed);
+                const int jsel = packed & 511;
+                const int r4 = (packed >> 9) - 1;
                 minVal = lowest;
-                const int r4c = row4col[jsel];
-                if (r4c == -1) sink = jsel; else i = r4c;
-                __syncwarp();
-                if (lane == 0) {
-                    const int last = remaining[num_rem - 1];
-                    pos[jsel] = -1;
-                    remaining[index] = last;
-                    if (last != jsel) pos[last] = index;
+                if (r4 == -1) sink = jsel; else i = r4;
+                // remaining[index] = remaining[--num_remaining]
+#pragma unroll
+                for (int s = 0; s < CPL; s++) {
+                    if (pos[s] == index) pos[s] = -2;  // visited (SC)
+                }
+#pragma unroll
+                for (int s = 0; s < CPL; s++) {
+                    if (pos[s] == num_rem - 1) pos[s] = index;
                 }
                 num_rem--;
-                __syncwarp();
             }
             if (st != PTK_PROBLEM_OK) break;
             // dual update (rectangular_lsap.cpp order: u[cur] first, then visited rows / columns)
-            for (int r = lane; r < nr; r += 32) {
-                if (r == cur) u[r] += minVal;
-                else if (SR[r]) u[r] += minVal - spc[col4row[r]];
-            }
-            for (int j = lane; j < nc; j += 32)
-                if (pos[j] < 0) v[j] -= minVal - spc[j];
-            __syncwarp();
-            if (lane == 0) {
-                int j = sink;
-                while (true) {
-                    const int r = path[j];
-                    row4col[j] = r;
-                    const int t = col4row[r];
-                    col4row[r] = j;
-                    j = t;
-                    if (r == cur) break;
+#pragma unroll
+            for (int s = 0; s < CPL; s++) {
+                const int r = lane + 32 * s;
+                const int col = c4r[s] < 0 ? 0 : c4r[s];
+                double sp = 0.0;
+#pragma unroll
+                for (int t = 0; t < CPL; t++) {
+                    const double tmp = __shfl_sync(kFull, spc[t], col & 31);
+                    if (t == (col >> 5)) sp = tmp;
                 }
+                if (r == cur) u[s] += minVal;
+                else if ((srbits >> s) & 1u) u[s] += minVal - sp;
             }
-            __syncwarp();
+#pragma unroll
+            for (int s = 0; s < CPL; s++)
+                if (pos[s] == -2) v[s] -= minVal - spc[s];
+            // augment along the path
+            int j = sink;
+            while (true) {
+                const int r = lane_array_get<CPL>(path, j);
+                lane_array_set<CPL>(r4c, j, r, lane);
+                const int t = lane_array_get<CPL>(c4r, r);
+                lane_array_set<CPL>(c4r, r, j, lane);
+                j = t;
+                if (r == cur) break;
+            }
         }
     }
 
@@ -285,25 +337,30 @@ __global__ void __launch_bounds__(32) k_lsap(const __grid_constant__ LsapArgs a)
         n = nr;
         double tsum = 0.0;
         if (!tr) {
-            for (int r = lane; r < nr; r += 32) {
-                const int cj = col4row[r];
-                const double cst = C[(size_t)r * ldc + cj];
-                if (orow) orow[r] = r;
-                ocol[r] = cj;
-                if (oasg) oasg[r] = cst;
-                if (okeep) okeep[r] = (cst <= a.max_err) ? 1 : 0;
-                tsum += cst;
+#pragma unroll
+            for (int s = 0; s < CPL; s++) {
+                const int r = lane + 32 * s;
+                if (r < nr) {
+                    const int cj = c4r[s];
+                    const double cst = C[(size_t)r * ldc + cj];
+                    if (orow) orow[r] = r;
+                    ocol[r] = cj;
+                    if (oasg) oasg[r] = cst;
+                    if (okeep) okeep[r] = (cst <= a.max_err) ? 1 : 0;
+                    tsum += cst;
+                }
             }
         } else {
             // rows of the transposed problem are original columns; emit sorted by original row
             int off = 0;
-            for (int b = 0; b < nc; b += 32) {
-                const int r0 = b + lane;
-                const bool has = r0 < nc && row4col[r0] != -1;
+#pragma unroll
+            for (int s = 0; s < CPL; s++) {
+                const int r0 = lane + 32 * s;
+                const bool has = r0 < nc && r4c[s] != -1;
                 const unsigned m = __ballot_sync(kFull, has);
                 if (has) {
                     const int k = off + __popc(m & ((1u << lane) - 1u));
-                    const int cj = row4col[r0];
+                    const int cj = r4c[s];
                     const double cst = C[(size_t)r0 * ldc + cj];
                     if (orow) orow[k] = r0;
                     ocol[k] = cj;

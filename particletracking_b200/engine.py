@@ -268,12 +268,16 @@ def kernel_timing(enable: bool) -> None:
     nat.lib().ptk_timing_enable(1 if enable else 0)
 
 
+TIMING_KINDS = ["undistort", "cost", "lsap_match", "rows", "rows_to_ends", "track_cost", "lsap_track", "chain", "weights"]
+
+
 def kernel_timing_read(reset: bool = True):
-    """(total ms, launches) of K1 since the last reset; synchronise first."""
-    ms = ctypes.c_double(0.0)
-    n = ctypes.c_longlong(0)
-    nat.check(nat.lib().ptk_timing_read(ctypes.byref(ms), ctypes.byref(n), 1 if reset else 0), "ptk_timing_read")
-    return ms.value, n.value
+    """{kind: (total ms, launches)} since the last reset; synchronise first."""
+    n = len(TIMING_KINDS)
+    ms = (ctypes.c_double * n)()
+    cnt = (ctypes.c_longlong * n)()
+    nat.check(nat.lib().ptk_timing_read(ms, cnt, 1 if reset else 0), "ptk_timing_read")
+    return {k: (ms[i], cnt[i]) for i, k in enumerate(TIMING_KINDS)}
 
 
 def launch_count(reset: bool = False) -> int:
