@@ -72,7 +72,12 @@ struct CostArgs {
 
 __device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
 
-__global__ void __launch_bounds__(128) k_cost(const __grid_constant__ DevRig rig, const __grid_constant__ CostArgs a)
+// 5 CTAs x 4 warps per SM (96 registers, ~90 B of spill outside the Jacobi loop) measured 3 %
+// faster than 4 CTAs at 126 registers (tools/ab_bench.py, profiles/README.md).
+#ifndef PTK_KCOST_MINBLOCKS
+#define PTK_KCOST_MINBLOCKS 5
+#endif
+__global__ void __launch_bounds__(128, PTK_KCOST_MINBLOCKS) k_cost(const __grid_constant__ DevRig rig, const __grid_constant__ CostArgs a)
 {
     const long long blk = blockIdx.x;
     const int p = (int)(blk / a.tiles);
