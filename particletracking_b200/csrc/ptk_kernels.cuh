@@ -273,26 +273,34 @@ __global__ void __launch_bounds__(32) k_lsap(const __grid_constant__ LsapArgs a)
                         lmin = fmin(lmin, spc[s]);
                     }
                 }
-                const double lowest = warp_min_redux(lmin);
+                // warp argmin with SciPy's tie rule in three REDUX ops: (1) high word and (2) low
+                // word of the order-preserving key of the shortest-path cost, then (3) one packed
+                // integer whose order is the tie rule: unassigned columns first (largest list
+                // position wins), then assigned ones (smallest position wins); its low bits carry
+                // row4col+1 and the column so that the winner needs no further broadcast.
+                unsigned long long k = (unsigned long long)__double_as_longlong(lmin);
+                k = (k >> 63) ? ~k : (k | 0x8000000000000000ull);
+                const unsigned mh = __reduce_min_sync(kFull, (unsigned)(k >> 32));
+                const unsigned ml = __reduce_min_sync(kFull, (unsigned)(k >> 32) == mh ? (unsigned)k : 0xffffffffu);
+                unsigned long long m64 = ((unsigned long long)mh << 32) | ml;
+                m64 = (m64 >> 63) ? (m64 & 0x7fffffffffffffffull) : ~m64;
+                const double lowest = __longlong_as_double((long long)m64);
                 if (lowest == INFINITY) { st = PTK_PROBLEM_INFEASIBLE; break; }
-                int un_pos = -1, as_pos = INT_MAX;
+                unsigned key3 = 0xffffffffu;
 #pragma unroll
                 for (int s = 0; s < CPL; s++) {
                     if (pos[s] >= 0 && spc[s] == lowest) {
-                        if (r4c[s] == -1) un_pos = max(un_pos, pos[s]);
-                        else as_pos = min(as_pos, pos[s]);
+                        const unsigned un = (r4c[s] == -1);
+                        const unsigned rank = un ? (unsigned)(511 - pos[s]) : (unsigned)(512 + pos[s]);
+                        const unsigned cand = (rank << 18) | ((unsigned)(r4c[s] + 1) << 9) | (unsigned)(lane + 32 * s);
+                        key3 = min(key3, cand);
                     }
                 }
-                const int un = __reduce_max_sync(kFull, un_pos);
-                const int index = (un >= 0) ? un : __reduce_min_sync(kFull, as_pos);
-                // the column sitting at `index`: pack (row4col+1, column) and broadcast
-                int packed = 0;
-#pragma unroll
-                for (int s = 0; s < CPL; s++)
-                    if (pos[s] == index) packed = ((r4c[s] + 1) << 9) | (lane + 32 * s);
-                packed = __reduce_max_sync(kFull, packed);
-                const int jsel = packed & 511;
-                const int r4 = (packed >> 9) - 1;
+                key3 = __reduce_min_sync(kFull, key3);
+                const int jsel = (int)(key3 & 511u);
+                const int r4 = (int)((key3 >> 9) & 511u) - 1;
+                const unsigned rank = key3 >> 18;
+                const int index = rank < 512u ? (int)(511u - rank) : (int)(rank - 512u);
                 minVal = lowest;
                 if (r4 == -1) sink = jsel; else i = r4;
                 // remaining[index] = remaining[--num_remaining]

@@ -8,7 +8,7 @@
 #include <float.h>
 #include <string.h>
 
-typedef struct { double eps; int sort_first; int small_angle; int fixed_sweeps; } Var;
+typedef struct { double eps; int sort_first; int small_angle; int fixed_sweeps; int rr; } Var;
 
 static void tri(const double* P1, const double* P2, const double* q, Var v, double* X, long* rot, long* swp, long* chk)
 {
@@ -39,8 +39,10 @@ static void tri(const double* P1, const double* P2, const double* q, Var v, doub
     double eps2 = v.eps * v.eps;
     for (int iter = 0; iter < 30; iter++) {
         int changed = 0;
-        for (int i = 0; i < 3; i++)
-            for (int j = i + 1; j < 4; j++) {
+        static const int ORD[2][6][2] = {{{0,1},{0,2},{0,3},{1,2},{1,3},{2,3}}, {{0,1},{2,3},{0,2},{1,3},{0,3},{1,2}}};
+        for (int pi = 0; pi < 6; pi++) {
+            {
+                int i = ORD[v.rr][pi][0], j = ORD[v.rr][pi][1];
                 double a = W[i], b = W[j], p = 0;
                 for (int k = 0; k < 4; k++) p += At[i][k] * At[j][k];
                 (*chk)++;
@@ -62,6 +64,7 @@ static void tri(const double* P1, const double* P2, const double* q, Var v, doub
                 W[i] = a; W[j] = b;
                 changed = 1; (*rot)++;
             }
+        }
         (*swp)++;
         if (v.fixed_sweeps ? (iter + 1 >= v.fixed_sweeps) : !changed) break;
     }
@@ -81,7 +84,7 @@ int main(int argc, char** argv)
     if (fread(q, 8, M * 4, f) != (size_t)(M * 4)) return 1;
     Var vars[] = {{10 * DBL_EPSILON, 0, 0, 0}, {1e-13, 0, 0, 0}, {1e-12, 0, 0, 0}, {1e-11, 0, 0, 0}, {1e-10, 0, 0, 0},
                   {10 * DBL_EPSILON, 1, 0, 0}, {1e-12, 1, 0, 0}, {10 * DBL_EPSILON, 0, 1, 0}, {1e-12, 0, 1, 0},
-                  {10 * DBL_EPSILON, 1, 1, 0}, {1e-12, 1, 1, 0}, {1e-300, 0, 0, 3}, {1e-300, 0, 0, 4}, {1e-300, 1, 0, 4}};
+                  {10 * DBL_EPSILON, 1, 1, 0}, {1e-12, 1, 1, 0}, {10 * DBL_EPSILON, 1, 0, 0, 1}, {10 * DBL_EPSILON, 0, 0, 0, 1}};
     int nv = sizeof(vars) / sizeof(vars[0]);
     double* base = malloc(M * 3 * 8);
     for (int v = 0; v < nv; v++) {
@@ -102,8 +105,8 @@ int main(int argc, char** argv)
         }
         long big = 0;
         for (long m = 0; m < M; m++) if (errs[m] > 1e-10) big++;
-        printf("eps=%.1e sort=%d small=%d fixed=%d : rot/combo %.2f sweeps %.2f (max %d) checks %.1f  max_rel_err %.2e  n(err>1e-10)=%ld of %ld\n",
-               vars[v].eps, vars[v].sort_first, vars[v].small_angle, vars[v].fixed_sweeps, (double)rot / M, (double)swp / M, maxs,
+        printf("eps=%.1e sort=%d small=%d fixed=%d rr=%d : rot/combo %.2f sweeps %.2f (max %d) checks %.1f  max_rel_err %.2e  n(err>1e-10)=%ld of %ld\n",
+               vars[v].eps, vars[v].sort_first, vars[v].small_angle, vars[v].fixed_sweeps, vars[v].rr, (double)rot / M, (double)swp / M, maxs,
                (double)chk / M, worst, big, M);
         free(errs);
     }

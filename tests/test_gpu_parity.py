@@ -362,3 +362,77 @@ def test_full_size_c2_properties(eng, crig):
     np.testing.assert_array_equal(col[sel], o["col_ind"])
     assert rel_err(rows[sel][..., :10], o["rows"][..., :10]) < TOL
     np.testing.assert_array_equal(rows[sel][..., 10:], o["rows"][..., 10:])
+
+
+# ------------------------------------------------------------------ large N (BASELINE config 5: 8 -> 256 rods)
+@pytest.mark.parametrize("n,P", [(8, 40), (128, 6), (256, 2)])
+def test_match_large_n_vs_c_oracle(eng, crig, n, P):
+    from oracle import c_oracle as co
+    from particletracking_b200 import synthetic as syn
+
+    data = syn.make_stereo(P, 1, n, seed=500 + n, p_drop=0.02 if n > 8 else 0.0)
+    c1, c2, n1, n2 = data.problems()
+    o = co.match_batch(crig, c1, c2, n1, n2)
+    r = run_match(eng, crig, c1, c2, n1, n2)
+    np.testing.assert_array_equal(r.status.cpu().numpy(), o["status"])
+    np.testing.assert_array_equal(r.col_ind.cpu().numpy(), o["col_ind"])
+    np.testing.assert_array_equal(r.row_ind.cpu().numpy(), o["row_ind"])
+    rows = r.rows.cpu().numpy()
+    for p in range(P):
+        k = o["n_out"][p]
+        assert rel_err(rows[p, :k, :10], o["rows"][p, :k, :10]) < TOL
+        np.testing.assert_array_equal(rows[p, :k, 10:], o["rows"][p, :k, 10:])
+    assert rel_err(r.match_cost.cpu().numpy()[:, :8], o["match_cost"][:, :8]) < TOL
+
+
+# ------------------------------------------------------------------ BASELINE config 3 (ragged, dummies, threshold)
+def test_config3_ragged_properties(eng, crig):
+    """Noisy / missing detections (N1 != N2), 2 % dummy rods, sigma 0.5 px, 5 px threshold:
+    sampled problems against the C oracle, properties on all of them."""
+    from oracle import c_oracle as co
+    from particletracking_b200 import synthetic as syn
+
+    data = syn.make_stereo(600, 8, 32, seed=3, p_drop=0.05, p_dummy=0.02, sigma_px=0.5)
+    c1, c2, n1, n2 = data.problems()
+    r = run_match(eng, crig, c1, c2, n1, n2, max_repr_err=5.0)
+    n_out = r.n_out.cpu().numpy()
+    col, row = r.col_ind.cpu().numpy(), r.row_ind.cpu().numpy()
+    mc, keep = r.match_cost.cpu().numpy(), r.keep.cpu().numpy()
+    assert (r.status.cpu().numpy() == 0).all()
+    np.testing.assert_array_equal(n_out, np.minimum(n1, n2))
+    assert (n1 != n2).mean() > 0.5  # the config really is ragged
+    for p in range(0, len(n1), 97):
+        k = n_out[p]
+        assert len(set(col[p, :k])) == k and (col[p, :k] < n2[p]).all() and (col[p, k:] == -1).all()
+        assert (np.diff(row[p, :k]) > 0).all() and (row[p, :k] < n1[p]).all()
+    np.testing.assert_array_equal(keep.astype(bool), np.nan_to_num(mc, nan=np.inf) <= 5.0)
+    sel = np.arange(0, len(n1), 61)
+    o = co.match_batch(crig, c1[sel], c2[sel], n1[sel], n2[sel])
+    np.testing.assert_array_equal(col[sel], o["col_ind"])
+    np.testing.assert_array_equal(row[sel], o["row_ind"])
+    assert rel_err(np.nan_to_num(mc[sel]), np.nan_to_num(np.where(o["row_ind"] >= 0, o["match_cost"], np.nan))) < TOL
+
+
+# ------------------------------------------------------------------ BASELINE config 4 shape (8 colours x 64 rods, match + track)
+def test_config4_shape_match_and_track(eng, crig):
+    import torch
+    from oracle import c_oracle as co
+    from particletracking_b200 import synthetic as syn
+
+    F, C, N = 40, 8, 64
+    data = syn.make_stereo(F, C, N, seed=4)
+    c1, c2, n1, n2 = data.problems()
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    m, col, tot, tid, st = eng.reconstruct_device(crig, t(c1), t(c2), t(n1), t(n2), F, C, track=True)
+    torch.cuda.synchronize()
+    assert (m.status.cpu().numpy() == 0).all() and (st.cpu().numpy() == 0).all()
+    o = co.match_batch(crig, c1, c2, n1, n2)
+    np.testing.assert_array_equal(m.col_ind.cpu().numpy(), o["col_ind"])
+    rows = m.rows.cpu().numpy()
+    assert rel_err(rows[..., :10], o["rows"][..., :10]) < TOL
+    # tracking on the SAME 3D input the GPU tracked (its own rows): bit-exact vs the oracle
+    ends = rows[..., :6].reshape(F, C, N, 2, 3).transpose(1, 0, 2, 3, 4).copy()
+    ot = co.track_batch(ends)
+    np.testing.assert_array_equal(col.cpu().numpy(), ot["col_ind"])
+    np.testing.assert_array_equal(tid.cpu().numpy(), co.chain_tracks(ot["col_ind"]))
+    assert rel_err(tot.cpu().numpy(), ot["total_cost"]) < 1e-13
