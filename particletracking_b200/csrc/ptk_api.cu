@@ -109,13 +109,21 @@ DevRig make_devrig(const ptk_rig* r)
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
-// Problems per internal pass of ptk_match_batch: the cost-matrix chunk is kept around 64 MB so
-// it stays L2-resident (126 MB) between K1 writing it and K2 reading it.
+// Problems per internal pass of ptk_match_batch / ptk_track_batch.  Two constraints:
+//  - small problems: keep the cost-matrix chunk around 64 MB so that it is still L2 resident
+//    (126 MB) when K2 reads what K1 / K4 wrote;
+//  - large problems: K2 is one warp per problem, so a pass needs thousands of problems to fill
+//    148 SMs x 32 warps -- at least 4736 per pass, as long as the chunk stays below 2 GB
+//    (a 296-problem pass of 256x256 matrices left 146 SMs' worth of warp slots empty and made
+//    the N=256 tracking LSAP 10x slower; profiles/README.md).
 long long match_chunk(long long P, int Nmax)
 {
     const size_t per = (size_t)Nmax * Nmax * sizeof(double);
     long long c = (long long)((64ull << 20) / (per ? per : 1));
-    if (c < 296) c = 296;  // >= 2 CTAs per SM worth of problems even for N = 256
+    if (c < 4736) c = 4736;
+    const long long cap = (long long)((2048ull << 20) / (per ? per : 1));
+    if (c > cap) c = cap;
+    if (c < 296) c = 296;
     if (c > P) c = P;
     if (c < 1) c = 1;
     return c;
@@ -189,7 +197,7 @@ int launch_lsap(long long P, LsapArgs a, cudaStream_t st)
     const int M = a.ld_rows > a.ld_cols ? a.ld_rows : a.ld_cols;
     const size_t bytes = (size_t)a.ld_rows * a.ld_cols * sizeof(double);
     a.stage = bytes <= (size_t)kLsapStageBytes ? 1 : 0;
-    const size_t smem = a.stage ? bytes : 0;
+    const size_t smem = ((lsap_row_state_bytes(M) + 15) / 16) * 16 + (a.stage ? bytes : 0);
     const long long max_p = 1ll << 30;
     for (long long p0 = 0; p0 < P; p0 += max_p) {
         const long long np = (P - p0) < max_p ? (P - p0) : max_p;

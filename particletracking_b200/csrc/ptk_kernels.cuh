@@ -163,18 +163,16 @@ __device__ __forceinline__ double warp_sum(double x)
     return x;
 }
 
-// warp-wide minimum of a double in two REDUX ops: map to an order-preserving unsigned key,
-// reduce the high words, then the low words among the lanes that hold the winning high word.
-__device__ __forceinline__ double warp_min_redux(double x)
+// order-preserving map double -> unsigned 64 (for REDUX-based min / equality)
+__device__ __forceinline__ unsigned long long ordered_key(double x)
 {
-    unsigned long long k = (unsigned long long)__double_as_longlong(x);
-    k = (k >> 63) ? ~k : (k | 0x8000000000000000ull);
-    const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
-    const unsigned mh = __reduce_min_sync(kFull, hi);
-    const unsigned ml = __reduce_min_sync(kFull, hi == mh ? lo : 0xffffffffu);
-    unsigned long long m = ((unsigned long long)mh << 32) | ml;
-    m = (m >> 63) ? (m & 0x7fffffffffffffffull) : ~m;
-    return __longlong_as_double((long long)m);
+    const unsigned long long k = (unsigned long long)__double_as_longlong(x);
+    return (k >> 63) ? ~k : (k | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double ordered_value(unsigned long long k)
+{
+    k = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)k);
 }
 
 // value of arr[idx >> 5] held by lane (idx & 31), broadcast to the warp (idx is warp-uniform)
@@ -200,16 +198,22 @@ __device__ __forceinline__ void lane_array_set(T (&arr)[CPL], int idx, T val, in
 
 constexpr int kLsapStageBytes = 16 * 1024;  // stage the cost matrix in shared memory up to this size
 
-// CPL = columns (and rows) per lane: the problem must satisfy max(nr, nc) <= 32*CPL.
-// All solver state lives in registers: lane l owns columns l, l+32, ... (v, shortest path cost,
-// path, row4col, position in SciPy's `remaining` list) and rows l, l+32, ... (u, col4row, visited
-// bit).  The `remaining` list itself is never stored: only each column's position in it, which
-// is all the tie rule needs; removal = "the column at the last position takes the freed one".
+__host__ __device__ inline size_t lsap_row_state_bytes(int M) { return (size_t)M * (sizeof(double) + sizeof(int32_t)) + 16; }
+
+// CPL = columns per lane: the problem must satisfy max(nr, nc) <= 32*CPL.
+// Lane l owns columns l, l+32, ...: v, shortest-path cost, path, row4col and the column's position
+// in SciPy's `remaining` list live in registers (the list itself is never stored: only positions,
+// which is all the tie rule needs; removal = "the column at the last position takes the freed
+// one").  Row duals u and col4row sit in shared memory (one read per Dijkstra step).  A step is
+// ~60 warp instructions + ~25 per owned column; the kernel is issue bound, not latency bound.
 template <int CPL>
 __global__ void __launch_bounds__(32) k_lsap(const __grid_constant__ LsapArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* sm = reinterpret_cast<double*>(smem_raw);
+    const int M = a.ld_rows > a.ld_cols ? a.ld_rows : a.ld_cols;
+    double* u = reinterpret_cast<double*>(smem_raw);
+    int32_t* c4r = reinterpret_cast<int32_t*>(u + M);
+    double* sm = reinterpret_cast<double*>(smem_raw + ((lsap_row_state_bytes(M) + 15) / 16) * 16);
     const int lane = threadIdx.x;
     const long long p = blockIdx.x;
     const int nr0 = a.nr ? a.nr[p] : a.ld_rows;
@@ -240,17 +244,18 @@ __global__ void __launch_bounds__(32) k_lsap(const __grid_constant__ LsapArgs a)
             if (staged) sm[tr ? (j * nc + i) : (i * nc + j)] = c;
         }
         if (__any_sync(kFull, bad)) st = PTK_PROBLEM_INVALID;
+        for (int r = lane; r < nr; r += 32) { u[r] = 0.0; c4r[r] = -1; }
         __syncwarp();
     }
 
-    double u[CPL], v[CPL], spc[CPL];
-    int path[CPL], r4c[CPL], c4r[CPL], pos[CPL];
+    double v[CPL], spc[CPL];
+    int path[CPL], r4c[CPL], pos[CPL];
 #pragma unroll
-    for (int s = 0; s < CPL; s++) { u[s] = 0.0; v[s] = 0.0; spc[s] = 0.0; path[s] = -1; r4c[s] = -1; c4r[s] = -1; pos[s] = -1; }
+    for (int s = 0; s < CPL; s++) { v[s] = 0.0; spc[s] = 0.0; path[s] = -1; r4c[s] = -1; pos[s] = -1; }
+    const unsigned long long kInfKey = 0xfff0000000000000ull;  // ordered_key(+inf)
 
     if (st == PTK_PROBLEM_OK) {
         for (int cur = 0; cur < nr; cur++) {
-            unsigned srbits = 0;
 #pragma unroll
             for (int s = 0; s < CPL; s++) {
                 const int j = lane + 32 * s;
@@ -260,38 +265,35 @@ __global__ void __launch_bounds__(32) k_lsap(const __grid_constant__ LsapArgs a)
             double minVal = 0.0;
             int i = cur, num_rem = nc, sink = -1;
             while (sink == -1) {
-                if (lane == (i & 31)) srbits |= 1u << (i >> 5);
-                const double ui = lane_array_get<CPL>(u, i);
-                double lmin = INFINITY;
+                const double ui = u[i];
+                unsigned long long kmin = ~0ull;
+                unsigned long long key[CPL];
 #pragma unroll
                 for (int s = 0; s < CPL; s++) {
-                    const int j = lane + 32 * s;
+                    key[s] = ~0ull;
                     if (pos[s] >= 0) {
+                        const int j = lane + 32 * s;
                         const double c = staged ? sm[i * nc + j] : (tr ? C[(size_t)j * ldc + i] : C[(size_t)i * ldc + j]);
                         const double r = ((minVal + c) - ui) - v[s];
                         if (r < spc[s]) { spc[s] = r; path[s] = i; }
-                        lmin = fmin(lmin, spc[s]);
+                        key[s] = ordered_key(spc[s]);
+                        kmin = key[s] < kmin ? key[s] : kmin;
                     }
                 }
-                // warp argmin with SciPy's tie rule in three REDUX ops: (1) high word and (2) low
-                // word of the order-preserving key of the shortest-path cost, then (3) one packed
-                // integer whose order is the tie rule: unassigned columns first (largest list
-                // position wins), then assigned ones (smallest position wins); its low bits carry
-                // row4col+1 and the column so that the winner needs no further broadcast.
-                unsigned long long k = (unsigned long long)__double_as_longlong(lmin);
-                k = (k >> 63) ? ~k : (k | 0x8000000000000000ull);
-                const unsigned mh = __reduce_min_sync(kFull, (unsigned)(k >> 32));
-                const unsigned ml = __reduce_min_sync(kFull, (unsigned)(k >> 32) == mh ? (unsigned)k : 0xffffffffu);
-                unsigned long long m64 = ((unsigned long long)mh << 32) | ml;
-                m64 = (m64 >> 63) ? (m64 & 0x7fffffffffffffffull) : ~m64;
-                const double lowest = __longlong_as_double((long long)m64);
-                if (lowest == INFINITY) { st = PTK_PROBLEM_INFEASIBLE; break; }
+                // warp argmin with SciPy's tie rule in three REDUX ops: (1) high and (2) low word
+                // of the order-preserving key of the shortest-path cost, then (3) one packed
+                // integer whose order is the tie rule -- unassigned columns first (largest list
+                // position wins), then assigned ones (smallest position wins) -- and whose low
+                // bits carry row4col+1 and the column, so the winner needs no further broadcast.
+                const unsigned mh = __reduce_min_sync(kFull, (unsigned)(kmin >> 32));
+                const unsigned ml = __reduce_min_sync(kFull, (unsigned)(kmin >> 32) == mh ? (unsigned)kmin : 0xffffffffu);
+                const unsigned long long m64 = ((unsigned long long)mh << 32) | ml;
+                if (m64 == kInfKey) { st = PTK_PROBLEM_INFEASIBLE; break; }
                 unsigned key3 = 0xffffffffu;
 #pragma unroll
                 for (int s = 0; s < CPL; s++) {
-                    if (pos[s] >= 0 && spc[s] == lowest) {
-                        const unsigned un = (r4c[s] == -1);
-                        const unsigned rank = un ? (unsigned)(511 - pos[s]) : (unsigned)(512 + pos[s]);
+                    if (key[s] == m64) {  // implies pos[s] >= 0
+                        const unsigned rank = (r4c[s] == -1) ? (unsigned)(511 - pos[s]) : (unsigned)(512 + pos[s]);
                         const unsigned cand = (rank << 18) | ((unsigned)(r4c[s] + 1) << 9) | (unsigned)(lane + 32 * s);
                         key3 = min(key3, cand);
                     }
@@ -301,47 +303,43 @@ __global__ void __launch_bounds__(32) k_lsap(const __grid_constant__ LsapArgs a)
                 const int r4 = (int)((key3 >> 9) & 511u) - 1;
                 const unsigned rank = key3 >> 18;
                 const int index = rank < 512u ? (int)(511u - rank) : (int)(rank - 512u);
-                minVal = lowest;
+                minVal = ordered_value(m64);
                 if (r4 == -1) sink = jsel; else i = r4;
-                // remaining[index] = remaining[--num_remaining]
-#pragma unroll
-                for (int s = 0; s < CPL; s++) {
-                    if (pos[s] == index) pos[s] = -2;  // visited (SC)
-                }
-#pragma unroll
-                for (int s = 0; s < CPL; s++) {
-                    if (pos[s] == num_rem - 1) pos[s] = index;
-                }
+                // remaining[index] = remaining[--num_remaining]; -2 marks "visited" (SC)
                 num_rem--;
+#pragma unroll
+                for (int s = 0; s < CPL; s++) {
+                    const int ps = pos[s];
+                    pos[s] = (ps == index) ? -2 : ((ps == num_rem) ? index : ps);
+                }
             }
             if (st != PTK_PROBLEM_OK) break;
-            // dual update (rectangular_lsap.cpp order: u[cur] first, then visited rows / columns)
+            // dual update.  SciPy: u[cur] += minVal; u[i] += minVal - spc[col4row[i]] for the other
+            // visited rows; v[j] -= minVal - spc[j] for visited columns.  Every visited row other
+            // than cur was entered through its assigned (visited) column, so the row update is
+            // done from the column side with the same operands.
+            if (lane == 0) u[cur] += minVal;
 #pragma unroll
             for (int s = 0; s < CPL; s++) {
-                const int r = lane + 32 * s;
-                const int col = c4r[s] < 0 ? 0 : c4r[s];
-                double sp = 0.0;
-#pragma unroll
-                for (int t = 0; t < CPL; t++) {
-                    const double tmp = __shfl_sync(kFull, spc[t], col & 31);
-                    if (t == (col >> 5)) sp = tmp;
+                if (pos[s] == -2) {
+                    const double d = minVal - spc[s];
+                    if (r4c[s] >= 0) u[r4c[s]] += d;
+                    v[s] -= d;
                 }
-                if (r == cur) u[s] += minVal;
-                else if ((srbits >> s) & 1u) u[s] += minVal - sp;
             }
-#pragma unroll
-            for (int s = 0; s < CPL; s++)
-                if (pos[s] == -2) v[s] -= minVal - spc[s];
+            __syncwarp();
             // augment along the path
             int j = sink;
             while (true) {
                 const int r = lane_array_get<CPL>(path, j);
                 lane_array_set<CPL>(r4c, j, r, lane);
-                const int t = lane_array_get<CPL>(c4r, r);
-                lane_array_set<CPL>(c4r, r, j, lane);
+                const int t = c4r[r];
+                __syncwarp();
+                if (lane == 0) c4r[r] = j;
                 j = t;
                 if (r == cur) break;
             }
+            __syncwarp();
         }
     }
 
@@ -350,18 +348,14 @@ __global__ void __launch_bounds__(32) k_lsap(const __grid_constant__ LsapArgs a)
         n = nr;
         double tsum = 0.0;
         if (!tr) {
-#pragma unroll
-            for (int s = 0; s < CPL; s++) {
-                const int r = lane + 32 * s;
-                if (r < nr) {
-                    const int cj = c4r[s];
-                    const double cst = C[(size_t)r * ldc + cj];
-                    if (orow) orow[r] = r;
-                    ocol[r] = cj;
-                    if (oasg) oasg[r] = cst;
-                    if (okeep) okeep[r] = (cst <= a.max_err) ? 1 : 0;
-                    tsum += cst;
-                }
+            for (int r = lane; r < nr; r += 32) {
+                const int cj = c4r[r];
+                const double cst = C[(size_t)r * ldc + cj];
+                if (orow) orow[r] = r;
+                ocol[r] = cj;
+                if (oasg) oasg[r] = cst;
+                if (okeep) okeep[r] = (cst <= a.max_err) ? 1 : 0;
+                tsum += cst;
             }
         } else {
             // rows of the transposed problem are original columns; emit sorted by original row
