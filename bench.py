@@ -228,12 +228,13 @@ def run_b200(args):
             host_batches.append(tuple(torch.from_numpy(np.ascontiguousarray(x)).pin_memory()
                                       for x in (data.cam1, data.cam2, data.n1, data.n2)))
     sharded = pdist.ShardedReconstructor(rig, F, C, N, dev) if world > 1 else None
+    pipe_dev = engine.DevicePipeline(rig, F, C, N, dev, track=True) if world == 1 else None
 
     def step(i):
         c1, c2, n1, n2 = batches[i % N_BATCHES]
         if sharded is not None:
             return sharded.step(c1, c2, n1, n2)
-        return engine.reconstruct_device(rig, c1, c2, n1, n2, F, C, track=True)
+        return pipe_dev.run(c1, c2, n1, n2)
 
     def barrier():
         if world > 1:
@@ -244,7 +245,7 @@ def run_b200(args):
     for i in range(W):
         out = step(i)
     barrier()
-    st = out[0].status if sharded is None else out["status"]
+    st = out.status if sharded is None else out["status"]
     assert int((st != 0).sum().item()) == 0, "matching reported invalid problems"
 
     clocks = ClockSampler(local)

@@ -179,6 +179,24 @@ int ptk_create_weights(int Np, int N1, int N2, const double* p_3D, const double*
 #define PTK_WS_WEIGHTS 4
 size_t ptk_workspace_bytes(int kind, long long n_problems, int Nmax);
 
+/* ---- the whole path on DEVICE buffers, one call ----------------------------------------
+ * ptk_match_batch -> ptk_rows_to_ends -> ptk_track_batch -> chain pass, enqueued on `stream`
+ * (replaces the match2D.py:600-625 driver loop + tracking.py:70-138 for F frames x C colours;
+ * problem index = f*C + c).  Outputs as in ptk_reconstruct_host but in device memory; tracking
+ * (do_track != 0) expects n_out == Nmax for every problem, like tracking.py:97.  Only kernel
+ * launches are enqueued (no allocation, no synchronisation), so the call can be captured in a
+ * CUDA graph.  workspace: ptk_reconstruct_device_workspace_bytes(F, C, Nmax, do_track). */
+size_t ptk_reconstruct_device_workspace_bytes(int F, int C, int Nmax, int do_track);
+int ptk_reconstruct_device(const ptk_rig* rig, int F, int C, int Nmax,
+                           const double* cam1, const double* cam2,
+                           const int32_t* n1, const int32_t* n2,
+                           double* rows, double* match_cost,
+                           int32_t* row_ind, int32_t* col_ind, int32_t* n_out, int32_t* status,
+                           double max_repr_err, uint8_t* keep_mask,
+                           int do_track, int32_t* track_col, double* track_total,
+                           int32_t* track_id, int32_t* track_status,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- host-buffer pipeline (what bench.py's `e2e` and match_csv_complex call) ----------
  * A ptk_ctx owns a device, streams, pinned staging and device buffers sized on demand. */
 typedef struct ptk_ctx ptk_ctx;

@@ -27,6 +27,7 @@ SYMBOLS = [
     "ptk_undistort_batch", "ptk_cost_batch", "ptk_lsap_batch", "ptk_match_batch",
     "ptk_rows_batch", "ptk_rows_to_ends", "ptk_track_batch", "ptk_chain_tracks", "ptk_create_weights", "ptk_workspace_bytes",
     "ptk_ctx_create", "ptk_ctx_destroy", "ptk_reconstruct_host",
+    "ptk_reconstruct_device", "ptk_reconstruct_device_workspace_bytes",
     "ptk_measure_fp64_peak", "ptk_launch_count", "ptk_timing_enable", "ptk_timing_read",
 ]
 
@@ -81,6 +82,9 @@ def lib() -> ctypes.CDLL:
     L.ptk_ctx_create.argtypes = [i32, ctypes.POINTER(vp)]
     L.ptk_ctx_destroy.argtypes = [vp]
     L.ptk_ctx_destroy.restype = None
+    L.ptk_reconstruct_device_workspace_bytes.restype = sz
+    L.ptk_reconstruct_device_workspace_bytes.argtypes = [i32, i32, i32, i32]
+    L.ptk_reconstruct_device.argtypes = [rigp, i32, i32, i32] + [vp] * 10 + [dbl, vp, i32] + [vp] * 4 + [vp, sz, vp]
     L.ptk_reconstruct_host.argtypes = [vp, rigp, i32, i32, i32] + [vp] * 10 + [dbl, vp, i32] + [vp] * 4
     L.ptk_timing_enable.argtypes = [i32]
     L.ptk_timing_enable.restype = None

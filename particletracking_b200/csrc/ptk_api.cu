@@ -525,6 +525,61 @@ PTK_API int ptk_chain_tracks(int C, int F, int N, const int32_t* col_ind, const 
     return rc;
 }
 
+// ------------------------------------------------------------------------------------ whole path, device buffers
+namespace {
+struct DevWs { size_t match, ends, track, chain, total; };
+DevWs device_ws(int F, int C, int Nmax, int do_track)
+{
+    DevWs w{};
+    const long long P = (long long)F * C, Q = (long long)C * (F > 0 ? F - 1 : 0);
+    w.match = align_up(ptk_workspace_bytes(PTK_WS_MATCH, P, Nmax));
+    if (do_track) {
+        w.ends = align_up((size_t)C * F * Nmax * 6 * sizeof(double));
+        w.track = align_up(ptk_workspace_bytes(PTK_WS_TRACK, Q > 0 ? Q : 1, Nmax));
+        w.chain = align_up(chain_scratch_ints(C, F, Nmax) * sizeof(int32_t) + 16);
+    }
+    w.total = w.match + w.ends + w.track + w.chain + 256;
+    return w;
+}
+}  // namespace
+
+PTK_API size_t ptk_reconstruct_device_workspace_bytes(int F, int C, int Nmax, int do_track)
+{
+    if (F < 0 || C < 0 || bad_n(Nmax)) return 0;
+    return device_ws(F, C, Nmax, do_track).total;
+}
+
+PTK_API int ptk_reconstruct_device(const ptk_rig* rig, int F, int C, int Nmax, const double* cam1, const double* cam2,
+                                   const int32_t* n1, const int32_t* n2, double* rows, double* match_cost,
+                                   int32_t* row_ind, int32_t* col_ind, int32_t* n_out, int32_t* status,
+                                   double max_repr_err, uint8_t* keep_mask, int do_track, int32_t* track_col,
+                                   double* track_total, int32_t* track_id, int32_t* track_status, void* workspace,
+                                   size_t workspace_bytes, void* stream)
+{
+    if (!rig || F < 0 || C < 0 || bad_n(Nmax)) return PTK_ERR_INVALID_ARG;
+    if (do_track && (!track_col || !track_total || F < 1)) return PTK_ERR_INVALID_ARG;
+    const long long P = (long long)F * C;
+    if (P == 0) return PTK_OK;
+    const DevWs w = device_ws(F, C, Nmax, do_track);
+    if (!workspace || workspace_bytes < w.total) return PTK_ERR_WORKSPACE;
+    char* base = (char*)align_up((size_t)workspace);
+    int rc = ptk_match_batch(rig, (int)P, Nmax, cam1, cam2, n1, n2, nullptr, nullptr, row_ind, col_ind, n_out, status, rows,
+                             match_cost, max_repr_err, keep_mask, base, w.match, stream);
+    if (rc || !do_track) return rc;
+    double* ends = reinterpret_cast<double*>(base + w.match);
+    rc = ptk_rows_to_ends(F, C, Nmax, Nmax, rows, ends, stream);
+    if (rc) return rc;
+    if (F > 1) {
+        rc = ptk_track_batch(C, F, Nmax, ends, nullptr, track_col, track_total, track_status, base + w.match + w.ends, w.track,
+                             stream);
+        if (rc) return rc;
+    }
+    if (track_id)
+        rc = chain_impl(C, F, Nmax, track_col, nullptr, track_id, reinterpret_cast<int32_t*>(base + w.match + w.ends + w.track),
+                        (cudaStream_t)stream);
+    return rc;
+}
+
 // ------------------------------------------------------------------------------------ K6
 PTK_API int ptk_create_weights(int Np, int N1, int N2, const double* p_3D, const double* p_prev, const double* rep_errs,
                                double* weights, double* choices, void* workspace, size_t workspace_bytes, void* stream)

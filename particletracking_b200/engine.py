@@ -205,6 +205,46 @@ def reconstruct_device(rig: PtkRig, cam1, cam2, n1, n2, F: int, C: int, track: b
     return m, col, tot, tid, st
 
 
+class DevicePipeline:
+    """The whole path on device-resident tensors through ONE library call
+    (``ptk_reconstruct_device``) with outputs and workspace allocated once for a given
+    (F, C, Nmax): no per-step allocation, a single ctypes call per step, capturable in a CUDA
+    graph.  This is what bench.py times as `value`."""
+
+    def __init__(self, rig: PtkRig, F: int, C: int, Nmax: int, device=None, track: bool = True,
+                 max_repr_err: Optional[float] = None):
+        _require_cuda()
+        self.rig, self.F, self.C, self.N, self.track = rig, F, C, Nmax, track
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.device = dev
+        P = F * C
+        self.rows = torch.empty((P, Nmax, nat.ROW_COLS), dtype=_f64, device=dev)
+        self.match_cost = torch.empty((P, Nmax), dtype=_f64, device=dev)
+        self.row_ind = torch.empty((P, Nmax), dtype=_i32, device=dev)
+        self.col_ind = torch.empty((P, Nmax), dtype=_i32, device=dev)
+        self.n_out = torch.empty((P,), dtype=_i32, device=dev)
+        self.status = torch.empty((P,), dtype=_i32, device=dev)
+        self.keep = torch.empty((P, Nmax), dtype=_u8, device=dev) if max_repr_err is not None else None
+        self.thr = float("inf") if max_repr_err is None else float(max_repr_err)
+        self.track_col = torch.empty((C, max(F - 1, 0), Nmax), dtype=_i32, device=dev) if track else None
+        self.track_total = torch.empty((C, max(F - 1, 0)), dtype=_f64, device=dev) if track else None
+        self.track_id = torch.empty((C, F, Nmax), dtype=_i32, device=dev) if track else None
+        self.track_status = torch.empty((C, max(F - 1, 0)), dtype=_i32, device=dev) if track else None
+        nb = nat.lib().ptk_reconstruct_device_workspace_bytes(F, C, Nmax, 1 if track else 0)
+        self.ws = torch.empty(nb, dtype=_u8, device=dev)
+
+    def run(self, cam1, cam2, n1, n2):
+        """Enqueue one pass on the current stream; results are in the pipeline's tensors."""
+        with torch.cuda.device(self.device):
+            nat.check(nat.lib().ptk_reconstruct_device(
+                ctypes.byref(self.rig), self.F, self.C, self.N, _ptr(cam1), _ptr(cam2), _ptr(n1), _ptr(n2),
+                _ptr(self.rows), _ptr(self.match_cost), _ptr(self.row_ind), _ptr(self.col_ind), _ptr(self.n_out),
+                _ptr(self.status), self.thr, _ptr(self.keep), 1 if self.track else 0, _ptr(self.track_col),
+                _ptr(self.track_total), _ptr(self.track_id), _ptr(self.track_status), _ptr(self.ws), self.ws.numel(),
+                _stream()), "ptk_reconstruct_device")
+        return self
+
+
 def track_batch(ends: torch.Tensor, want_cost=False):
     """K4+K2: ``tracking_global_assignment`` (tracking.py:97-123,136-137) for C colours.
     ends[C,F,N,2,3] -> col_ind[C,F-1,N], total_cost[C,F-1], status[C,F-1] (, cost[C,F-1,N,N])."""

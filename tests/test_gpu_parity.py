@@ -436,3 +436,41 @@ def test_config4_shape_match_and_track(eng, crig):
     np.testing.assert_array_equal(col.cpu().numpy(), ot["col_ind"])
     np.testing.assert_array_equal(tid.cpu().numpy(), co.chain_tracks(ot["col_ind"]))
     assert rel_err(tot.cpu().numpy(), ot["total_cost"]) < 1e-13
+
+
+def test_device_pipeline_single_call_and_cuda_graph(eng, crig):
+    """ptk_reconstruct_device == the composition of the separate entry points (same kernels,
+    same bits); the call only enqueues kernels, so it can be captured in a CUDA graph."""
+    import torch
+    from particletracking_b200 import synthetic as syn
+
+    F, C, N = 50, 4, 16
+    data = syn.make_stereo(F, C, N, seed=21)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    c1, c2, n1, n2 = (t(x) for x in data.problems())
+    m, col, tot, tid, st = eng.reconstruct_device(crig, c1, c2, n1, n2, F, C, track=True)
+    pipe = eng.DevicePipeline(crig, F, C, N, track=True, max_repr_err=3.0)
+    pipe.run(c1, c2, n1, n2)
+    torch.cuda.synchronize()
+    for a, b in ((pipe.rows, m.rows), (pipe.col_ind, m.col_ind), (pipe.match_cost, m.match_cost),
+                 (pipe.track_col, col), (pipe.track_id, tid), (pipe.track_total, tot)):
+        np.testing.assert_array_equal(a.cpu().numpy(), b.cpu().numpy())
+    np.testing.assert_array_equal(pipe.keep.cpu().numpy().astype(bool), pipe.match_cost.cpu().numpy() <= 3.0)
+    # graph capture + replay on new inputs
+    data2 = syn.make_stereo(F, C, N, seed=22)
+    d1, d2, _, _ = (t(x) for x in data2.problems())
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(s):
+        pipe.run(c1, c2, n1, n2)  # warm-up on the side stream
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g, stream=s):
+            pipe.run(c1, c2, n1, n2)
+    c1.copy_(d1)
+    c2.copy_(d2)
+    g.replay()
+    torch.cuda.synchronize()
+    m2 = eng.match_batch(crig, d1, d2, n1, n2)
+    np.testing.assert_array_equal(pipe.rows.cpu().numpy(), m2.rows.cpu().numpy())
+    np.testing.assert_array_equal(pipe.col_ind.cpu().numpy(), m2.col_ind.cpu().numpy())
