@@ -211,6 +211,7 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("PTK_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     F, C, N = args.frames, args.colors, args.rods
     K, W = args.steps, max(args.warmup, 3)

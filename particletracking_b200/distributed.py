@@ -111,11 +111,13 @@ class ShardedReconstructor:
             w.wait()
         return recv
 
-    def _gather(self, t: torch.Tensor, cache_name: str, frame_dim: int):
+    def _gather(self, t: torch.Tensor, cache_name: str, frame_dim: int, async_op: bool = False):
         """Gather ``t`` (frames along ``frame_dim``) to rank 0; returns the list of per-rank
-        shards there, None elsewhere.  Shards of unequal length are padded for the collective."""
+        shards there, None elsewhere.  Shards of unequal length are padded for the collective.
+        With ``async_op`` returns ``(result, work)``: the collective runs on NCCL's stream while
+        the caller keeps enqueueing compute; ``work.wait()`` orders the current stream after it."""
         if self.world == 1:
-            return [t]
+            return ([t], None) if async_op else [t]
         fmax = max(self.shard_sizes)
         if t.shape[frame_dim] < fmax:
             pad_shape = list(t.shape)
@@ -127,10 +129,11 @@ class ShardedReconstructor:
             if buf is None or buf[0].shape != t.shape:
                 buf = [torch.empty_like(t) for _ in range(self.world)]
                 setattr(self, cache_name, buf)
-            dist.gather(t, buf, dst=0, group=self.group)
-            return [b.narrow(frame_dim, 0, n) for b, n in zip(buf, self.shard_sizes)]
-        dist.gather(t, None, dst=0, group=self.group)
-        return None
+            work = dist.gather(t, buf, dst=0, group=self.group, async_op=async_op)
+            res = [b.narrow(frame_dim, 0, n) for b, n in zip(buf, self.shard_sizes)]
+            return (res, work) if async_op else res
+        work = dist.gather(t, None, dst=0, group=self.group, async_op=async_op)
+        return (None, work) if async_op else None
 
     # -- one pass over this rank's frames ----------------------------------------------------
     def step(self, cam1, cam2, n1, n2):
@@ -138,6 +141,10 @@ class ShardedReconstructor:
         Returns a dict; on rank 0 ``rows_all`` / ``track_id_all`` hold every rank's shard."""
         F, C, N = self.F, self.C, self.N
         rows, col_m, status = self.ops.match(cam1, cam2, n1, n2)
+        rows_all = rows_work = None
+        if self.gather_to_root:
+            # the big gather (rows) starts as soon as matching is enqueued and overlaps tracking
+            rows_all, rows_work = self._gather(rows.view(F, C, -1, rows.shape[-1]), "_rows_all", 0, async_op=True)
         ends = self.ops.rows_to_ends(rows, F, C)  # [C,F,N,2,3]
         halo = self._halo(ends[:, 0].contiguous())
         if halo is not None:
@@ -158,6 +165,8 @@ class ShardedReconstructor:
         out = dict(rows=rows, col_ind=col_m, status=status, track_col=col, track_total=total,
                    track_status=tstatus, track_id=track_id)
         if self.gather_to_root:
-            out["rows_all"] = self._gather(rows.view(F, C, -1, rows.shape[-1]), "_rows_all", 0)  # [F,C,Nmax,18] per rank
-            out["track_id_all"] = self._gather(track_id, "_tid_all", 1)                         # [C,F,N] per rank
+            out["track_id_all"] = self._gather(track_id, "_tid_all", 1)  # [C,F,N] per rank
+            if rows_work is not None:
+                rows_work.wait()
+            out["rows_all"] = rows_all                                     # [F,C,Nmax,18] per rank
         return out
