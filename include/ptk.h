@@ -164,6 +164,13 @@ int ptk_track_batch(int C, int F, int N, const double* ends,
 int ptk_chain_tracks(int C, int F, int N, const int32_t* col_ind, const int32_t* ids_in,
                      int32_t* track_id, void* stream);
 
+/* Multi-GPU part of the chain pass: every rank chains its own frames from the identity
+ * (ptk_chain_tracks with ids_in = NULL, last frame = next rank's first frame), the per-rank boundary
+ * maps are all-gathered (maps[W,C,N]: position in rank r+1's first frame -> local id on rank r), and
+ * this call composes them up to `rank` (start[C,N], written) and re-bases track_id[C,F,N] in place. */
+int ptk_chain_rebase(int W, int C, int F, int N, int rank, const int32_t* maps, int32_t* start,
+                     int32_t* track_id, void* stream);
+
 /* ---- K6: matchND.create_weights ("next" row) --------------------------
  * Replaces matchND.py:141-217.  p_3D[N1,N2,4,3], p_prev[Np,2,3], rep_errs[N1,N2,4,2] ->
  * weights[Np,N1,N2] (= max(w) - w), choices[Np,N1,N2] (float64 0..3, as the reference).

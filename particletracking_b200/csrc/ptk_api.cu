@@ -525,6 +525,27 @@ PTK_API int ptk_chain_tracks(int C, int F, int N, const int32_t* col_ind, const 
     return rc;
 }
 
+PTK_API int ptk_chain_rebase(int W, int C, int F, int N, int rank, const int32_t* maps, int32_t* start,
+                             int32_t* track_id, void* stream)
+{
+    if (W < 1 || C < 0 || F < 0 || bad_n(N) || rank < 0 || rank >= W || !maps || !start || !track_id)
+        return PTK_ERR_INVALID_ARG;
+    if (C == 0) return PTK_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int threads = N < 32 ? 32 : ((N + 31) / 32 * 32);
+    {
+        LaunchTimer lt(K_CHAIN, st);
+        k_chain_compose<<<C, threads, 2 * (size_t)N * sizeof(int32_t), st>>>(W, C, N, rank, maps, start);
+        LAUNCHED("k_chain_compose");
+        const long long total = (long long)C * F * N;
+        if (total > 0) {
+            k_chain_rebase<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(F, N, start, track_id, total);
+            LAUNCHED("k_chain_rebase");
+        }
+    }
+    return PTK_OK;
+}
+
 // ------------------------------------------------------------------------------------ whole path, device buffers
 namespace {
 struct DevWs { size_t match, ends, track, chain, total; };

@@ -602,6 +602,36 @@ __global__ void k_chain_apply(int F, int N, int nseg, const int32_t* __restrict_
     track_id[t] = seg_start[((size_t)c * nseg + s) * N + track_id[t]];
 }
 
+// Multi-GPU chain pass: compose the all-gathered per-rank boundary maps up to `rank`
+// (start[c][x] = global track id of local id x on this rank) and re-base the local ids.
+// maps[W,C,N]: position x in rank r+1's first frame -> local id on rank r.
+__global__ void k_chain_compose(int W, int C, int N, int rank, const int32_t* __restrict__ maps,
+                                int32_t* __restrict__ start)
+{
+    extern __shared__ int32_t sh[];
+    int32_t* cur = sh;
+    int32_t* nxt = sh + N;
+    const int c = blockIdx.x;
+    for (int a = threadIdx.x; a < N; a += blockDim.x) cur[a] = a;
+    __syncthreads();
+    for (int r = 0; r < rank && r < W; r++) {
+        const int32_t* mp = maps + ((size_t)r * C + c) * N;
+        for (int a = threadIdx.x; a < N; a += blockDim.x) nxt[a] = cur[mp[a]];
+        __syncthreads();
+        int32_t* t = cur; cur = nxt; nxt = t;
+    }
+    for (int a = threadIdx.x; a < N; a += blockDim.x) start[(size_t)c * N + a] = cur[a];
+}
+
+__global__ void k_chain_rebase(int F, int N, const int32_t* __restrict__ start, int32_t* __restrict__ track_id,
+                               long long total)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int c = (int)(t / ((long long)F * N));
+    track_id[t] = start[(size_t)c * N + track_id[t]];
+}
+
 // ------------------------------------------------------------------------------------- K6
 // matchND.create_weights (matchND.py:141-217), one thread per (prev rod i, cam1 rod j, cam2 rod k).
 __device__ __forceinline__ double dist3(const double* a, const double* b)

@@ -68,6 +68,11 @@ class _CudaOps:
     def chain(self, col, ids_in=None):
         return self.e.chain_tracks(col, ids_in)
 
+    def rebase(self, maps, rank, local):
+        """compose the gathered boundary maps and re-base ``local`` [C,F',N] in place"""
+        self.e.chain_rebase(maps, rank, local)
+        return local
+
 
 class ShardedReconstructor:
     """match -> track -> chain for one rank's frame range, with the halo / boundary-map /
@@ -92,8 +97,12 @@ class ShardedReconstructor:
         self.shard_sizes = [b - a for a, b in (shard_frames(total, self.world, r) for r in range(self.world))]
         if self.shard_sizes[self.rank] != n_frames_local:
             raise ValueError("n_frames_local does not match shard_frames(n_frames_total, world, rank)")
-        self._rows_all = None
-        self._tid_all = None
+        # final-gather pipelining: two sets of receive buffers; the gather of step k runs on
+        # NCCL's stream while step k+1 computes, and is waited for before its buffers are reused
+        self._rows_all0 = self._rows_all1 = None
+        self._tid_all0 = self._tid_all1 = None
+        self._pending = [None, None]
+        self._step_idx = 0
 
     # -- exchanges ------------------------------------------------------------------------
     def _halo(self, first_frame_ends: torch.Tensor) -> Optional[torch.Tensor]:
@@ -142,9 +151,12 @@ class ShardedReconstructor:
         F, C, N = self.F, self.C, self.N
         rows, col_m, status = self.ops.match(cam1, cam2, n1, n2)
         rows_all = rows_work = None
+        slot = self._step_idx % 2
+        self._step_idx += 1
         if self.gather_to_root:
+            self._wait(slot)  # this slot's receive buffers are free again
             # the big gather (rows) starts as soon as matching is enqueued and overlaps tracking
-            rows_all, rows_work = self._gather(rows.view(F, C, -1, rows.shape[-1]), "_rows_all", 0, async_op=True)
+            rows_all, rows_work = self._gather(rows.view(F, C, -1, rows.shape[-1]), f"_rows_all{slot}", 0, async_op=True)
         ends = self.ops.rows_to_ends(rows, F, C)  # [C,F,N,2,3]
         halo = self._halo(ends[:, 0].contiguous())
         if halo is not None:
@@ -158,15 +170,31 @@ class ShardedReconstructor:
                 my_map = torch.arange(N, dtype=local.dtype, device=local.device).expand(C, N).contiguous()
             maps = torch.empty((self.world * C, N), dtype=local.dtype, device=local.device)
             dist.all_gather_into_tensor(maps, my_map, group=self.group)
-            start = compose_rank_maps(maps.view(self.world, C, N))[self.rank].contiguous()
-            track_id = self.ops.chain(col, start)[:, :F].contiguous()
+            maps = maps.view(self.world, C, N)
+            if hasattr(self.ops, "rebase"):
+                track_id = self.ops.rebase(maps, self.rank, local)[:, :F].contiguous()
+            else:  # back ends without a fused kernel: same composition with torch ops
+                start = compose_rank_maps(maps)[self.rank].contiguous()
+                track_id = self.ops.chain(col, start)[:, :F].contiguous()
         else:
             track_id = local
         out = dict(rows=rows, col_ind=col_m, status=status, track_col=col, track_total=total,
                    track_status=tstatus, track_id=track_id)
         if self.gather_to_root:
-            out["track_id_all"] = self._gather(track_id, "_tid_all", 1)  # [C,F,N] per rank
-            if rows_work is not None:
-                rows_work.wait()
-            out["rows_all"] = rows_all                                     # [F,C,Nmax,18] per rank
+            tid_all, tid_work = self._gather(track_id, f"_tid_all{slot}", 1, async_op=True)
+            self._pending[slot] = [w for w in (rows_work, tid_work) if w is not None]
+            out["rows_all"] = rows_all        # [F,C,Nmax,18] per rank   } valid after finish()
+            out["track_id_all"] = tid_all     # [C,F,N] per rank         } (or the next-but-one step)
         return out
+
+    def _wait(self, slot: int):
+        if self._pending[slot]:
+            for w in self._pending[slot]:
+                w.wait()
+        self._pending[slot] = None
+
+    def finish(self):
+        """Order the current stream after every outstanding gather (call before reading
+        ``rows_all`` / ``track_id_all`` of the latest steps)."""
+        self._wait(0)
+        self._wait(1)

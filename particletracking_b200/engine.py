@@ -278,6 +278,20 @@ def chain_tracks(col_ind: torch.Tensor, ids_in: Optional[torch.Tensor] = None) -
     return out
 
 
+def chain_rebase(maps: torch.Tensor, rank: int, track_id: torch.Tensor) -> torch.Tensor:
+    """Multi-GPU chain pass: compose the all-gathered boundary maps[W,C,N] up to ``rank`` and
+    re-base the local ids track_id[C,F,N] in place; returns the rank's start ids [C,N]."""
+    _require_cuda()
+    maps, track_id = _chk(maps, _i32, "maps"), _chk(track_id, _i32, "track_id")
+    W, C, N = maps.shape
+    F = track_id.shape[1]
+    start = torch.empty((C, N), dtype=_i32, device=maps.device)
+    with torch.cuda.device(maps.device):
+        nat.check(nat.lib().ptk_chain_rebase(W, C, F, N, int(rank), _ptr(maps), _ptr(start), _ptr(track_id), _stream()),
+                  "ptk_chain_rebase")
+    return start
+
+
 def create_weights(p_3D: torch.Tensor, p_prev: torch.Tensor, rep_errs: torch.Tensor):
     """K6: ``matchND.create_weights`` (matchND.py:141-217)."""
     _require_cuda()

@@ -80,6 +80,7 @@ def _worker(rank, world, port, F, C, N, out_path):
     rec = pdist.ShardedReconstructor(rig, Fl, C, N, "cpu", ops=OracleOps(rig), n_frames_total=F)
     out = rec.step(t(data.cam1[sl].reshape(Fl * C, N, 2, 2)), t(data.cam2[sl].reshape(Fl * C, N, 2, 2)),
                    t(data.n1[sl].reshape(-1)), t(data.n2[sl].reshape(-1)))
+    rec.finish()
     if rank == 0:
         rows = torch.cat(list(out["rows_all"]), dim=0).numpy()
         tid = torch.cat(list(out["track_id_all"]), dim=1).numpy()

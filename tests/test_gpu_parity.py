@@ -474,3 +474,31 @@ def test_device_pipeline_single_call_and_cuda_graph(eng, crig):
     m2 = eng.match_batch(crig, d1, d2, n1, n2)
     np.testing.assert_array_equal(pipe.rows.cpu().numpy(), m2.rows.cpu().numpy())
     np.testing.assert_array_equal(pipe.col_ind.cpu().numpy(), m2.col_ind.cpu().numpy())
+
+
+def test_chain_rebase_emulated_ranks(eng):
+    """Multi-GPU chain pass on one GPU: W emulated ranks chain their own frame ranges (+ the halo
+    pair) from the identity, the boundary maps are 'gathered' and ptk_chain_rebase re-bases the
+    local ids -- must equal the single-pass chain over all frames."""
+    import torch
+    from particletracking_b200.distributed import shard_frames
+
+    rng = np.random.default_rng(9)
+    C, F, N, W = 3, 37, 11, 4
+    col = np.stack([np.stack([rng.permutation(N) for _ in range(F - 1)]) for _ in range(C)]).astype(np.int32)
+    full = eng.chain_tracks(dev(col)).cpu().numpy()
+    locals_, maps = [], []
+    for r in range(W):
+        f0, f1 = shard_frames(F, W, r)
+        hi = f1 if r < W - 1 else f1 - 1  # pairs f0..hi-1 (the last one is the halo pair)
+        loc = eng.chain_tracks(dev(col[:, f0:hi]))
+        locals_.append(loc)
+        maps.append(loc[:, -1] if r < W - 1 else torch.arange(N, dtype=torch.int32, device="cuda").expand(C, N))
+    maps = torch.stack([m.contiguous() for m in maps]).contiguous()
+    out = []
+    for r in range(W):
+        f0, f1 = shard_frames(F, W, r)
+        loc = locals_[r].clone()
+        eng.chain_rebase(maps, r, loc)
+        out.append(loc[:, : f1 - f0].cpu().numpy())
+    np.testing.assert_array_equal(np.concatenate(out, axis=1), full)
