@@ -179,6 +179,27 @@ int ptk_create_weights(int Np, int N1, int N2, const double* p_3D, const double*
                        const double* rep_errs, double* weights, double* choices,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- K7: end-point re-ordering ("next" row) ------------------------------
+ * Replaces the numeric body of match2D.reorder_endpoints_csv (match2D.py:1055-1137): per particle,
+ * frame after frame, the two end points are swapped when the swapped displacement to the previous,
+ * already re-ordered frame is strictly smaller (match2D.py:1102).
+ *   ends[C,F,N,2,3] (rows sorted by particle within each frame); pts2d[C,F,N,2(cam),2(end),2(xy)]
+ *   optional -> out_ends, out_2d (same shapes), swapped[C,F,N] (uint8; frame 0 is never swapped),
+ *   mincost[C,F-1,N] = min(comb1, comb2) (the reference's mincosts_T, transposed). */
+int ptk_reorder_endpoints(int C, int F, int N, const double* ends, const double* pts2d,
+                          double* out_ends, double* out_2d, uint8_t* swapped, double* mincost, void* stream);
+
+/* ---- K8 / K9: stand-alone triangulation / projection ("next" row) ----------
+ * ptk_triangulate_points replaces calibrate_cameras.project_points (calibrate_cameras.py:137-199):
+ *   cv2.triangulatePoints(P1, P2, p1, p2) on the points as given (no undistortion), p[0:3]/p[3],
+ *   optional world transform.  p1, p2 [n,2] -> out [n,3].
+ * ptk_project_points replaces calibrate_cameras.reproject_points (calibrate_cameras.py:202-262):
+ *   optional inverse world transform, then cv2.projectPoints into both cameras.  X [n,3] -> uv1, uv2 [n,2]. */
+int ptk_triangulate_points(const ptk_rig* rig, long long n, const double* p1, const double* p2,
+                           int to_world, double* out, void* stream);
+int ptk_project_points(const ptk_rig* rig, long long n, const double* X, int from_world,
+                       double* uv1, double* uv2, void* stream);
+
 /* ---- workspace sizing ---------------------------------------------------------------- */
 #define PTK_WS_COST 1
 #define PTK_WS_MATCH 2

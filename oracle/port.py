@@ -360,3 +360,61 @@ def create_weights(p_3D: np.ndarray, p_3D_prev: np.ndarray, repr_errs: np.ndarra
     w = s.min(axis=0)
     choice = s.argmin(axis=0).astype(np.float64)
     return w.max() - w, choice
+
+
+# --------------------------------------------------------------------------
+# "next" rows: reorder_endpoints_csv, project_points / reproject_points
+# --------------------------------------------------------------------------
+def reorder_endpoints_arrays(ends: np.ndarray, pts2d: Optional[np.ndarray] = None):
+    """match2D.py:1055-1137 on ``ends[F,N,2,3]`` (rows sorted by particle): frame after frame,
+    swap the end points of a particle when the swapped displacement to the previous, already
+    re-ordered frame is strictly smaller.  Returns ``(out_ends, out_2d, swapped[F,N],
+    mincost[F-1,N])``; ``pts2d[F,N,2(cam),2(end),2]`` follows the swaps."""
+    F, N = ends.shape[:2]
+    out = ends.copy()
+    o2 = None if pts2d is None else pts2d.copy()
+    swapped = np.zeros((F, N), dtype=bool)
+    mincost = np.zeros((max(F - 1, 0), N))
+    for f in range(1, F):
+        for n in range(N):
+            a0, b0 = out[f - 1, n]
+            a1, b1 = ends[f, n]
+            comb1 = np.linalg.norm(a0 - a1) + np.linalg.norm(b0 - b1)
+            comb2 = np.linalg.norm(b0 - a1) + np.linalg.norm(a0 - b1)
+            mincost[f - 1, n] = min(comb1, comb2)
+            if comb2 < comb1:
+                out[f, n] = ends[f, n, ::-1]
+                swapped[f, n] = True
+                if o2 is not None:
+                    o2[f, n] = pts2d[f, n, :, ::-1]
+    return out, o2, swapped, mincost
+
+
+def project_points(p_cam1, p_cam2, calibration, transforms=None):
+    """calibrate_cameras.py:137-199."""
+    import cv2
+    from scipy.spatial.transform import Rotation
+
+    from particletracking_b200.synthetic import projection_matrices
+
+    P1, P2, *_ = projection_matrices(calibration)
+    p = cv2.triangulatePoints(P1, P2, np.asarray(p_cam1, dtype=np.float64), np.asarray(p_cam2, dtype=np.float64))
+    p = p[0:3] / p[3]
+    if transforms is not None:
+        p = (Rotation.from_matrix(transforms["rotation"]).apply(p.T) + transforms["translation"]).T
+    return p
+
+
+def reproject_points(points, calibration, transforms=None):
+    """calibrate_cameras.py:202-262."""
+    import cv2
+    from scipy.spatial.transform import Rotation
+
+    from particletracking_b200.synthetic import projection_matrices
+
+    _, _, r1, r2, t1, t2 = projection_matrices(calibration)
+    if transforms is not None:
+        points = Rotation.from_matrix(transforms["rotation"]).inv().apply(points - transforms["translation"])
+    a = cv2.projectPoints(points, r1, t1, calibration["CM1"], calibration["dist1"])[0].squeeze()
+    b = cv2.projectPoints(points, r2, t2, calibration["CM2"], calibration["dist2"])[0].squeeze()
+    return a, b

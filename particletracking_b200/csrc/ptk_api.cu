@@ -619,6 +619,49 @@ PTK_API int ptk_create_weights(int Np, int N1, int N2, const double* p_3D, const
     return PTK_OK;
 }
 
+// ------------------------------------------------------------------------------------ K7
+PTK_API int ptk_reorder_endpoints(int C, int F, int N, const double* ends, const double* pts2d, double* out_ends,
+                                  double* out_2d, uint8_t* swapped, double* mincost, void* stream)
+{
+    if (C < 0 || F < 1 || N < 0 || !ends || !out_ends || !swapped || (pts2d && !out_2d) || (F > 1 && !mincost))
+        return PTK_ERR_INVALID_ARG;
+    const long long total = (long long)C * F * N;
+    if (total == 0) return PTK_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (F > 1) {
+        const long long t1 = (long long)C * (F - 1) * N;
+        k_reorder_costs<<<(unsigned)((t1 + 255) / 256), 256, 0, st>>>(F, N, t1, ends, swapped, mincost);
+        LAUNCHED("k_reorder_costs");
+    }
+    const int CN = C * N;
+    k_reorder_scan<<<(CN + 127) / 128, 128, 0, st>>>(F, N, CN, swapped);
+    LAUNCHED("k_reorder_scan");
+    k_reorder_apply<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(total, swapped, ends, pts2d, out_ends, out_2d);
+    LAUNCHED("k_reorder_apply");
+    return PTK_OK;
+}
+
+// ------------------------------------------------------------------------------------ K8 / K9
+PTK_API int ptk_triangulate_points(const ptk_rig* rig, long long n, const double* p1, const double* p2, int to_world,
+                                   double* out, void* stream)
+{
+    if (!rig || n < 0 || !p1 || !p2 || !out) return PTK_ERR_INVALID_ARG;
+    if (n == 0) return PTK_OK;
+    k_triangulate_points<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(make_devrig(rig), n, to_world, p1, p2, out);
+    LAUNCHED("k_triangulate_points");
+    return PTK_OK;
+}
+
+PTK_API int ptk_project_points(const ptk_rig* rig, long long n, const double* X, int from_world, double* uv1, double* uv2,
+                               void* stream)
+{
+    if (!rig || n < 0 || !X || !uv1 || !uv2) return PTK_ERR_INVALID_ARG;
+    if (n == 0) return PTK_OK;
+    k_project_points<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(make_devrig(rig), n, from_world, X, uv1, uv2);
+    LAUNCHED("k_project_points");
+    return PTK_OK;
+}
+
 // ------------------------------------------------------------------------------------ FP64 peak
 PTK_API int ptk_measure_fp64_peak(int iters, double* flops, void* stream)
 {

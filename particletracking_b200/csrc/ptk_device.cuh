@@ -188,11 +188,10 @@ __device__ __forceinline__ void dlt_triangulate(const double* __restrict__ P1, c
     Z = vz / vw;
 }
 
-// cv2.projectPoints for one point (match2D.py:898-903) and the distance to
-// the original (distorted) detection (match2D.py:905-910).
-__device__ __forceinline__ double reproject_dist(const double* __restrict__ R, const double* __restrict__ t,
-                                                 const double* __restrict__ cm, const double* __restrict__ k,
-                                                 double X, double Y, double Z, double ou, double ov)
+// cv2.projectPoints for one point (match2D.py:898-903)
+__device__ __forceinline__ void project_point(const double* __restrict__ R, const double* __restrict__ t,
+                                              const double* __restrict__ cm, const double* __restrict__ k,
+                                              double X, double Y, double Z, double& u, double& v)
 {
     double x = fma(R[2], Z, fma(R[1], Y, R[0] * X)) + t[0];
     double y = fma(R[5], Z, fma(R[4], Y, R[3] * X)) + t[1];
@@ -207,8 +206,19 @@ __device__ __forceinline__ double reproject_dist(const double* __restrict__ R, c
     const double rad = cdist * icdist2;
     const double xd = fma(k[9], r4, fma(k[8], r2, fma(k[3], a2, fma(k[2], a1, x * rad))));
     const double yd = fma(k[11], r4, fma(k[10], r2, fma(k[3], a1, fma(k[2], a3, y * rad))));
-    const double ex = ou - fma(xd, cm[0], cm[2]);
-    const double ey = ov - fma(yd, cm[1], cm[3]);
+    u = fma(xd, cm[0], cm[2]);
+    v = fma(yd, cm[1], cm[3]);
+}
+
+// ... and the distance of the reprojection to the original (distorted) detection (match2D.py:905-910)
+__device__ __forceinline__ double reproject_dist(const double* __restrict__ R, const double* __restrict__ t,
+                                                 const double* __restrict__ cm, const double* __restrict__ k,
+                                                 double X, double Y, double Z, double ou, double ov)
+{
+    double u, v;
+    project_point(R, t, cm, k, X, Y, Z, u, v);
+    const double ex = ou - u;
+    const double ey = ov - v;
     return sqrt(fma(ex, ex, ey * ey));
 }
 

@@ -637,7 +637,7 @@ __global__ void k_chain_rebase(int F, int N, const int32_t* __restrict__ start, 
 __device__ __forceinline__ double dist3(const double* a, const double* b)
 {
     const double dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
-    return sqrt(dx * dx + dy * dy + dz * dz);
+    return sqrt((dx * dx + dy * dy) + dz * dz);
 }
 
 __global__ void __launch_bounds__(256) k_weights_raw(int Np, int N1, int N2, const double* __restrict__ p3,
@@ -701,6 +701,119 @@ __global__ void __launch_bounds__(256) k_weights_finish(long long tot, int nbloc
     __syncthreads();
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < tot) w[t] = wmax - w[t];  // matchND.py:216
+}
+
+// ------------------------------------------------------------------------------------- K7
+// match2D.reorder_endpoints_csv (match2D.py:1001-1146): per particle, frame after frame, swap the
+// two end points when the swapped displacement to the previous, already re-ordered frame is
+// strictly smaller.  Whether frame f ends up swapped depends on the state s of frame f-1:
+//   s = 0: swap iff comb2 < comb1;   s = 1: swap iff comb1 < comb2      (raw, un-swapped costs)
+// i.e. each frame is one of four maps {0,1} -> {0,1}; composing them along the frames is a scan.
+// pass A (parallel over frames x particles): the two raw costs, the map bits and min cost;
+// pass B (thread per particle): compose the maps along the frames;
+// pass C (parallel): apply the swaps to the 3D ends and the 2D end points of both cameras.
+// ends[C,F,N,2,3]; pts2d[C,F,N,2(cam),2(end),2(xy)] optional.
+__global__ void __launch_bounds__(256) k_reorder_costs(int F, int N, long long total, const double* __restrict__ ends,
+                                                       uint8_t* __restrict__ bits, double* __restrict__ mincost)
+{
+    // t indexes (c, f>=1, particle); bits[c,f,n] = (comb2<comb1) | (comb1<comb2)<<1
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int n = (int)(t % N);
+    const long long r = t / N;
+    const int f = (int)(r % (F - 1)) + 1;
+    const int c = (int)(r / (F - 1));
+    const double* e0 = ends + (((size_t)c * F + (f - 1)) * N + n) * 6;
+    const double* e1 = ends + (((size_t)c * F + f) * N + n) * 6;
+    // np.linalg.norm of a 3-vector (dot product, then sqrt) -- match2D.py:1093-1098
+    const double c1 = dist3(e0, e1) + dist3(e0 + 3, e1 + 3);
+    const double c2 = dist3(e0 + 3, e1) + dist3(e0, e1 + 3);
+    bits[((size_t)c * F + f) * N + n] = (uint8_t)((c2 < c1 ? 1 : 0) | (c1 < c2 ? 2 : 0));
+    mincost[((size_t)c * (F - 1) + (f - 1)) * N + n] = (c2 < c1) ? c2 : c1;  // Python's min(comb1, comb2)
+}
+
+__global__ void k_reorder_scan(int F, int N, int CN, uint8_t* __restrict__ bits)
+{
+    // thread per (colour, particle): bits[c,f,n] <- swap state of frame f (0/1); frame 0 is never swapped
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= CN) return;
+    const int c = t / N, n = t - c * N;
+    uint8_t* b = bits + (size_t)c * F * N + n;
+    int s = 0;
+    b[0] = 0;
+    for (int f = 1; f < F; f++) {
+        const int m = b[(size_t)f * N];
+        s = s ? ((m >> 1) & 1) : (m & 1);
+        b[(size_t)f * N] = (uint8_t)s;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_reorder_apply(long long total, const uint8_t* __restrict__ state,
+                                                       const double* __restrict__ ends, const double* __restrict__ pts2d,
+                                                       double* __restrict__ out_ends, double* __restrict__ out_2d)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (c, f, n)
+    if (t >= total) return;
+    const int s = state[t];
+    const double* e = ends + (size_t)t * 6;
+    double* o = out_ends + (size_t)t * 6;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        o[k] = s ? e[3 + k] : e[k];
+        o[3 + k] = s ? e[k] : e[3 + k];
+    }
+    if (pts2d) {
+        const double* q = pts2d + (size_t)t * 8;
+        double* w = out_2d + (size_t)t * 8;
+#pragma unroll
+        for (int cam = 0; cam < 2; cam++) {
+            w[cam * 4 + 0] = s ? q[cam * 4 + 2] : q[cam * 4 + 0];
+            w[cam * 4 + 1] = s ? q[cam * 4 + 3] : q[cam * 4 + 1];
+            w[cam * 4 + 2] = s ? q[cam * 4 + 0] : q[cam * 4 + 2];
+            w[cam * 4 + 3] = s ? q[cam * 4 + 1] : q[cam * 4 + 3];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------- K8 / K9
+// calibrate_cameras.project_points (calibrate_cameras.py:137-199): cv2.triangulatePoints on raw
+// (not undistorted) points, optional world transform.  p1, p2 [n,2] -> out [n,3].
+__global__ void __launch_bounds__(128) k_triangulate_points(const __grid_constant__ DevRig rig, long long n, int to_world_,
+                                                            const double* __restrict__ p1, const double* __restrict__ p2,
+                                                            double* __restrict__ out)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    double X, Y, Z;
+    dlt_triangulate(rig.P1, rig.P2, p1[2 * t], p1[2 * t + 1], p2[2 * t], p2[2 * t + 1], X, Y, Z);
+    if (to_world_) {
+        double wx, wy, wz;
+        to_world(rig, X, Y, Z, wx, wy, wz);
+        X = wx; Y = wy; Z = wz;
+    }
+    out[3 * t] = X; out[3 * t + 1] = Y; out[3 * t + 2] = Z;
+}
+
+// calibrate_cameras.reproject_points (calibrate_cameras.py:202-262): optional inverse world
+// transform rot_inv.apply(X - trans) = Rw^T (X - tw), then cv2.projectPoints into both cameras.
+__global__ void __launch_bounds__(128) k_project_points(const __grid_constant__ DevRig rig, long long n, int from_world,
+                                                        const double* __restrict__ X3, double* __restrict__ uv1,
+                                                        double* __restrict__ uv2)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    double X = X3[3 * t], Y = X3[3 * t + 1], Z = X3[3 * t + 2];
+    if (from_world) {
+        const double dx = X - rig.tw[0], dy = Y - rig.tw[1], dz = Z - rig.tw[2];
+        X = fma(rig.Rw[6], dz, fma(rig.Rw[3], dy, rig.Rw[0] * dx));
+        Y = fma(rig.Rw[7], dz, fma(rig.Rw[4], dy, rig.Rw[1] * dx));
+        Z = fma(rig.Rw[8], dz, fma(rig.Rw[5], dy, rig.Rw[2] * dx));
+    }
+    double u, v;
+    project_point(rig.R1, rig.t1, rig.CM1, rig.k1, X, Y, Z, u, v);
+    uv1[2 * t] = u; uv1[2 * t + 1] = v;
+    project_point(rig.R2, rig.t2, rig.CM2, rig.k2, X, Y, Z, u, v);
+    uv2[2 * t] = u; uv2[2 * t + 1] = v;
 }
 
 // ------------------------------------------------------------------------- FP64 peak probe

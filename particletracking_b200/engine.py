@@ -309,6 +309,52 @@ def create_weights(p_3D: torch.Tensor, p_prev: torch.Tensor, rep_errs: torch.Ten
     return w, ch
 
 
+def reorder_endpoints(ends: torch.Tensor, pts2d: Optional[torch.Tensor] = None):
+    """K7: ``match2D.reorder_endpoints_csv``'s numeric body (match2D.py:1055-1137).
+    ends[C,F,N,2,3] (, pts2d[C,F,N,2,2,2]) -> (out_ends, out_2d | None, swapped[C,F,N] uint8,
+    mincost[C,F-1,N])."""
+    _require_cuda()
+    ends = _chk(ends, _f64, "ends")
+    C, F, N = ends.shape[:3]
+    dev = ends.device
+    out_ends = torch.empty_like(ends)
+    out_2d = None
+    if pts2d is not None:
+        pts2d = _chk(pts2d, _f64, "pts2d")
+        out_2d = torch.empty_like(pts2d)
+    swapped = torch.zeros((C, F, N), dtype=_u8, device=dev)
+    mincost = torch.empty((C, max(F - 1, 0), N), dtype=_f64, device=dev)
+    with torch.cuda.device(dev):
+        nat.check(nat.lib().ptk_reorder_endpoints(C, F, N, _ptr(ends), _ptr(pts2d), _ptr(out_ends), _ptr(out_2d),
+                                                  _ptr(swapped), _ptr(mincost), _stream()), "ptk_reorder_endpoints")
+    return out_ends, out_2d, swapped, mincost
+
+
+def triangulate_points(rig: PtkRig, p1: torch.Tensor, p2: torch.Tensor, to_world: bool = False) -> torch.Tensor:
+    """K8: ``calibrate_cameras.project_points`` (calibrate_cameras.py:137-199). p1, p2 [n,2] -> [n,3]."""
+    _require_cuda()
+    p1, p2 = _chk(p1, _f64, "p1"), _chk(p2, _f64, "p2")
+    n = p1.shape[0]
+    out = torch.empty((n, 3), dtype=_f64, device=p1.device)
+    with torch.cuda.device(p1.device):
+        nat.check(nat.lib().ptk_triangulate_points(ctypes.byref(rig), n, _ptr(p1), _ptr(p2), 1 if to_world else 0,
+                                                   _ptr(out), _stream()), "ptk_triangulate_points")
+    return out
+
+
+def project_points(rig: PtkRig, X: torch.Tensor, from_world: bool = False):
+    """K9: ``calibrate_cameras.reproject_points`` (calibrate_cameras.py:202-262). X [n,3] -> uv1, uv2 [n,2]."""
+    _require_cuda()
+    X = _chk(X, _f64, "X")
+    n = X.shape[0]
+    uv1 = torch.empty((n, 2), dtype=_f64, device=X.device)
+    uv2 = torch.empty((n, 2), dtype=_f64, device=X.device)
+    with torch.cuda.device(X.device):
+        nat.check(nat.lib().ptk_project_points(ctypes.byref(rig), n, _ptr(X), 1 if from_world else 0, _ptr(uv1), _ptr(uv2),
+                                               _stream()), "ptk_project_points")
+    return uv1, uv2
+
+
 def measure_fp64_peak(iters: int = 20000) -> float:
     """FLOP/s of a dependency-free DFMA loop on the current device (roofline denominator)."""
     _require_cuda()

@@ -3,4 +3,4 @@
 ``tracking.tracking_global_assignment`` and ``matchND.create_weights`` -- same names,
 arguments, return values and error behaviour, computed by the sm_100a kernels in
 ``libptk.so``."""
-from . import match2D, matchND, tracking  # noqa: F401
+from . import calibrate_cameras, match2D, matchND, tracking  # noqa: F401

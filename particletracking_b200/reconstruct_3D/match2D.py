@@ -245,3 +245,62 @@ def match_csv_complex(input_folder, output_folder, colors, cam1_name="gp1", cam2
         df_out.reset_index(drop=True, inplace=True)
         df_out.to_csv(os.path.join(output_folder, f"rods_df_{color}.csv"), sep=",")
     return np.array(all_repr_errs), np.array(all_rod_lengths)
+
+
+def _reorder_tensors(data: pd.DataFrame, frame_numbers, cam1_name: str, cam2_name: str):
+    """Frames x particles tensors for the re-ordering kernel: per frame the rows sorted by
+    ``particle`` (match2D.py:1057,1064); every frame must hold the same particle ids."""
+    fidx = _FrameIndex(data)
+    pcol = data["particle"].to_numpy()
+    idx = []
+    ref_ids = None
+    for f in frame_numbers:
+        rows = fidx.rows(f)
+        rows = rows[np.argsort(pcol[rows], kind="stable")]
+        ids = pcol[rows]
+        if ref_ids is None:
+            ref_ids = ids
+        elif len(ids) != len(ref_ids) or (ids != ref_ids).any():
+            raise ValueError("reorder_endpoints needs the same particle ids in every frame")
+        idx.append(rows)
+    idx = np.stack(idx)  # [F, N] positions into data
+    ends = data[COLS_3D[:6]].to_numpy(dtype=np.float64)[idx].reshape(len(idx), -1, 2, 3)
+    c2d = [*_cam_cols(cam1_name), *_cam_cols(cam2_name)]
+    pts = data[c2d].to_numpy(dtype=np.float64)[idx].reshape(len(idx), -1, 2, 2, 2)
+    return idx, ends, pts, c2d
+
+
+def reorder_endpoints(data: pd.DataFrame, frame_numbers, cam1_name: str = "gp1", cam2_name: str = "gp2"):
+    """DataFrame form of ``reorder_endpoints_csv``: returns ``(df_out, mincosts_T)``."""
+    engine._require_cuda()
+    frames = list(frame_numbers)
+    idx, ends, pts, c2d = _reorder_tensors(data, frames, cam1_name, cam2_name)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a[None])).to(dev)
+    out_ends, out_2d, _, mincost = engine.reorder_endpoints(t(ends), t(pts))
+    flat = idx.reshape(-1)
+    df_out = data.iloc[flat].copy()
+    df_out[COLS_3D[:6]] = out_ends[0].cpu().numpy().reshape(len(flat), 6)
+    df_out[c2d] = out_2d[0].cpu().numpy().reshape(len(flat), 8)
+    df_out.reset_index(drop=True, inplace=True)
+    # mincosts_T[particle, frame - frame_numbers[1]] (match2D.py:1058,1100)
+    return df_out, mincost[0].cpu().numpy().T.copy()
+
+
+def reorder_endpoints_csv(input_folder: str, output_folder: str, colors: Iterable[str], cam1_name: str = "gp1",
+                          cam2_name: str = "gp2", frame_numbers: Iterable[int] = None):
+    """Reorders rod end points in ``rods_df_{color}.csv`` files such that their displacement
+    between consecutive frames is minimal (reference match2D.py:1001-1146): one device scan per
+    colour instead of O(frames x particles) pandas look-ups.  Writes files of the same layout and
+    returns the costs of the last colour, ``mincosts_T[particle, frame]``, as the reference does.
+
+    The reference hard-codes the 2D column names ``*_gp1`` / ``*_gp2`` (match2D.py:1083-1091);
+    here ``cam1_name`` / ``cam2_name`` are honoured (identical for the default names)."""
+    if not os.path.exists(output_folder):
+        os.mkdir(output_folder)
+    mincosts_T = None
+    for color in colors:
+        data = pd.read_csv(input_folder + f"/rods_df_{color}.csv", sep=",", index_col=0)
+        df_out, mincosts_T = reorder_endpoints(data, frame_numbers, cam1_name, cam2_name)
+        df_out.to_csv(os.path.join(output_folder, f"rods_df_{color}.csv"), sep=",")
+    return mincosts_T

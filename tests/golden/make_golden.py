@@ -129,6 +129,57 @@ def golden_weights(name, seed):
     print(name, "ok")
 
 
+def golden_reorder(name, F, N, seed):
+    """reference match2D.reorder_endpoints_csv on a 3D-matched experiment with random end-point flips."""
+    import tempfile
+
+    import pandas as pd
+
+    m2d = refload.load()[0]
+    cal, trf, args = rig_args()
+    data = syn.make_stereo(F, 1, N, seed=seed)
+    df = syn.to_dataframes(data)["black"]
+    m = m2d.match_complex(df, list(data.frames), "black", cal, trf)[0]
+    m["particle"] = np.concatenate([np.arange(N) for _ in range(F)])
+    flip = np.random.default_rng(seed).random(len(m)) < 0.4
+    a = ["x1", "y1", "z1", "x1_gp1", "y1_gp1", "x1_gp2", "y1_gp2"]
+    b = ["x2", "y2", "z2", "x2_gp1", "y2_gp1", "x2_gp2", "y2_gp2"]
+    va, vb = m.loc[flip, a].to_numpy(), m.loc[flip, b].to_numpy()
+    m.loc[flip, a] = vb
+    m.loc[flip, b] = va
+    c2d = [f"{k}_{c}" for c in ("gp1", "gp2") for k in ("x1", "y1", "x2", "y2")]
+    c3d = ["x1", "y1", "z1", "x2", "y2", "z2"]
+    with tempfile.TemporaryDirectory() as tmp:
+        os.mkdir(os.path.join(tmp, "in"))
+        m.to_csv(os.path.join(tmp, "in", "rods_df_black.csv"), sep=",")
+        src = pd.read_csv(os.path.join(tmp, "in", "rods_df_black.csv"), index_col=0)
+        mc = m2d.reorder_endpoints_csv(os.path.join(tmp, "in"), os.path.join(tmp, "out"), ["black"], "gp1", "gp2", list(range(F)))
+        out = pd.read_csv(os.path.join(tmp, "out", "rods_df_black.csv"), index_col=0, float_precision="round_trip")
+    np.savez_compressed(
+        os.path.join(OUT, name), ends=src[c3d].to_numpy().reshape(F, N, 2, 3), pts2d=src[c2d].to_numpy().reshape(F, N, 2, 2, 2),
+        out_ends=out[c3d].to_numpy().reshape(F, N, 2, 3), out_2d=out[c2d].to_numpy().reshape(F, N, 2, 2, 2),
+        mincosts_T=mc, versions=versions(), params=np.array([F, N, seed]))
+    print(name, "ok", int((out[c3d].to_numpy() != src[c3d].to_numpy()).any(axis=1).sum()), "rows swapped")
+
+
+def golden_project(name, seed):
+    """reference calibrate_cameras.project_points / reproject_points (needs a matplotlib stub to import)."""
+    import types
+
+    sys.modules.setdefault("matplotlib", types.ModuleType("matplotlib"))
+    refload.load()
+    import ParticleDetection.reconstruct_3D.calibrate_cameras as cc
+
+    cal, trf, _ = rig_args()
+    X = np.random.default_rng(seed).uniform([-40, -30, 260], [40, 30, 320], size=(64, 3))
+    a, b = cc.reproject_points(X, cal, None)
+    aw, bw = cc.reproject_points(X, cal, trf)
+    np.savez_compressed(os.path.join(OUT, name), X=X, uv1=a, uv2=b, uv1_w=aw, uv2_w=bw,
+                        p3d=cc.project_points(a.T.copy(), b.T.copy(), cal, None),
+                        p3d_w=cc.project_points(a.T.copy(), b.T.copy(), cal, trf), versions=versions())
+    print(name, "ok")
+
+
 if __name__ == "__main__":
     assert refload.available(), "needs /root/reference"
     # C1 of BASELINE.json: one stereo frame pair, 3 colours x 12 rods (+ one more frame)
@@ -142,3 +193,5 @@ if __name__ == "__main__":
     golden_tracking("track_12.npz", 6, 12, seed=21)
     golden_tracking("track_25.npz", 4, 25, seed=22)
     golden_weights("weights.npz", seed=5)
+    golden_reorder("reorder.npz", 9, 10, seed=41)
+    golden_project("project.npz", seed=6)

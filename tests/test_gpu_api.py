@@ -192,3 +192,81 @@ def test_matchnd_weights_and_block(api, rig):
     assert rel_err(w, ew) < 1e-8  # products of two 1e-9-accurate factors
     with pytest.raises(NotImplementedError):
         mnd.match_frame(df, df, "gp1", "gp2", 1, "black", *_args(rig))
+
+
+def test_reorder_endpoints_vs_reference_golden(api):
+    """K7 against the output of the reference's reorder_endpoints_csv (golden) -- swap decisions
+    and re-ordered values identical, costs within tolerance -- and through the CSV entry point."""
+    import torch
+    from conftest import GOLDEN
+    from particletracking_b200 import engine
+
+    g = np.load(os.path.join(GOLDEN, "reorder.npz"))
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a[None])).cuda()
+    oe, o2, sw, mc = engine.reorder_endpoints(t(g["ends"]), t(g["pts2d"]))
+    np.testing.assert_array_equal(oe.cpu().numpy()[0], g["out_ends"])
+    np.testing.assert_array_equal(o2.cpu().numpy()[0], g["out_2d"])
+    assert rel_err(mc.cpu().numpy()[0].T, g["mincosts_T"]) < 1e-14
+    assert sw.cpu().numpy()[0, 0].sum() == 0
+
+
+def test_reorder_endpoints_csv_api_and_long_sequence(api, tmp_path):
+    import torch
+    from oracle import port
+    from particletracking_b200 import engine
+
+    m2d = api[0]
+    rng = np.random.default_rng(5)
+    F, N = 40, 6
+    base = rng.normal(size=(1, N, 2, 3)) * 30
+    ends = base + np.cumsum(rng.normal(size=(F, N, 2, 3)) * 0.3, axis=0)
+    pts = rng.uniform(100, 900, size=(F, N, 2, 2, 2))
+    flip = rng.random((F, N)) < 0.5
+    ends[flip] = ends[flip][:, ::-1]
+    pts[flip] = pts[flip][:, :, ::-1]
+    cols3 = ["x1", "y1", "z1", "x2", "y2", "z2"]
+    c2d = [f"{k}_{c}" for c in ("gp1", "gp2") for k in ("x1", "y1", "x2", "y2")]
+    df = pd.DataFrame(ends.reshape(F * N, 6), columns=cols3)
+    df[c2d] = pts.reshape(F * N, 8)
+    df["frame"] = np.repeat(np.arange(10, 10 + F), N)
+    df["particle"] = np.tile(np.arange(N), F)
+    df = df.sample(frac=1.0, random_state=1)  # row order must not matter: rows are sorted by particle per frame
+    inp, outp = tmp_path / "in", tmp_path / "out"
+    inp.mkdir()
+    df.to_csv(inp / "rods_df_red.csv", sep=",")
+    mc = m2d.reorder_endpoints_csv(str(inp), str(outp), ["red"], "gp1", "gp2", list(range(10, 10 + F)))
+    res = pd.read_csv(outp / "rods_df_red.csv", index_col=0, float_precision="round_trip")
+    src = pd.read_csv(inp / "rods_df_red.csv", index_col=0)
+    src = src.sort_values(["frame", "particle"])
+    oe, o2, sw, omc = port.reorder_endpoints_arrays(src[cols3].to_numpy().reshape(F, N, 2, 3), src[c2d].to_numpy().reshape(F, N, 2, 2, 2))
+    np.testing.assert_array_equal(res[cols3].to_numpy().reshape(F, N, 2, 3), oe)
+    np.testing.assert_array_equal(res[c2d].to_numpy().reshape(F, N, 2, 2, 2), o2)
+    assert mc.shape == (N, F - 1) and rel_err(mc, omc.T) < 1e-14
+    assert list(res["frame"]) == list(np.repeat(np.arange(10, 10 + F), N))
+    # property at a length the Python loop would crawl through: idempotence (re-ordering the output changes nothing)
+    Fl, Nl = 20000, 64
+    big = rng.normal(size=(1, 1, Nl, 2, 3)) * 30 + np.cumsum(rng.normal(size=(1, Fl, Nl, 2, 3)) * 0.2, axis=1)
+    fl = rng.random((1, Fl, Nl)) < 0.5
+    big[fl] = big[fl][:, ::-1]
+    o1, _, s1, _ = engine.reorder_endpoints(torch.from_numpy(big).cuda())
+    o2_, _, s2, _ = engine.reorder_endpoints(o1)
+    assert s1.sum().item() > 0 and s2.sum().item() == 0
+    np.testing.assert_array_equal(o1.cpu().numpy(), o2_.cpu().numpy())
+
+
+def test_project_and_reproject_points_api(api, rig):
+    from conftest import GOLDEN
+    from particletracking_b200.reconstruct_3D import calibrate_cameras as cc
+
+    g = np.load(os.path.join(GOLDEN, "project.npz"))
+    cal, trf = rig["calibration"], rig["transformation"]
+    a, b = cc.reproject_points(g["X"], cal, None)
+    assert rel_err(a, g["uv1"]) < 1e-12 and rel_err(b, g["uv2"]) < 1e-12
+    aw, bw = cc.reproject_points(g["X"], cal, trf)
+    assert rel_err(aw, g["uv1_w"]) < 1e-12 and rel_err(bw, g["uv2_w"]) < 1e-12
+    p = cc.project_points(g["uv1"].T.copy(), g["uv2"].T.copy(), cal, None)
+    assert p.shape == (3, 64) and rel_err(p, g["p3d"]) < TOL
+    pw = cc.project_points(g["uv1"].T.copy(), g["uv2"].T.copy(), cal, trf)
+    assert rel_err(pw, g["p3d_w"]) < TOL
+    # reference test_calibrate_cameras.py: shapes
+    assert a.shape == (64, 2) and b.shape == (64, 2)

@@ -266,3 +266,17 @@ def test_synthetic_data_is_matchable(rig, crig):
     assert ok >= 0.98 * truth.size
     assert 0.3 < np.median(o["match_cost"]) < 3.0
     assert abs(np.median(o["rows"][..., 9]) - 10.0) < 0.2
+
+
+def test_reorder_and_project_goldens():
+    g = np.load(os.path.join(GOLDEN, "reorder.npz"))
+    oe, o2, sw, mc = port.reorder_endpoints_arrays(g["ends"], g["pts2d"])
+    np.testing.assert_array_equal(oe, g["out_ends"])
+    np.testing.assert_array_equal(o2, g["out_2d"])
+    np.testing.assert_array_equal(mc.T, g["mincosts_T"])
+    assert sw[1:].any()
+    g = np.load(os.path.join(GOLDEN, "project.npz"))
+    cal, trf = syn.synthetic_calibration(), syn.synthetic_transformation()
+    a, b = port.reproject_points(g["X"], cal, None)
+    np.testing.assert_array_equal(a, g["uv1"])
+    np.testing.assert_array_equal(port.project_points(a.T.copy(), b.T.copy(), cal, trf), g["p3d_w"])

@@ -128,3 +128,61 @@ def test_create_weights_matches_reference(ref, rig):
     ow, oc = port.create_weights(p3, prev, re)
     np.testing.assert_array_equal(rc, oc)
     assert rel_err(ow, rw) < 1e-14
+
+
+def _matched_with_flips(rig, F, N, seed):
+    """3D-matched DataFrame whose end-point order flips at random from frame to frame."""
+    data = syn.make_stereo(F, 1, N, seed=seed)
+    df = syn.to_dataframes(data)["black"]
+    m = port.match_complex(df, list(data.frames), "black", rig["calibration"], rig["transformation"])[0]
+    # give every rod a persistent particle id (the planted correspondence) so that rows of
+    # consecutive frames refer to the same physical rod
+    ids = np.concatenate([np.arange(N) for _ in range(F)])
+    m["particle"] = ids
+    flip = np.random.default_rng(seed).random(len(m)) < 0.4
+    a = ["x1", "y1", "z1", "x1_gp1", "y1_gp1", "x1_gp2", "y1_gp2"]
+    b = ["x2", "y2", "z2", "x2_gp1", "y2_gp1", "x2_gp2", "y2_gp2"]
+    va, vb = m.loc[flip, a].to_numpy(), m.loc[flip, b].to_numpy()
+    m.loc[flip, a] = vb
+    m.loc[flip, b] = va
+    return m
+
+
+def test_reorder_endpoints_matches_reference(ref, rig, tmp_path):
+    m2d = ref[0]
+    F, N = 6, 7
+    m = _matched_with_flips(rig, F, N, seed=31)
+    inp, outp = tmp_path / "in", tmp_path / "out"
+    inp.mkdir()
+    m.to_csv(inp / "rods_df_black.csv", sep=",")
+    frames = list(range(F))
+    rmin = m2d.reorder_endpoints_csv(str(inp), str(outp), ["black"], "gp1", "gp2", frames)
+    rdf = pd.read_csv(outp / "rods_df_black.csv", index_col=0, float_precision="round_trip")
+    src = pd.read_csv(inp / "rods_df_black.csv", index_col=0)
+    ends = src[["x1", "y1", "z1", "x2", "y2", "z2"]].to_numpy().reshape(F, N, 2, 3)
+    c2d = [f"{k}_{c}" for c in ("gp1", "gp2") for k in ("x1", "y1", "x2", "y2")]
+    pts = src[c2d].to_numpy().reshape(F, N, 2, 2, 2)
+    oe, o2, sw, mc = port.reorder_endpoints_arrays(ends, pts)
+    assert sw.any() and not sw.all()
+    np.testing.assert_array_equal(rdf[["x1", "y1", "z1", "x2", "y2", "z2"]].to_numpy().reshape(F, N, 2, 3), oe)
+    np.testing.assert_array_equal(rdf[c2d].to_numpy().reshape(F, N, 2, 2, 2), o2)
+    np.testing.assert_array_equal(rmin, mc.T)
+
+
+def test_project_reproject_points_match_reference(ref, rig):
+    import sys
+
+    sys.modules.setdefault("matplotlib", __import__("types").ModuleType("matplotlib"))
+    import ParticleDetection.reconstruct_3D.calibrate_cameras as cc
+
+    rng = np.random.default_rng(2)
+    X = rng.uniform([-40, -30, 260], [40, 30, 320], size=(50, 3))
+    cal, trf = rig["calibration"], rig["transformation"]
+    for tr in (None, trf):
+        a, b = cc.reproject_points(X, cal, tr)
+        oa, ob = port.reproject_points(X, cal, tr)
+        np.testing.assert_array_equal(a, oa)
+        np.testing.assert_array_equal(b, ob)
+        p = cc.project_points(a.T.copy(), b.T.copy(), cal, tr)
+        op = port.project_points(a.T.copy(), b.T.copy(), cal, tr)
+        np.testing.assert_array_equal(p, op)
