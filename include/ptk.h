@@ -200,6 +200,17 @@ int ptk_triangulate_points(const ptk_rig* rig, long long n, const double* p1, co
 int ptk_project_points(const ptk_rig* rig, long long n, const double* X, int from_world,
                        double* uv1, double* uv2, void* stream);
 
+/* ---- CSV writer (host; "next" row) ---------------------------------------
+ * Replaces df_out.to_csv(...) at match2D.py:626-629 for the output layout of match_frame
+ * (match2D.py:986-997): an unnamed RangeIndex column, `n_float_cols` float columns (Python repr()
+ * formatting, NaN -> empty field), frame, color, particle, and `n_seen` columns that are all 1.
+ * `header` is the full first line (starting with the empty index name, i.e. with a comma).
+ * ptk_format_double is the float formatter alone (test hook; buf >= 32 bytes, returns the length). */
+int ptk_csv_write_rods(const char* path, const char* header, long long n_rows, int n_float_cols,
+                       const double* values, const int64_t* frame, const char* color,
+                       const int64_t* particle, int n_seen);
+int ptk_format_double(double x, char* buf);
+
 /* ---- workspace sizing ---------------------------------------------------------------- */
 #define PTK_WS_COST 1
 #define PTK_WS_MATCH 2

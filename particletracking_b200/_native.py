@@ -26,7 +26,7 @@ SYMBOLS = [
     "ptk_version", "ptk_strerror", "ptk_last_cuda_error", "ptk_device_count",
     "ptk_undistort_batch", "ptk_cost_batch", "ptk_lsap_batch", "ptk_match_batch",
     "ptk_rows_batch", "ptk_rows_to_ends", "ptk_track_batch", "ptk_chain_tracks", "ptk_chain_rebase", "ptk_create_weights", "ptk_reorder_endpoints", "ptk_triangulate_points", "ptk_project_points",
-    "ptk_workspace_bytes",
+    "ptk_csv_write_rods", "ptk_format_double", "ptk_workspace_bytes",
     "ptk_ctx_create", "ptk_ctx_destroy", "ptk_reconstruct_host",
     "ptk_reconstruct_device", "ptk_reconstruct_device_workspace_bytes",
     "ptk_measure_fp64_peak", "ptk_launch_count", "ptk_timing_enable", "ptk_timing_read",
@@ -84,6 +84,8 @@ def lib() -> ctypes.CDLL:
     L.ptk_reorder_endpoints.argtypes = [i32, i32, i32] + [vp] * 6 + [vp]
     L.ptk_triangulate_points.argtypes = [rigp, ll, vp, vp, i32, vp, vp]
     L.ptk_project_points.argtypes = [rigp, ll, vp, i32, vp, vp, vp]
+    L.ptk_csv_write_rods.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ll, i32, vp, vp, ctypes.c_char_p, vp, i32]
+    L.ptk_format_double.argtypes = [dbl, ctypes.c_char_p]
     L.ptk_ctx_create.argtypes = [i32, ctypes.POINTER(vp)]
     L.ptk_ctx_destroy.argtypes = [vp]
     L.ptk_ctx_destroy.restype = None

@@ -11,6 +11,7 @@
 #include <utility>
 #include <vector>
 
+#include "ptk_csv.cuh"
 #include "ptk_kernels.cuh"
 
 using namespace ptk;
@@ -661,6 +662,51 @@ PTK_API int ptk_project_points(const ptk_rig* rig, long long n, const double* X,
     LAUNCHED("k_project_points");
     return PTK_OK;
 }
+
+// ------------------------------------------------------------------------------------ CSV writer (host)
+PTK_API int ptk_csv_write_rods(const char* path, const char* header, long long n_rows, int n_float_cols,
+                               const double* values, const int64_t* frame, const char* color, const int64_t* particle,
+                               int n_seen)
+{
+    if (!path || !header || n_rows < 0 || n_float_cols < 0 || (n_rows && (!values || !frame || !particle)) || !color ||
+        n_seen < 0)
+        return PTK_ERR_INVALID_ARG;
+    FILE* f = fopen(path, "wb");
+    if (!f) return PTK_ERR_INVALID_ARG;
+    std::vector<char> buf(1 << 22);
+    size_t used = 0;
+    const size_t clen = strlen(color);
+    auto flush = [&]() { if (used) fwrite(buf.data(), 1, used, f); used = 0; };
+    fwrite(header, 1, strlen(header), f);
+    fputc('\n', f);
+    const size_t worst = (size_t)n_float_cols * 26 + clen + 3 * 24 + (size_t)n_seen * 2 + 16;
+    for (long long r = 0; r < n_rows; r++) {
+        if (used + worst > buf.size()) flush();
+        char* o = buf.data() + used;
+        o += format_int(r, o);
+        const double* v = values + (size_t)r * n_float_cols;
+        for (int c = 0; c < n_float_cols; c++) {
+            *o++ = ',';
+            o += format_double_repr(v[c], o);
+        }
+        *o++ = ',';
+        o += format_int(frame[r], o);
+        *o++ = ',';
+        memcpy(o, color, clen); o += clen;
+        *o++ = ',';
+        o += format_int(particle[r], o);
+        for (int k = 0; k < n_seen; k++) { *o++ = ','; *o++ = '1'; }
+        *o++ = '\n';
+        used = (size_t)(o - buf.data());
+    }
+    flush();
+    const int bad = ferror(f);
+    fclose(f);
+    return bad ? PTK_ERR_INVALID_ARG : PTK_OK;
+}
+
+// test hook: Python repr() of one double (returns the length; buf needs 32 bytes)
+PTK_API int ptk_format_double(double x, char* buf) { return format_double_repr(x, buf); }
 
 // ------------------------------------------------------------------------------------ FP64 peak
 PTK_API int ptk_measure_fp64_peak(int iters, double* flops, void* stream)
