@@ -92,8 +92,30 @@ inline int cuda_fail(cudaError_t e, const char* what)
 DevRig make_devrig(const ptk_rig* r)
 {
     DevRig d;
-    memcpy(d.P1, r->P1, sizeof(d.P1));
-    memcpy(d.P2, r->P2, sizeof(d.P2));
+    // Static de Rijk ordering: norms of the DLT matrix's columns at the two principal points decide
+    // the column order the Jacobi starts from; the columns of P1/P2 are permuted accordingly (the
+    // kernel verifies the order per point and re-sorts the rare exception).
+    {
+        const double x1 = r->CM1[2], y1 = r->CM1[5], x2 = r->CM2[2], y2 = r->CM2[5];
+        double w[4];
+        for (int k = 0; k < 4; k++) {
+            const double a0 = x1 * r->P1[8 + k] - r->P1[k], a1 = y1 * r->P1[8 + k] - r->P1[4 + k];
+            const double a2 = x2 * r->P2[8 + k] - r->P2[k], a3 = y2 * r->P2[8 + k] - r->P2[4 + k];
+            w[k] = a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3;
+            d.perm[k] = k;
+        }
+        for (int i = 0; i < 3; i++) {
+            int j = i;
+            for (int k = i + 1; k < 4; k++)
+                if (w[d.perm[k]] > w[d.perm[j]]) j = k;
+            const int t = d.perm[i]; d.perm[i] = d.perm[j]; d.perm[j] = t;
+        }
+        for (int k = 0; k < 4; k++)
+            for (int row = 0; row < 3; row++) {
+                d.P1[row * 4 + k] = r->P1[row * 4 + d.perm[k]];
+                d.P2[row * 4 + k] = r->P2[row * 4 + d.perm[k]];
+            }
+    }
     memcpy(d.R1, r->R1, sizeof(d.R1));
     memcpy(d.t1, r->t1, sizeof(d.t1));
     memcpy(d.R2, r->R2, sizeof(d.R2));

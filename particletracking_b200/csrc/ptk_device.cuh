@@ -21,7 +21,8 @@ namespace ptk {
 
 // Device-side copy of the rig, pre-digested (reciprocal focal lengths etc.).
 struct DevRig {
-    double P1[12], P2[12];
+    double P1[12], P2[12];  // columns permuted by `perm` (host-side static de Rijk ordering, see make_devrig)
+    int perm[4];            // column k of the permuted matrices is original column perm[k]
     double R1[9], t1[3], R2[9], t2[3];
     double CM1[4], CM2[4];  // fx, fy, cx, cy
     double k1[12], k2[12];  // k1 k2 p1 p2 k3 k4 k5 k6 s1 s2 s3 s4
@@ -145,9 +146,59 @@ __device__ __forceinline__ bool jacobi_pair(double (&Ai)[4], double (&Aj)[4], do
     return true;
 }
 
+// The same rotation without the skip test, for the first two sweeps: on DLT matrices every pair
+// needs its rotation there anyway (measured: identical rotation counts with and without the test,
+// profiles/experiments), and straight-line code lets the compiler keep the 36 doubles of state in
+// place instead of shuffling registers at every if-merge (16 moves per rotation) -- this kernel
+// is co-limited by instruction issue, not only by the FP64 pipe.  A rotation of an already
+// orthogonal pair is the identity (s = 0); the only singular case, p == 0 with equal norms, is
+// mapped to the identity explicitly.
+__device__ __forceinline__ void jacobi_pair_always(double (&Ai)[4], double (&Aj)[4], double (&Vi)[4], double (&Vj)[4],
+                                                   double& Wi, double& Wj)
+{
+    double p = Ai[0] * Aj[0];
+    p = fma(Ai[1], Aj[1], p);
+    p = fma(Ai[2], Aj[2], p);
+    p = fma(Ai[3], Aj[3], p);
+    const double beta = Wi - Wj;
+    const double p2 = p + p;
+    const double x1 = fma(p2, p2, beta * beta);
+    const double hb = 0.5 * fabs(beta);
+    const double g0 = rsqrt_seed(x1);
+    const double r0 = rsqrt_seed(fma(hb, g0, 0.5));
+    const double g = rsqrt_refine(x1, g0);
+    const double t = fma(hb, g, 0.5);
+    const double rt = rsqrt_refine(t, r0);
+    const double big = t * rt;
+    const double small_ = p * g * rt;
+    const bool ok = x1 > 0.0;
+    const double c = ok ? (beta < 0 ? small_ : big) : 1.0;
+    const double s = ok ? (beta < 0 ? big : small_) : 0.0;
+    double na = 0, nb = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const double x = Ai[k], y = Aj[k];
+        const double t0 = fma(c, x, s * y);
+        const double t1 = fma(c, y, -(s * x));
+        Ai[k] = t0;
+        Aj[k] = t1;
+        na = fma(t0, t0, na);
+        nb = fma(t1, t1, nb);
+    }
+    Wi = na;
+    Wj = nb;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const double x = Vi[k], y = Vj[k];
+        Vi[k] = fma(c, x, s * y);
+        Vj[k] = fma(c, y, -(s * x));
+    }
+}
+
 // cv2.triangulatePoints for one point (match2D.py:889) + the reference's p[0:3]/p[3]
 // (match2D.py:895).  Returns the point in camera-1 coordinates.
 __device__ __forceinline__ void dlt_triangulate(const double* __restrict__ P1, const double* __restrict__ P2,
+                                                const int* __restrict__ perm,
                                                 double x1, double y1, double x2, double y2,
                                                 double& X, double& Y, double& Z, int* n_rot = nullptr)
 {
@@ -164,13 +215,15 @@ __device__ __forceinline__ void dlt_triangulate(const double* __restrict__ P1, c
     double W0, W1, W2, W3;
 #define PTK_NRM(Ak) fma(Ak[3], Ak[3], fma(Ak[2], Ak[2], fma(Ak[1], Ak[1], Ak[0] * Ak[0])))
     W0 = PTK_NRM(A0); W1 = PTK_NRM(A1); W2 = PTK_NRM(A2); W3 = PTK_NRM(A3);
-    // de Rijk ordering: sort the columns by decreasing norm before the first sweep.  OpenCV does
-    // not, but the singular vectors do not depend on the column order, and on DLT matrices (one
-    // column ~ f*T dominates) it cuts the rotations from 19.6 to 13.9 and the sweeps from 4.8 to
-    // 3.9 per point at the same 1e-15 accuracy (profiles/experiments/jacobi_variants.c).  Branch
-    // free 5-comparator network on registers; V starts as the identity in the permuted basis and
-    // the selected vector is un-permuted at the end.
-    int q0 = 0, q1 = 1, q2 = 2, q3 = 3;
+    // de Rijk ordering: the columns are taken by decreasing norm before the first sweep.  OpenCV
+    // does not, but the singular vectors do not depend on the column order, and on DLT matrices
+    // (one column ~ f*T dominates) it cuts the rotations from 19.6 to 13.9 and the sweeps from 4.8
+    // to 3.9 per point at the same 1e-15 accuracy (profiles/experiments/jacobi_variants.c).
+    // The order is fixed by the rig, so the host already permuted the columns of P1/P2
+    // (make_devrig); here it is only verified, and the rare point that disagrees (e.g. a dummy
+    // detection far off the image) goes through a branch-free 5-comparator network.  V starts as
+    // the identity in the permuted basis and the selected vector is un-permuted at the end.
+    int q0 = perm[0], q1 = perm[1], q2 = perm[2], q3 = perm[3];
 #define PTK_CSWAP(a, b)                                                      \
     {                                                                        \
         const bool sw = W##b > W##a;                                         \
@@ -186,11 +239,23 @@ __device__ __forceinline__ void dlt_triangulate(const double* __restrict__ P1, c
         q##a = sw ? q##b : q##a;                                             \
         q##b = ql;                                                           \
     }
-    PTK_CSWAP(0, 1) PTK_CSWAP(2, 3) PTK_CSWAP(0, 2) PTK_CSWAP(1, 3) PTK_CSWAP(1, 2)
+    if (!(W0 >= W1 && W1 >= W2 && W2 >= W3)) {
+        PTK_CSWAP(0, 1) PTK_CSWAP(2, 3) PTK_CSWAP(0, 2) PTK_CSWAP(1, 3) PTK_CSWAP(1, 2)
+    }
 #undef PTK_CSWAP
-    int rot = 0;
+    // sweeps 1 and 2: every pair, no skip test (see jacobi_pair_always)
 #pragma unroll 1
-    for (int iter = 0; iter < 30; iter++) {
+    for (int iter = 0; iter < 2; iter++) {
+        jacobi_pair_always(A0, A1, V0, V1, W0, W1);
+        jacobi_pair_always(A0, A2, V0, V2, W0, W2);
+        jacobi_pair_always(A0, A3, V0, V3, W0, W3);
+        jacobi_pair_always(A1, A2, V1, V2, W1, W2);
+        jacobi_pair_always(A1, A3, V1, V3, W1, W3);
+        jacobi_pair_always(A2, A3, V2, V3, W2, W3);
+    }
+    int rot = 12;
+#pragma unroll 1
+    for (int iter = 2; iter < 30; iter++) {
         bool ch = false;
         bool r;
         r = jacobi_pair(A0, A1, V0, V1, W0, W1); ch |= r; rot += r;
@@ -259,7 +324,7 @@ __device__ __forceinline__ void eval_combo(const DevRig& rig, double u1x, double
                                            double o1x, double o1y, double o2x, double o2y,
                                            double& d1, double& d2, double& X, double& Y, double& Z)
 {
-    dlt_triangulate(rig.P1, rig.P2, u1x, u1y, u2x, u2y, X, Y, Z);
+    dlt_triangulate(rig.P1, rig.P2, rig.perm, u1x, u1y, u2x, u2y, X, Y, Z);
     d1 = reproject_dist(rig.R1, rig.t1, rig.CM1, rig.k1, X, Y, Z, o1x, o1y);
     d2 = reproject_dist(rig.R2, rig.t2, rig.CM2, rig.k2, X, Y, Z, o2x, o2y);
 }

@@ -785,7 +785,7 @@ __global__ void __launch_bounds__(128) k_triangulate_points(const __grid_constan
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     double X, Y, Z;
-    dlt_triangulate(rig.P1, rig.P2, p1[2 * t], p1[2 * t + 1], p2[2 * t], p2[2 * t + 1], X, Y, Z);
+    dlt_triangulate(rig.P1, rig.P2, rig.perm, p1[2 * t], p1[2 * t + 1], p2[2 * t], p2[2 * t + 1], X, Y, Z);
     if (to_world_) {
         double wx, wy, wz;
         to_world(rig, X, Y, Z, wx, wy, wz);
