@@ -92,6 +92,8 @@ inline int cuda_fail(cudaError_t e, const char* what)
 DevRig make_devrig(const ptk_rig* r)
 {
     DevRig d;
+    memcpy(d.P1o, r->P1, sizeof(d.P1o));
+    memcpy(d.P2o, r->P2, sizeof(d.P2o));
     // Static de Rijk ordering: norms of the DLT matrix's columns at the two principal points decide
     // the column order the Jacobi starts from; the columns of P1/P2 are permuted accordingly (the
     // kernel verifies the order per point and re-sorts the rare exception).

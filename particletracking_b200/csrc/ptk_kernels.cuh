@@ -72,10 +72,11 @@ struct CostArgs {
 
 __device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
 
-// 5 CTAs x 4 warps per SM (96 registers, ~90 B of spill outside the Jacobi loop) measured 3 %
-// faster than 4 CTAs at 126 registers (tools/ab_bench.py, profiles/README.md).
+// 6 CTAs x 4 warps per SM (80 registers; the Jacobi state is 16 + 4 doubles since V is no longer
+// accumulated) measured fastest: 2.67 / 2.57 / 2.53 / 2.55 / 2.54 ms at 4 / 5 / 6 / 7 / 8 CTAs
+// (tools/ab_bench.py, profiles/README.md).
 #ifndef PTK_KCOST_MINBLOCKS
-#define PTK_KCOST_MINBLOCKS 5
+#define PTK_KCOST_MINBLOCKS 6
 #endif
 __global__ void __launch_bounds__(128, PTK_KCOST_MINBLOCKS) k_cost(const __grid_constant__ DevRig rig, const __grid_constant__ CostArgs a)
 {
@@ -785,7 +786,7 @@ __global__ void __launch_bounds__(128) k_triangulate_points(const __grid_constan
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     double X, Y, Z;
-    dlt_triangulate(rig.P1, rig.P2, rig.perm, p1[2 * t], p1[2 * t + 1], p2[2 * t], p2[2 * t + 1], X, Y, Z);
+    dlt_triangulate(rig, p1[2 * t], p1[2 * t + 1], p2[2 * t], p2[2 * t + 1], X, Y, Z);
     if (to_world_) {
         double wx, wy, wz;
         to_world(rig, X, Y, Z, wx, wy, wz);
