@@ -502,3 +502,28 @@ def test_chain_rebase_emulated_ranks(eng):
         eng.chain_rebase(maps, r, loc)
         out.append(loc[:, : f1 - f0].cpu().numpy())
     np.testing.assert_array_equal(np.concatenate(out, axis=1), full)
+
+
+def test_full_distortion_model_vs_c_oracle(eng, rig):
+    """Rig with tangential, k3 and rational (k4..k6) and thin-prism (s1..s4) coefficients: exercises
+    every term of the undistortion / projection formulas."""
+    from oracle import c_oracle as co
+    from particletracking_b200 import rig as rigmod
+    from particletracking_b200 import synthetic as syn
+
+    cal = dict(syn.synthetic_calibration())
+    cal["dist1"] = np.array([-0.11, 1.2, 1e-3, -2e-3, 0.3, 0.02, -0.01, 0.005, 1e-3, -1e-3, 2e-3, 5e-4])
+    cal["dist2"] = np.array([-0.41, 10.1, -1e-3, 1e-3, 0.0, 0.01, 0.02, 0.0])
+    trf = syn.synthetic_transformation()
+    r = rigmod.rig_from_dicts(cal, trf)
+    data = syn.make_stereo(3, 2, 16, seed=44, calibration=cal)
+    c1, c2, n1, n2 = data.problems()
+    o = co.match_batch(r, c1, c2, n1, n2, want_cost=True)
+    g = run_match(eng, r, c1, c2, n1, n2, want_cost=True)
+    np.testing.assert_array_equal(g.col_ind.cpu().numpy(), o["col_ind"])
+    assert rel_err(g.cost.cpu().numpy(), o["cost"]) < TOL
+    assert rel_err(g.rows.cpu().numpy()[..., :10], o["rows"][..., :10]) < TOL
+    u1, u2 = eng.undistort_batch(r, dev(c1), dev(c2), dev(n1), dev(n2))
+    for p in range(len(n1)):
+        np.testing.assert_array_equal(u1.cpu().numpy()[p], co.undistort_rods(cal["CM1"], cal["dist1"], c1[p]))
+        np.testing.assert_array_equal(u2.cpu().numpy()[p], co.undistort_rods(cal["CM2"], cal["dist2"], c2[p]))
