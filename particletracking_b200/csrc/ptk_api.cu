@@ -483,15 +483,13 @@ PTK_API int ptk_track_batch(int C, int F, int N, const double* ends, double* cos
     cudaStream_t st = (cudaStream_t)stream;
     const size_t NN = (size_t)N * N;
     long long chunk = cost ? Q : match_chunk(Q, N);
-    if (chunk > 65535) chunk = 65535;  // gridDim.y
     double* wcost = cost ? cost : reinterpret_cast<double*>(align_up((size_t)workspace));
     for (long long q0 = 0; q0 < Q; q0 += chunk) {
         const long long nq = (Q - q0) < chunk ? (Q - q0) : chunk;
         double* cchunk = cost ? cost + (size_t)q0 * NN : wcost;
-        dim3 grid((unsigned)((NN + 255) / 256), (unsigned)nq);
         {
             LaunchTimer lt(K_TRACK_COST, st);
-            k_track_cost<<<grid, 256, 0, st>>>(N, F, q0, ends, cchunk);
+            k_track_cost<<<(unsigned)nq, 256, (size_t)14 * N * sizeof(double), st>>>(N, F, q0, ends, cchunk);
         }
         LAUNCHED("k_track_cost");
         LsapArgs a{};

@@ -506,26 +506,43 @@ __device__ __forceinline__ double norm3(double ax, double ay, double az, double 
     return sqrt((dx * dx + dy * dy) + dz * dz);
 }
 
+// One CTA per frame pair.  The first candidate d0 = |q1[a]-p1[a]| + |q2[b]-p2[b]| is separable, so
+// its 2N norms are computed once into shared memory (same arithmetic, same bits) and only the
+// cross term costs two norms per (a,b); the 2 x N x 6 doubles of the two frames are staged in
+// shared memory as well.
 __global__ void __launch_bounds__(256) k_track_cost(int N, int F, long long q0, const double* __restrict__ ends,
                                                     double* __restrict__ cost)
 {
-    const long long ql = blockIdx.y;  // problem within this launch
+    extern __shared__ double tsm[];  // cur[6N] | nxt[6N] | n1[N] | n2[N]
+    double* cur = tsm;
+    double* nxt = tsm + 6 * N;
+    double* n1 = tsm + 12 * N;
+    double* n2 = n1 + N;
+    const long long ql = blockIdx.x;  // problem within this launch
     const long long q = q0 + ql;
     const int c = (int)(q / (F - 1)), f = (int)(q - (long long)c * (F - 1));
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= N * N) return;
-    const int aa = e / N, bb = e - aa * N;
-    const double* cur = ends + ((size_t)c * F + f) * N * 6;
-    const double* nxt = cur + (size_t)N * 6;
-    const double* p1a = cur + 6 * aa;
-    const double* p2b = cur + 6 * bb + 3;
-    const double* q1a = nxt + 6 * aa;
-    const double* q2b = nxt + 6 * bb + 3;
-    const double d0 = norm3(q1a[0], q1a[1], q1a[2], p1a[0], p1a[1], p1a[2]) +
-                      norm3(q2b[0], q2b[1], q2b[2], p2b[0], p2b[1], p2b[2]);
-    const double d1 = norm3(p1a[0], p1a[1], p1a[2], q2b[0], q2b[1], q2b[2]) +
-                      norm3(p2b[0], p2b[1], p2b[2], q1a[0], q1a[1], q1a[2]);
-    cost[(size_t)ql * N * N + e] = np_min(d0, d1);
+    const double* g = ends + ((size_t)c * F + f) * N * 6;
+    for (int k = threadIdx.x; k < 12 * N; k += blockDim.x) tsm[k] = g[k];  // frames f and f+1 are contiguous
+    __syncthreads();
+    for (int k = threadIdx.x; k < 2 * N; k += blockDim.x) {
+        const int r = k >> 1, e = (k & 1) * 3;  // rod r, end point 1 or 2
+        const double v = norm3(nxt[6 * r + e], nxt[6 * r + e + 1], nxt[6 * r + e + 2],
+                               cur[6 * r + e], cur[6 * r + e + 1], cur[6 * r + e + 2]);
+        if (k & 1) n2[r] = v; else n1[r] = v;
+    }
+    __syncthreads();
+    double* out = cost + (size_t)ql * N * N;
+    for (int e = threadIdx.x; e < N * N; e += blockDim.x) {
+        const int aa = e / N, bb = e - aa * N;
+        const double* p1a = cur + 6 * aa;
+        const double* p2b = cur + 6 * bb + 3;
+        const double* q1a = nxt + 6 * aa;
+        const double* q2b = nxt + 6 * bb + 3;
+        const double d0 = n1[aa] + n2[bb];
+        const double d1 = norm3(p1a[0], p1a[1], p1a[2], q2b[0], q2b[1], q2b[2]) +
+                          norm3(p2b[0], p2b[1], p2b[2], q1a[0], q1a[1], q1a[2]);
+        out[e] = np_min(d0, d1);
+    }
 }
 
 // ------------------------------------------------------------------------------------- K5
