@@ -245,6 +245,27 @@ def run_b200(args):
     fp64_peak = engine.measure_fp64_peak(20000)  # also warms the clocks
     for i in range(W):
         out = step(i)
+    # Settling: on a fresh box the first process that brings up NCCL / the allocator keeps paying
+    # one-time host-side costs for a few dozen steps (measured: 14 ms/step of host enqueue time
+    # instead of 0.8).  Keep stepping, untimed, until three consecutive synchronised steps agree
+    # within 10 % (at most 60 extra steps); the timed region below is still exactly K steps.
+    extra, hist = 0, []
+    while extra < 60:
+        t_s = time.perf_counter()
+        out = step(W + extra)
+        if sharded is not None:
+            sharded.finish()
+        torch.cuda.synchronize()
+        hist.append(time.perf_counter() - t_s)
+        extra += 1
+        stable = len(hist) >= 3 and max(hist[-3:]) <= 1.10 * min(hist[-3:])
+        if world > 1:
+            flag = torch.tensor([1.0 if stable else 0.0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            stable = bool(flag.item() == 1.0)
+        if stable and extra >= 5:
+            break
+    W_total = W + extra
     if sharded is not None:
         sharded.finish()
     barrier()
@@ -262,10 +283,11 @@ def run_b200(args):
     t_wall0 = time.perf_counter()
     e0.record()
     for i in range(K):
-        step(W + i)
+        step(W_total + i)
     if sharded is not None:
         sharded.finish()  # the last steps' result gathers are part of the timed region
     e1.record()
+    t_enq = time.perf_counter() - t_wall0  # host time to enqueue K steps (no synchronisation inside)
     barrier()
     t_wall1 = time.perf_counter()
     ms = e0.elapsed_time(e1)
@@ -333,7 +355,7 @@ def run_b200(args):
     }
 
     line = {
-        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W, "warmup_settle_steps": extra,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "frames_per_gpu": F, "colours": C, "rods": N, "problems_per_step": P,
@@ -347,6 +369,7 @@ def run_b200(args):
         "clocks": clk,
         "kernel_ms_per_step": {k: v[0] / K for k, v in timing.items() if v[1]},
         "wall_s": t_wall1 - t_wall0,
+        "host_enqueue_ms_per_step": t_enq / K * 1e3,
     }
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
