@@ -513,8 +513,8 @@ int chain_impl(int C, int F, int N, const int32_t* col_ind, const int32_t* ids_i
     const int nseg = (F + kChainSeg - 1) / kChainSeg;
     int32_t* seg_map = scratch;
     int32_t* seg_start = scratch + (size_t)C * nseg * N;
-    const int threads = N < 32 ? 32 : ((N + 31) / 32 * 32);
-    const size_t smem = 2 * (size_t)N * sizeof(int32_t);
+    const int threads = N < 128 ? 128 : ((N + 31) / 32 * 32);
+    const size_t smem = (2 + (size_t)kChainSeg) * N * sizeof(int32_t);
     const long long total = (long long)C * F * N;
     {
         LaunchTimer lt(K_CHAIN, st);

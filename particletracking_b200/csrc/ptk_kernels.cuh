@@ -561,22 +561,27 @@ constexpr int kChainSeg = 32;
 __global__ void k_chain_local(int F, int N, int nseg, const int32_t* __restrict__ col_ind,
                               int32_t* __restrict__ track_id, int32_t* __restrict__ seg_map)
 {
-    extern __shared__ int32_t sh[];  // two id buffers of N
+    extern __shared__ int32_t sh[];  // cur[N] | nxt[N] | the segment's assignments [<=kChainSeg][N]
     int32_t* cur = sh;
     int32_t* nxt = sh + N;
+    int32_t* cols = sh + 2 * N;
     const int c = blockIdx.y, s = blockIdx.x;
     const int f0 = s * kChainSeg;
     const int fl = min(f0 + kChainSeg, F) - 1;  // last frame of the segment
+    // pairs f0..fl-1 stay inside the segment; pair fl (if any) leaves it
+    const int f_end = (fl < F - 1) ? fl + 1 : fl;
     int32_t* tid = track_id + (size_t)c * F * N;
+    // all assignments of the segment in one coalesced sweep (independent loads), then the
+    // dependent chain runs out of shared memory
+    const int32_t* g = col_ind + ((size_t)c * (F - 1) + f0) * N;
+    for (int k = threadIdx.x; k < (f_end - f0) * N; k += blockDim.x) cols[k] = g[k];
     for (int a = threadIdx.x; a < N; a += blockDim.x) {
         cur[a] = a;
         tid[(size_t)f0 * N + a] = a;
     }
     __syncthreads();
-    // pairs f0..fl-1 stay inside the segment; pair fl (if any) leaves it
-    const int f_end = (fl < F - 1) ? fl + 1 : fl;
     for (int f = f0; f < f_end; f++) {
-        const int32_t* col = col_ind + ((size_t)c * (F - 1) + f) * N;
+        const int32_t* col = cols + (size_t)(f - f0) * N;
         for (int a = threadIdx.x; a < N; a += blockDim.x) nxt[col[a]] = cur[a];
         __syncthreads();
         if (f < fl) {
@@ -592,19 +597,29 @@ __global__ void k_chain_local(int F, int N, int nseg, const int32_t* __restrict_
 __global__ void k_chain_scan(int N, int nseg, const int32_t* __restrict__ ids_in, const int32_t* __restrict__ seg_map,
                              int32_t* __restrict__ seg_start)
 {
-    extern __shared__ int32_t sh[];
+    extern __shared__ int32_t sh[];  // cur[N] | nxt[N] | a block of kChainSeg segment maps
     int32_t* cur = sh;
     int32_t* nxt = sh + N;
+    int32_t* maps = sh + 2 * N;
     const int c = blockIdx.x;
     for (int a = threadIdx.x; a < N; a += blockDim.x) cur[a] = ids_in ? ids_in[(size_t)c * N + a] : a;
     __syncthreads();
-    for (int s = 0; s < nseg; s++) {
-        for (int a = threadIdx.x; a < N; a += blockDim.x) seg_start[((size_t)c * nseg + s) * N + a] = cur[a];
-        if (s + 1 == nseg) break;
-        const int32_t* mp = seg_map + ((size_t)c * nseg + s) * N;
-        for (int a = threadIdx.x; a < N; a += blockDim.x) nxt[a] = cur[mp[a]];
+    for (int s0 = 0; s0 < nseg; s0 += kChainSeg) {
+        const int ns = min(kChainSeg, nseg - s0);
+        const int32_t* g = seg_map + ((size_t)c * nseg + s0) * N;
+        // the last segment of all has no map (nothing follows it): do not read it
+        const int nload = (s0 + ns == nseg) ? ns - 1 : ns;
+        for (int k = threadIdx.x; k < nload * N; k += blockDim.x) maps[k] = g[k];
         __syncthreads();
-        int32_t* t = cur; cur = nxt; nxt = t;
+        for (int s = 0; s < ns; s++) {
+            for (int a = threadIdx.x; a < N; a += blockDim.x) seg_start[((size_t)c * nseg + s0 + s) * N + a] = cur[a];
+            if (s0 + s + 1 == nseg) break;
+            const int32_t* mp = maps + (size_t)s * N;
+            for (int a = threadIdx.x; a < N; a += blockDim.x) nxt[a] = cur[mp[a]];
+            __syncthreads();
+            int32_t* t = cur; cur = nxt; nxt = t;
+        }
+        __syncthreads();
     }
 }
 
