@@ -280,3 +280,34 @@ def test_reorder_and_project_goldens():
     a, b = port.reproject_points(g["X"], cal, None)
     np.testing.assert_array_equal(a, g["uv1"])
     np.testing.assert_array_equal(port.project_points(a.T.copy(), b.T.copy(), cal, trf), g["p3d_w"])
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_c_oracle_vs_cv2_on_random_rigs(seed):
+    """The C restatement against the cv2/scipy port on other stereo geometries than the bench rig."""
+    from scipy.spatial.transform import Rotation
+
+    rng = np.random.default_rng(seed)
+    trf = syn.synthetic_transformation()
+    f1, f2 = rng.uniform(800, 4000, size=2)
+    cal = {
+        "CM1": np.array([[f1, 0, rng.uniform(300, 900)], [0, f1 * 1.01, rng.uniform(250, 700)], [0, 0, 1.0]]),
+        "CM2": np.array([[f2, 0, rng.uniform(300, 900)], [0, f2 * 0.99, rng.uniform(250, 700)], [0, 0, 1.0]]),
+        "dist1": np.array([rng.uniform(-0.2, 0.1), rng.uniform(-0.5, 1.0), 1e-3, -1e-3]),
+        "dist2": np.array([rng.uniform(-0.2, 0.1), rng.uniform(-0.5, 1.0), 0.0, 0.0, 0.1]),
+    }
+    axis = rng.normal(size=3)
+    axis /= np.linalg.norm(axis)
+    R = Rotation.from_rotvec(axis * np.deg2rad(rng.uniform(15, 95))).as_matrix()
+    cal["R"] = R
+    cal["T"] = (np.array([0.0, 0.0, 350.0]) - R @ (-trf["rotation"].T @ trf["translation"])).reshape(3, 1)
+    r = rigmod.rig_from_dicts(cal, trf)
+    P1, P2, r1, r2, t1, t2 = syn.projection_matrices(cal)
+    data = syn.make_stereo(1, 1, 14, seed=seed, p_dummy=0.1, calibration=cal)
+    ref = port.match_arrays(data.cam1[0, 0], data.cam2[0, 0], cal, P1, P2, Rotation.from_matrix(trf["rotation"]),
+                            trf["translation"], r1, r2, t1, t2)
+    o = co.cost_problem(r, data.cam1[0, 0], data.cam2[0, 0], want_combos=True)
+    assert rel_err(o["cost"], ref["cost"]) < TOL
+    np.testing.assert_array_equal(o["choice"], ref["choice"])
+    d = np.abs(o["p_world"] - ref["p_world"]).max(axis=-1) / np.maximum(np.abs(ref["p_world"]).max(axis=-1), 1.0)
+    assert d.max() < TOL
