@@ -221,13 +221,16 @@ int launch_lsap(long long P, LsapArgs a, cudaStream_t st)
 {
     const int M = a.ld_rows > a.ld_cols ? a.ld_rows : a.ld_cols;
     const size_t bytes = (size_t)a.ld_rows * a.ld_cols * sizeof(double);
-    a.stage = bytes <= (size_t)kLsapStageBytes ? 1 : 0;
-    const size_t smem = ((lsap_row_state_bytes(M) + 15) / 16) * 16 + (a.stage ? bytes : 0);
+    const bool trk = a.trk_ends != nullptr;
+    a.stage = (!trk && bytes <= (size_t)kLsapStageBytes) ? 1 : 0;
+    const size_t smem = ((lsap_row_state_bytes(M) + 15) / 16) * 16 +
+                        (trk ? (size_t)14 * M * sizeof(double) : (a.stage ? bytes : 0));
     const long long max_p = 1ll << 30;
     for (long long p0 = 0; p0 < P; p0 += max_p) {
         const long long np = (P - p0) < max_p ? (P - p0) : max_p;
         LsapArgs b = a;
-        b.cost = a.cost + (size_t)p0 * a.cost_stride;
+        if (a.cost) b.cost = a.cost + (size_t)p0 * a.cost_stride;
+        if (trk && p0 != 0) return PTK_ERR_INVALID_ARG;  // TRK launches index frames by the launch-local problem id
         if (a.nr) b.nr = a.nr + p0;
         if (a.nc) b.nc = a.nc + p0;
         if (a.row_ind) b.row_ind = a.row_ind + (size_t)p0 * a.out_ld;
@@ -239,7 +242,11 @@ int launch_lsap(long long P, LsapArgs a, cudaStream_t st)
         if (a.keep) b.keep = a.keep + (size_t)p0 * a.out_ld;
         {
             LaunchTimer lt(a.total ? K_LSAP_TRACK : K_LSAP_MATCH, st);
-            if (M <= 32) k_lsap<1><<<(unsigned)np, 32, smem, st>>>(b);
+            if (trk) {
+                if (M <= 64) k_lsap<2, true><<<(unsigned)np, 32, smem, st>>>(b);
+                else if (M <= 128) k_lsap<4, true><<<(unsigned)np, 32, smem, st>>>(b);
+                else k_lsap<8, true><<<(unsigned)np, 32, smem, st>>>(b);
+            } else if (M <= 32) k_lsap<1><<<(unsigned)np, 32, smem, st>>>(b);
             else if (M <= 64) k_lsap<2><<<(unsigned)np, 32, smem, st>>>(b);
             else if (M <= 128) k_lsap<4><<<(unsigned)np, 32, smem, st>>>(b);
             else k_lsap<8><<<(unsigned)np, 32, smem, st>>>(b);
@@ -482,6 +489,20 @@ PTK_API int ptk_track_batch(int C, int F, int N, const double* ends, double* cos
     if (!cost && (!workspace || workspace_bytes < ptk_workspace_bytes(PTK_WS_TRACK, Q, N))) return PTK_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t NN = (size_t)N * N;
+    if (!cost && N > 64) {
+        // large N: solve straight from the end points (k_lsap<CPL, true>), no cost matrix in HBM at
+        // all.  Measured (profiles/README.md): N=128 96 -> 81 ms, N=256 382 -> 239 ms per 16000 /
+        // 4000 problems; at N=64 the matrix path is as fast (8.6 vs 8.9 ms), below it is faster.
+        LsapArgs a{};
+        a.ld_rows = N; a.ld_cols = N; a.cost_stride = 0; a.cost = nullptr;
+        a.out_ld = N;
+        a.col_ind = col_ind;
+        a.status = status;
+        a.total = total_cost;
+        a.max_err = INFINITY;
+        a.trk_ends = ends; a.trk_F = F;
+        return launch_lsap(Q, a, st);
+    }
     long long chunk = cost ? Q : match_chunk(Q, N);
     double* wcost = cost ? cost : reinterpret_cast<double*>(align_up((size_t)workspace));
     for (long long q0 = 0; q0 < Q; q0 += chunk) {

@@ -570,3 +570,30 @@ def test_random_rigs_vs_c_oracle(eng, seed):
         for k in range(o["n_out"][p]):
             for s in (slice(0, 3), slice(3, 6), slice(6, 9)):
                 assert rel_err(rows[p, k, s], o["rows"][p, k, s]) < TOL
+
+
+@pytest.mark.parametrize("C,F,N", [(1, 4, 100), (2, 3, 128), (1, 3, 256), (2, 5, 65)])
+def test_tracking_on_the_fly_large_n(eng, C, F, N):
+    """N > 64: the tracking LSAP evaluates costs on the fly from the end points (no cost matrix).
+    Must equal both the matrix path (cost output requested) and the oracle, incl. flipped rods
+    (cross term active) and a NaN frame."""
+    from oracle import c_oracle as co
+
+    rng = np.random.default_rng(N + F)
+    base = rng.normal(size=(C, 1, N, 2, 3)) * 30
+    ends = base + np.cumsum(rng.normal(size=(C, F, N, 2, 3)) * 0.2, axis=1)
+    flip = rng.random((C, F, N)) < 0.2
+    ends[flip] = ends[flip][:, ::-1]  # end points swapped in some frames -> the cross term wins there
+    o = co.track_batch(ends, want_cost=True)
+    col_m, tot_m, st_m, cost = eng.track_batch(dev(ends), want_cost=True)  # matrix path
+    col_f, tot_f, st_f, _ = eng.track_batch(dev(ends))                    # on-the-fly path
+    np.testing.assert_array_equal(cost.cpu().numpy(), o["cost"])
+    np.testing.assert_array_equal(col_m.cpu().numpy(), o["col_ind"])
+    np.testing.assert_array_equal(col_f.cpu().numpy(), o["col_ind"])
+    assert rel_err(tot_f.cpu().numpy(), o["total_cost"]) < 1e-13
+    assert (st_f.cpu().numpy() == 0).all()
+    bad = ends.copy()
+    bad[0, 1, 3, 0, 1] = np.nan
+    _, _, st_b, _ = eng.track_batch(dev(bad))
+    st_b = st_b.cpu().numpy()
+    assert st_b[0, 0] == 1 and (F < 3 or st_b[0, 1] == 1) and (st_b[0, 2:] == 0).all()
