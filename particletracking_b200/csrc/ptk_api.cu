@@ -129,6 +129,19 @@ DevRig make_devrig(const ptk_rig* r)
     memcpy(d.Rw, r->Rw, sizeof(d.Rw));
     memcpy(d.tw, r->tw, sizeof(d.tw));
     d.agg_sum = r->agg_sum;
+    const double eye[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    const double* Rs[2] = {r->R1, r->R2};
+    const double* ts[2] = {r->t1, r->t2};
+    const double* ks[2] = {r->dist1, r->dist2};
+    for (int c = 0; c < 2; c++) {
+        bool id = true;
+        for (int k = 0; k < 9; k++) id = id && (Rs[c][k] == eye[k]);
+        for (int k = 0; k < 3; k++) id = id && (ts[c][k] == 0.0);
+        d.ext_identity[c] = id ? 1 : 0;
+        bool tg = false;
+        for (int k : {2, 3, 8, 9, 10, 11}) tg = tg || (ks[c][k] != 0.0);
+        d.tangential[c] = tg ? 1 : 0;
+    }
     return d;
 }
 

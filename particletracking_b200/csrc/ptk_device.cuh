@@ -29,6 +29,9 @@ struct DevRig {
     double k1[12], k2[12];  // k1 k2 p1 p2 k3 k4 k5 k6 s1 s2 s3 s4
     double Rw[9], tw[3];
     int agg_sum;
+    // rig-constant shortcuts for the projection (set by make_devrig; warp-uniform branches):
+    int ext_identity[2];  // camera k has R = I, t = 0 (camera 1 of a stereo rig)
+    int tangential[2];    // camera k has any of p1, p2, s1..s4 non-zero
 };
 
 // ---------------------------------------------------------------------------------------
@@ -313,22 +316,29 @@ __device__ __forceinline__ void dlt_triangulate(const DevRig& rig, double x1, do
 // cv2.projectPoints for one point (match2D.py:898-903)
 __device__ __forceinline__ void project_point(const double* __restrict__ R, const double* __restrict__ t,
                                               const double* __restrict__ cm, const double* __restrict__ k,
-                                              double X, double Y, double Z, double& u, double& v)
+                                              double X, double Y, double Z, double& u, double& v,
+                                              bool ext_identity = false, bool tangential = true)
 {
-    double x = fma(R[2], Z, fma(R[1], Y, R[0] * X)) + t[0];
-    double y = fma(R[5], Z, fma(R[4], Y, R[3] * X)) + t[1];
-    double z = fma(R[8], Z, fma(R[7], Y, R[6] * X)) + t[2];
+    double x = X, y = Y, z = Z;
+    if (!ext_identity) {
+        x = fma(R[2], Z, fma(R[1], Y, R[0] * X)) + t[0];
+        y = fma(R[5], Z, fma(R[4], Y, R[3] * X)) + t[1];
+        z = fma(R[8], Z, fma(R[7], Y, R[6] * X)) + t[2];
+    }
     z = (z != 0.0) ? fast_rcp(z) : 1.0;
     x *= z;
     y *= z;
     const double r2 = fma(x, x, y * y), r4 = r2 * r2, r6 = r4 * r2;
-    const double a1 = 2 * x * y, a2 = fma(2 * x, x, r2), a3 = fma(2 * y, y, r2);
     const double cdist = fma(k[4], r6, fma(k[1], r4, fma(k[0], r2, 1.0)));
     double rad = cdist;
     if (k[5] != 0.0 || k[6] != 0.0 || k[7] != 0.0)  // rational model (k4..k6); warp-uniform branch on rig constants
         rad = cdist * fast_rcp(fma(k[7], r6, fma(k[6], r4, fma(k[5], r2, 1.0))));
-    const double xd = fma(k[9], r4, fma(k[8], r2, fma(k[3], a2, fma(k[2], a1, x * rad))));
-    const double yd = fma(k[11], r4, fma(k[10], r2, fma(k[3], a1, fma(k[2], a3, y * rad))));
+    double xd = x * rad, yd = y * rad;
+    if (tangential) {  // p1, p2 and thin-prism s1..s4
+        const double a1 = 2 * x * y, a2 = fma(2 * x, x, r2), a3 = fma(2 * y, y, r2);
+        xd = fma(k[9], r4, fma(k[8], r2, fma(k[3], a2, fma(k[2], a1, xd))));
+        yd = fma(k[11], r4, fma(k[10], r2, fma(k[3], a1, fma(k[2], a3, yd))));
+    }
     u = fma(xd, cm[0], cm[2]);
     v = fma(yd, cm[1], cm[3]);
 }
@@ -336,10 +346,11 @@ __device__ __forceinline__ void project_point(const double* __restrict__ R, cons
 // ... and the distance of the reprojection to the original (distorted) detection (match2D.py:905-910)
 __device__ __forceinline__ double reproject_dist(const double* __restrict__ R, const double* __restrict__ t,
                                                  const double* __restrict__ cm, const double* __restrict__ k,
-                                                 double X, double Y, double Z, double ou, double ov)
+                                                 double X, double Y, double Z, double ou, double ov,
+                                                 bool ext_identity, bool tangential)
 {
     double u, v;
-    project_point(R, t, cm, k, X, Y, Z, u, v);
+    project_point(R, t, cm, k, X, Y, Z, u, v, ext_identity, tangential);
     const double ex = ou - u;
     const double ey = ov - v;
     return sqrt(fma(ex, ex, ey * ey));
@@ -352,8 +363,8 @@ __device__ __forceinline__ void eval_combo(const DevRig& rig, double u1x, double
                                            double& d1, double& d2, double& X, double& Y, double& Z)
 {
     dlt_triangulate(rig, u1x, u1y, u2x, u2y, X, Y, Z);
-    d1 = reproject_dist(rig.R1, rig.t1, rig.CM1, rig.k1, X, Y, Z, o1x, o1y);
-    d2 = reproject_dist(rig.R2, rig.t2, rig.CM2, rig.k2, X, Y, Z, o2x, o2y);
+    d1 = reproject_dist(rig.R1, rig.t1, rig.CM1, rig.k1, X, Y, Z, o1x, o1y, rig.ext_identity[0] != 0, rig.tangential[0] != 0);
+    d2 = reproject_dist(rig.R2, rig.t2, rig.CM2, rig.k2, X, Y, Z, o2x, o2y, rig.ext_identity[1] != 0, rig.tangential[1] != 0);
 }
 
 // match2D.py:913: X_w = rot.apply(X) + trans
