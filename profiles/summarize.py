@@ -30,6 +30,7 @@ KEYS = [
     "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_blocks",
     "sm__throughput.avg.pct_of_peak_sustained_elapsed",
     "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
     "smsp__issue_active.avg.pct_of_peak_sustained_active",
@@ -100,20 +101,24 @@ def kernel(tag, rep):
     ix = {h: i for i, h in enumerate(hdr)}
     out = []
     traffic = None
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    seen = set()
     for r in rows[2:]:
         name = r[ix["Kernel Name"]]
-        if "k_cost" not in name or "track" in name:
+        key = (name, r[ix["launch__grid_size"]])
+        if key in seen:
             continue
-        out.append(f"== {name}")
+        seen.add(key)
+        out.append(f"== {name}  grid {r[ix['launch__grid_size']]}")
         for k in KEYS:
             if k in ix:
                 out.append(f"{k:85s} {units[ix[k]]:16s} {r[ix[k]]}")
-        scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        rd = float(r[ix["dram__bytes_read.sum"]]) * scale[units[ix["dram__bytes_read.sum"]]]
-        wr = float(r[ix["dram__bytes_write.sum"]]) * scale[units[ix["dram__bytes_write.sum"]]]
-        traffic = {"dram_bytes_per_launch": rd + wr, "read": rd, "write": wr, "source": f"profiles/{tag}_k_cost_ncu.txt",
-                   "grid": r[ix["launch__grid_size"]]}
-        break
+        out.append("")
+        if "k_cost" in name and "track" not in name and traffic is None:
+            rd = float(r[ix["dram__bytes_read.sum"]]) * scale[units[ix["dram__bytes_read.sum"]]]
+            wr = float(r[ix["dram__bytes_write.sum"]]) * scale[units[ix["dram__bytes_write.sum"]]]
+            traffic = {"dram_bytes_per_launch": rd + wr, "read": rd, "write": wr, "source": f"profiles/{tag}_k_cost_ncu.txt",
+                       "grid": r[ix["launch__grid_size"]]}
     open(os.path.join(HERE, f"{tag}_k_cost_ncu.txt"), "w").write("\n".join(out) + "\n")
     if traffic:
         json.dump(traffic, open(os.path.join(HERE, "k_cost_traffic.json"), "w"), indent=1)
