@@ -159,7 +159,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.idx)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.idx)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -245,20 +245,23 @@ def run_b200(args):
     fp64_peak = engine.measure_fp64_peak(20000)  # also warms the clocks
     for i in range(W):
         out = step(i)
-    # Settling: on a fresh box the first process that brings up NCCL / the allocator keeps paying
-    # one-time host-side costs for a few dozen steps (measured: 14 ms/step of host enqueue time
-    # instead of 0.8).  Keep stepping, untimed, until three consecutive synchronised steps agree
-    # within 10 % (at most 60 extra steps); the timed region below is still exactly K steps.
-    extra, hist = 0, []
-    while extra < 60:
+    # Settling: on a fresh box the first process that brings up NCCL keeps paying host-side costs
+    # for a while (measured: 7-14 ms/step of host enqueue time instead of 0.9, for dozens of steps).
+    # Keep stepping, untimed, until three consecutive synchronised steps agree within 10 % AND the
+    # host enqueues a step in well under the time the GPUs need for it (i.e. the run is not
+    # host-bound); at most 400 extra steps / 4 s.  The timed region below is still exactly K steps.
+    extra, hist, t_settle0 = 0, [], time.perf_counter()
+    while extra < 400 and time.perf_counter() - t_settle0 < 4.0:
         t_s = time.perf_counter()
         out = step(W + extra)
         if sharded is not None:
             sharded.finish()
+        t_host = time.perf_counter() - t_s
         torch.cuda.synchronize()
-        hist.append(time.perf_counter() - t_s)
+        t_all = time.perf_counter() - t_s
+        hist.append(t_all)
         extra += 1
-        stable = len(hist) >= 3 and max(hist[-3:]) <= 1.10 * min(hist[-3:])
+        stable = len(hist) >= 3 and max(hist[-3:]) <= 1.10 * min(hist[-3:]) and t_host <= 0.5 * t_all
         if world > 1:
             flag = torch.tensor([1.0 if stable else 0.0], device=dev)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
@@ -273,7 +276,8 @@ def run_b200(args):
     assert int((st != 0).sum().item()) == 0, "matching reported invalid problems"
 
     clocks = ClockSampler(local)
-    clocks.start()
+    if rank == 0:  # one sampler per job: nvidia-smi polling from every rank perturbs the driver
+        clocks.start()
     time.sleep(0.3)
     engine.kernel_timing(True)
     engine.kernel_timing_read(reset=True)

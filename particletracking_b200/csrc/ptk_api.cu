@@ -5,6 +5,7 @@
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -876,7 +877,9 @@ PTK_API int ptk_reconstruct_host(ptk_ctx* c, const ptk_rig* rig, int F, int C, i
     const size_t nd = (size_t)Nmax * sizeof(double), ni = (size_t)Nmax * sizeof(int32_t);
 
     // frames per chunk: ~2048 problems, at most 32 chunks
-    int fchunk = (2048 + C - 1) / C;
+    const char* ce = getenv("PTK_HOST_CHUNK");  // tuning knob (problems per chunk)
+    const int want = ce ? atoi(ce) : 2048;
+    int fchunk = ((want > 0 ? want : 2048) + C - 1) / C;
     if ((F + fchunk - 1) / fchunk > 32) fchunk = (F + 31) / 32;
     const int nchunks = (F + fchunk - 1) / fchunk;
     const long long pchunk = (long long)fchunk * C;
