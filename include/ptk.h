@@ -211,6 +211,34 @@ int ptk_csv_write_rods(const char* path, const char* header, long long n_rows, i
                        const int64_t* particle, int n_seen);
 int ptk_format_double(double x, char* buf);
 
+/* ---- CSV reader (host; "next" row) ---------------------------------------
+ * Replaces pd.read_csv(f_in, sep=",", index_col=0) at match2D.py:601-602, 1053 and matchND.py:317
+ * with a memory-mapped, multi-threaded columnar parse.  Column kinds follow pandas' inference
+ * (int64 / float64 with NA strings -> NaN / bool / string); floats go through the arithmetic of
+ * pandas' default parser so values are bit-identical to what the reference reads.
+ * ptk_csv_open parses the whole file (n_threads <= 0: all cores) and returns a handle that must be
+ * closed with ptk_csv_close, also after a failure (ptk_csv_error says what went wrong).
+ * ptk_csv_col_copy copies a column into dst: int64[n_rows] (PTK_CSV_INT64, PTK_CSV_BOOL as 0/1),
+ * double[n_rows] (PTK_CSV_FLOAT64) or int32 codes[n_rows] into the column's dictionary
+ * (PTK_CSV_STRING; -1 = missing).  Column 0 is the index column of the rods_df layout.
+ * ptk_parse_double is the float parser alone (test hook; returns 1 if the field is a number). */
+#define PTK_CSV_INT64 0
+#define PTK_CSV_FLOAT64 1
+#define PTK_CSV_STRING 2
+#define PTK_CSV_BOOL 3
+typedef struct ptk_csv ptk_csv;
+int ptk_csv_open(const char* path, int n_threads, ptk_csv** out);
+void ptk_csv_close(ptk_csv* h);
+const char* ptk_csv_error(const ptk_csv* h);
+long long ptk_csv_n_rows(const ptk_csv* h);
+int ptk_csv_n_cols(const ptk_csv* h);
+const char* ptk_csv_col_name(const ptk_csv* h, int col);
+int ptk_csv_col_kind(const ptk_csv* h, int col);
+int ptk_csv_col_copy(const ptk_csv* h, int col, void* dst);
+int ptk_csv_col_dict_size(const ptk_csv* h, int col);
+const char* ptk_csv_col_dict(const ptk_csv* h, int col, int k, int* len);
+int ptk_parse_double(const char* s, int len, double* out);
+
 /* ---- workspace sizing ---------------------------------------------------------------- */
 #define PTK_WS_COST 1
 #define PTK_WS_MATCH 2

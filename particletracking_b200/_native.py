@@ -27,6 +27,8 @@ SYMBOLS = [
     "ptk_undistort_batch", "ptk_cost_batch", "ptk_lsap_batch", "ptk_match_batch",
     "ptk_rows_batch", "ptk_rows_to_ends", "ptk_track_batch", "ptk_chain_tracks", "ptk_chain_rebase", "ptk_create_weights", "ptk_reorder_endpoints", "ptk_triangulate_points", "ptk_project_points",
     "ptk_csv_write_rods", "ptk_format_double", "ptk_workspace_bytes",
+    "ptk_csv_open", "ptk_csv_close", "ptk_csv_error", "ptk_csv_n_rows", "ptk_csv_n_cols", "ptk_csv_col_name",
+    "ptk_csv_col_kind", "ptk_csv_col_copy", "ptk_csv_col_dict_size", "ptk_csv_col_dict", "ptk_parse_double",
     "ptk_ctx_create", "ptk_ctx_destroy", "ptk_reconstruct_host",
     "ptk_reconstruct_device", "ptk_reconstruct_device_workspace_bytes",
     "ptk_measure_fp64_peak", "ptk_launch_count", "ptk_timing_enable", "ptk_timing_read",
@@ -86,6 +88,22 @@ def lib() -> ctypes.CDLL:
     L.ptk_project_points.argtypes = [rigp, ll, vp, i32, vp, vp, vp]
     L.ptk_csv_write_rods.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ll, i32, vp, vp, ctypes.c_char_p, vp, i32]
     L.ptk_format_double.argtypes = [dbl, ctypes.c_char_p]
+    L.ptk_csv_open.argtypes = [ctypes.c_char_p, i32, ctypes.POINTER(vp)]
+    L.ptk_csv_close.argtypes = [vp]
+    L.ptk_csv_close.restype = None
+    L.ptk_csv_error.argtypes = [vp]
+    L.ptk_csv_error.restype = ctypes.c_char_p
+    L.ptk_csv_n_rows.argtypes = [vp]
+    L.ptk_csv_n_rows.restype = ll
+    L.ptk_csv_n_cols.argtypes = [vp]
+    L.ptk_csv_col_name.argtypes = [vp, i32]
+    L.ptk_csv_col_name.restype = ctypes.c_char_p
+    L.ptk_csv_col_kind.argtypes = [vp, i32]
+    L.ptk_csv_col_copy.argtypes = [vp, i32, vp]
+    L.ptk_csv_col_dict_size.argtypes = [vp, i32]
+    L.ptk_csv_col_dict.argtypes = [vp, i32, i32, ctypes.POINTER(i32)]
+    L.ptk_csv_col_dict.restype = vp
+    L.ptk_parse_double.argtypes = [ctypes.c_char_p, i32, ctypes.POINTER(dbl)]
     L.ptk_ctx_create.argtypes = [i32, ctypes.POINTER(vp)]
     L.ptk_ctx_destroy.argtypes = [vp]
     L.ptk_ctx_destroy.restype = None

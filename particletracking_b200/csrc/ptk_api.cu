@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "ptk_csv.cuh"
+#include "ptk_csv_reader.h"
 #include "ptk_kernels.cuh"
 
 using namespace ptk;
@@ -764,6 +765,76 @@ PTK_API int ptk_csv_write_rods(const char* path, const char* header, long long n
 
 // test hook: Python repr() of one double (returns the length; buf needs 32 bytes)
 PTK_API int ptk_format_double(double x, char* buf) { return format_double_repr(x, buf); }
+
+// ------------------------------------------------------------------------------------ CSV reader (host)
+struct ptk_csv {
+    ptk::CsvTable t;
+};
+
+PTK_API int ptk_csv_open(const char* path, int n_threads, ptk_csv** out)
+{
+    if (!path || !out) return PTK_ERR_INVALID_ARG;
+    ptk_csv* h = new (std::nothrow) ptk_csv();
+    if (!h) return PTK_ERR_INVALID_ARG;
+    int rc = -1;
+    try {
+        rc = ptk::csv_read_file(path, n_threads, &h->t);
+    } catch (...) {
+        h->t.error = "out of memory";
+    }
+    *out = h;  // kept on failure so that ptk_csv_error() can be read; the caller closes it
+    return rc == 0 ? PTK_OK : PTK_ERR_INVALID_ARG;
+}
+PTK_API void ptk_csv_close(ptk_csv* h) { delete h; }
+PTK_API const char* ptk_csv_error(const ptk_csv* h) { return h ? h->t.error.c_str() : "null handle"; }
+PTK_API long long ptk_csv_n_rows(const ptk_csv* h) { return h ? h->t.n_rows : -1; }
+PTK_API int ptk_csv_n_cols(const ptk_csv* h) { return h ? (int)h->t.cols.size() : -1; }
+static const ptk::CsvColumn* csv_col(const ptk_csv* h, int c)
+{
+    return (h && c >= 0 && c < (int)h->t.cols.size()) ? &h->t.cols[c] : nullptr;
+}
+PTK_API const char* ptk_csv_col_name(const ptk_csv* h, int c)
+{
+    const ptk::CsvColumn* col = csv_col(h, c);
+    return col ? col->name.c_str() : nullptr;
+}
+PTK_API int ptk_csv_col_kind(const ptk_csv* h, int c)
+{
+    const ptk::CsvColumn* col = csv_col(h, c);
+    return col ? col->kind : PTK_ERR_INVALID_ARG;
+}
+PTK_API int ptk_csv_col_copy(const ptk_csv* h, int c, void* dst)
+{
+    const ptk::CsvColumn* col = csv_col(h, c);
+    if (!col || (!dst && h->t.n_rows)) return PTK_ERR_INVALID_ARG;
+    const size_t n = (size_t)h->t.n_rows;
+    if (n == 0) return PTK_OK;
+    switch (col->kind) {
+    case ptk::CSV_INT64:
+    case ptk::CSV_BOOL: memcpy(dst, col->i64.data(), n * sizeof(int64_t)); break;
+    case ptk::CSV_FLOAT64: memcpy(dst, col->f64.data(), n * sizeof(double)); break;
+    default: memcpy(dst, col->codes.data(), n * sizeof(int32_t)); break;
+    }
+    return PTK_OK;
+}
+PTK_API int ptk_csv_col_dict_size(const ptk_csv* h, int c)
+{
+    const ptk::CsvColumn* col = csv_col(h, c);
+    return col ? (int)col->dict.size() : PTK_ERR_INVALID_ARG;
+}
+PTK_API const char* ptk_csv_col_dict(const ptk_csv* h, int c, int k, int* len)
+{
+    const ptk::CsvColumn* col = csv_col(h, c);
+    if (!col || k < 0 || k >= (int)col->dict.size()) return nullptr;
+    if (len) *len = (int)col->dict[k].size();
+    return col->dict[k].data();
+}
+// test hook: pandas' float parser on one field (returns 1 if the field is a number)
+PTK_API int ptk_parse_double(const char* s, int len, double* out)
+{
+    if (!s || len < 0 || !out) return PTK_ERR_INVALID_ARG;
+    return ptk::csv_parse_double(s, s + len, out) ? 1 : 0;
+}
 
 // ------------------------------------------------------------------------------------ FP64 peak
 PTK_API int ptk_measure_fp64_peak(int iters, double* flops, void* stream)
