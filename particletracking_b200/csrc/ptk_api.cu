@@ -731,34 +731,53 @@ PTK_API int ptk_csv_write_rods(const char* path, const char* header, long long n
         return PTK_ERR_INVALID_ARG;
     FILE* f = fopen(path, "wb");
     if (!f) return PTK_ERR_INVALID_ARG;
-    std::vector<char> buf(1 << 22);
-    size_t used = 0;
     const size_t clen = strlen(color);
-    auto flush = [&]() { if (used) fwrite(buf.data(), 1, used, f); used = 0; };
     fwrite(header, 1, strlen(header), f);
     fputc('\n', f);
+    // rows are formatted in parallel over contiguous ranges, then written in order
     const size_t worst = (size_t)n_float_cols * 26 + clen + 3 * 24 + (size_t)n_seen * 2 + 16;
-    for (long long r = 0; r < n_rows; r++) {
-        if (used + worst > buf.size()) flush();
-        char* o = buf.data() + used;
-        o += format_int(r, o);
-        const double* v = values + (size_t)r * n_float_cols;
-        for (int c = 0; c < n_float_cols; c++) {
-            *o++ = ',';
-            o += format_double_repr(v[c], o);
+    int T = (int)std::min<long long>(std::max(1u, std::thread::hardware_concurrency()), std::max<long long>(1, n_rows / 2048));
+    T = std::min(T, 32);
+    std::vector<std::vector<char>> bufs(T);
+    std::vector<size_t> used(T, 0);
+    std::atomic<int> oom{0};
+    auto work = [&](int w) {
+        const long long lo = n_rows * w / T, hi = n_rows * (w + 1) / T;
+        try {
+            bufs[w].resize((size_t)(hi - lo) * worst + 16);
+        } catch (...) {
+            oom = 1;
+            return;
         }
-        *o++ = ',';
-        o += format_int(frame[r], o);
-        *o++ = ',';
-        memcpy(o, color, clen); o += clen;
-        *o++ = ',';
-        o += format_int(particle[r], o);
-        for (int k = 0; k < n_seen; k++) { *o++ = ','; *o++ = '1'; }
-        *o++ = '\n';
-        used = (size_t)(o - buf.data());
+        char* o = bufs[w].data();
+        for (long long r = lo; r < hi; r++) {
+            o += format_int(r, o);
+            const double* v = values + (size_t)r * n_float_cols;
+            for (int c = 0; c < n_float_cols; c++) {
+                *o++ = ',';
+                o += format_double_repr(v[c], o);
+            }
+            *o++ = ',';
+            o += format_int(frame[r], o);
+            *o++ = ',';
+            memcpy(o, color, clen); o += clen;
+            *o++ = ',';
+            o += format_int(particle[r], o);
+            for (int k = 0; k < n_seen; k++) { *o++ = ','; *o++ = '1'; }
+            *o++ = '\n';
+        }
+        used[w] = (size_t)(o - bufs[w].data());
+    };
+    if (T == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int w = 0; w < T; w++) th.emplace_back(work, w);
+        for (auto& x : th) x.join();
     }
-    flush();
-    const int bad = ferror(f);
+    if (!oom)
+        for (int w = 0; w < T; w++)
+            if (used[w]) fwrite(bufs[w].data(), 1, used[w], f);
+    const int bad = ferror(f) || oom;
     fclose(f);
     return bad ? PTK_ERR_INVALID_ARG : PTK_OK;
 }

@@ -14,6 +14,7 @@ from __future__ import annotations
 import logging
 import os
 import pathlib
+import threading
 from typing import Iterable, List, Optional, Sequence
 
 import numpy as np
@@ -22,10 +23,12 @@ import torch
 
 from .. import engine
 from ..rig import make_rig
+from ..utils import csv_io
 from ..utils import data_loading as dl
 
 _logger = logging.getLogger(__name__)
 
+_CSV_WORKERS = 4  # colours of match_csv_complex in flight
 COLS_3D = ["x1", "y1", "z1", "x2", "y2", "z2", "x", "y", "z", "l"]
 
 
@@ -70,6 +73,102 @@ def _pack(problems: Sequence[tuple]):
     dev = torch.device("cuda", torch.cuda.current_device())
     t = lambda x: torch.from_numpy(x).to(dev)
     return t(c1.reshape(P, nmax, 2, 2)), t(c2.reshape(P, nmax, 2, 2)), t(n1), t(n2)
+
+
+class _Table:
+    """Column store the batched path works on: what the native CSV reader returns, without the
+    detour through a DataFrame (``index`` = the file's first column)."""
+
+    def __init__(self, names: Sequence[str], cols: dict):
+        self.index = cols[0]
+        self.columns = list(names[1:])
+        self._pos = {n: c for c, n in enumerate(names) if c > 0}
+        self._cols = cols
+
+    @classmethod
+    def read(cls, path: str) -> "_Table":
+        return cls(*csv_io.read_columns(path))
+
+    def __len__(self):
+        return len(self.index)
+
+    def to_frame(self) -> pd.DataFrame:
+        return pd.DataFrame({n: self._cols[c] for n, c in self._pos.items()}, index=pd.Index(self.index))
+
+    def col(self, name: str) -> np.ndarray:
+        try:
+            return self._cols[self._pos[name]]
+        except KeyError:
+            raise KeyError(name) from None
+
+
+def _col(data, name: str) -> np.ndarray:
+    return data.col(name) if isinstance(data, _Table) else data[name].to_numpy()
+
+
+def _cols(data, names: Sequence[str]) -> np.ndarray:
+    if isinstance(data, _Table):
+        return np.stack([np.asarray(data.col(n), dtype=np.float64) for n in names], axis=1)
+    return data[list(names)].to_numpy(dtype=np.float64)
+
+
+def _index(data) -> np.ndarray:
+    return data.index if isinstance(data, _Table) else data.index.to_numpy()
+
+
+def _select_pack(fr: np.ndarray, v1: np.ndarray, v2: np.ndarray, frames: Sequence[int], renumber: bool):
+    """match2D.py:824-844 for all requested frames at once (no Python loop over frames): returns
+    padded ``cam1, cam2 [P,nmax,4]``, ``n1, n2 [P]`` and, for ``renumber=False``, the row positions
+    kept per problem (concatenated in problem order).  None if this form does not apply
+    (frame numbers listed twice)."""
+    frames_a = np.asarray(frames)
+    P = len(frames_a)
+    order_f = np.argsort(frames_a, kind="stable")
+    fs = frames_a[order_f]
+    if P > 1 and (fs[1:] == fs[:-1]).any():
+        return None
+    pos = np.minimum(np.searchsorted(fs, fr), P - 1)
+    pidx = np.where(fs[pos] == fr, order_f[pos], -1)  # problem of every row, -1 = frame not requested
+    k1, k2 = _valid(v1), _valid(v2)
+    if not renumber:
+        k1 = k2 = k1 & k2
+
+    def pack(v, k):
+        sel = np.flatnonzero(k & (pidx >= 0))
+        o = np.argsort(pidx[sel], kind="stable")  # DataFrame order inside every frame
+        sel = sel[o]
+        ps = pidx[sel]
+        n = np.bincount(ps, minlength=P)
+        rank = np.arange(len(sel)) - np.repeat(np.cumsum(n) - n, n)
+        return sel, ps, rank, n
+
+    s1, p1, r1, n1 = pack(v1, k1)
+    s2, p2, r2, n2 = pack(v2, k2)
+    if P and ((n1 == 0).any() or (n2 == 0).any()):
+        # the reference's drivers unpack match_frame's None here (match2D.py:622, 733)
+        raise TypeError("cannot unpack non-iterable NoneType object")
+    nmax = int(max(1, n1.max(initial=0), n2.max(initial=0)))
+    if nmax > 256:
+        raise ValueError("more than 256 rods in one (frame, colour) problem")
+    c1 = np.full((P, nmax, 4), np.nan)
+    c2 = np.full((P, nmax, 4), np.nan)
+    c1[p1, r1] = v1[s1]
+    c2[p2, r2] = v2[s2]
+    return c1, c2, n1.astype(np.int32), n2.astype(np.int32), (s1 if not renumber else None)
+
+
+_pipelines = threading.local()
+
+
+def _host_pipeline() -> "engine.HostPipeline":
+    """One ``ptk_ctx`` (streams, pinned staging, device buffers) per calling thread: the reference
+    is driven from one thread per colour, so nothing is shared between calls."""
+    dev = torch.cuda.current_device()
+    hp = getattr(_pipelines, "hp", None)
+    if hp is None or hp.device != dev:
+        hp = engine.HostPipeline(dev)
+        _pipelines.hp = hp
+    return hp
 
 
 def _raise_for_status(status: np.ndarray):
@@ -168,14 +267,11 @@ def _derive_rig(calibration: dict, transform: dict):
     return rig_from_dicts(calibration, transform)
 
 
-def _match_arrays(data: pd.DataFrame, frame_numbers: Iterable[int], rig, cam1_name, cam2_name, renumber: bool,
-                  max_repr_err=None):
-    """All requested frames in one library call.  Returns a dict of flat arrays (rows of all
-    frames concatenated) plus the per-frame lists the reference returns."""
+def _match_arrays_loop(data: pd.DataFrame, frames, rig, cam1_name, cam2_name, renumber: bool, max_repr_err=None):
+    """Frame-by-frame selection (the general form: repeated frame numbers, non-unique index)."""
     fidx = _FrameIndex(data)
     v1 = data[_cam_cols(cam1_name)].to_numpy(dtype=np.float64)
     v2 = data[_cam_cols(cam2_name)].to_numpy(dtype=np.float64)
-    frames = list(frame_numbers)
     problems, kepts = [], []
     for f in frames:
         a, b, kept = _select(data, fidx, v1, v2, f, renumber)
@@ -184,8 +280,6 @@ def _match_arrays(data: pd.DataFrame, frame_numbers: Iterable[int], rig, cam1_na
             raise TypeError("cannot unpack non-iterable NoneType object")
         problems.append((a, b))
         kepts.append(kept)
-    if not problems:
-        return None
     res = _solve(problems, rig, renumber, max_repr_err)
     n_rows = [len(r[0]) for r in res]
     if (not renumber) and ("particle" in data.columns):
@@ -200,9 +294,68 @@ def _match_arrays(data: pd.DataFrame, frame_numbers: Iterable[int], rig, cam1_na
         costs=[r[1] for r in res],
         lens=[r[0][:, 9].copy() for r in res],
         keeps=[r[2] for r in res],
-        cols=[*COLS_3D, *_cam_cols(cam1_name), *_cam_cols(cam2_name)],
-        seen_cols=[c for c in data.columns if "seen" in c],
+        costs2d=None, lens2d=None,
     )
+
+
+def _match_arrays(data, frame_numbers: Iterable[int], rig, cam1_name, cam2_name, renumber: bool,
+                  max_repr_err=None, copy_rows: bool = True):
+    """All requested frames in one library call.  ``data`` is a DataFrame or a ``_Table``.
+    Returns a dict of flat arrays (rows of all frames concatenated) plus the per-frame lists the
+    reference returns; with ``copy_rows=False`` ``rows`` may alias the pipeline's pinned output
+    buffer, valid until this thread's next call."""
+    frames = list(frame_numbers)
+    if not frames:
+        return None
+    common = dict(cols=[*COLS_3D, *_cam_cols(cam1_name), *_cam_cols(cam2_name)],
+                  seen_cols=[c for c in data.columns if "seen" in c])
+    packed = None
+    if renumber or len(np.unique(_index(data))) == len(data):
+        v1, v2 = _cols(data, _cam_cols(cam1_name)), _cols(data, _cam_cols(cam2_name))
+        packed = _select_pack(np.asarray(_col(data, "frame")), v1, v2, frames, renumber)
+    if packed is None:
+        if isinstance(data, _Table):
+            data = data.to_frame()
+        return {**_match_arrays_loop(data, frames, rig, cam1_name, cam2_name, renumber, max_repr_err), **common}
+    engine._require_cuda()
+    c1, c2, n1, n2, kept = packed
+    P, nmax = c1.shape[:2]
+    if renumber:
+        r = _host_pipeline().reconstruct(rig, c1.reshape(P, 1, nmax, 2, 2), c2.reshape(P, 1, nmax, 2, 2), n1.reshape(P, 1),
+                                         n2.reshape(P, 1), track=False, max_repr_err=max_repr_err, raise_on_invalid=False)
+        _raise_for_status(r["status"].numpy().reshape(P))
+        rows, costs = r["rows"].numpy().reshape(P, nmax, -1), r["match_cost"].numpy().reshape(P, nmax)
+        n_out = r["n_out"].numpy().reshape(P)
+        keep = r["keep"].numpy().reshape(P, nmax).astype(bool) if r["keep"] is not None else None
+    else:
+        # match2D.py:876-884, 941-955: pairs are kept (zip), only end-point combos are evaluated
+        dev = torch.device("cuda", torch.cuda.current_device())
+        t = lambda x: torch.from_numpy(x).to(dev)
+        d1, d2, dn = t(c1.reshape(P, nmax, 2, 2)), t(c2.reshape(P, nmax, 2, 2)), t(n1)
+        col = torch.arange(nmax, dtype=torch.int32, device=dev).expand(P, nmax).contiguous()
+        rows_t, pc = engine.rows_batch(rig, d1, d2, dn, dn, col, dn)
+        rows, costs, n_out = rows_t.cpu().numpy(), pc.cpu().numpy(), n1
+        keep = (costs <= max_repr_err) if max_repr_err is not None else None
+        copy_rows = False
+    n0 = int(n_out[0])
+    if (n_out == n0).all():  # the usual case: every frame holds the same number of rods
+        flat = rows[:, :n0].reshape(P * n0, -1)
+        costs2d, lens2d = costs[:, :n0].copy(), rows[:, :n0, 9].copy()
+        out = dict(rows=flat.copy() if copy_rows and np.shares_memory(flat, rows) else flat,
+                   costs=list(costs2d), lens=list(lens2d), costs2d=costs2d, lens2d=lens2d,
+                   keeps=[None] * P if keep is None else list(keep[:, :n0]),
+                   particle=np.tile(np.arange(n0), P))
+    else:
+        mask = np.arange(nmax)[None, :] < n_out[:, None]
+        cuts = np.cumsum(n_out)[:-1]
+        flat = rows[mask]
+        out = dict(rows=flat, costs=np.split(costs[mask], cuts), lens=np.split(flat[:, 9].copy(), cuts), costs2d=None,
+                   lens2d=None, keeps=[None] * P if keep is None else np.split(keep[mask], cuts),
+                   particle=np.broadcast_to(np.arange(nmax), (P, nmax))[mask])
+    if (not renumber) and ("particle" in data.columns):
+        out["particle"] = np.asarray(_col(data, "particle"))[kept]  # match2D.py:990-993
+    out["frame"] = np.repeat(np.asarray(frames), n_out)
+    return {**out, **common}
 
 
 def _match_many(data: pd.DataFrame, frame_numbers: Iterable[int], color: str, rig, cam1_name, cam2_name,
@@ -267,18 +420,37 @@ def match_csv_complex(input_folder, output_folder, colors, cam1_name="gp1", cam2
     calibration = dl.load_camera_calibration(str(pathlib.Path(calibration_file)))
     transforms = dl.load_world_transformation(str(pathlib.Path(transformation_file)))
     rig = _derive_rig(calibration, transforms)
-    all_repr_errs, all_rod_lengths = [], []
-    for color in colors:
-        f_in = input_folder + f"/rods_df_{color}.csv"
-        data = pd.read_csv(f_in, sep=",", index_col=0)
-        m = _match_arrays(data, frame_numbers, rig, cam1_name, cam2_name, rematching)
-        out_path = os.path.join(output_folder, f"rods_df_{color}.csv")
-        if m is None:
-            pd.DataFrame().to_csv(out_path, sep=",")
-            continue
-        all_repr_errs.extend(m["costs"])
-        all_rod_lengths.extend(m["lens"])
-        _write_csv(out_path, color, m)
+    engine._require_cuda()
+    dev = torch.cuda.current_device()
+    frames = list(frame_numbers)
+
+    def one_color(color):
+        # native reader -> vectorised selection -> one library call -> native writer; every stage
+        # releases the GIL, so colours overlap (one ptk_ctx per worker thread)
+        with torch.cuda.device(dev):
+            data = _Table.read(input_folder + f"/rods_df_{color}.csv")
+            m = _match_arrays(data, frames, rig, cam1_name, cam2_name, rematching, copy_rows=False)
+            out_path = os.path.join(output_folder, f"rods_df_{color}.csv")
+            if m is None:
+                pd.DataFrame().to_csv(out_path, sep=",")
+                return None
+            _write_csv(out_path, color, m)
+            return (m["costs2d"], m["lens2d"]) if m["costs2d"] is not None else (m["costs"], m["lens"])
+
+    colors = list(colors)
+    if len(colors) > 1:
+        from concurrent.futures import ThreadPoolExecutor
+
+        with ThreadPoolExecutor(max_workers=min(len(colors), _CSV_WORKERS)) as pool:
+            results = list(pool.map(one_color, colors))
+    else:
+        results = [one_color(c) for c in colors]
+    results = [r for r in results if r is not None]
+    if results and all(isinstance(r[0], np.ndarray) for r in results) and len({r[0].shape[1] for r in results}) == 1:
+        return np.concatenate([r[0] for r in results]), np.concatenate([r[1] for r in results])
+    # ragged frames: np.array over per-frame arrays, as the reference builds it (match2D.py:631)
+    all_repr_errs = [c for r in results for c in list(r[0])]
+    all_rod_lengths = [l for r in results for l in list(r[1])]
     return np.array(all_repr_errs), np.array(all_rod_lengths)
 
 
@@ -335,7 +507,7 @@ def reorder_endpoints_csv(input_folder: str, output_folder: str, colors: Iterabl
         os.mkdir(output_folder)
     mincosts_T = None
     for color in colors:
-        data = pd.read_csv(input_folder + f"/rods_df_{color}.csv", sep=",", index_col=0)
+        data = csv_io.read_rods_csv(input_folder + f"/rods_df_{color}.csv")
         df_out, mincosts_T = reorder_endpoints(data, frame_numbers, cam1_name, cam2_name)
         df_out.to_csv(os.path.join(output_folder, f"rods_df_{color}.csv"), sep=",")
     return mincosts_T
