@@ -200,6 +200,30 @@ int ptk_triangulate_points(const ptk_rig* rig, long long n, const double* p1, co
 int ptk_project_points(const ptk_rig* rig, long long n, const double* X, int from_world,
                        double* uv1, double* uv2, void* stream);
 
+/* ---- K10: 3-index assignment ("next" row) ----------------------------------
+ * Replaces matchND.npartite_matching (matchND.py:45-138; a 0/1 programme handed to pulp/CBC) for
+ * the three-group case matchND.match_frame poses (matchND.py:562): B independent problems
+ * weights[B,D0,D1,D2] (actual sizes n0,n1,n2[B], NULL = full), every axis <= 64.  Chooses triples
+ * (i,j,k), every index of every axis used at most once, with maximal summed weight.
+ *   sol[B,3,min(D0,D1,D2)]  index arrays per axis (the reference's np.where(x): sorted by i), -1 padded
+ *   n_sol[B]                number of triples (min(n0,n1,n2) when all weights are >= 0)
+ *   value[B], bound[B]      summed weight of sol and the proven upper bound
+ *   status[B]               PTK_AP3_OK: proven optimal (bound - value within rounding);
+ *                           PTK_AP3_GAP: work limits hit, sol is the best found and bound its bound;
+ *                           PTK_AP3_INVALID: NaN/inf weights or sizes out of range; PTK_AP3_EMPTY
+ *   stats[B,4] (optional)   dual-descent steps, search nodes, candidate triples, step that proved it
+ * max_steps / node_limit <= 0 select the defaults (60 / 20e6).
+ * workspace: ptk_workspace_bytes(PTK_WS_AP3, B, 0). */
+#define PTK_AP3_OK 0
+#define PTK_AP3_GAP 1
+#define PTK_AP3_INVALID 2
+#define PTK_AP3_EMPTY 3
+int ptk_npartite3_batch(int B, int D0, int D1, int D2, const double* weights,
+                        const int32_t* n0, const int32_t* n1, const int32_t* n2,
+                        int32_t* sol, int32_t* n_sol, double* value, double* bound,
+                        int32_t* status, int32_t* stats, int max_steps, long long node_limit,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- CSV writer (host; "next" row) ---------------------------------------
  * Replaces df_out.to_csv(...) at match2D.py:626-629 for the output layout of match_frame
  * (match2D.py:986-997): an unnamed RangeIndex column, `n_float_cols` float columns (Python repr()
@@ -244,6 +268,7 @@ int ptk_parse_double(const char* s, int len, double* out);
 #define PTK_WS_MATCH 2
 #define PTK_WS_TRACK 3
 #define PTK_WS_WEIGHTS 4
+#define PTK_WS_AP3 5
 size_t ptk_workspace_bytes(int kind, long long n_problems, int Nmax);
 
 /* ---- the whole path on DEVICE buffers, one call ----------------------------------------
@@ -297,8 +322,8 @@ int ptk_measure_fp64_peak(int iters, double* flops, void* stream);
  * launching stream around every kernel launch, by kind.  ptk_timing_read sums durations and counts
  * per kind into arrays of PTK_TIMING_KINDS entries (call after synchronising); off by default.
  * kinds: 0 undistort, 1 cost (K1), 2 lsap (matching), 3 rows, 4 rows_to_ends, 5 track_cost,
- *        6 lsap (tracking), 7 chain (3 launches), 8 create_weights */
-#define PTK_TIMING_KINDS 9
+ *        6 lsap (tracking), 7 chain (3 launches), 8 create_weights, 9 npartite3 */
+#define PTK_TIMING_KINDS 10
 void ptk_timing_enable(int on);
 int ptk_timing_read(double* ms_by_kind, long long* launches_by_kind, int reset);
 

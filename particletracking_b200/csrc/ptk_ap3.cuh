@@ -1,0 +1,537 @@
+// ptk_ap3.cuh -- K10 k_ap3: exact 3-index (axial) assignment, one CTA per problem.
+//
+// Replaces matchND.npartite_matching (matchND.py:45-138) for the three-group case that
+// matchND.match_frame poses (:562): choose triples t = (i, j, k) from w[n0, n1, n2] such that every
+// index of every axis is used at most once and the summed weight is maximal.  The reference writes
+// this as a 0/1 programme with n0*n1*n2 variables and shells out to CBC (seconds per frame at 32
+// rods); here the structure of the programme is used instead:
+//
+//  1. Dual block-coordinate descent.  The LP dual is  min sum(y0)+sum(y1)+sum(y2)  s.t.
+//     y0[i]+y1[j]+y2[k] >= w[i,j,k], y >= 0.  With one block fixed, e.g. y0, the best other two
+//     blocks are the duals of a 2-D assignment on c[j,k] = max(0, max_i (w[i,j,k] - y0[i])), so every
+//     step is: a max-reduction over one axis (all threads), then a shortest-augmenting-path LSAP by
+//     one warp (columns in registers, two per lane).  The upper bound never increases.
+//  2. Every step's pairs are completed to a feasible solution by a second LSAP over the remaining
+//     axis (lower bound).  On rod data the first step already closes the gap: the pair (j,k) that
+//     triangulates a rod also prefers the right previous rod, so bound == value and the solution is
+//     proven optimal without any search.
+//  3. If the descent stalls with a gap, only triples whose dual slack y0+y1+y2-w is below the gap can
+//     be part of a better solution; they are listed (sorted per i) and a depth-first search over the
+//     first axis with slack-sum pruning finishes the proof.  Work limits (candidates, nodes) turn into
+//     status PTK_AP3_GAP with the best solution found and its bound, never into a silent answer.
+//
+// Sizes: every axis <= 64 (w <= 2 MB per problem, L2-resident); B problems per launch (colours).
+#pragma once
+#include <cfloat>
+#include <cstdint>
+
+namespace ptk {
+
+constexpr int AP3_MAXN = 64;
+constexpr int AP3_THREADS = 256;
+constexpr int AP3_OK = 0, AP3_GAP = 1, AP3_INVALID = 2, AP3_EMPTY = 3;
+
+struct Ap3Cand {
+    double slack;
+    int16_t j, k;
+    int32_t pad;
+};
+
+struct Ap3Args {
+    const double* w;  // [B, D0, D1, D2]
+    int D0, D1, D2;
+    const int32_t* n0;  // [B] actual sizes (nullptr: D0 / D1 / D2)
+    const int32_t* n1;
+    const int32_t* n2;
+    int32_t* sol;     // [B, 3, Dmin], -1 beyond n_sol; triples sorted by the first index
+    int32_t* n_sol;   // [B]
+    double* value;    // [B] summed weight of the returned triples
+    double* bound;    // [B] proven upper bound
+    int32_t* status;  // [B]
+    int32_t* stats;   // [B, 4] descent steps, search nodes (saturating), candidates, proven-at-step (optional)
+    Ap3Cand* cand;    // workspace [B, 2, cand_cap]
+    int cand_cap;
+    int max_steps;
+    long long node_limit;
+};
+
+struct Ap3Smem {
+    double cneg[AP3_MAXN * AP3_MAXN];  // LSAP cost (negated benefit), row-major, leading dimension m
+    double y[3][AP3_MAXN];             // duals per axis
+    double uu[AP3_MAXN], vv[AP3_MAXN], sp[AP3_MAXN];
+    double ub_hist[4];
+    double red[AP3_THREADS / 32];
+    int path[AP3_MAXN], col4row[AP3_MAXN], row4col[AP3_MAXN];
+    int pair_p[AP3_MAXN], pair_q[AP3_MAXN];
+    int16_t best[3][AP3_MAXN];
+    int16_t cur[3][AP3_MAXN];
+    int cnt[AP3_MAXN + 1], off[AP3_MAXN + 1], order[AP3_MAXN];
+    // search
+    double acc[AP3_MAXN + 1], usum[AP3_MAXN + 1], suffix[AP3_MAXN + 1];
+    int pos[AP3_MAXN + 1];
+    int16_t chj[AP3_MAXN + 1], chk[AP3_MAXN + 1];
+    int n_best, n_pairs, flag, total_cand;
+    double best_val, ub, wmax;
+};
+
+__device__ __forceinline__ double ap3_inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+
+// Min-cost square assignment on cost[m x m] (shared memory) by one warp: shortest augmenting paths
+// with duals uu (rows), vv (columns); lanes own columns lane and lane+32.  Ties go to the lowest
+// column.  Result: col4row / row4col and the duals (cost[i][j] - uu[i] - vv[j] >= 0, = 0 on the
+// assignment).
+__device__ void ap3_lsap_warp(const double* __restrict__ cost, int m, Ap3Smem& s)
+{
+    const int lane = threadIdx.x & 31;
+    const double INF = ap3_inf();
+    for (int j = lane; j < AP3_MAXN; j += 32) {
+        s.uu[j] = 0.0;
+        s.vv[j] = 0.0;
+        s.col4row[j] = -1;
+        s.row4col[j] = -1;
+    }
+    __syncwarp();
+    const int j0 = lane, j1 = lane + 32;
+    const bool in0 = j0 < m, in1 = j1 < m;
+    for (int cur = 0; cur < m; cur++) {
+        double sp0 = INF, sp1 = INF;
+        unsigned long long SC = 0ull, SR = 0ull;
+        int i = cur, sink = -1;
+        double minv = 0.0;
+        const double v0 = s.vv[j0], v1 = s.vv[j1];
+        while (sink < 0) {
+            SR |= 1ull << i;
+            const double ui = s.uu[i];
+            double c0 = INF, c1 = INF;
+            if (in0 && !((SC >> j0) & 1ull)) {
+                const double r = minv + cost[i * m + j0] - ui - v0;
+                if (r < sp0) { sp0 = r; s.path[j0] = i; }
+                c0 = sp0;
+            }
+            if (in1 && !((SC >> j1) & 1ull)) {
+                const double r = minv + cost[i * m + j1] - ui - v1;
+                if (r < sp1) { sp1 = r; s.path[j1] = i; }
+                c1 = sp1;
+            }
+            double bv = c0;
+            int bj = j0;
+            if (c1 < bv) { bv = c1; bj = j1; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+                if (ov < bv || (ov == bv && oj < bj)) { bv = ov; bj = oj; }
+            }
+            if (!(bv < INF)) { sink = bj; minv = bv; break; }  // cannot happen for finite costs
+            minv = bv;
+            SC |= 1ull << bj;
+            const int r4 = s.row4col[bj];
+            if (r4 < 0) sink = bj;
+            else i = r4;
+        }
+        if (in0) s.sp[j0] = sp0;
+        if (in1) s.sp[j1] = sp1;
+        __syncwarp();
+        for (int r = lane; r < m; r += 32)
+            if ((SR >> r) & 1ull) s.uu[r] += (r == cur) ? minv : (minv - s.sp[s.col4row[r]]);
+        if (in0 && ((SC >> j0) & 1ull)) s.vv[j0] = v0 - (minv - sp0);
+        if (in1 && ((SC >> j1) & 1ull)) s.vv[j1] = v1 - (minv - sp1);
+        __syncwarp();
+        if (lane == 0) {
+            int j = sink;
+            while (true) {
+                const int i2 = s.path[j];
+                s.row4col[j] = i2;
+                const int t = s.col4row[i2];
+                s.col4row[i2] = j;
+                j = t;
+                if (i2 == cur) break;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+__device__ __forceinline__ double ap3_block_max(double v, Ap3Smem& s)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) s.red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = s.red[0];
+    for (int k = 1; k < AP3_THREADS / 32; k++) r = fmax(r, s.red[k]);
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(AP3_THREADS) k_ap3(const __grid_constant__ Ap3Args a)
+{
+    extern __shared__ __align__(16) unsigned char ap3_smem_raw[];
+    Ap3Smem& s = *reinterpret_cast<Ap3Smem*>(ap3_smem_raw);
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n[3] = {a.n0 ? a.n0[b] : a.D0, a.n1 ? a.n1[b] : a.D1, a.n2 ? a.n2[b] : a.D2};
+    const long long st[3] = {(long long)a.D1 * a.D2, a.D2, 1};
+    const double* __restrict__ w = a.w + (size_t)b * a.D0 * a.D1 * a.D2;
+    const int Dmin = min(a.D0, min(a.D1, a.D2));
+    int32_t* sol = a.sol + (size_t)b * 3 * Dmin;
+    const int nmin = min(n[0], min(n[1], n[2]));
+    const double INF = ap3_inf();
+
+    for (int t = tid; t < 3 * Dmin; t += AP3_THREADS) sol[t] = -1;
+    if (tid == 0) {
+        a.n_sol[b] = 0;
+        a.value[b] = 0.0;
+        a.bound[b] = 0.0;
+        if (a.stats) { a.stats[b * 4 + 0] = 0; a.stats[b * 4 + 1] = 0; a.stats[b * 4 + 2] = 0; a.stats[b * 4 + 3] = -1; }
+    }
+    if (n[0] < 0 || n[1] < 0 || n[2] < 0 || n[0] > a.D0 || n[1] > a.D1 || n[2] > a.D2) {
+        if (tid == 0) a.status[b] = AP3_INVALID;
+        return;
+    }
+    if (nmin == 0) {
+        if (tid == 0) a.status[b] = AP3_EMPTY;
+        return;
+    }
+    // ---- validate, scale
+    {
+        double mx = 0.0;
+        bool bad = false;
+        const int tot = n[0] * n[1] * n[2];
+        for (int e = tid; e < tot; e += AP3_THREADS) {
+            const int k = e % n[2], j = (e / n[2]) % n[1], i = e / (n[2] * n[1]);
+            const double v = w[i * st[0] + j * st[1] + k];
+            if (!(fabs(v) < INF)) bad = true;
+            mx = fmax(mx, fabs(v));
+        }
+        mx = ap3_block_max(bad ? INF : mx, s);
+        if (!(mx < INF)) {
+            if (tid == 0) a.status[b] = AP3_INVALID;
+            return;
+        }
+        if (tid == 0) {
+            s.wmax = mx;
+            s.best_val = -1.0;
+            s.n_best = 0;
+            s.ub = INF;
+            s.flag = 0;
+            for (int q = 0; q < 4; q++) s.ub_hist[q] = INF;
+        }
+        for (int t = tid; t < 3 * AP3_MAXN; t += AP3_THREADS) s.y[t / AP3_MAXN][t % AP3_MAXN] = 0.0;
+        __syncthreads();
+    }
+    const double eps = 16.0 * DBL_EPSILON * (double)nmin * fmax(s.wmax, 1e-300);
+
+    int steps = 0, proven_at = -1;
+    for (int step = 0; step < a.max_steps; step++) {
+        // axis r is the fixed block, (p, q) the two that are re-optimised
+        const int r = step % 3, p = r == 0 ? 1 : 0, q = r == 2 ? 1 : 2;
+        const int np = n[p], nq = n[q], nr = n[r];
+        const int m = max(np, nq);
+        // ---- c[p,q] = max(0, max_r (w - y_r)), stored negated, padded with zeros to m x m
+        for (int e = tid; e < m * m; e += AP3_THREADS) {
+            const int iq = e % m, ip = e / m;
+            double best = 0.0;
+            if (ip < np && iq < nq) {
+                const double* base = w + ip * st[p] + iq * st[q];
+                for (int ir = 0; ir < nr; ir++) best = fmax(best, base[ir * st[r]] - s.y[r][ir]);
+            }
+            s.cneg[e] = -best;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            ap3_lsap_warp(s.cneg, m, s);
+            // duals of the max problem: a = -uu, b = -vv; shift so that both are >= 0 (possible
+            // because every c >= 0); dummy rows / columns end at zero
+            double amin = INF;
+            for (int j = lane; j < m; j += 32) amin = fmin(amin, -s.uu[j]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) amin = fmin(amin, __shfl_xor_sync(0xffffffffu, amin, o));
+            double sum = 0.0;
+            for (int j = lane; j < AP3_MAXN; j += 32) {
+                const double ya = j < np ? fmax(0.0, -s.uu[j] - amin) : 0.0;
+                const double yb = j < nq ? fmax(0.0, -s.vv[j] + amin) : 0.0;
+                s.y[p][j] = ya;
+                s.y[q][j] = yb;
+                sum += ya + yb + (j < nr ? s.y[r][j] : 0.0);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            if (lane == 0) {
+                s.ub = fmin(s.ub, sum);
+                int np_ = 0;
+                for (int ip = 0; ip < np; ip++) {
+                    const int iq = s.col4row[ip];
+                    if (iq >= 0 && iq < nq) { s.pair_p[np_] = ip; s.pair_q[np_] = iq; np_++; }
+                }
+                s.n_pairs = np_;
+            }
+        }
+        __syncthreads();
+        // ---- complete the pairs over axis r: second assignment on max(w[r, pair], 0)
+        const int K = s.n_pairs;
+        if (K > 0) {
+            const int m2 = max(K, nr);
+            for (int e = tid; e < m2 * m2; e += AP3_THREADS) {
+                const int ir = e % m2, ik = e / m2;
+                double v = 0.0;
+                if (ik < K && ir < nr) v = fmax(0.0, w[ir * st[r] + s.pair_p[ik] * st[p] + s.pair_q[ik] * st[q]]);
+                s.cneg[e] = -v;
+            }
+            __syncthreads();
+            if (warp == 0) {
+                ap3_lsap_warp(s.cneg, m2, s);
+                double val = 0.0;
+                for (int ik = lane; ik < K; ik += 32) {
+                    const int ir = s.col4row[ik];
+                    if (ir >= 0 && ir < nr) val += -s.cneg[ik * m2 + ir];
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+                if (val > s.best_val) {  // uniform
+                    __syncwarp();
+                    if (lane == 0) {
+                        int nb = 0;
+                        for (int ik = 0; ik < K; ik++) {
+                            const int ir = s.col4row[ik];
+                            if (ir < 0 || ir >= nr) continue;
+                            if (w[ir * st[r] + s.pair_p[ik] * st[p] + s.pair_q[ik] * st[q]] < 0.0) continue;
+                            s.best[r][nb] = (int16_t)ir;
+                            s.best[p][nb] = (int16_t)s.pair_p[ik];
+                            s.best[q][nb] = (int16_t)s.pair_q[ik];
+                            nb++;
+                        }
+                        s.n_best = nb;
+                        s.best_val = val;
+                    }
+                }
+            }
+        } else if (tid == 0 && s.best_val < 0.0) {
+            s.best_val = 0.0;
+            s.n_best = 0;
+        }
+        __syncthreads();
+        steps = step + 1;
+        // ---- stop rules (uniform: everything read from shared memory)
+        const double gap = s.ub - s.best_val;
+        if (gap <= eps) { proven_at = step; break; }
+        const double prev3 = s.ub_hist[(step + 1) & 3];  // bound three steps ago (INF until then)
+        __syncthreads();
+        if (tid == 0) s.ub_hist[step & 3] = s.ub;
+        __syncthreads();
+        if (step >= 5 && !(prev3 - s.ub > 1e-13 * fabs(s.ub) + eps)) break;  // one full cycle without progress
+    }
+
+    int status = AP3_OK;
+    long long nodes = 0;
+    int total_cand = 0;
+    if (proven_at < 0) {
+        // ---- reduced-cost search: only triples with slack below the gap can improve the incumbent
+        const double gap = s.ub - s.best_val;
+        const double thr = gap + eps;
+        Ap3Cand* c0 = a.cand + (size_t)b * 2 * a.cand_cap;
+        Ap3Cand* c1 = c0 + a.cand_cap;
+        for (int t = tid; t <= AP3_MAXN; t += AP3_THREADS) s.cnt[t] = 0;
+        __syncthreads();
+        const int tot = n[0] * n[1] * n[2];
+        for (int e = tid; e < tot; e += AP3_THREADS) {
+            const int k = e % n[2], j = (e / n[2]) % n[1], i = e / (n[2] * n[1]);
+            const double sl = s.y[0][i] + s.y[1][j] + s.y[2][k] - w[i * st[0] + j * st[1] + k];
+            if (sl < thr) atomicAdd(&s.cnt[i], 1);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int o = 0;
+            for (int i = 0; i < n[0]; i++) { s.off[i] = o; o += s.cnt[i]; }
+            s.off[n[0]] = o;
+            s.total_cand = o;
+        }
+        __syncthreads();
+        total_cand = s.total_cand;
+        if (total_cand > a.cand_cap) {
+            status = AP3_GAP;
+        } else {
+            for (int t = tid; t <= AP3_MAXN; t += AP3_THREADS) s.cnt[t] = 0;
+            __syncthreads();
+            for (int e = tid; e < tot; e += AP3_THREADS) {
+                const int k = e % n[2], j = (e / n[2]) % n[1], i = e / (n[2] * n[1]);
+                const double sl = s.y[0][i] + s.y[1][j] + s.y[2][k] - w[i * st[0] + j * st[1] + k];
+                if (sl < thr) {
+                    const int at = s.off[i] + atomicAdd(&s.cnt[i], 1);
+                    c0[at].slack = fmax(sl, 0.0);
+                    c0[at].j = (int16_t)j;
+                    c0[at].k = (int16_t)k;
+                }
+            }
+            __syncthreads();
+            // rank sort inside every i (ascending slack, then (j,k)): makes the list deterministic
+            for (int i = 0; i < n[0]; i++) {
+                const int lo = s.off[i], L = s.cnt[i];
+                for (int e = tid; e < L; e += AP3_THREADS) {
+                    const Ap3Cand me = c0[lo + e];
+                    const int mekey = me.j * AP3_MAXN + me.k;
+                    int rank = 0;
+                    for (int f = 0; f < L; f++) {
+                        const Ap3Cand ot = c0[lo + f];
+                        const int okey = ot.j * AP3_MAXN + ot.k;
+                        rank += (ot.slack < me.slack || (ot.slack == me.slack && okey < mekey)) ? 1 : 0;
+                    }
+                    c1[lo + rank] = me;
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                // depth order: fewest candidates first
+                for (int i = 0; i < n[0]; i++) s.order[i] = i;
+                for (int x = 1; x < n[0]; x++) {
+                    const int v = s.order[x];
+                    int y = x - 1;
+                    while (y >= 0 && s.cnt[s.order[y]] > s.cnt[v]) { s.order[y + 1] = s.order[y]; y--; }
+                    s.order[y + 1] = v;
+                }
+                s.suffix[n[0]] = 0.0;
+                for (int d = n[0] - 1; d >= 0; d--) {
+                    const int i = s.order[d];
+                    double mn = s.y[0][i];  // leaving i unused costs its dual
+                    if (s.cnt[i] > 0) mn = fmin(mn, c1[s.off[i]].slack);
+                    s.suffix[d] = s.suffix[d + 1] + mn;
+                }
+                double ysum12 = 0.0;
+                for (int j = 0; j < n[1]; j++) ysum12 += s.y[1][j];
+                for (int k = 0; k < n[2]; k++) ysum12 += s.y[2][k];
+                unsigned long long usedJ = 0ull, usedK = 0ull;
+                double bestslack = gap;  // a better solution has total slack < gap
+                const int D = n[0];
+                int d = 0;
+                s.acc[0] = 0.0;
+                s.usum[0] = 0.0;
+                s.pos[0] = 0;
+                s.chj[0] = -1;
+                bool limit = false;
+                while (d >= 0) {
+                    if (++nodes > a.node_limit) { limit = true; break; }
+                    if (d == D) {
+                        const double total = s.acc[d] + (ysum12 - s.usum[d]);
+                        if (total < bestslack - eps) {
+                            // candidate solution: take it if its true value beats the incumbent
+                            double val = 0.0;
+                            int nb = 0;
+                            for (int x = 0; x < D; x++)
+                                if (s.chj[x] >= 0) val += w[s.order[x] * st[0] + s.chj[x] * st[1] + s.chk[x]];
+                            if (val > s.best_val) {
+                                for (int x = 0; x < D; x++)
+                                    if (s.chj[x] >= 0) {
+                                        s.best[0][nb] = (int16_t)s.order[x];
+                                        s.best[1][nb] = s.chj[x];
+                                        s.best[2][nb] = s.chk[x];
+                                        nb++;
+                                    }
+                                s.n_best = nb;
+                                s.best_val = val;
+                                bestslack = fmin(total, s.ub - val);
+                            }
+                        }
+                        d--;
+                        continue;
+                    }
+                    const int i = s.order[d];
+                    if (s.chj[d] >= 0) {  // undo the choice this depth holds
+                        usedJ &= ~(1ull << s.chj[d]);
+                        usedK &= ~(1ull << s.chk[d]);
+                        s.chj[d] = -1;
+                    }
+                    const int L = s.cnt[i], lo = s.off[i];
+                    int t = s.pos[d];
+                    bool went = false;
+                    while (t < L) {
+                        const Ap3Cand c = c1[lo + t];
+                        if (s.acc[d] + c.slack + s.suffix[d + 1] >= bestslack) { t = L; break; }  // sorted: nothing later fits
+                        if (!((usedJ >> c.j) & 1ull) && !((usedK >> c.k) & 1ull)) {
+                            usedJ |= 1ull << c.j;
+                            usedK |= 1ull << c.k;
+                            s.chj[d] = c.j;
+                            s.chk[d] = c.k;
+                            s.pos[d] = t + 1;
+                            s.acc[d + 1] = s.acc[d] + c.slack;
+                            s.usum[d + 1] = s.usum[d] + s.y[1][c.j] + s.y[2][c.k];
+                            went = true;
+                            break;
+                        }
+                        t++;
+                    }
+                    if (!went && t == L) {  // last option: leave i unused
+                        if (s.acc[d] + s.y[0][i] + s.suffix[d + 1] < bestslack) {
+                            s.pos[d] = L + 1;
+                            s.acc[d + 1] = s.acc[d] + s.y[0][i];
+                            s.usum[d + 1] = s.usum[d];
+                            went = true;
+                        }
+                    }
+                    if (went) {
+                        d++;
+                        if (d < D) { s.pos[d] = 0; s.chj[d] = -1; }
+                    } else {
+                        d--;
+                    }
+                }
+                s.flag = limit ? 1 : 0;
+            }
+            __syncthreads();
+            if (s.flag) status = AP3_GAP;
+        }
+    }
+
+    // ---- output: triples sorted by the first index, then completed with unused indices (weight
+    // >= 0 only) up to min(n0, n1, n2) -- at an optimum these can only be zero-weight triples
+    __syncthreads();
+    if (tid == 0) {
+        const int nb = s.n_best;
+        unsigned long long u0 = 0ull, u1 = 0ull, u2 = 0ull;
+        for (int x = 0; x < nb; x++) { u0 |= 1ull << s.best[0][x]; u1 |= 1ull << s.best[1][x]; u2 |= 1ull << s.best[2][x]; }
+        int cnt_ = nb;
+        double val = 0.0;
+        for (int x = 0; x < nb; x++) val += w[s.best[0][x] * st[0] + s.best[1][x] * st[1] + s.best[2][x]];
+        for (int i = 0; i < n[0] && cnt_ < nmin; i++) {
+            if ((u0 >> i) & 1ull) continue;
+            for (int j = 0; j < n[1] && !((u0 >> i) & 1ull); j++) {
+                if ((u1 >> j) & 1ull) continue;
+                for (int k = 0; k < n[2]; k++) {
+                    if ((u2 >> k) & 1ull) continue;
+                    const double v = w[i * st[0] + j * st[1] + k];
+                    if (v < 0.0) continue;
+                    s.best[0][cnt_] = (int16_t)i; s.best[1][cnt_] = (int16_t)j; s.best[2][cnt_] = (int16_t)k;
+                    cnt_++;
+                    val += v;
+                    u0 |= 1ull << i; u1 |= 1ull << j; u2 |= 1ull << k;
+                    break;
+                }
+            }
+        }
+        // insertion sort by first index
+        for (int x = 1; x < cnt_; x++) {
+            const int16_t i0 = s.best[0][x], i1 = s.best[1][x], i2 = s.best[2][x];
+            int y = x - 1;
+            while (y >= 0 && s.best[0][y] > i0) {
+                s.best[0][y + 1] = s.best[0][y]; s.best[1][y + 1] = s.best[1][y]; s.best[2][y + 1] = s.best[2][y];
+                y--;
+            }
+            s.best[0][y + 1] = i0; s.best[1][y + 1] = i1; s.best[2][y + 1] = i2;
+        }
+        for (int x = 0; x < cnt_; x++) {
+            sol[0 * Dmin + x] = s.best[0][x];
+            sol[1 * Dmin + x] = s.best[1][x];
+            sol[2 * Dmin + x] = s.best[2][x];
+        }
+        a.n_sol[b] = cnt_;
+        a.value[b] = val;
+        a.bound[b] = status == AP3_OK ? fmax(val, fmin(s.ub, val + eps)) : s.ub;
+        a.status[b] = status;
+        if (a.stats) {
+            a.stats[b * 4 + 0] = steps;
+            a.stats[b * 4 + 1] = (int32_t)(nodes > 0x7fffffffLL ? 0x7fffffff : nodes);
+            a.stats[b * 4 + 2] = total_cand;
+            a.stats[b * 4 + 3] = proven_at;
+        }
+    }
+}
+
+}  // namespace ptk

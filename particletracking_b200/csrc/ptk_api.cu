@@ -15,6 +15,7 @@
 #include "ptk_csv.cuh"
 #include "ptk_csv_reader.h"
 #include "ptk_kernels.cuh"
+#include "ptk_ap3.cuh"
 
 using namespace ptk;
 
@@ -29,7 +30,7 @@ std::atomic<long long> g_launches{0};
 // stream around every kernel launch, by kernel kind, so bench.py can report the dominant
 // kernel's duration (and the step's breakdown) measured inside the timed region.  Off by default
 // (no events are recorded).
-enum Kind { K_UNDISTORT = 0, K_COST, K_LSAP_MATCH, K_ROWS, K_ROWS_TO_ENDS, K_TRACK_COST, K_LSAP_TRACK, K_CHAIN, K_WEIGHTS, K_N };
+enum Kind { K_UNDISTORT = 0, K_COST, K_LSAP_MATCH, K_ROWS, K_ROWS_TO_ENDS, K_TRACK_COST, K_LSAP_TRACK, K_CHAIN, K_WEIGHTS, K_AP3, K_N };
 std::atomic<int> g_timing{0};
 std::mutex g_timing_mu;
 struct TimedLaunch { int kind; cudaEvent_t t0, t1; };
@@ -375,6 +376,8 @@ PTK_API size_t ptk_workspace_bytes(int kind, long long n_problems, int Nmax)
         }
         case PTK_WS_WEIGHTS:
             return align_up((size_t)((n_problems + 255) / 256) * sizeof(double)) + 256;
+        case PTK_WS_AP3:
+            return align_up((size_t)n_problems * 2 * 32768 * sizeof(Ap3Cand)) + 256;
         default: return 0;
     }
 }
@@ -675,6 +678,36 @@ PTK_API int ptk_create_weights(int Np, int N1, int N2, const double* p_3D, const
     LAUNCHED("k_weights_raw");
     k_weights_finish<<<nb, 256, 0, st>>>(tot, nb, bm, weights);
     LAUNCHED("k_weights_finish");
+    return PTK_OK;
+}
+
+// ------------------------------------------------------------------------------------ K10
+static const int kAp3CandCap = 32768;
+PTK_API int ptk_npartite3_batch(int B, int D0, int D1, int D2, const double* weights, const int32_t* n0, const int32_t* n1,
+                                const int32_t* n2, int32_t* sol, int32_t* n_sol, double* value, double* bound,
+                                int32_t* status, int32_t* stats, int max_steps, long long node_limit, void* workspace,
+                                size_t workspace_bytes, void* stream)
+{
+    if (B < 0 || D0 < 0 || D1 < 0 || D2 < 0 || D0 > AP3_MAXN || D1 > AP3_MAXN || D2 > AP3_MAXN) return PTK_ERR_INVALID_ARG;
+    if (!n_sol || !value || !bound || !status) return PTK_ERR_INVALID_ARG;
+    if (B == 0) return PTK_OK;
+    const long long tot = (long long)D0 * D1 * D2;
+    if (tot > 0 && (!weights || !sol)) return PTK_ERR_INVALID_ARG;
+    if (!workspace || workspace_bytes < ptk_workspace_bytes(PTK_WS_AP3, B, 0)) return PTK_ERR_WORKSPACE;
+    Ap3Args a;
+    a.w = weights;
+    a.D0 = D0; a.D1 = D1; a.D2 = D2;
+    a.n0 = n0; a.n1 = n1; a.n2 = n2;
+    a.sol = sol; a.n_sol = n_sol; a.value = value; a.bound = bound; a.status = status; a.stats = stats;
+    a.cand = reinterpret_cast<Ap3Cand*>(align_up((size_t)workspace));
+    a.cand_cap = kAp3CandCap;
+    a.max_steps = max_steps > 0 ? max_steps : 60;
+    a.node_limit = node_limit > 0 ? node_limit : 20000000LL;
+    static_assert(sizeof(Ap3Smem) <= 48 * 1024, "k_ap3 shared memory");
+    cudaStream_t st = (cudaStream_t)stream;
+    LaunchTimer tm(K_AP3, st);
+    k_ap3<<<B, AP3_THREADS, sizeof(Ap3Smem), st>>>(a);
+    LAUNCHED("k_ap3");
     return PTK_OK;
 }
 

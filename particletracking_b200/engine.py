@@ -309,6 +309,41 @@ def create_weights(p_3D: torch.Tensor, p_prev: torch.Tensor, rep_errs: torch.Ten
     return w, ch
 
 
+class Npartite3Result:
+    """sol[B,3,Dmin] (-1 padded), n_sol[B], value[B], bound[B], status[B], stats[B,4]."""
+
+    def __init__(self, sol, n_sol, value, bound, status, stats):
+        self.sol, self.n_sol, self.value, self.bound, self.status, self.stats = sol, n_sol, value, bound, status, stats
+
+
+def npartite3_batch(weights: torch.Tensor, n0=None, n1=None, n2=None, max_steps: int = 0, node_limit: int = 0) -> Npartite3Result:
+    """K10: the 3-group ``matchND.npartite_matching`` (matchND.py:45-138) for ``weights[B,D0,D1,D2]``."""
+    _require_cuda()
+    weights = _chk(weights, _f64, "weights")
+    if weights.dim() != 4:
+        raise ValueError("weights must be [B, D0, D1, D2]")
+    B, D0, D1, D2 = weights.shape
+    if max(D0, D1, D2) > nat.AP3_MAXN:
+        raise ValueError(f"npartite3: more than {nat.AP3_MAXN} members in a group")
+    dev = weights.device
+    dmin = min(D0, D1, D2)
+    sol = torch.empty((B, 3, dmin), dtype=_i32, device=dev)
+    n_sol = torch.empty((B,), dtype=_i32, device=dev)
+    value = torch.empty((B,), dtype=_f64, device=dev)
+    bound = torch.empty((B,), dtype=_f64, device=dev)
+    status = torch.empty((B,), dtype=_i32, device=dev)
+    stats = torch.empty((B, 4), dtype=_i32, device=dev)
+    ns = [None if x is None else _chk(x, _i32, "n") for x in (n0, n1, n2)]
+    nb = nat.lib().ptk_workspace_bytes(nat.WS_AP3, B, 0)
+    ws = _ws.get(nb, dev)
+    with torch.cuda.device(dev):
+        nat.check(nat.lib().ptk_npartite3_batch(B, D0, D1, D2, _ptr(weights), _ptr(ns[0]), _ptr(ns[1]), _ptr(ns[2]), _ptr(sol),
+                                                _ptr(n_sol), _ptr(value), _ptr(bound), _ptr(status), _ptr(stats),
+                                                int(max_steps), int(node_limit), _ptr(ws), ws.numel(), _stream()),
+                  "ptk_npartite3_batch")
+    return Npartite3Result(sol, n_sol, value, bound, status, stats)
+
+
 def reorder_endpoints(ends: torch.Tensor, pts2d: Optional[torch.Tensor] = None):
     """K7: ``match2D.reorder_endpoints_csv``'s numeric body (match2D.py:1055-1137).
     ends[C,F,N,2,3] (, pts2d[C,F,N,2,2,2]) -> (out_ends, out_2d | None, swapped[C,F,N] uint8,
@@ -368,7 +403,7 @@ def kernel_timing(enable: bool) -> None:
     nat.lib().ptk_timing_enable(1 if enable else 0)
 
 
-TIMING_KINDS = ["undistort", "cost", "lsap_match", "rows", "rows_to_ends", "track_cost", "lsap_track", "chain", "weights"]
+TIMING_KINDS = ["undistort", "cost", "lsap_match", "rows", "rows_to_ends", "track_cost", "lsap_track", "chain", "weights", "npartite3"]
 
 
 def kernel_timing_read(reset: bool = True):

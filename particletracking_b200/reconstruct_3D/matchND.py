@@ -1,22 +1,77 @@
-"""The parts of the reference's ``matchND`` (``reconstruct_3D/matchND.py``) on the hot path:
-the shared triangulation block with SUM aggregation (:446-551) and ``create_weights``
-(:141-217), both on the B200.
+"""The reference's ``matchND`` (``reconstruct_3D/matchND.py``) on the B200: the shared
+triangulation block with SUM aggregation (:446-551), ``create_weights`` (:141-217),
+``npartite_matching`` (:45-138) for two and three groups, ``match_frame`` (:372-632) and the
+``assign`` CSV driver (:220-369).
 
-``npartite_matching`` (:45-138, a 3-index assignment ILP solved by pulp/CBC) is a "next" row
-(SURVEY.md 8f.2): no oracle for it can run here (pulp and CBC are absent) and it is not the
-LSAP the north star names.  ``match_frame`` therefore takes the solver as an argument.
+The reference hands the 3-index assignment to pulp/CBC as a 0/1 programme; here it is solved
+exactly on the GPU (``libptk.so``: dual block-coordinate descent over 2-D assignments, then a
+reduced-cost search if a gap is left -- ``csrc/ptk_ap3.cuh``).  Where several optima exist the
+returned one may differ from CBC's; the optimal value cannot.
 """
 from __future__ import annotations
 
-from typing import Callable, Optional, Tuple
+import os
+import pathlib
+import warnings
+from typing import Callable, Iterable, Optional, Tuple
 
 import numpy as np
 import pandas as pd
 import torch
 
+from .. import _native as nat
 from .. import engine
 from ..rig import make_rig
+from ..utils import csv_io
+from ..utils import data_loading as dl
 from . import match2D
+
+
+class NpartiteGapWarning(RuntimeWarning):
+    """The solver hit its work limits: the matching returned is feasible and the best found, but
+    not proven optimal (``npartite_matching.last`` holds value and bound)."""
+
+
+def npartite_matching(weights: np.ndarray, maximize: bool = True, solver=None) -> Tuple[np.ndarray, ...]:
+    """Solve an n-partite matching problem (reference matchND.py:45-138) for 2 or 3 groups.
+
+    Returns one index array per axis of ``weights`` (what ``np.where`` of the reference's 0/1
+    solution gives: sorted by the first axis).  ``solver`` is accepted for signature
+    compatibility and ignored (there is no LP solver here).  ``maximize=False`` solves the same
+    programme the reference poses for it -- with "at most once" constraints that is the empty
+    matching for positive weights, which is the bug the reference warns about."""
+    if not maximize:
+        warnings.warn("Minimization is currently not fully supported.Results might be incorrect.")
+    w = np.ascontiguousarray(weights, dtype=np.float64)
+    if not maximize:
+        w = -w
+    engine._require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    if w.ndim == 3:
+        r = engine.npartite3_batch(torch.from_numpy(w[None]).to(dev))
+        status, n = int(r.status[0]), int(r.n_sol[0])
+        npartite_matching.last = dict(status=status, value=float(r.value[0]), bound=float(r.bound[0]),
+                                      stats=r.stats[0].cpu().numpy())
+        if status == nat.AP3_INVALID:
+            raise ValueError("weights contain invalid numeric entries")
+        if status == nat.AP3_GAP:
+            warnings.warn(f"npartite_matching: work limit reached, value {float(r.value[0])!r} <= optimum <= "
+                          f"{float(r.bound[0])!r}", NpartiteGapWarning)
+        sol = r.sol[0, :, :n].cpu().numpy().astype(np.int64)
+        return sol[0], sol[1], sol[2]
+    if w.ndim == 2:
+        n0, n1 = w.shape
+        if n0 == 0 or n1 == 0:
+            return np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)
+        if not np.isfinite(w).all():
+            raise ValueError("weights contain invalid numeric entries")
+        # "at most once" lets negative weights stay unmatched: clamp them, drop them afterwards
+        row, col, n_out, _ = engine.lsap_batch(torch.from_numpy(-np.maximum(w, 0.0)[None]).to(dev))
+        n = int(n_out[0])
+        ri, ci = row[0, :n].cpu().numpy().astype(np.int64), col[0, :n].cpu().numpy().astype(np.int64)
+        keep = w[ri, ci] >= 0
+        return ri[keep], ci[keep]
+    raise NotImplementedError("npartite_matching: only 2 and 3 groups are implemented (the reference's callers use 3)")
 
 
 def create_weights(p_3D: np.ndarray, p_3D_prev: np.ndarray, repr_errs: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
@@ -54,12 +109,11 @@ def match_frame(data: pd.DataFrame, data_last_frame: pd.DataFrame, cam1_name: st
                 solver: Optional[Callable[[np.ndarray], Tuple[np.ndarray, np.ndarray, np.ndarray]]] = None):
     """Matches, triangulates and tracks the rods of one frame (reference matchND.py:372-632).
 
-    Everything but the 3-index assignment runs on the GPU; ``solver(weights) -> (rod, cam1_ind,
-    cam2_ind)`` must maximise the summed weights (the reference's ``npartite_matching``)."""
+    ``solver(weights) -> (rod, cam1_ind, cam2_ind)`` defaults to this module's
+    ``npartite_matching``; row bookkeeping follows matchND.py:564-632 (rows indexed by the previous
+    frame's rod id, NaN fill-in, ``ValueError`` for unbalanced data)."""
     if solver is None:
-        raise NotImplementedError(
-            "matchND.match_frame needs a 3-index assignment solver (the reference's pulp/CBC npartite_matching is "
-            "out of scope, SURVEY.md 8f.2); pass solver=callable(weights) -> (rod, cam1_ind, cam2_ind)")
+        solver = npartite_matching
     tri = triangulate_frame(data, cam1_name, cam2_name, frame, calibration, P1, P2, rot, trans, r1, r2, t1, t2)
     if tri is None:
         return None
@@ -100,3 +154,50 @@ def match_frame(data: pd.DataFrame, data_last_frame: pd.DataFrame, cam1_name: st
     if seen_cols:
         df[seen_cols] = 1
     return df, costs[idx_out[1, :], idx_out[2, :]], out[:, 9]
+
+
+def assign(input_folder: str, output_folder: str, colors: Iterable[str], cam1_name: str = "gp1", cam2_name: str = "gp2",
+           frame_numbers: Iterable[int] = None, calibration_file: str = None, transformation_file: str = None, solver=None):
+    """Matches, triangulates and tracks rods over frames from ``rods_df_{color}.csv`` files
+    (reference matchND.py:220-369): the first frame through ``match2D.match_frame``, every later
+    frame through ``match_frame`` against the previous result.  Frames are sequential by
+    construction ("replicas only" along frames).  Returns ``(reprojection errors, rod
+    lengths)``."""
+    if calibration_file is None or transformation_file is None:
+        raise FileNotFoundError("calibration_file / transformation_file: the reference's defaults "
+                                "(example_calibration/Matlab/*.json) are not part of this package; pass them explicitly")
+    if not os.path.exists(output_folder):
+        os.mkdir(output_folder)
+    calibration = dl.load_camera_calibration(str(pathlib.Path(calibration_file)))
+    transforms = dl.load_world_transformation(str(pathlib.Path(transformation_file)))
+    from scipy.spatial.transform import Rotation
+
+    # matchND.py:297-312
+    r1 = np.eye(3)
+    t1 = np.expand_dims(np.array([0.0, 0.0, 0.0]), 1)
+    P1 = (np.vstack((r1.T, t1.T)) @ calibration["CM1"].T).T
+    r2, t2 = calibration["R"], calibration["T"]
+    P2 = (np.vstack((r2.T, t2.T)) @ calibration["CM2"].T).T
+    rot = Rotation.from_matrix(transforms["rotation"])
+    trans = transforms["translation"]
+    all_repr_errs, all_rod_lengths = [], []
+    for color in colors:
+        data = csv_io.read_rods_csv(input_folder + f"/rods_df_{color}.csv")
+        parts = []
+        tmp_df = None
+        for fn in range(len(frame_numbers)):
+            frame = frame_numbers[fn]
+            if fn == 0:
+                res = match2D.match_frame(data, cam1_name, cam2_name, frame, color, calibration, P1, P2, rot, trans, r1, r2,
+                                          t1, t2, renumber=True)
+            else:
+                res = match_frame(data, tmp_df, cam1_name, cam2_name, frame, color, calibration, P1, P2, rot, trans, r1, r2,
+                                  t1, t2, solver=solver)
+            tmp_df, tmp_costs, tmp_lengths = res  # TypeError on None, as in the reference (:322, :341)
+            parts.append(tmp_df)
+            all_repr_errs.append(tmp_costs)
+            all_rod_lengths.append(tmp_lengths)
+        df_out = pd.concat(parts) if parts else pd.DataFrame()
+        df_out.reset_index(drop=True, inplace=True)
+        df_out.to_csv(os.path.join(output_folder, f"rods_df_{color}.csv"), sep=",")
+    return np.asarray(all_repr_errs), np.asarray(all_rod_lengths)
