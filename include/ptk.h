@@ -224,6 +224,34 @@ int ptk_npartite3_batch(int B, int D0, int D1, int D2, const double* weights,
                         int32_t* status, int32_t* stats, int max_steps, long long node_limit,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- matchND.assign: a whole frame sequence, enqueue-only ------------------------------------
+ * Replaces the frame loop of matchND.assign (matchND.py:318-360) for C colours at once: frame 0
+ * through the match2D path (ptk_match_batch, mean error), every later frame f through
+ * matchND.match_frame (matchND.py:372-632) against frame f-1's rows: K0 + K1 with the summed error
+ * and per-combo outputs -> create_weights (matchND.py:141-217) -> 3-index assignment (K10) -> index
+ * bookkeeping and rows (matchND.py:568-632).  All sizes are read on the device, so nothing
+ * synchronises; frames are sequential by construction (5 launches per frame).
+ *   cam1, cam2 [F,C,Nmax,2,2]; n1, n2 [F,C]; Nmax <= 64
+ *   rows[F,C,Nmax,18] (NaN beyond n_rows), costs[F,C,Nmax], n_rows[F,C]
+ *   status[F,C]: PTK_PROBLEM_* for frame 0; later frames PTK_ND_OK, PTK_ND_INVALID (NaN weights),
+ *     PTK_ND_EMPTY (a camera without rods: match_frame returns None), PTK_ND_UNBALANCED (the
+ *     reference's ValueError, matchND.py:592-598), PTK_ND_GAP (solver work limit: rows are the best
+ *     matching found), PTK_ND_ABORTED (an earlier frame of this colour failed)
+ *   solver_stats[C,4] (optional): summed descent steps, search nodes, candidates, problems that
+ *     needed the search
+ * workspace: ptk_matchnd_sequence_workspace_bytes(F, C, Nmax). */
+#define PTK_ND_OK 0
+#define PTK_ND_INVALID 1
+#define PTK_ND_EMPTY 3
+#define PTK_ND_UNBALANCED 6
+#define PTK_ND_GAP 7
+#define PTK_ND_ABORTED 8
+size_t ptk_matchnd_sequence_workspace_bytes(int F, int C, int Nmax);
+int ptk_matchnd_sequence(const ptk_rig* rig, int F, int C, int Nmax,
+                         const double* cam1, const double* cam2, const int32_t* n1, const int32_t* n2,
+                         double* rows, double* costs, int32_t* n_rows, int32_t* status,
+                         int32_t* solver_stats, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- CSV writer (host; "next" row) ---------------------------------------
  * Replaces df_out.to_csv(...) at match2D.py:626-629 for the output layout of match_frame
  * (match2D.py:986-997): an unnamed RangeIndex column, `n_float_cols` float columns (Python repr()

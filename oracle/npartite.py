@@ -108,3 +108,17 @@ def match_frame_rows(p_triang: np.ndarray, rods1: np.ndarray, rods2: np.ndarray,
         out[idx_r, 10:14] = rods1[i1].ravel()
         out[idx_r, 14:] = rods2[i2].ravel()
     return out, costs[idx_out[1, :], idx_out[2, :]]
+
+
+def match_frame_arrays(rods1: np.ndarray, rods2: np.ndarray, prev_ends: np.ndarray, calibration, P1, P2, rot, trans,
+                       r1, r2, t1, t2, solver=npartite_matching):
+    """matchND.match_frame (matchND.py:446-632) on arrays: ``rods1[N1,2,2]``, ``rods2[N2,2,2]`` (already
+    filtered), ``prev_ends[Np,2,3]`` = the previous frame's ``x1..z2``.  Returns
+    ``(rows[Np,18], costs[Np], lengths[Np], weights, sol)``."""
+    from . import port
+
+    m = port.match_arrays(rods1, rods2, calibration, P1, P2, rot, trans, r1, r2, t1, t2, agg="sum")
+    weights, choices = port.create_weights(m["p_world"], prev_ends, m["rep_errs"])
+    sol = solver(weights)
+    out, costs = match_frame_rows(m["p_world"], rods1, rods2, m["cost"], choices, sol, weights.shape[0])
+    return out, costs, out[:, 9].copy(), weights, sol

@@ -20,6 +20,7 @@ PROBLEM_OK, PROBLEM_INVALID, PROBLEM_INFEASIBLE, PROBLEM_EMPTY = 0, 1, 2, 3
 WS_COST, WS_MATCH, WS_TRACK, WS_WEIGHTS, WS_AP3 = 1, 2, 3, 4, 5
 AP3_OK, AP3_GAP, AP3_INVALID, AP3_EMPTY = 0, 1, 2, 3
 AP3_MAXN = 64
+ND_OK, ND_INVALID, ND_INFEASIBLE, ND_EMPTY, ND_UNBALANCED, ND_GAP, ND_ABORTED = 0, 1, 2, 3, 6, 7, 8
 ROW_COLS = 18
 MAX_RODS = 256
 
@@ -27,7 +28,7 @@ MAX_RODS = 256
 SYMBOLS = [
     "ptk_version", "ptk_strerror", "ptk_last_cuda_error", "ptk_device_count",
     "ptk_undistort_batch", "ptk_cost_batch", "ptk_lsap_batch", "ptk_match_batch",
-    "ptk_rows_batch", "ptk_rows_to_ends", "ptk_track_batch", "ptk_chain_tracks", "ptk_chain_rebase", "ptk_create_weights", "ptk_reorder_endpoints", "ptk_triangulate_points", "ptk_project_points", "ptk_npartite3_batch",
+    "ptk_rows_batch", "ptk_rows_to_ends", "ptk_track_batch", "ptk_chain_tracks", "ptk_chain_rebase", "ptk_create_weights", "ptk_reorder_endpoints", "ptk_triangulate_points", "ptk_project_points", "ptk_npartite3_batch", "ptk_matchnd_sequence", "ptk_matchnd_sequence_workspace_bytes",
     "ptk_csv_write_rods", "ptk_format_double", "ptk_workspace_bytes",
     "ptk_csv_open", "ptk_csv_close", "ptk_csv_error", "ptk_csv_n_rows", "ptk_csv_n_cols", "ptk_csv_col_name",
     "ptk_csv_col_kind", "ptk_csv_col_copy", "ptk_csv_col_dict_size", "ptk_csv_col_dict", "ptk_parse_double",
@@ -89,6 +90,9 @@ def lib() -> ctypes.CDLL:
     L.ptk_triangulate_points.argtypes = [rigp, ll, vp, vp, i32, vp, vp]
     L.ptk_project_points.argtypes = [rigp, ll, vp, i32, vp, vp, vp]
     L.ptk_npartite3_batch.argtypes = [i32] * 4 + [vp] * 10 + [i32, ll, vp, sz, vp]
+    L.ptk_matchnd_sequence_workspace_bytes.restype = sz
+    L.ptk_matchnd_sequence_workspace_bytes.argtypes = [i32, i32, i32]
+    L.ptk_matchnd_sequence.argtypes = [rigp, i32, i32, i32] + [vp] * 9 + [vp, sz, vp]
     L.ptk_csv_write_rods.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ll, i32, vp, vp, ctypes.c_char_p, vp, i32]
     L.ptk_format_double.argtypes = [dbl, ctypes.c_char_p]
     L.ptk_csv_open.argtypes = [ctypes.c_char_p, i32, ctypes.POINTER(vp)]

@@ -534,4 +534,183 @@ __global__ void __launch_bounds__(AP3_THREADS) k_ap3(const __grid_constant__ Ap3
     }
 }
 
+// ------------------------------------------------------------------------------------- K11 / K12
+// matchND.match_frame around the solver, batched over the colours of one frame with every size read
+// from device memory, so that a whole frame sequence (matchND.assign, matchND.py:318-360) is enqueued
+// without a host round trip:
+//   k_nd_weights_raw / _finish : create_weights (matchND.py:141-217) from the previous frame's rows
+//   k_nd_rows                  : index bookkeeping and rows (matchND.py:568-632)
+constexpr int ND_OK = 0, ND_INVALID = 1, ND_EMPTY = 3, ND_UNBALANCED = 6, ND_GAP = 7, ND_ABORTED = 8;
+__device__ __forceinline__ bool nd_usable(int st) { return st == ND_OK || st == ND_GAP; }
+
+struct NdArgs {
+    int D;                      // padded rods per problem (Nmax <= 64)
+    const double* prev_rows;    // [C, D, 18] rows of frame f-1 (x1..z2 = columns 0..5)
+    const int32_t* prev_n;      // [C]
+    const int32_t* prev_status; // [C]
+    const int32_t* n1;          // [C] frame f
+    const int32_t* n2;
+    const double* cam1;         // [C, D, 2, 2] frame f (distorted detections, as read)
+    const double* cam2;
+    const double* p_world;      // [C, D, D, 4, 3]
+    const double* rep_errs;     // [C, D, D, 4, 2]
+    const double* cost;         // [C, D, D]
+    double* w;                  // [C, D, D, D]
+    uint8_t* choices;           // [C, D, D, D]
+    unsigned long long* wkey;   // [C] ordered key of the running maximum (zeroed by the caller)
+    const int32_t* sol;         // [C, 3, D]
+    const int32_t* n_sol;       // [C]
+    const int32_t* ap3_status;  // [C]
+    double* rows;               // [C, D, 18] frame f
+    double* costs;              // [C, D]
+    int32_t* n_rows;            // [C]
+    int32_t* status;            // [C]
+};
+
+__device__ __forceinline__ double nd_weight(const double* q1, const double* q2, const double* p, const double* r, int& am)
+{
+    const double *c1p1 = p, *c2p1 = p + 3, *c2p2 = p + 6, *c1p2 = p + 9;  // matchND.py:184-187
+    const double c1_re = ((r[0] + r[1]) + r[6]) + r[7];                   // combos 0 and 3
+    const double c2_re = r[2] + r[3];                                     // combo 1 only: the 1:2 slice
+    const double s0 = (dist3(c1p1, q1) + dist3(c1p2, q2)) * c1_re;
+    const double s1 = (dist3(c2p1, q1) + dist3(c2p2, q2)) * c2_re;
+    const double s2 = (dist3(c2p1, q2) + dist3(c2p2, q1)) * c2_re;
+    const double s3 = (dist3(c1p1, q2) + dist3(c1p2, q1)) * c1_re;
+    am = 0;
+    double best = s0;
+    if (s1 < best) { best = s1; am = 1; }
+    if (s2 < best) { best = s2; am = 2; }
+    if (s3 < best) { best = s3; am = 3; }
+    return best;
+}
+
+__global__ void __launch_bounds__(256) k_nd_weights_raw(const __grid_constant__ NdArgs a)
+{
+    __shared__ double red[8];
+    const int c = blockIdx.y, D = a.D;
+    const int np = nd_usable(a.prev_status[c]) ? a.prev_n[c] : 0, n1 = a.n1[c], n2 = a.n2[c];
+    const int tot = np * n1 * n2;
+    double mine = -INFINITY;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += gridDim.x * blockDim.x) {
+        const int k = e % n2, j = (e / n2) % n1, i = e / (n2 * n1);
+        const double* q1 = a.prev_rows + ((size_t)c * D + i) * 18;
+        const size_t jk = ((size_t)c * D + j) * D + k;
+        int am;
+        const double v = nd_weight(q1, q1 + 3, a.p_world + jk * 12, a.rep_errs + jk * 8, am);
+        const size_t o = (((size_t)c * D + i) * D + j) * D + k;
+        a.w[o] = v;
+        a.choices[o] = (uint8_t)am;
+        mine = fmax(mine, v);  // NaN-ignoring here; NaN weights are caught by the solver's validation
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine = fmax(mine, __shfl_xor_sync(kFull, mine, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0 && tot > 0) {
+        double m = red[0];
+        for (int k = 1; k < 8; k++) m = fmax(m, red[k]);
+        if (m > -INFINITY) atomicMax(a.wkey + c, ordered_key(m));
+    }
+}
+
+__global__ void __launch_bounds__(256) k_nd_weights_finish(const __grid_constant__ NdArgs a)
+{
+    const int c = blockIdx.y, D = a.D;
+    const int np = nd_usable(a.prev_status[c]) ? a.prev_n[c] : 0, n1 = a.n1[c], n2 = a.n2[c];
+    const int tot = np * n1 * n2;
+    const double wmax = ordered_value(a.wkey[c]);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += gridDim.x * blockDim.x) {
+        const int k = e % n2, j = (e / n2) % n1, i = e / (n2 * n1);
+        const size_t o = (((size_t)c * D + i) * D + j) * D + k;
+        a.w[o] = wmax - a.w[o];  // matchND.py:216
+    }
+}
+
+__global__ void __launch_bounds__(64) k_nd_rows(const __grid_constant__ NdArgs a)
+{
+    __shared__ int idx[3][AP3_MAXN];
+    __shared__ int st_s;
+    const int c = blockIdx.x, D = a.D, tid = threadIdx.x;
+    const int np = a.prev_n[c], n1 = a.n1[c], n2 = a.n2[c];
+    double* rows = a.rows + (size_t)c * D * 18;
+    double* costs = a.costs + (size_t)c * D;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int t = tid; t < D * 18; t += blockDim.x) rows[t] = nan;
+    for (int t = tid; t < D; t += blockDim.x) costs[t] = nan;
+    if (tid == 0) {
+        int st = ND_OK;
+        if (!nd_usable(a.prev_status[c])) st = ND_ABORTED;
+        else if (np <= 0 || n1 <= 0 || n2 <= 0) st = ND_EMPTY;  // match_frame returns None (matchND.py:465-467)
+        else if (a.ap3_status[c] == AP3_INVALID) st = ND_INVALID;
+        else {
+            const int ns = a.n_sol[c];
+            const int32_t* sol = a.sol + (size_t)c * 3 * D;
+            // matchND.py:570-583: idx_out[:, rod] = triples; rods without a triple take the indices
+            // (< nprev) that no triple uses, in increasing order
+            unsigned long long u1 = 0ull, u2 = 0ull;
+            for (int r = 0; r < np; r++) { idx[0][r] = r; idx[1][r] = -1; idx[2][r] = -1; }
+            for (int x = 0; x < ns; x++) {
+                const int r = sol[x];
+                idx[1][r] = sol[D + x];
+                idx[2][r] = sol[2 * D + x];
+                u1 |= 1ull << sol[D + x];
+                u2 |= 1ull << sol[2 * D + x];
+            }
+            if (ns < np) {
+                int f1 = 0, f2 = 0, miss = 0, free1 = 0, free2 = 0;
+                for (int r = 0; r < np; r++) { free1 += !((u1 >> r) & 1ull); free2 += !((u2 >> r) & 1ull); }
+                miss = np - ns;
+                if (free1 != miss || free2 != miss) st = ND_UNBALANCED;  // numpy: shape mismatch in the fill-in
+                else
+                    for (int r = 0; r < np; r++) {
+                        if (idx[1][r] >= 0) continue;
+                        while ((u1 >> f1) & 1ull) f1++;
+                        while ((u2 >> f2) & 1ull) f2++;
+                        idx[1][r] = f1++;
+                        idx[2][r] = f2++;
+                    }
+            }
+            if (st == ND_OK)
+                for (int r = 0; r < np; r++)
+                    if (idx[1][r] >= n1 || idx[2][r] >= n2) st = ND_UNBALANCED;  // IndexError -> ValueError (matchND.py:592-598)
+            if (st == ND_OK && a.ap3_status[c] == AP3_GAP) st = ND_GAP;
+        }
+        st_s = st;
+        a.status[c] = st;
+        a.n_rows[c] = (st == ND_OK || st == ND_GAP) ? np : 0;
+    }
+    __syncthreads();
+    if (st_s != ND_OK && st_s != ND_GAP) return;
+    for (int r = tid; r < np; r += blockDim.x) {
+        const int i1 = idx[1][r], i2 = idx[2][r];
+        const int i3 = a.choices[(((size_t)c * D + r) * D + i1) * D + i2];
+        const double* pw = a.p_world + (((size_t)c * D + i1) * D + i2) * 12;
+        const double* e1 = pw + 3 * i3;
+        const double* e2 = pw + 3 * (3 - i3);
+        double* o = rows + (size_t)r * 18;
+        for (int q = 0; q < 3; q++) {
+            o[q] = e1[q];
+            o[3 + q] = e2[q];
+            o[6 + q] = (e1[q] + e2[q]) / 2.0;
+        }
+        o[9] = dist3(e1, e2);
+        const double* r1 = a.cam1 + ((size_t)c * D + i1) * 4;
+        const double* r2 = a.cam2 + ((size_t)c * D + i2) * 4;
+        for (int q = 0; q < 4; q++) { o[10 + q] = r1[q]; o[14 + q] = r2[q]; }
+        costs[r] = a.cost[((size_t)c * D + i1) * D + i2];
+    }
+}
+
+// running totals of the solver statistics over the frames of a sequence: steps, nodes, candidates,
+// and the number of problems that needed the search
+__global__ void k_nd_stats(int C, const int32_t* __restrict__ stats, int32_t* __restrict__ total)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    total[c * 4 + 0] += stats[c * 4 + 0];
+    total[c * 4 + 1] = (int32_t)min(0x7fffffffLL, (long long)total[c * 4 + 1] + stats[c * 4 + 1]);
+    total[c * 4 + 2] = (int32_t)min(0x7fffffffLL, (long long)total[c * 4 + 2] + stats[c * 4 + 2]);
+    total[c * 4 + 3] += stats[c * 4 + 3] < 0 ? 1 : 0;
+}
+
 }  // namespace ptk

@@ -3,6 +3,7 @@
 //
 // Build (see particletracking_b200/csrc/Makefile):
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -708,6 +709,132 @@ PTK_API int ptk_npartite3_batch(int B, int D0, int D1, int D2, const double* wei
     LaunchTimer tm(K_AP3, st);
     k_ap3<<<B, AP3_THREADS, sizeof(Ap3Smem), st>>>(a);
     LAUNCHED("k_ap3");
+    return PTK_OK;
+}
+
+// ------------------------------------------------------------------------------------ matchND.assign
+namespace {
+struct NdWs {
+    double *und1, *und2, *cost, *pw, *re, *w, *value, *bound;
+    uint8_t* choices;
+    unsigned long long* wkey;
+    int32_t *sol, *n_sol, *ap3_status, *stats, *row_ind, *col_ind;
+    Ap3Cand* cand;
+    void* match_ws;
+    size_t match_ws_bytes;
+    size_t bytes;
+};
+NdWs carve_nd(void* base, int F, int C, int D)
+{
+    NdWs w;
+    char* b = static_cast<char*>(base);
+    size_t o = 0;
+    auto take = [&](size_t n) { char* p = b + o; o += align_up(n); return p; };
+    const size_t CD = (size_t)C * D, CDD = CD * D, CDDD = CDD * D;
+    w.und1 = (double*)take(CD * 4 * sizeof(double));
+    w.und2 = (double*)take(CD * 4 * sizeof(double));
+    w.cost = (double*)take(CDD * sizeof(double));
+    w.pw = (double*)take(CDD * 12 * sizeof(double));
+    w.re = (double*)take(CDD * 8 * sizeof(double));
+    w.w = (double*)take(CDDD * sizeof(double));
+    w.choices = (uint8_t*)take(CDDD);
+    w.wkey = (unsigned long long*)take((size_t)F * C * sizeof(unsigned long long));
+    w.sol = (int32_t*)take(CD * 3 * sizeof(int32_t));
+    w.n_sol = (int32_t*)take((size_t)C * sizeof(int32_t));
+    w.ap3_status = (int32_t*)take((size_t)C * sizeof(int32_t));
+    w.stats = (int32_t*)take((size_t)C * 4 * sizeof(int32_t));
+    w.value = (double*)take((size_t)C * sizeof(double));
+    w.bound = (double*)take((size_t)C * sizeof(double));
+    w.row_ind = (int32_t*)take(CD * sizeof(int32_t));
+    w.col_ind = (int32_t*)take(CD * sizeof(int32_t));
+    w.cand = (Ap3Cand*)take((size_t)C * 2 * kAp3CandCap * sizeof(Ap3Cand));
+    w.match_ws_bytes = ptk_workspace_bytes(PTK_WS_MATCH, C, D);
+    w.match_ws = take(w.match_ws_bytes);
+    w.bytes = o;
+    return w;
+}
+}  // namespace
+
+PTK_API size_t ptk_matchnd_sequence_workspace_bytes(int F, int C, int Nmax)
+{
+    if (F <= 0 || C <= 0 || Nmax <= 0 || Nmax > AP3_MAXN) return 0;
+    return carve_nd(nullptr, F, C, Nmax).bytes + 256;
+}
+
+PTK_API int ptk_matchnd_sequence(const ptk_rig* rig, int F, int C, int Nmax, const double* cam1, const double* cam2,
+                                 const int32_t* n1, const int32_t* n2, double* rows, double* costs, int32_t* n_rows,
+                                 int32_t* status, int32_t* solver_stats, void* workspace, size_t workspace_bytes,
+                                 void* stream)
+{
+    if (!rig || F < 0 || C < 0 || Nmax <= 0 || Nmax > AP3_MAXN || !cam1 || !cam2 || !n1 || !n2 || !rows || !costs ||
+        !n_rows || !status)
+        return PTK_ERR_INVALID_ARG;
+    if (F == 0 || C == 0) return PTK_OK;
+    if (!workspace || workspace_bytes < ptk_matchnd_sequence_workspace_bytes(F, C, Nmax)) return PTK_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int D = Nmax;
+    NdWs w = carve_nd((void*)align_up((size_t)workspace), F, C, D);
+    ptk_rig rmean = *rig, rsum = *rig;
+    rmean.agg_sum = 0;  // frame 0: match2D.match_frame (matchND.py:322-340)
+    rsum.agg_sum = 1;   // later frames: matchND.match_frame sums the two cameras' errors (matchND.py:525)
+    const DevRig dsum = make_devrig(&rsum);
+    const size_t fr4 = (size_t)C * D * 4, frR = (size_t)C * D * PTK_ROW_COLS, frD = (size_t)C * D;
+    int rc = ptk_match_batch(&rmean, C, D, cam1, cam2, n1, n2, nullptr, nullptr, w.row_ind, w.col_ind, n_rows, status, rows,
+                             costs, INFINITY, nullptr, w.match_ws, w.match_ws_bytes, stream);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(w.wkey, 0, (size_t)F * C * sizeof(unsigned long long), st));
+    if (solver_stats) CK(cudaMemsetAsync(solver_stats, 0, (size_t)C * 4 * sizeof(int32_t), st));
+    for (int f = 1; f < F; f++) {
+        const double* c1 = cam1 + f * fr4;
+        const double* c2 = cam2 + f * fr4;
+        const int32_t* m1 = n1 + (size_t)f * C;
+        const int32_t* m2 = n2 + (size_t)f * C;
+        rc = launch_undistort(dsum, C, D, c1, c2, m1, m2, w.und1, w.und2, st);
+        if (rc) return rc;
+        rc = launch_cost(dsum, C, D, c1, c2, w.und1, w.und2, m1, m2, w.cost, nullptr, w.pw, w.re, st);
+        if (rc) return rc;
+        NdArgs a;
+        a.D = D;
+        a.prev_rows = rows + (size_t)(f - 1) * frR;
+        a.prev_n = n_rows + (size_t)(f - 1) * C;
+        a.prev_status = status + (size_t)(f - 1) * C;
+        a.n1 = m1; a.n2 = m2; a.cam1 = c1; a.cam2 = c2;
+        a.p_world = w.pw; a.rep_errs = w.re; a.cost = w.cost; a.w = w.w; a.choices = w.choices;
+        a.wkey = w.wkey + (size_t)f * C;
+        a.sol = w.sol; a.n_sol = w.n_sol; a.ap3_status = w.ap3_status;
+        a.rows = rows + (size_t)f * frR;
+        a.costs = costs + (size_t)f * frD;
+        a.n_rows = n_rows + (size_t)f * C;
+        a.status = status + (size_t)f * C;
+        const int gx = std::max(1, std::min(64, (D * D * D + 2047) / 2048));
+        {
+            LaunchTimer lt(K_WEIGHTS, st);
+            k_nd_weights_raw<<<dim3(gx, C), 256, 0, st>>>(a);
+        }
+        LAUNCHED("k_nd_weights_raw");
+        {
+            LaunchTimer lt(K_WEIGHTS, st);
+            k_nd_weights_finish<<<dim3(gx, C), 256, 0, st>>>(a);
+        }
+        LAUNCHED("k_nd_weights_finish");
+        Ap3Args s;
+        s.w = w.w; s.D0 = D; s.D1 = D; s.D2 = D;
+        s.n0 = a.prev_n; s.n1 = m1; s.n2 = m2;
+        s.sol = w.sol; s.n_sol = w.n_sol; s.value = w.value; s.bound = w.bound; s.status = w.ap3_status;
+        s.stats = w.stats;
+        s.cand = w.cand; s.cand_cap = kAp3CandCap; s.max_steps = 60; s.node_limit = 20000000LL;
+        {
+            LaunchTimer lt(K_AP3, st);
+            k_ap3<<<C, AP3_THREADS, sizeof(Ap3Smem), st>>>(s);
+        }
+        LAUNCHED("k_ap3");
+        k_nd_rows<<<C, 64, 0, st>>>(a);
+        LAUNCHED("k_nd_rows");
+        if (solver_stats) {
+            k_nd_stats<<<(C + 63) / 64, 64, 0, st>>>(C, w.stats, solver_stats);
+            LAUNCHED("k_nd_stats");
+        }
+    }
     return PTK_OK;
 }
 

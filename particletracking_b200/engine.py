@@ -344,6 +344,31 @@ def npartite3_batch(weights: torch.Tensor, n0=None, n1=None, n2=None, max_steps:
     return Npartite3Result(sol, n_sol, value, bound, status, stats)
 
 
+def matchnd_sequence(rig: PtkRig, cam1, cam2, n1, n2):
+    """``matchND.assign``'s frame loop (matchND.py:318-360) for ``cam1, cam2 [F,C,Nmax,2,2]``,
+    ``n1, n2 [F,C]`` on the device: returns ``rows[F,C,Nmax,18], costs[F,C,Nmax], n_rows[F,C],
+    status[F,C], solver_stats[C,4]``."""
+    _require_cuda()
+    cam1, cam2 = _chk(cam1, _f64, "cam1"), _chk(cam2, _f64, "cam2")
+    n1, n2 = _chk(n1, _i32, "n1"), _chk(n2, _i32, "n2")
+    F, C, Nmax = cam1.shape[:3]
+    if Nmax > nat.AP3_MAXN:
+        raise ValueError(f"matchND: more than {nat.AP3_MAXN} rods per (frame, colour)")
+    dev = cam1.device
+    rows = torch.empty((F, C, Nmax, nat.ROW_COLS), dtype=_f64, device=dev)
+    costs = torch.empty((F, C, Nmax), dtype=_f64, device=dev)
+    n_rows = torch.empty((F, C), dtype=_i32, device=dev)
+    status = torch.empty((F, C), dtype=_i32, device=dev)
+    stats = torch.zeros((C, 4), dtype=_i32, device=dev)
+    nb = nat.lib().ptk_matchnd_sequence_workspace_bytes(F, C, Nmax)
+    ws = _ws.get(nb, dev)
+    with torch.cuda.device(dev):
+        nat.check(nat.lib().ptk_matchnd_sequence(ctypes.byref(rig), F, C, Nmax, _ptr(cam1), _ptr(cam2), _ptr(n1), _ptr(n2),
+                                                 _ptr(rows), _ptr(costs), _ptr(n_rows), _ptr(status), _ptr(stats), _ptr(ws),
+                                                 ws.numel(), _stream()), "ptk_matchnd_sequence")
+    return rows, costs, n_rows, status, stats
+
+
 def reorder_endpoints(ends: torch.Tensor, pts2d: Optional[torch.Tensor] = None):
     """K7: ``match2D.reorder_endpoints_csv``'s numeric body (match2D.py:1055-1137).
     ends[C,F,N,2,3] (, pts2d[C,F,N,2,2,2]) -> (out_ends, out_2d | None, swapped[C,F,N] uint8,

@@ -180,6 +180,10 @@ def assign(input_folder: str, output_folder: str, colors: Iterable[str], cam1_na
     P2 = (np.vstack((r2.T, t2.T)) @ calibration["CM2"].T).T
     rot = Rotation.from_matrix(transforms["rotation"])
     trans = transforms["translation"]
+    colors = list(colors)
+    if solver is None and colors and len(frame_numbers) > 0:
+        return _assign_device(input_folder, output_folder, colors, cam1_name, cam2_name, list(frame_numbers), calibration,
+                              P1, P2, rot, trans, r1, r2, t1, t2)
     all_repr_errs, all_rod_lengths = [], []
     for color in colors:
         data = csv_io.read_rods_csv(input_folder + f"/rods_df_{color}.csv")
@@ -200,4 +204,77 @@ def assign(input_folder: str, output_folder: str, colors: Iterable[str], cam1_na
         df_out = pd.concat(parts) if parts else pd.DataFrame()
         df_out.reset_index(drop=True, inplace=True)
         df_out.to_csv(os.path.join(output_folder, f"rods_df_{color}.csv"), sep=",")
+    return np.asarray(all_repr_errs), np.asarray(all_rod_lengths)
+
+
+def _raise_for_nd_status(status: np.ndarray):
+    """status[F, C] of ptk_matchnd_sequence -> the exception the reference's loop would have raised
+    first (colours outer, frames inner, matchND.py:314-360)."""
+    F, C = status.shape
+    for c in range(C):
+        for f in range(F):
+            st = int(status[f, c])
+            if st in (nat.ND_OK, nat.ND_GAP):
+                continue
+            if st == nat.ND_EMPTY:  # match_frame returned None (match2D.py:838-840, matchND.py:465-467)
+                raise TypeError("cannot unpack non-iterable NoneType object")
+            if st == nat.ND_UNBALANCED:
+                raise ValueError("Unbalanced dataset given. Please use dataset with the same number of rods on every frame.")
+            if st == nat.ND_INFEASIBLE:
+                raise ValueError("cost matrix is infeasible")
+            if st == nat.ND_INVALID:
+                raise ValueError("matrix contains invalid numeric entries" if f == 0 else
+                                 "weights contain invalid numeric entries")
+            raise RuntimeError(f"matchND sequence: status {st} at frame index {f}, colour index {c}")
+
+
+def _assign_device(input_folder, output_folder, colors, cam1_name, cam2_name, frames, calibration, P1, P2, rot, trans,
+                   r1, r2, t1, t2):
+    """``assign`` with every colour's whole frame sequence in one enqueue-only library call
+    (``ptk_matchnd_sequence``): native CSV reader -> vectorised selection -> device loop -> native
+    CSV writer."""
+    engine._require_cuda()
+    rig = make_rig(calibration, P1, P2, rot, trans, r1, r2, t1, t2)
+    tables, packs = [], []
+    for color in colors:
+        data = match2D._Table.read(input_folder + f"/rods_df_{color}.csv")
+        v1 = match2D._cols(data, match2D._cam_cols(cam1_name))
+        v2 = match2D._cols(data, match2D._cam_cols(cam2_name))
+        packed = match2D._select_pack(np.asarray(match2D._col(data, "frame")), v1, v2, frames, True)
+        if packed is None:
+            raise ValueError("frame numbers must be unique")
+        tables.append(data)
+        packs.append(packed)
+    F, C = len(frames), len(colors)
+    nmax = max(p[0].shape[1] for p in packs)
+    c1 = np.full((F, C, nmax, 4), np.nan)
+    c2 = np.full((F, C, nmax, 4), np.nan)
+    n1 = np.zeros((F, C), dtype=np.int32)
+    n2 = np.zeros((F, C), dtype=np.int32)
+    for ci, (a, b, m1, m2, _) in enumerate(packs):
+        c1[:, ci, : a.shape[1]] = a
+        c2[:, ci, : b.shape[1]] = b
+        n1[:, ci], n2[:, ci] = m1, m2
+    dev = torch.device("cuda", torch.cuda.current_device())
+    t = lambda x: torch.from_numpy(x).to(dev)
+    rows, costs, n_rows, status, stats = engine.matchnd_sequence(rig, t(c1.reshape(F, C, nmax, 2, 2)), t(c2.reshape(F, C, nmax, 2, 2)),
+                                                                 t(n1), t(n2))
+    rows, costs, n_rows, status = rows.cpu().numpy(), costs.cpu().numpy(), n_rows.cpu().numpy(), status.cpu().numpy()
+    assign.last = dict(status=status, solver_stats=stats.cpu().numpy())
+    _raise_for_nd_status(status)
+    if (status == nat.ND_GAP).any():
+        warnings.warn(f"matchND.assign: the 3-index assignment hit its work limit in {int((status == nat.ND_GAP).sum())} "
+                      "(frame, colour) problems; their matchings are the best found, not proven optimal", NpartiteGapWarning)
+    all_repr_errs, all_rod_lengths = [], []
+    cols = [*match2D.COLS_3D, *match2D._cam_cols(cam1_name), *match2D._cam_cols(cam2_name)]
+    for ci, color in enumerate(colors):
+        n = n_rows[:, ci]
+        mask = np.arange(nmax)[None, :] < n[:, None]
+        flat = rows[:, ci][mask]
+        m = dict(rows=flat, frame=np.repeat(np.asarray(frames), n), particle=np.broadcast_to(np.arange(nmax), (F, nmax))[mask],
+                 cols=cols, seen_cols=[c for c in tables[ci].columns if "seen" in c])
+        match2D._write_csv(os.path.join(output_folder, f"rods_df_{color}.csv"), color, m)
+        cuts = np.cumsum(n)[:-1]
+        all_repr_errs.extend(np.split(costs[:, ci][mask], cuts))
+        all_rod_lengths.extend(np.split(flat[:, 9].copy(), cuts))
     return np.asarray(all_repr_errs), np.asarray(all_rod_lengths)

@@ -180,6 +180,52 @@ def golden_project(name, seed):
     print(name, "ok")
 
 
+def golden_matchnd(name, F, N, seed, **kw):
+    """reference matchND.match_frame / assign chain with ``npartite_matching`` replaced by the HiGHS
+    restatement of the same programme (oracle/npartite.py; pulp and CBC are absent here).  Everything
+    around the solver -- triangulation block, create_weights, index bookkeeping, rows -- is the
+    reference's own code.  Stored: input frames, every frame's weights / solution / output rows."""
+    from oracle import npartite as onp
+
+    m2d, mnd = refload.load()[:2]
+    cal, trf, args = rig_args()
+    data = syn.make_stereo(F, 1, N, seed=seed, **kw)
+    color = data.colors[0]
+    df = syn.to_dataframes(data)[color]
+    seen = []
+    orig_solver = mnd.npartite_matching
+
+    def solver(weights, maximize=True, solver=None):
+        sol = onp.npartite_matching(weights, maximize)
+        seen.append((np.array(weights, copy=True), np.stack(sol)))
+        return sol
+
+    mnd.npartite_matching = solver
+    frames = [int(f) for f in data.frames]
+    outs, costs, lens = [], [], []
+    tmp = None
+    for fn, frame in enumerate(frames):  # matchND.py:318-360
+        if fn == 0:
+            tmp, c, l = m2d.match_frame(df, "gp1", "gp2", frame, color, *args, renumber=True)
+        else:
+            tmp, c, l = mnd.match_frame(df, tmp, "gp1", "gp2", frame, color, *args)
+        outs.append(tmp[[*m2d_cols(m2d)]].to_numpy())
+        costs.append(c)
+        lens.append(l)
+    mnd.npartite_matching = orig_solver
+    np.savez_compressed(
+        os.path.join(OUT, name), cam1=data.cam1[:, 0], cam2=data.cam2[:, 0], n1=data.n1[:, 0], n2=data.n2[:, 0],
+        frames=np.array(frames), rows=np.stack(outs), costs=np.stack(costs), lens=np.stack(lens),
+        weights=np.stack([w for w, _ in seen]), sols=np.stack([s_ for _, s_ in seen]),
+        values=np.array([onp.objective(w, s_) for w, s_ in seen]), versions=versions(), params=np.array([F, N, seed]))
+    print(name, "ok", [float(v) for v in np.array([onp.objective(w, s_) for w, s_ in seen])[:2]])
+
+
+def m2d_cols(m2d):
+    return ["x1", "y1", "z1", "x2", "y2", "z2", "x", "y", "z", "l", "x1_gp1", "y1_gp1", "x2_gp1", "y2_gp1",
+            "x1_gp2", "y1_gp2", "x2_gp2", "y2_gp2"]
+
+
 if __name__ == "__main__":
     assert refload.available(), "needs /root/reference"
     # C1 of BASELINE.json: one stereo frame pair, 3 colours x 12 rods (+ one more frame)
@@ -195,3 +241,5 @@ if __name__ == "__main__":
     golden_weights("weights.npz", seed=5)
     golden_reorder("reorder.npz", 9, 10, seed=41)
     golden_project("project.npz", seed=6)
+    golden_matchnd("matchnd_12.npz", 4, 12, seed=51)
+    golden_matchnd("matchnd_25.npz", 3, 25, seed=52, sigma_px=0.5)
