@@ -28,7 +28,7 @@
 namespace ptk {
 
 constexpr int AP3_MAXN = 64;
-constexpr int AP3_THREADS = 256;
+constexpr int AP3_THREADS = 1024;
 constexpr int AP3_OK = 0, AP3_GAP = 1, AP3_INVALID = 2, AP3_EMPTY = 3;
 
 struct Ap3Cand {
@@ -64,36 +64,78 @@ struct Ap3Smem {
     int path[AP3_MAXN], col4row[AP3_MAXN], row4col[AP3_MAXN];
     int pair_p[AP3_MAXN], pair_q[AP3_MAXN];
     int16_t best[3][AP3_MAXN];
-    int16_t cur[3][AP3_MAXN];
+    double vals[AP3_MAXN];
+    int16_t cur3[3][AP3_MAXN];
+    uint8_t argr[AP3_MAXN * AP3_MAXN];  // argmax over the fixed axis behind every c[p,q] (255: none positive)
     int cnt[AP3_MAXN + 1], off[AP3_MAXN + 1], order[AP3_MAXN];
     // search
     double acc[AP3_MAXN + 1], usum[AP3_MAXN + 1], suffix[AP3_MAXN + 1];
     int pos[AP3_MAXN + 1];
     int16_t chj[AP3_MAXN + 1], chk[AP3_MAXN + 1];
     int n_best, n_pairs, flag, total_cand;
-    double best_val, ub, wmax;
+    double best_val, ub;
 };
 
 __device__ __forceinline__ double ap3_inf() { return __longlong_as_double(0x7ff0000000000000LL); }
 
-// Min-cost square assignment on cost[m x m] (shared memory) by one warp: shortest augmenting paths
+// Min-cost square assignment on cost[m x m] (shared memory): shortest augmenting paths by one warp
 // with duals uu (rows), vv (columns); lanes own columns lane and lane+32.  Ties go to the lowest
 // column.  Result: col4row / row4col and the duals (cost[i][j] - uu[i] - vv[j] >= 0, = 0 on the
 // assignment).
-__device__ void ap3_lsap_warp(const double* __restrict__ cost, int m, Ap3Smem& s)
+__device__ void ap3_lsap_augment(const double* __restrict__ cost, int m, Ap3Smem& s);
+
+// Called by the whole CTA.  Row reduction first (every warp takes rows: uu[i] = min_j cost[i][j], row i
+// keeps its arg-min column if no lower row wants it -- on rod data that already is the assignment),
+// then warp 0 augments the rows left over.
+__device__ void ap3_lsap(const double* __restrict__ cost, int m, Ap3Smem& s)
 {
-    const int lane = threadIdx.x & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double INF = ap3_inf();
-    for (int j = lane; j < AP3_MAXN; j += 32) {
+    for (int j = tid; j < AP3_MAXN; j += AP3_THREADS) {
         s.uu[j] = 0.0;
         s.vv[j] = 0.0;
         s.col4row[j] = -1;
-        s.row4col[j] = -1;
+        s.row4col[j] = 0x7fffffff;
     }
-    __syncwarp();
+    __syncthreads();
+    for (int i = warp; i < m; i += AP3_THREADS / 32) {
+        double bv = lane < m ? cost[i * m + lane] : INF;
+        int bj = lane;
+        if (lane + 32 < m) {
+            const double c1 = cost[i * m + lane + 32];
+            if (c1 < bv) { bv = c1; bj = lane + 32; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+            if (ov < bv || (ov == bv && oj < bj)) { bv = ov; bj = oj; }
+        }
+        if (lane == 0) {
+            s.uu[i] = bv;
+            s.path[i] = bj;  // scratch: the row's arg-min column
+            atomicMin(&s.row4col[bj], i);
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < m; i += AP3_THREADS)
+        if (s.row4col[s.path[i]] == i) s.col4row[i] = s.path[i];
+    __syncthreads();
+    for (int j = tid; j < AP3_MAXN; j += AP3_THREADS)
+        if (s.row4col[j] == 0x7fffffff) s.row4col[j] = -1;
+    __syncthreads();
+    if (warp == 0) ap3_lsap_augment(cost, m, s);
+    __syncthreads();
+}
+
+__device__ void ap3_lsap_augment(const double* __restrict__ cost, int m, Ap3Smem& s)
+{
+    const int lane = threadIdx.x & 31;
+    const double INF = ap3_inf();
     const int j0 = lane, j1 = lane + 32;
     const bool in0 = j0 < m, in1 = j1 < m;
     for (int cur = 0; cur < m; cur++) {
+        if (s.col4row[cur] >= 0) continue;  // assigned by the row reduction (uniform)
         double sp0 = INF, sp1 = INF;
         unsigned long long SC = 0ull, SR = 0ull;
         int i = cur, sink = -1;
@@ -192,34 +234,17 @@ __global__ void __launch_bounds__(AP3_THREADS) k_ap3(const __grid_constant__ Ap3
         if (tid == 0) a.status[b] = AP3_EMPTY;
         return;
     }
-    // ---- validate, scale
-    {
-        double mx = 0.0;
-        bool bad = false;
-        const int tot = n[0] * n[1] * n[2];
-        for (int e = tid; e < tot; e += AP3_THREADS) {
-            const int k = e % n[2], j = (e / n[2]) % n[1], i = e / (n[2] * n[1]);
-            const double v = w[i * st[0] + j * st[1] + k];
-            if (!(fabs(v) < INF)) bad = true;
-            mx = fmax(mx, fabs(v));
-        }
-        mx = ap3_block_max(bad ? INF : mx, s);
-        if (!(mx < INF)) {
-            if (tid == 0) a.status[b] = AP3_INVALID;
-            return;
-        }
-        if (tid == 0) {
-            s.wmax = mx;
-            s.best_val = -1.0;
-            s.n_best = 0;
-            s.ub = INF;
-            s.flag = 0;
-            for (int q = 0; q < 4; q++) s.ub_hist[q] = INF;
-        }
-        for (int t = tid; t < 3 * AP3_MAXN; t += AP3_THREADS) s.y[t / AP3_MAXN][t % AP3_MAXN] = 0.0;
-        __syncthreads();
+    if (tid == 0) {
+        s.best_val = -1.0;
+        s.n_best = 0;
+        s.ub = INF;
+        s.flag = 0;
+        for (int q = 0; q < 4; q++) s.ub_hist[q] = INF;
     }
-    const double eps = 16.0 * DBL_EPSILON * (double)nmin * fmax(s.wmax, 1e-300);
+    for (int t = tid; t < 3 * AP3_MAXN; t += AP3_THREADS) s.y[t / AP3_MAXN][t % AP3_MAXN] = 0.0;
+    __syncthreads();
+    double eps = 0.0, wabs = 0.0;
+    bool bad = false;
 
     int steps = 0, proven_at = -1;
     for (int step = 0; step < a.max_steps; step++) {
@@ -231,15 +256,34 @@ __global__ void __launch_bounds__(AP3_THREADS) k_ap3(const __grid_constant__ Ap3
         for (int e = tid; e < m * m; e += AP3_THREADS) {
             const int iq = e % m, ip = e / m;
             double best = 0.0;
+            int arg = 255;
             if (ip < np && iq < nq) {
                 const double* base = w + ip * st[p] + iq * st[q];
-                for (int ir = 0; ir < nr; ir++) best = fmax(best, base[ir * st[r]] - s.y[r][ir]);
+#pragma unroll 4
+                for (int ir = 0; ir < nr; ir++) {
+                    const double wv = base[ir * st[r]];
+                    if (step == 0) {
+                        if (!(fabs(wv) < INF)) bad = true;
+                        wabs = fmax(wabs, fabs(wv));
+                    }
+                    const double v = wv - s.y[r][ir];
+                    if (v > best) { best = v; arg = ir; }
+                }
             }
             s.cneg[e] = -best;
+            s.argr[e] = (uint8_t)arg;
         }
         __syncthreads();
+        if (step == 0) {  // the first reduction saw every weight: validate and scale here
+            const double mx = ap3_block_max(bad ? INF : wabs, s);
+            if (!(mx < INF)) {
+                if (tid == 0) a.status[b] = AP3_INVALID;
+                return;
+            }
+            eps = 16.0 * DBL_EPSILON * (double)nmin * fmax(mx, 1e-300);
+        }
+        ap3_lsap(s.cneg, m, s);
         if (warp == 0) {
-            ap3_lsap_warp(s.cneg, m, s);
             // duals of the max problem: a = -uu, b = -vv; shift so that both are >= 0 (possible
             // because every c >= 0); dummy rows / columns end at zero
             double amin = INF;
@@ -258,18 +302,40 @@ __global__ void __launch_bounds__(AP3_THREADS) k_ap3(const __grid_constant__ Ap3
             for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
             if (lane == 0) {
                 s.ub = fmin(s.ub, sum);
-                int np_ = 0;
+                int np_ = 0, nt = 0;
+                unsigned long long used = 0ull;
+                bool distinct = true;
+                double v = 0.0;
                 for (int ip = 0; ip < np; ip++) {
                     const int iq = s.col4row[ip];
-                    if (iq >= 0 && iq < nq) { s.pair_p[np_] = ip; s.pair_q[np_] = iq; np_++; }
+                    if (iq < 0 || iq >= nq) continue;
+                    s.pair_p[np_] = ip;
+                    s.pair_q[np_] = iq;
+                    np_++;
+                    // the pair's own best partner on the fixed axis: if these are all different the
+                    // pairs are a feasible solution as they stand (w = c + y up to rounding)
+                    const int ar = s.argr[ip * m + iq];
+                    if (ar == 255) continue;
+                    if ((used >> ar) & 1ull) distinct = false;
+                    used |= 1ull << ar;
+                    v += -s.cneg[ip * m + iq] + s.y[r][ar];
+                    s.cur3[r][nt] = (int16_t)ar; s.cur3[p][nt] = (int16_t)ip; s.cur3[q][nt] = (int16_t)iq;
+                    nt++;
                 }
                 s.n_pairs = np_;
+                if (distinct && v > s.best_val) {
+                    for (int x = 0; x < nt; x++) { s.best[0][x] = s.cur3[0][x]; s.best[1][x] = s.cur3[1][x]; s.best[2][x] = s.cur3[2][x]; }
+                    s.n_best = nt;
+                    s.best_val = v;
+                }
             }
         }
         __syncthreads();
         // ---- complete the pairs over axis r: second assignment on max(w[r, pair], 0)
         const int K = s.n_pairs;
-        if (K > 0) {
+        if (s.ub - s.best_val <= eps) {
+            // proven by the pairs themselves
+        } else if (K > 0) {
             const int m2 = max(K, nr);
             for (int e = tid; e < m2 * m2; e += AP3_THREADS) {
                 const int ir = e % m2, ik = e / m2;
@@ -278,8 +344,8 @@ __global__ void __launch_bounds__(AP3_THREADS) k_ap3(const __grid_constant__ Ap3
                 s.cneg[e] = -v;
             }
             __syncthreads();
+            ap3_lsap(s.cneg, m2, s);
             if (warp == 0) {
-                ap3_lsap_warp(s.cneg, m2, s);
                 double val = 0.0;
                 for (int ik = lane; ik < K; ik += 32) {
                     const int ir = s.col4row[ik];
@@ -294,7 +360,7 @@ __global__ void __launch_bounds__(AP3_THREADS) k_ap3(const __grid_constant__ Ap3
                         for (int ik = 0; ik < K; ik++) {
                             const int ir = s.col4row[ik];
                             if (ir < 0 || ir >= nr) continue;
-                            if (w[ir * st[r] + s.pair_p[ik] * st[p] + s.pair_q[ik] * st[q]] < 0.0) continue;
+                            if (!(s.cneg[ik * m2 + ir] < 0.0)) continue;  // w <= 0: leave it out (zero-weight triples are re-added at the end)
                             s.best[r][nb] = (int16_t)ir;
                             s.best[p][nb] = (int16_t)s.pair_p[ik];
                             s.best[q][nb] = (int16_t)s.pair_q[ik];
@@ -488,19 +554,15 @@ __global__ void __launch_bounds__(AP3_THREADS) k_ap3(const __grid_constant__ Ap3
         unsigned long long u0 = 0ull, u1 = 0ull, u2 = 0ull;
         for (int x = 0; x < nb; x++) { u0 |= 1ull << s.best[0][x]; u1 |= 1ull << s.best[1][x]; u2 |= 1ull << s.best[2][x]; }
         int cnt_ = nb;
-        double val = 0.0;
-        for (int x = 0; x < nb; x++) val += w[s.best[0][x] * st[0] + s.best[1][x] * st[1] + s.best[2][x]];
         for (int i = 0; i < n[0] && cnt_ < nmin; i++) {
             if ((u0 >> i) & 1ull) continue;
             for (int j = 0; j < n[1] && !((u0 >> i) & 1ull); j++) {
                 if ((u1 >> j) & 1ull) continue;
                 for (int k = 0; k < n[2]; k++) {
                     if ((u2 >> k) & 1ull) continue;
-                    const double v = w[i * st[0] + j * st[1] + k];
-                    if (v < 0.0) continue;
+                    if (w[i * st[0] + j * st[1] + k] < 0.0) continue;
                     s.best[0][cnt_] = (int16_t)i; s.best[1][cnt_] = (int16_t)j; s.best[2][cnt_] = (int16_t)k;
                     cnt_++;
-                    val += v;
                     u0 |= 1ull << i; u1 |= 1ull << j; u2 |= 1ull << k;
                     break;
                 }
@@ -516,11 +578,20 @@ __global__ void __launch_bounds__(AP3_THREADS) k_ap3(const __grid_constant__ Ap3
             }
             s.best[0][y + 1] = i0; s.best[1][y + 1] = i1; s.best[2][y + 1] = i2;
         }
-        for (int x = 0; x < cnt_; x++) {
-            sol[0 * Dmin + x] = s.best[0][x];
-            sol[1 * Dmin + x] = s.best[1][x];
-            sol[2 * Dmin + x] = s.best[2][x];
-        }
+        s.n_best = cnt_;
+    }
+    __syncthreads();
+    const int cnt_ = s.n_best;
+    for (int x = tid; x < cnt_; x += AP3_THREADS) {
+        s.vals[x] = w[s.best[0][x] * st[0] + s.best[1][x] * st[1] + s.best[2][x]];
+        sol[0 * Dmin + x] = s.best[0][x];
+        sol[1 * Dmin + x] = s.best[1][x];
+        sol[2 * Dmin + x] = s.best[2][x];
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double val = 0.0;
+        for (int x = 0; x < cnt_; x++) val += s.vals[x];
         a.n_sol[b] = cnt_;
         a.value[b] = val;
         a.bound[b] = status == AP3_OK ? fmax(val, fmin(s.ub, val + eps)) : s.ub;

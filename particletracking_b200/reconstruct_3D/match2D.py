@@ -15,6 +15,7 @@ import logging
 import os
 import pathlib
 import threading
+import time
 from typing import Iterable, List, Optional, Sequence
 
 import numpy as np
@@ -424,17 +425,23 @@ def match_csv_complex(input_folder, output_folder, colors, cam1_name="gp1", cam2
     dev = torch.cuda.current_device()
     frames = list(frame_numbers)
 
+    stages = []
+
     def one_color(color):
         # native reader -> vectorised selection -> one library call -> native writer; every stage
         # releases the GIL, so colours overlap (one ptk_ctx per worker thread)
         with torch.cuda.device(dev):
+            t0 = time.perf_counter()
             data = _Table.read(input_folder + f"/rods_df_{color}.csv")
+            t1 = time.perf_counter()
             m = _match_arrays(data, frames, rig, cam1_name, cam2_name, rematching, copy_rows=False)
+            t2 = time.perf_counter()
             out_path = os.path.join(output_folder, f"rods_df_{color}.csv")
             if m is None:
                 pd.DataFrame().to_csv(out_path, sep=",")
                 return None
             _write_csv(out_path, color, m)
+            stages.append((color, t1 - t0, t2 - t1, time.perf_counter() - t2))
             return (m["costs2d"], m["lens2d"]) if m["costs2d"] is not None else (m["costs"], m["lens"])
 
     colors = list(colors)
@@ -445,6 +452,7 @@ def match_csv_complex(input_folder, output_folder, colors, cam1_name="gp1", cam2
             results = list(pool.map(one_color, colors))
     else:
         results = [one_color(c) for c in colors]
+    match_csv_complex.last_stage_seconds = {c: dict(read=a, match=b, write=w) for c, a, b, w in stages}
     results = [r for r in results if r is not None]
     if results and all(isinstance(r[0], np.ndarray) for r in results) and len({r[0].shape[1] for r in results}) == 1:
         return np.concatenate([r[0] for r in results]), np.concatenate([r[1] for r in results])

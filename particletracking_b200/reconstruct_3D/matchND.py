@@ -235,16 +235,21 @@ def _assign_device(input_folder, output_folder, colors, cam1_name, cam2_name, fr
     CSV writer."""
     engine._require_cuda()
     rig = make_rig(calibration, P1, P2, rot, trans, r1, r2, t1, t2)
-    tables, packs = [], []
-    for color in colors:
+    from concurrent.futures import ThreadPoolExecutor
+
+    def load(color):
         data = match2D._Table.read(input_folder + f"/rods_df_{color}.csv")
         v1 = match2D._cols(data, match2D._cam_cols(cam1_name))
         v2 = match2D._cols(data, match2D._cam_cols(cam2_name))
         packed = match2D._select_pack(np.asarray(match2D._col(data, "frame")), v1, v2, frames, True)
         if packed is None:
             raise ValueError("frame numbers must be unique")
-        tables.append(data)
-        packs.append(packed)
+        return data, packed
+
+    # reader and writer release the GIL: colours are read / written side by side
+    pool = ThreadPoolExecutor(max_workers=min(len(colors), match2D._CSV_WORKERS))
+    loaded = list(pool.map(load, colors))
+    tables, packs = [l[0] for l in loaded], [l[1] for l in loaded]
     F, C = len(frames), len(colors)
     nmax = max(p[0].shape[1] for p in packs)
     c1 = np.full((F, C, nmax, 4), np.nan)
@@ -265,16 +270,20 @@ def _assign_device(input_folder, output_folder, colors, cam1_name, cam2_name, fr
     if (status == nat.ND_GAP).any():
         warnings.warn(f"matchND.assign: the 3-index assignment hit its work limit in {int((status == nat.ND_GAP).sum())} "
                       "(frame, colour) problems; their matchings are the best found, not proven optimal", NpartiteGapWarning)
-    all_repr_errs, all_rod_lengths = [], []
     cols = [*match2D.COLS_3D, *match2D._cam_cols(cam1_name), *match2D._cam_cols(cam2_name)]
-    for ci, color in enumerate(colors):
+
+    def store(ci):
         n = n_rows[:, ci]
         mask = np.arange(nmax)[None, :] < n[:, None]
         flat = rows[:, ci][mask]
         m = dict(rows=flat, frame=np.repeat(np.asarray(frames), n), particle=np.broadcast_to(np.arange(nmax), (F, nmax))[mask],
                  cols=cols, seen_cols=[c for c in tables[ci].columns if "seen" in c])
-        match2D._write_csv(os.path.join(output_folder, f"rods_df_{color}.csv"), color, m)
+        match2D._write_csv(os.path.join(output_folder, f"rods_df_{colors[ci]}.csv"), colors[ci], m)
         cuts = np.cumsum(n)[:-1]
-        all_repr_errs.extend(np.split(costs[:, ci][mask], cuts))
-        all_rod_lengths.extend(np.split(flat[:, 9].copy(), cuts))
+        return np.split(costs[:, ci][mask], cuts), np.split(flat[:, 9].copy(), cuts)
+
+    stored = list(pool.map(store, range(C)))
+    pool.shutdown()
+    all_repr_errs = [e for s_ in stored for e in s_[0]]
+    all_rod_lengths = [l for s_ in stored for l in s_[1]]
     return np.asarray(all_repr_errs), np.asarray(all_rod_lengths)

@@ -36,7 +36,9 @@ def main():
         errs, lens = match2D.match_csv_complex(inp, outp, data.colors, "gp1", "gp2", frames, cal, trf)
         dt = time.perf_counter() - t0
         size = sum(os.path.getsize(os.path.join(outp, f)) for f in os.listdir(outp))
-    print(json.dumps({"call": "match2D.match_csv_complex", "frames": a.frames, "colours": a.colors, "rods": a.rods,
+    st = getattr(match2D.match_csv_complex, "last_stage_seconds", {})
+    stage_ms = {k: round(1e3 * sum(v[k] for v in st.values()) / max(len(st), 1), 2) for k in ("read", "match", "write")}
+    print(json.dumps({"call": "match2D.match_csv_complex", "mean_stage_ms_per_colour": stage_ms, "frames": a.frames, "colours": a.colors, "rods": a.rods,
                       "seconds": dt, "frames_per_s": a.frames / dt, "output_MB": size / 1e6,
                       "errs_shape": list(errs.shape)}))
 
