@@ -248,42 +248,44 @@ def _assign_device(input_folder, output_folder, colors, cam1_name, cam2_name, fr
 
     # reader and writer release the GIL: colours are read / written side by side
     pool = ThreadPoolExecutor(max_workers=min(len(colors), match2D._CSV_WORKERS))
-    loaded = list(pool.map(load, colors))
-    tables, packs = [l[0] for l in loaded], [l[1] for l in loaded]
-    F, C = len(frames), len(colors)
-    nmax = max(p[0].shape[1] for p in packs)
-    c1 = np.full((F, C, nmax, 4), np.nan)
-    c2 = np.full((F, C, nmax, 4), np.nan)
-    n1 = np.zeros((F, C), dtype=np.int32)
-    n2 = np.zeros((F, C), dtype=np.int32)
-    for ci, (a, b, m1, m2, _) in enumerate(packs):
-        c1[:, ci, : a.shape[1]] = a
-        c2[:, ci, : b.shape[1]] = b
-        n1[:, ci], n2[:, ci] = m1, m2
-    dev = torch.device("cuda", torch.cuda.current_device())
-    t = lambda x: torch.from_numpy(x).to(dev)
-    rows, costs, n_rows, status, stats = engine.matchnd_sequence(rig, t(c1.reshape(F, C, nmax, 2, 2)), t(c2.reshape(F, C, nmax, 2, 2)),
-                                                                 t(n1), t(n2))
-    rows, costs, n_rows, status = rows.cpu().numpy(), costs.cpu().numpy(), n_rows.cpu().numpy(), status.cpu().numpy()
-    assign.last = dict(status=status, solver_stats=stats.cpu().numpy())
-    _raise_for_nd_status(status)
-    if (status == nat.ND_GAP).any():
-        warnings.warn(f"matchND.assign: the 3-index assignment hit its work limit in {int((status == nat.ND_GAP).sum())} "
-                      "(frame, colour) problems; their matchings are the best found, not proven optimal", NpartiteGapWarning)
-    cols = [*match2D.COLS_3D, *match2D._cam_cols(cam1_name), *match2D._cam_cols(cam2_name)]
+    try:
+        loaded = list(pool.map(load, colors))
+        tables, packs = [l[0] for l in loaded], [l[1] for l in loaded]
+        F, C = len(frames), len(colors)
+        nmax = max(p[0].shape[1] for p in packs)
+        c1 = np.full((F, C, nmax, 4), np.nan)
+        c2 = np.full((F, C, nmax, 4), np.nan)
+        n1 = np.zeros((F, C), dtype=np.int32)
+        n2 = np.zeros((F, C), dtype=np.int32)
+        for ci, (a, b, m1, m2, _) in enumerate(packs):
+            c1[:, ci, : a.shape[1]] = a
+            c2[:, ci, : b.shape[1]] = b
+            n1[:, ci], n2[:, ci] = m1, m2
+        dev = torch.device("cuda", torch.cuda.current_device())
+        t = lambda x: torch.from_numpy(x).to(dev)
+        rows, costs, n_rows, status, stats = engine.matchnd_sequence(rig, t(c1.reshape(F, C, nmax, 2, 2)), t(c2.reshape(F, C, nmax, 2, 2)),
+                                                                     t(n1), t(n2))
+        rows, costs, n_rows, status = rows.cpu().numpy(), costs.cpu().numpy(), n_rows.cpu().numpy(), status.cpu().numpy()
+        assign.last = dict(status=status, solver_stats=stats.cpu().numpy())
+        _raise_for_nd_status(status)
+        if (status == nat.ND_GAP).any():
+            warnings.warn(f"matchND.assign: the 3-index assignment hit its work limit in {int((status == nat.ND_GAP).sum())} "
+                          "(frame, colour) problems; their matchings are the best found, not proven optimal", NpartiteGapWarning)
+        cols = [*match2D.COLS_3D, *match2D._cam_cols(cam1_name), *match2D._cam_cols(cam2_name)]
 
-    def store(ci):
-        n = n_rows[:, ci]
-        mask = np.arange(nmax)[None, :] < n[:, None]
-        flat = rows[:, ci][mask]
-        m = dict(rows=flat, frame=np.repeat(np.asarray(frames), n), particle=np.broadcast_to(np.arange(nmax), (F, nmax))[mask],
-                 cols=cols, seen_cols=[c for c in tables[ci].columns if "seen" in c])
-        match2D._write_csv(os.path.join(output_folder, f"rods_df_{colors[ci]}.csv"), colors[ci], m)
-        cuts = np.cumsum(n)[:-1]
-        return np.split(costs[:, ci][mask], cuts), np.split(flat[:, 9].copy(), cuts)
+        def store(ci):
+            n = n_rows[:, ci]
+            mask = np.arange(nmax)[None, :] < n[:, None]
+            flat = rows[:, ci][mask]
+            m = dict(rows=flat, frame=np.repeat(np.asarray(frames), n), particle=np.broadcast_to(np.arange(nmax), (F, nmax))[mask],
+                     cols=cols, seen_cols=[c for c in tables[ci].columns if "seen" in c])
+            match2D._write_csv(os.path.join(output_folder, f"rods_df_{colors[ci]}.csv"), colors[ci], m)
+            cuts = np.cumsum(n)[:-1]
+            return np.split(costs[:, ci][mask], cuts), np.split(flat[:, 9].copy(), cuts)
 
-    stored = list(pool.map(store, range(C)))
-    pool.shutdown()
+        stored = list(pool.map(store, range(C)))
+    finally:
+        pool.shutdown()
     all_repr_errs = [e for s_ in stored for e in s_[0]]
     all_rod_lengths = [l for s_ in stored for l in s_[1]]
     return np.asarray(all_repr_errs), np.asarray(all_rod_lengths)
