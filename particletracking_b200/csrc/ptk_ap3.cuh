@@ -30,6 +30,8 @@ namespace ptk {
 constexpr int AP3_MAXN = 64;
 constexpr int AP3_THREADS = 1024;
 constexpr int AP3_OK = 0, AP3_GAP = 1, AP3_INVALID = 2, AP3_EMPTY = 3;
+constexpr int AP3_SG_ROUND = 300, AP3_SG_PATIENCE = 30;
+constexpr double AP3_SG_LAMBDA = 2.0;  // Polyak step factor at the start of a round (tools/ap3_proto.py: the sweep behind these three)
 
 struct Ap3Cand {
     double slack;
@@ -51,13 +53,16 @@ struct Ap3Args {
     int32_t* stats;   // [B, 4] descent steps, search nodes (saturating), candidates, proven-at-step (optional)
     Ap3Cand* cand;    // workspace [B, 2, cand_cap]
     int cand_cap;
-    int max_steps;
+    int max_steps;         // dual block-coordinate descent steps
+    int max_sg;            // subgradient iterations after the descent has stalled
     long long node_limit;
 };
 
 struct Ap3Smem {
     double cneg[AP3_MAXN * AP3_MAXN];  // LSAP cost (negated benefit), row-major, leading dimension m
     double y[3][AP3_MAXN];             // duals per axis
+    double ybest[3][AP3_MAXN];         // the duals behind the best bound so far (sum = ub)
+    int gcnt[AP3_MAXN];                // how many of the step's pairs prefer index r of the fixed axis
     double uu[AP3_MAXN], vv[AP3_MAXN], sp[AP3_MAXN];
     double ub_hist[4];
     double red[AP3_THREADS / 32];
@@ -72,8 +77,8 @@ struct Ap3Smem {
     double acc[AP3_MAXN + 1], usum[AP3_MAXN + 1], suffix[AP3_MAXN + 1];
     int pos[AP3_MAXN + 1];
     int16_t chj[AP3_MAXN + 1], chk[AP3_MAXN + 1];
-    int n_best, n_pairs, flag, total_cand;
-    double best_val, ub;
+    int n_best, n_pairs, flag, total_cand, improved, signif;
+    double best_val, ub, curL, gg;
 };
 
 __device__ __forceinline__ double ap3_inf() { return __longlong_as_double(0x7ff0000000000000LL); }
@@ -247,9 +252,18 @@ __global__ void __launch_bounds__(AP3_THREADS) k_ap3(const __grid_constant__ Ap3
     bool bad = false;
 
     int steps = 0, proven_at = -1;
-    for (int step = 0; step < a.max_steps; step++) {
+    // mode 0: descent (the fixed block cycles); mode 1: subgradient on the fixed block r_sg (Polyak
+    // steps towards the incumbent, halved after AP3_SG_PATIENCE steps without a better bound; the
+    // block changes every AP3_SG_ROUND iterations).  The descent can stall at a non-optimal dual
+    // when rows of the cube are identical (the detector's dummy rods); the subgradient phase does
+    // not, and every iteration is the same reduction + 2-D assignment, so the incumbent heuristics
+    // keep running on its duals.
+    int mode = 0, r_sg = 0, sg_it = 0, since = 0;
+    double lam = 1.0;
+    const int max_iter = a.max_steps + a.max_sg;
+    for (int step = 0; step < max_iter; step++) {
         // axis r is the fixed block, (p, q) the two that are re-optimised
-        const int r = step % 3, p = r == 0 ? 1 : 0, q = r == 2 ? 1 : 2;
+        const int r = mode == 0 ? step % 3 : r_sg, p = r == 0 ? 1 : 0, q = r == 2 ? 1 : 2;
         const int np = n[p], nq = n[q], nr = n[r];
         const int m = max(np, nq);
         // ---- c[p,q] = max(0, max_r (w - y_r)), stored negated, padded with zeros to m x m
@@ -300,7 +314,12 @@ __global__ void __launch_bounds__(AP3_THREADS) k_ap3(const __grid_constant__ Ap3
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            for (int j = lane; j < AP3_MAXN; j += 32) s.gcnt[j] = 0;
+            __syncwarp();
             if (lane == 0) {
+                s.curL = sum;
+                s.improved = sum < s.ub;
+                s.signif = sum < s.ub - 1e-13 * fabs(sum);
                 s.ub = fmin(s.ub, sum);
                 int np_ = 0, nt = 0;
                 unsigned long long used = 0ull;
@@ -316,6 +335,7 @@ __global__ void __launch_bounds__(AP3_THREADS) k_ap3(const __grid_constant__ Ap3
                     // pairs are a feasible solution as they stand (w = c + y up to rounding)
                     const int ar = s.argr[ip * m + iq];
                     if (ar == 255) continue;
+                    s.gcnt[ar]++;
                     if ((used >> ar) & 1ull) distinct = false;
                     used |= 1ull << ar;
                     v += -s.cneg[ip * m + iq] + s.y[r][ar];
@@ -329,8 +349,16 @@ __global__ void __launch_bounds__(AP3_THREADS) k_ap3(const __grid_constant__ Ap3
                     s.best_val = v;
                 }
             }
+            __syncwarp();
+            double gg = 0.0;  // squared norm of the subgradient 1 - gcnt over the fixed axis
+            for (int j = lane; j < nr; j += 32) { const double g = 1.0 - (double)s.gcnt[j]; gg += g * g; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) gg += __shfl_xor_sync(0xffffffffu, gg, o);
+            if (lane == 0) s.gg = gg;
         }
         __syncthreads();
+        if (s.improved)
+            for (int t = tid; t < 3 * AP3_MAXN; t += AP3_THREADS) s.ybest[t / AP3_MAXN][t % AP3_MAXN] = s.y[t / AP3_MAXN][t % AP3_MAXN];
         // ---- complete the pairs over axis r: second assignment on max(w[r, pair], 0)
         const int K = s.n_pairs;
         if (s.ub - s.best_val <= eps) {
@@ -380,11 +408,41 @@ __global__ void __launch_bounds__(AP3_THREADS) k_ap3(const __grid_constant__ Ap3
         // ---- stop rules (uniform: everything read from shared memory)
         const double gap = s.ub - s.best_val;
         if (gap <= eps) { proven_at = step; break; }
-        const double prev3 = s.ub_hist[(step + 1) & 3];  // bound three steps ago (INF until then)
+        bool restore = false;
+        if (mode == 0) {
+            const double prev3 = s.ub_hist[(step + 1) & 3];  // bound three steps ago (INF until then)
+            __syncthreads();
+            if (tid == 0) s.ub_hist[step & 3] = s.ub;
+            __syncthreads();
+            const bool stalled = step >= 5 && !(prev3 - s.ub > 1e-13 * fabs(s.ub) + eps);  // one full cycle without progress
+            if (!stalled && step + 1 < a.max_steps) continue;
+            if (a.max_sg <= 0) break;
+            mode = 1; r_sg = r; lam = AP3_SG_LAMBDA; since = 0; sg_it = 0;  // this step doubles as the first subgradient iteration
+        } else {
+            since = s.signif ? 0 : since + 1;
+            sg_it++;
+            if (sg_it >= a.max_sg || lam < AP3_SG_LAMBDA / 1024.0 || gap <= 1e-10 * fabs(s.ub)) break;
+            if (sg_it % AP3_SG_ROUND == 0) { r_sg = (r_sg + 1) % 3; lam = AP3_SG_LAMBDA; since = 0; restore = true; }
+            else if (since >= AP3_SG_PATIENCE) { lam *= 0.5; since = 0; restore = true; }
+        }
+        if (restore || !(s.gg > 0.0)) {
+            if (!restore) lam *= 0.5;  // every index of the fixed axis used once, yet a gap: rounding of c; shrink and go on
+            __syncthreads();
+            for (int t = tid; t < 3 * AP3_MAXN; t += AP3_THREADS) s.y[t / AP3_MAXN][t % AP3_MAXN] = s.ybest[t / AP3_MAXN][t % AP3_MAXN];
+            __syncthreads();
+            continue;
+        }
+        {
+            const double tstep = lam * (s.curL - s.best_val) / s.gg;
+            __syncthreads();
+            for (int j = tid; j < nr; j += AP3_THREADS) s.y[r][j] = fmax(0.0, s.y[r][j] - tstep * (1.0 - (double)s.gcnt[j]));
+            __syncthreads();
+        }
+    }
+    if (proven_at < 0) {  // the search below works on the duals of the best bound
         __syncthreads();
-        if (tid == 0) s.ub_hist[step & 3] = s.ub;
+        for (int t = tid; t < 3 * AP3_MAXN; t += AP3_THREADS) s.y[t / AP3_MAXN][t % AP3_MAXN] = s.ybest[t / AP3_MAXN][t % AP3_MAXN];
         __syncthreads();
-        if (step >= 5 && !(prev3 - s.ub > 1e-13 * fabs(s.ub) + eps)) break;  // one full cycle without progress
     }
 
     int status = AP3_OK;

@@ -683,7 +683,8 @@ PTK_API int ptk_create_weights(int Np, int N1, int N2, const double* p_3D, const
 }
 
 // ------------------------------------------------------------------------------------ K10
-static const int kAp3CandCap = 32768;
+static const int kAp3CandCap = 32768, kAp3Steps = 60, kAp3Subgradient = 1200;
+static const long long kAp3Nodes = 20000000LL;
 PTK_API int ptk_npartite3_batch(int B, int D0, int D1, int D2, const double* weights, const int32_t* n0, const int32_t* n1,
                                 const int32_t* n2, int32_t* sol, int32_t* n_sol, double* value, double* bound,
                                 int32_t* status, int32_t* stats, int max_steps, long long node_limit, void* workspace,
@@ -702,8 +703,9 @@ PTK_API int ptk_npartite3_batch(int B, int D0, int D1, int D2, const double* wei
     a.sol = sol; a.n_sol = n_sol; a.value = value; a.bound = bound; a.status = status; a.stats = stats;
     a.cand = reinterpret_cast<Ap3Cand*>(align_up((size_t)workspace));
     a.cand_cap = kAp3CandCap;
-    a.max_steps = max_steps > 0 ? max_steps : 60;
-    a.node_limit = node_limit > 0 ? node_limit : 20000000LL;
+    a.max_steps = max_steps > 0 ? max_steps : kAp3Steps;
+    a.max_sg = kAp3Subgradient;
+    a.node_limit = node_limit > 0 ? node_limit : kAp3Nodes;
     static_assert(sizeof(Ap3Smem) <= 48 * 1024, "k_ap3 shared memory");
     cudaStream_t st = (cudaStream_t)stream;
     LaunchTimer tm(K_AP3, st);
@@ -822,7 +824,7 @@ PTK_API int ptk_matchnd_sequence(const ptk_rig* rig, int F, int C, int Nmax, con
         s.n0 = a.prev_n; s.n1 = m1; s.n2 = m2;
         s.sol = w.sol; s.n_sol = w.n_sol; s.value = w.value; s.bound = w.bound; s.status = w.ap3_status;
         s.stats = w.stats;
-        s.cand = w.cand; s.cand_cap = kAp3CandCap; s.max_steps = 60; s.node_limit = 20000000LL;
+        s.cand = w.cand; s.cand_cap = kAp3CandCap; s.max_steps = kAp3Steps; s.max_sg = kAp3Subgradient; s.node_limit = kAp3Nodes;
         {
             LaunchTimer lt(K_AP3, st);
             k_ap3<<<C, AP3_THREADS, sizeof(Ap3Smem), st>>>(s);

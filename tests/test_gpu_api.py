@@ -190,7 +190,8 @@ def test_matchnd_weights_and_block(api, rig):
     ew, ech = port.create_weights(ref["p_world"], prev, ref["rep_errs"])
     np.testing.assert_array_equal(ch, ech)
     assert rel_err(w, ew) < 1e-8  # products of two 1e-9-accurate factors
-    with pytest.raises(NotImplementedError):
+    # a previous frame without 3D columns gives NaN weights: refused, never solved silently
+    with pytest.raises(ValueError):
         mnd.match_frame(df, df, "gp1", "gp2", 1, "black", *_args(rig))
 
 
