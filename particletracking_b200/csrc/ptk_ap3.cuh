@@ -31,6 +31,7 @@ constexpr int AP3_MAXN = 64;
 constexpr int AP3_THREADS = 1024;
 constexpr int AP3_OK = 0, AP3_GAP = 1, AP3_INVALID = 2, AP3_EMPTY = 3;
 constexpr int AP3_SG_ROUND = 300, AP3_SG_PATIENCE = 30;
+constexpr double AP3_SG_DEFLECT = 0.7;
 constexpr double AP3_SG_LAMBDA = 2.0;  // Polyak step factor at the start of a round (tools/ap3_proto.py: the sweep behind these three)
 
 struct Ap3Cand {
@@ -63,6 +64,8 @@ struct Ap3Smem {
     double y[3][AP3_MAXN];             // duals per axis
     double ybest[3][AP3_MAXN];         // the duals behind the best bound so far (sum = ub)
     int gcnt[AP3_MAXN];                // how many of the step's pairs prefer index r of the fixed axis
+    double dir[AP3_MAXN];              // deflected subgradient direction on the fixed axis
+    int dir_valid;
     double uu[AP3_MAXN], vv[AP3_MAXN], sp[AP3_MAXN];
     double ub_hist[4];
     double red[AP3_THREADS / 32];
@@ -244,6 +247,7 @@ __global__ void __launch_bounds__(AP3_THREADS) k_ap3(const __grid_constant__ Ap3
         s.n_best = 0;
         s.ub = INF;
         s.flag = 0;
+        s.dir_valid = 0;
         for (int q = 0; q < 4; q++) s.ub_hist[q] = INF;
     }
     for (int t = tid; t < 3 * AP3_MAXN; t += AP3_THREADS) s.y[t / AP3_MAXN][t % AP3_MAXN] = 0.0;
@@ -350,8 +354,16 @@ __global__ void __launch_bounds__(AP3_THREADS) k_ap3(const __grid_constant__ Ap3
                 }
             }
             __syncwarp();
-            double gg = 0.0;  // squared norm of the subgradient 1 - gcnt over the fixed axis
-            for (int j = lane; j < nr; j += 32) { const double g = 1.0 - (double)s.gcnt[j]; gg += g * g; }
+            // subgradient 1 - gcnt over the fixed axis, deflected by the previous direction
+            // (Camerini-Fratta-Maffioli: damps the zig-zag that otherwise leaves some cubes unconverged)
+            double gg = 0.0;
+            const double beta = s.dir_valid ? AP3_SG_DEFLECT : 0.0;
+            for (int j = lane; j < nr; j += 32) {
+                double g = 1.0 - (double)s.gcnt[j];
+                if (beta != 0.0) g += beta * s.dir[j];
+                s.dir[j] = g;
+                gg += g * g;
+            }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) gg += __shfl_xor_sync(0xffffffffu, gg, o);
             if (lane == 0) s.gg = gg;
@@ -427,6 +439,7 @@ __global__ void __launch_bounds__(AP3_THREADS) k_ap3(const __grid_constant__ Ap3
         }
         if (restore || !(s.gg > 0.0)) {
             if (!restore) lam *= 0.5;  // every index of the fixed axis used once, yet a gap: rounding of c; shrink and go on
+            if (restore && tid == 0) s.dir_valid = 0;
             __syncthreads();
             for (int t = tid; t < 3 * AP3_MAXN; t += AP3_THREADS) s.y[t / AP3_MAXN][t % AP3_MAXN] = s.ybest[t / AP3_MAXN][t % AP3_MAXN];
             __syncthreads();
@@ -435,7 +448,8 @@ __global__ void __launch_bounds__(AP3_THREADS) k_ap3(const __grid_constant__ Ap3
         {
             const double tstep = lam * (s.curL - s.best_val) / s.gg;
             __syncthreads();
-            for (int j = tid; j < nr; j += AP3_THREADS) s.y[r][j] = fmax(0.0, s.y[r][j] - tstep * (1.0 - (double)s.gcnt[j]));
+            for (int j = tid; j < nr; j += AP3_THREADS) s.y[r][j] = fmax(0.0, s.y[r][j] - tstep * s.dir[j]);
+            if (tid == 0) s.dir_valid = 1;
             __syncthreads();
         }
     }

@@ -684,7 +684,7 @@ PTK_API int ptk_create_weights(int Np, int N1, int N2, const double* p_3D, const
 
 // ------------------------------------------------------------------------------------ K10
 static const int kAp3CandCap = 32768, kAp3Steps = 60, kAp3Subgradient = 1200;
-static const long long kAp3Nodes = 20000000LL;
+static const long long kAp3Nodes = 2000000LL;
 PTK_API int ptk_npartite3_batch(int B, int D0, int D1, int D2, const double* weights, const int32_t* n0, const int32_t* n1,
                                 const int32_t* n2, int32_t* sol, int32_t* n_sol, double* value, double* bound,
                                 int32_t* status, int32_t* stats, int max_steps, long long node_limit, void* workspace,

@@ -97,6 +97,53 @@ def test_batch_with_ragged_sizes_and_flags(gpu):
         assert n == min(n0[b], n1[b], n2[b]) and onp.is_feasible(w.shape, r.sol[b, :, :n].cpu().numpy())
 
 
+def _rod_optima():
+    with open(os.path.join(GOLDEN, "ap3_rod_optima.json")) as f:
+        return json.load(f)
+
+
+def test_dropped_and_dummy_detections_batch(gpu):
+    """Cubes from frames with dropped and dummy (-1,-1,-1,-1) detections: identical rows / columns make
+    the dual descent stall, the subgradient phase has to close the bound.  All sizes differ, so they go
+    through one ragged batch; optima are HiGHS's (tools/ap3_optima.py)."""
+    from oracle import npartite as onp
+    from tools.ap3_check import rod_weights
+
+    torch, engine = gpu
+    table = _rod_optima()
+    names = ["d16_0", "d16_1", "d32_1", "dd25_1", "drop16_2", "e24_0", "e24_4", "e32_1", "e32_2", "e32_4"]
+    cubes = [rod_weights(**table[k]["args"]) for k in names]
+    D = max(max(c.shape) for c in cubes)
+    W = np.zeros((len(cubes), D, D, D))
+    n = np.zeros((3, len(cubes)), np.int32)
+    for b, c in enumerate(cubes):
+        W[b, : c.shape[0], : c.shape[1], : c.shape[2]] = c
+        n[:, b] = c.shape
+    r = engine.npartite3_batch(torch.from_numpy(W).cuda(), *(torch.from_numpy(x.copy()).cuda() for x in n))
+    for b, (k, c) in enumerate(zip(names, cubes)):
+        ref = table[k]["milp"]
+        ns = int(r.n_sol[b])
+        sol = r.sol[b, :, :ns].cpu().numpy()
+        assert int(r.status[b]) == 0, (k, r.stats[b].tolist())
+        assert onp.is_feasible(c.shape, sol) and ns == min(c.shape)
+        assert abs(float(r.value[b]) - ref) <= 1e-9 * abs(ref), (k, float(r.value[b]) - ref)
+        assert abs(onp.objective(c, sol) - float(r.value[b])) <= 1e-9 * abs(ref)
+        assert float(r.bound[b]) >= ref * (1 - 1e-12)
+
+
+def test_integrality_gap_is_reported(gpu):
+    """e32_5: the LP relaxation of this cube is 306 above the integer optimum, so no dual can prove
+    it and the reduced-cost search runs into its node limit: the (here optimal) incumbent comes back
+    with status GAP and value <= optimum <= bound."""
+    from tools.ap3_check import rod_weights
+
+    rec = _rod_optima()["e32_5"]
+    r = _solve(gpu, rod_weights(**rec["args"]), node_limit=100000)
+    assert int(r.status[0]) in (0, 1)
+    assert float(r.value[0]) <= rec["milp"] * (1 + 1e-12) <= float(r.bound[0]) * (1 + 1e-12)
+    assert float(r.value[0]) >= rec["milp"] - 400.0  # within the LP gap
+
+
 def test_work_limit_is_reported_not_hidden(gpu):
     from oracle import npartite as onp
 
