@@ -207,8 +207,8 @@ __device__ __forceinline__ void jacobi_pair_always(double (&Ai)[4], double (&Aj)
 // instead of 16 per rotation (~220), and 32 fewer live registers; measured agreement with the
 // V-accumulating Jacobi on 327 680 combinations incl. dummy rods: max 1.0e-15 relative on the
 // triangulated point (profiles/experiments/jacobi_no_v.c).
-__device__ __forceinline__ void dlt_triangulate(const DevRig& rig, double x1, double y1, double x2, double y2,
-                                                double& X, double& Y, double& Z, int* n_rot = nullptr)
+__device__ __forceinline__ void dlt_triangulate_jacobi(const DevRig& rig, double x1, double y1, double x2, double y2,
+                                                       double& X, double& Y, double& Z, int* n_rot = nullptr)
 {
     const double* __restrict__ P1 = rig.P1;
     const double* __restrict__ P2 = rig.P2;
@@ -311,6 +311,173 @@ __device__ __forceinline__ void dlt_triangulate(const DevRig& rig, double x1, do
     X = vx * rw;
     Y = vy * rw;
     Z = vz * rw;
+}
+
+// ---------------------------------------------------------------------------------------
+// The same null vector without any SVD iteration: QR + inverse power by repeated squaring.
+//
+//   A = Q R (modified Gram-Schmidt on the 4 columns),  S = R^-1 (upper triangular),
+//   B = S S^T = (A^T A)^-1 = V diag(1/sigma_k^2) V^T.
+// The wanted right singular vector v_4 (smallest sigma) is the DOMINANT eigenvector of B, and
+// on DLT matrices it dominates strongly: rho = (sigma_4/sigma_3)^2 is 0.005 in the median and
+// below 0.07 for every rod pair of the synthetic and the reference's example data (mis-paired
+// rods and end points included; profiles/experiments/dlt_invpower.py).  Three symmetric
+// squarings give B^8, one more product with its largest-diagonal column gives B^16 e_j, in which
+// every other direction is down by rho^16 < 1e-18: v_4 to rounding accuracy in ~340 straight-line
+// FP64 instructions, against ~790 for the Jacobi above, with no data-dependent trip count (no
+// warp divergence).  Forming S S^T is harmless here although it squares the spectrum: rounding
+// errors are relative to |B| = 1/sigma_4^2, i.e. to the eigenvalue that is wanted, not to the
+// large singular values as they would be in A^T A.  R itself comes from a backward-stable QR of A
+// (not of A^T A), so the vector is as accurate as the one-sided Jacobi's: max 1.8e-15 relative on
+// the triangulated point against cv2.triangulatePoints over 1.1 M combinations.
+//
+// Convergence is CHECKED, not assumed: with C = B^8 / tr(B^8), 1 - tr(C^2) ~ 2 rho^8.  A point
+// with rho^8 > 2.5e-7 (sigma_4/sigma_3 > 0.39: near-degenerate geometry), or whose R is singular
+// (NaN), reports false and the caller falls back to the Jacobi, which reproduces OpenCV there.
+// ---------------------------------------------------------------------------------------
+#define PTK_INVPOWER_TOL 5e-7
+
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ double ptk_rsqrt(double x) { return rsqrt_refine(x, rsqrt_seed(x)); }
+// 2^-floor(log2 x) for finite positive x (garbage otherwise: caught by the convergence check)
+__device__ __forceinline__ double ptk_pow2_inv(double x)
+{
+    const int e = (__double2hiint(x) >> 20) & 0x7ff;
+    return __hiloint2double((2046 - e) << 20, 0);
+}
+#define PTK_HD __host__ __device__ __forceinline__
+#else
+static inline double ptk_rsqrt(double x) { return 1.0 / sqrt(x); }
+static inline double ptk_pow2_inv(double x)
+{
+    int e;
+    frexp(x, &e);
+    return ldexp(1.0, 1 - e);
+}
+#define PTK_HD __host__ __device__ inline
+#endif
+
+// P1o, P2o: 3x4 row-major projection matrices in the caller's column order.  v: the null vector
+// (any scale).  Returns whether the power iteration has converged.
+PTK_HD bool dlt_null_invpower(const double* __restrict__ Q1, const double* __restrict__ Q2, double x1, double y1,
+                              double x2, double y2, double (&v)[4])
+{
+    double a0[4], a1[4], a2[4], a3[4];
+#define PTK_COL(Ak, k)                      \
+    Ak[0] = fma(x1, Q1[8 + k], -Q1[0 + k]); \
+    Ak[1] = fma(y1, Q1[8 + k], -Q1[4 + k]); \
+    Ak[2] = fma(x2, Q2[8 + k], -Q2[0 + k]); \
+    Ak[3] = fma(y2, Q2[8 + k], -Q2[4 + k]);
+    PTK_COL(a0, 0) PTK_COL(a1, 1) PTK_COL(a2, 2) PTK_COL(a3, 3)
+#undef PTK_COL
+#define PTK_DOT(x, y) fma(x[3], y[3], fma(x[2], y[2], fma(x[1], y[1], x[0] * y[0])))
+#define PTK_AXPY(y, r, q) { y[0] = fma(-r, q[0], y[0]); y[1] = fma(-r, q[1], y[1]); y[2] = fma(-r, q[2], y[2]); y[3] = fma(-r, q[3], y[3]); }
+#define PTK_SCAL(q, s) { q[0] *= s; q[1] *= s; q[2] *= s; q[3] *= s; }
+    // modified Gram-Schmidt; i_k = 1/r_kk
+    const double i0 = ptk_rsqrt(PTK_DOT(a0, a0));
+    PTK_SCAL(a0, i0)
+    const double r01 = PTK_DOT(a0, a1), r02 = PTK_DOT(a0, a2), r03 = PTK_DOT(a0, a3);
+    PTK_AXPY(a1, r01, a0) PTK_AXPY(a2, r02, a0) PTK_AXPY(a3, r03, a0)
+    const double i1 = ptk_rsqrt(PTK_DOT(a1, a1));
+    PTK_SCAL(a1, i1)
+    const double r12 = PTK_DOT(a1, a2), r13 = PTK_DOT(a1, a3);
+    PTK_AXPY(a2, r12, a1) PTK_AXPY(a3, r13, a1)
+    const double i2 = ptk_rsqrt(PTK_DOT(a2, a2));
+    PTK_SCAL(a2, i2)
+    const double r23 = PTK_DOT(a2, a3);
+    PTK_AXPY(a3, r23, a2)
+    const double i3 = ptk_rsqrt(PTK_DOT(a3, a3));
+#undef PTK_DOT
+#undef PTK_AXPY
+#undef PTK_SCAL
+    // S = R^-1
+    const double s01 = -(r01 * i1) * i0;
+    const double s12 = -(r12 * i2) * i1;
+    const double s23 = -(r23 * i3) * i2;
+    const double s02 = -fma(r01, s12, r02 * i2) * i0;
+    const double s13 = -fma(r12, s23, r13 * i3) * i1;
+    const double s03 = -fma(r01, s13, fma(r02, s23, r03 * i3)) * i0;
+    // B = S S^T, scaled by a power of two so that 1 <= tr(B) < 2 (then B^16 stays within 2^-32 .. 2^16)
+    double b00 = fma(s03, s03, fma(s02, s02, fma(s01, s01, i0 * i0)));
+    double b01 = fma(s03, s13, fma(s02, s12, s01 * i1));
+    double b02 = fma(s03, s23, s02 * i2);
+    double b03 = s03 * i3;
+    double b11 = fma(s13, s13, fma(s12, s12, i1 * i1));
+    double b12 = fma(s13, s23, s12 * i2);
+    double b13 = s13 * i3;
+    double b22 = fma(s23, s23, i2 * i2);
+    double b23 = s23 * i3;
+    double b33 = i3 * i3;
+    {
+        const double sc = ptk_pow2_inv((b00 + b11) + (b22 + b33));
+        b00 *= sc; b01 *= sc; b02 *= sc; b03 *= sc; b11 *= sc;
+        b12 *= sc; b13 *= sc; b22 *= sc; b23 *= sc; b33 *= sc;
+    }
+#pragma unroll
+    for (int sq = 0; sq < 3; sq++) {
+        const double c00 = fma(b03, b03, fma(b02, b02, fma(b01, b01, b00 * b00)));
+        const double c01 = fma(b03, b13, fma(b02, b12, fma(b01, b11, b00 * b01)));
+        const double c02 = fma(b03, b23, fma(b02, b22, fma(b01, b12, b00 * b02)));
+        const double c03 = fma(b03, b33, fma(b02, b23, fma(b01, b13, b00 * b03)));
+        const double c11 = fma(b13, b13, fma(b12, b12, fma(b11, b11, b01 * b01)));
+        const double c12 = fma(b13, b23, fma(b12, b22, fma(b11, b12, b01 * b02)));
+        const double c13 = fma(b13, b33, fma(b12, b23, fma(b11, b13, b01 * b03)));
+        const double c22 = fma(b23, b23, fma(b22, b22, fma(b12, b12, b02 * b02)));
+        const double c23 = fma(b23, b33, fma(b22, b23, fma(b12, b13, b02 * b03)));
+        const double c33 = fma(b33, b33, fma(b23, b23, fma(b13, b13, b03 * b03)));
+        b00 = c00; b01 = c01; b02 = c02; b03 = c03; b11 = c11;
+        b12 = c12; b13 = c13; b22 = c22; b23 = c23; b33 = c33;
+    }
+    // converged?  |B^8|_F^2 >= (1 - tol) tr(B^8)^2
+    const double tr = (b00 + b11) + (b22 + b33);
+    const double od = fma(b23, b23, fma(b13, b13, fma(b12, b12, fma(b03, b03, fma(b02, b02, b01 * b01)))));
+    const double fr = fma(2.0, od, fma(b33, b33, fma(b22, b22, fma(b11, b11, b00 * b00))));
+    const bool ok = fr >= (1.0 - PTK_INVPOWER_TOL) * (tr * tr);
+    // v = B^8 (column of B^8 with the largest diagonal entry: |v_4[j]|^2 >= 1/4 there)
+    double u0 = b00, u1 = b01, u2 = b02, u3 = b03, dm = b00;
+    if (b11 > dm) { dm = b11; u0 = b01; u1 = b11; u2 = b12; u3 = b13; }
+    if (b22 > dm) { dm = b22; u0 = b02; u1 = b12; u2 = b22; u3 = b23; }
+    if (b33 > dm) { u0 = b03; u1 = b13; u2 = b23; u3 = b33; }
+    v[0] = fma(b03, u3, fma(b02, u2, fma(b01, u1, b00 * u0)));
+    v[1] = fma(b13, u3, fma(b12, u2, fma(b11, u1, b01 * u0)));
+    v[2] = fma(b23, u3, fma(b22, u2, fma(b12, u1, b02 * u0)));
+    v[3] = fma(b33, u3, fma(b23, u2, fma(b13, u1, b03 * u0)));
+    return ok;
+}
+
+// The Jacobi as an out-of-line call: only points whose inverse power iteration did not converge
+// get here, so its 80 registers must not set the register budget of the callers.
+__device__ __noinline__ void dlt_triangulate_fallback(const DevRig& rig, double x1, double y1, double x2, double y2,
+                                                      double* __restrict__ xyz)
+{
+    double X, Y, Z;
+    dlt_triangulate_jacobi(rig, x1, y1, x2, y2, X, Y, Z);
+    xyz[0] = X;
+    xyz[1] = Y;
+    xyz[2] = Z;
+}
+
+// cv2.triangulatePoints for one point (match2D.py:889) + p[0:3]/p[3] (match2D.py:895).
+__device__ __forceinline__ void dlt_triangulate(const DevRig& rig, double x1, double y1, double x2, double y2,
+                                                double& X, double& Y, double& Z)
+{
+#ifdef PTK_DLT_JACOBI  // A/B switch (tools/ab_bench.py): the one-sided Jacobi for every point
+    dlt_triangulate_jacobi(rig, x1, y1, x2, y2, X, Y, Z);
+#else
+    double v[4];
+    if (dlt_null_invpower(rig.P1o, rig.P2o, x1, y1, x2, y2, v)) {
+        const double rw = fast_rcp(v[3]);
+        X = v[0] * rw;
+        Y = v[1] * rw;
+        Z = v[2] * rw;
+    } else {
+        double xyz[3];
+        dlt_triangulate_fallback(rig, x1, y1, x2, y2, xyz);
+        X = xyz[0];
+        Y = xyz[1];
+        Z = xyz[2];
+    }
+#endif
 }
 
 // cv2.projectPoints for one point (match2D.py:898-903)
