@@ -572,6 +572,32 @@ def test_random_rigs_vs_c_oracle(eng, seed):
                 assert rel_err(rows[p, k, s], o["rows"][p, k, s]) < TOL
 
 
+@pytest.mark.parametrize("scale", [2e-3, 1e-3])
+def test_near_degenerate_rig_takes_jacobi_fallback(eng, scale):
+    """A stereo rig whose baseline is shrunk to (almost) nothing: sigma_4/sigma_3 of the DLT matrices
+    is above 0.39 for 15 % (scale 2e-3) or 44 % (1e-3) of the end-point combinations, so K1's inverse
+    power iteration reports "not converged" there and the one-sided Jacobi (OpenCV's algorithm) takes
+    over per thread.  Mixed warps must give what the C oracle (OpenCV's Jacobi for every point) gives;
+    profiles/experiments/dlt_invpower.py counts the fallbacks for this geometry on the CPU."""
+    from oracle import c_oracle as co
+    from particletracking_b200 import rig as rigmod
+    from particletracking_b200 import synthetic as syn
+
+    cal = dict(syn.synthetic_calibration())
+    cal["R"] = np.eye(3)
+    cal["T"] = np.asarray(cal["T"], dtype=np.float64) * scale
+    r = rigmod.rig_from_dicts(cal, syn.synthetic_transformation())
+    data = syn.make_stereo(2, 2, 24, seed=77)  # detections of the ordinary rig: geometrically inconsistent here
+    c1, c2, n1, n2 = data.problems()
+    o = co.match_batch(r, c1, c2, n1, n2, want_cost=True)
+    g = run_match(eng, r, c1, c2, n1, n2, want_cost=True)
+    np.testing.assert_array_equal(g.status.cpu().numpy(), o["status"])
+    cost = g.cost.cpu().numpy()
+    # ill-conditioned null vectors: both sides lose digits with 1/(1 - sigma_4/sigma_3)
+    assert rel_err(cost, o["cost"]) < 1e-7
+    np.testing.assert_array_equal(g.col_ind.cpu().numpy(), o["col_ind"])
+
+
 @pytest.mark.parametrize("C,F,N", [(1, 4, 100), (2, 3, 128), (1, 3, 256), (2, 5, 65)])
 def test_tracking_on_the_fly_large_n(eng, C, F, N):
     """N > 64: the tracking LSAP evaluates costs on the fly from the end points (no cost matrix).
