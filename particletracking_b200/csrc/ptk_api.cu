@@ -1128,13 +1128,25 @@ PTK_API int ptk_reconstruct_host(ptk_ctx* c, const ptk_rig* rig, int F, int C, i
     const size_t n4 = (size_t)Nmax * 4 * sizeof(double), n18 = (size_t)Nmax * PTK_ROW_COLS * sizeof(double);
     const size_t nd = (size_t)Nmax * sizeof(double), ni = (size_t)Nmax * sizeof(int32_t);
 
-    // frames per chunk: ~2048 problems, at most 32 chunks
+    // frames per chunk: ~2048 problems, at most 32 full chunks.  The first chunks are smaller
+    // (1/8, 1/4, 1/2 of a full one): the very first host-to-device copy is the one transfer no
+    // kernel can hide, so it is kept short and the pipeline ramps up behind it.
     const char* ce = getenv("PTK_HOST_CHUNK");  // tuning knob (problems per chunk)
     const int want = ce ? atoi(ce) : 2048;
     int fchunk = ((want > 0 ? want : 2048) + C - 1) / C;
     if ((F + fchunk - 1) / fchunk > 32) fchunk = (F + 31) / 32;
-    const int nchunks = (F + fchunk - 1) / fchunk;
     const long long pchunk = (long long)fchunk * C;
+    int chunk_f0[40], nchunks = 0;
+    {
+        const char* re = getenv("PTK_HOST_RAMP");  // 0 disables the ramp (A/B)
+        int f = 0, step = (re && atoi(re) == 0) ? fchunk : (fchunk + 7) / 8;
+        while (f < F) {
+            chunk_f0[nchunks++] = f;
+            f += step;
+            step = step * 2 < fchunk ? step * 2 : fchunk;
+        }
+        chunk_f0[nchunks] = F;
+    }
 
     int rc;
     if ((rc = c->cam1.ensure(P * n4))) return rc;
@@ -1172,8 +1184,8 @@ PTK_API int ptk_reconstruct_host(ptk_ctx* c, const ptk_rig* rig, int F, int C, i
     }
 
     for (int k = 0; k < nchunks; k++) {
-        const int f0 = k * fchunk;
-        const int fn = (F - f0) < fchunk ? (F - f0) : fchunk;
+        const int f0 = chunk_f0[k];
+        const int fn = chunk_f0[k + 1] - f0;
         const long long p0 = (long long)f0 * C, np = (long long)fn * C;
         // H2D
         CK(cudaMemcpyAsync(c->cam1.as<char>() + p0 * n4, (const char*)cam1 + p0 * n4, np * n4, cudaMemcpyHostToDevice, c->s_in));

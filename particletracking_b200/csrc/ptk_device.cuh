@@ -317,7 +317,7 @@ __device__ __forceinline__ void dlt_triangulate_jacobi(const DevRig& rig, double
 // The same null vector without any SVD iteration: QR + inverse power by repeated squaring.
 //
 //   A = Q R (modified Gram-Schmidt on the 4 columns),  S = R^-1 (upper triangular),
-//   B = S S^T = (A^T A)^-1 = V diag(1/sigma_k^2) V^T.
+//   B = S S^T = (A^T A)^-1 = V diag(1/sigma_k^2) V^T   (formed without square roots, see below).
 // The wanted right singular vector v_4 (smallest sigma) is the DOMINANT eigenvector of B, and
 // on DLT matrices it dominates strongly: rho = (sigma_4/sigma_3)^2 is 0.005 in the median and
 // below 0.07 for every rod pair of the synthetic and the reference's example data (mis-paired
@@ -339,6 +339,7 @@ __device__ __forceinline__ void dlt_triangulate_jacobi(const DevRig& rig, double
 
 #if defined(__CUDA_ARCH__)
 __device__ __forceinline__ double ptk_rsqrt(double x) { return rsqrt_refine(x, rsqrt_seed(x)); }
+__device__ __forceinline__ double ptk_rcp(double x) { return fast_rcp(x); }
 // 2^-floor(log2 x) for finite positive x (garbage otherwise: caught by the convergence check)
 __device__ __forceinline__ double ptk_pow2_inv(double x)
 {
@@ -348,6 +349,7 @@ __device__ __forceinline__ double ptk_pow2_inv(double x)
 #define PTK_HD __host__ __device__ __forceinline__
 #else
 static inline double ptk_rsqrt(double x) { return 1.0 / sqrt(x); }
+static inline double ptk_rcp(double x) { return 1.0 / x; }
 static inline double ptk_pow2_inv(double x)
 {
     int e;
@@ -372,42 +374,40 @@ PTK_HD bool dlt_null_invpower(const double* __restrict__ Q1, const double* __res
 #undef PTK_COL
 #define PTK_DOT(x, y) fma(x[3], y[3], fma(x[2], y[2], fma(x[1], y[1], x[0] * y[0])))
 #define PTK_AXPY(y, r, q) { y[0] = fma(-r, q[0], y[0]); y[1] = fma(-r, q[1], y[1]); y[2] = fma(-r, q[2], y[2]); y[3] = fma(-r, q[3], y[3]); }
-#define PTK_SCAL(q, s) { q[0] *= s; q[1] *= s; q[2] *= s; q[3] *= s; }
-    // modified Gram-Schmidt; i_k = 1/r_kk
-    const double i0 = ptk_rsqrt(PTK_DOT(a0, a0));
-    PTK_SCAL(a0, i0)
-    const double r01 = PTK_DOT(a0, a1), r02 = PTK_DOT(a0, a2), r03 = PTK_DOT(a0, a3);
+    // modified Gram-Schmidt WITHOUT normalising: q_k = a_k^(k) (orthogonal, |q_k|^2 = n_k),
+    // A = Q~ R~ with R~ unit upper triangular, r~_kj = (q_k . a_j) / n_k.  Then
+    // (A^T A)^-1 = T diag(1/n_k) T^T with T = R~^-1 (unit upper triangular): no square root anywhere,
+    // four reciprocals w_k = 1/n_k.
+    const double w0 = ptk_rcp(PTK_DOT(a0, a0));
+    const double r01 = PTK_DOT(a0, a1) * w0, r02 = PTK_DOT(a0, a2) * w0, r03 = PTK_DOT(a0, a3) * w0;
     PTK_AXPY(a1, r01, a0) PTK_AXPY(a2, r02, a0) PTK_AXPY(a3, r03, a0)
-    const double i1 = ptk_rsqrt(PTK_DOT(a1, a1));
-    PTK_SCAL(a1, i1)
-    const double r12 = PTK_DOT(a1, a2), r13 = PTK_DOT(a1, a3);
+    const double w1 = ptk_rcp(PTK_DOT(a1, a1));
+    const double r12 = PTK_DOT(a1, a2) * w1, r13 = PTK_DOT(a1, a3) * w1;
     PTK_AXPY(a2, r12, a1) PTK_AXPY(a3, r13, a1)
-    const double i2 = ptk_rsqrt(PTK_DOT(a2, a2));
-    PTK_SCAL(a2, i2)
-    const double r23 = PTK_DOT(a2, a3);
+    const double w2 = ptk_rcp(PTK_DOT(a2, a2));
+    const double r23 = PTK_DOT(a2, a3) * w2;
     PTK_AXPY(a3, r23, a2)
-    const double i3 = ptk_rsqrt(PTK_DOT(a3, a3));
+    const double w3 = ptk_rcp(PTK_DOT(a3, a3));
 #undef PTK_DOT
 #undef PTK_AXPY
-#undef PTK_SCAL
-    // S = R^-1
-    const double s01 = -(r01 * i1) * i0;
-    const double s12 = -(r12 * i2) * i1;
-    const double s23 = -(r23 * i3) * i2;
-    const double s02 = -fma(r01, s12, r02 * i2) * i0;
-    const double s13 = -fma(r12, s23, r13 * i3) * i1;
-    const double s03 = -fma(r01, s13, fma(r02, s23, r03 * i3)) * i0;
-    // B = S S^T, scaled by a power of two so that 1 <= tr(B) < 2 (then B^16 stays within 2^-32 .. 2^16)
-    double b00 = fma(s03, s03, fma(s02, s02, fma(s01, s01, i0 * i0)));
-    double b01 = fma(s03, s13, fma(s02, s12, s01 * i1));
-    double b02 = fma(s03, s23, s02 * i2);
-    double b03 = s03 * i3;
-    double b11 = fma(s13, s13, fma(s12, s12, i1 * i1));
-    double b12 = fma(s13, s23, s12 * i2);
-    double b13 = s13 * i3;
-    double b22 = fma(s23, s23, i2 * i2);
-    double b23 = s23 * i3;
-    double b33 = i3 * i3;
+    // T = R~^-1: t01 = -r01, t12 = -r12, t23 = -r23 and
+    const double t02 = fma(r01, r12, -r02);                  // -(r02 + r01 t12)
+    const double t13 = fma(r12, r23, -r13);                  // -(r13 + r12 t23)
+    const double t03 = fma(r02, r23, -fma(r01, t13, r03));   // -(r03 + r01 t13 + r02 t23)
+    // B = T diag(w) T^T.  Columns of T scaled by w: c1 = w1 T[:,1], c2 = w2 T[:,2], c3 = w3 T[:,3]
+    const double c01 = -r01 * w1;
+    const double c02 = t02 * w2, c12 = -r12 * w2;
+    const double c03 = t03 * w3, c13 = t13 * w3, c23 = -r23 * w3;
+    double b00 = fma(t03, c03, fma(t02, c02, fma(-r01, c01, w0)));
+    double b01 = fma(t03, c13, fma(t02, c12, c01));
+    double b02 = fma(t03, c23, c02);
+    double b03 = c03;
+    double b11 = fma(t13, c13, fma(-r12, c12, w1));
+    double b12 = fma(t13, c23, c12);
+    double b13 = c13;
+    double b22 = fma(-r23, c23, w2);
+    double b23 = c23;
+    double b33 = w3;
     {
         const double sc = ptk_pow2_inv((b00 + b11) + (b22 + b33));
         b00 *= sc; b01 *= sc; b02 *= sc; b03 *= sc; b11 *= sc;
@@ -520,7 +520,10 @@ __device__ __forceinline__ double reproject_dist(const double* __restrict__ R, c
     project_point(R, t, cm, k, X, Y, Z, u, v, ext_identity, tangential);
     const double ex = ou - u;
     const double ey = ov - v;
-    return sqrt(fma(ex, ex, ey * ey));
+    const double q = fma(ex, ex, ey * ey);
+    // sqrt as q * rsqrt(q) (seed + one third-order step: an ulp or two, 7 instructions instead of
+    // the ~14 of the IEEE sequence); zero, denormal, infinite and NaN arguments take the library path
+    return (q > 1e-300 && q < 1e300) ? q * rsqrt_refine(q, rsqrt_seed(q)) : sqrt(q);
 }
 
 // One end-point combination (match2D.py:889-913): triangulate the undistorted pair, reproject
