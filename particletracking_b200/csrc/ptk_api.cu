@@ -1128,9 +1128,10 @@ PTK_API int ptk_reconstruct_host(ptk_ctx* c, const ptk_rig* rig, int F, int C, i
     const size_t n4 = (size_t)Nmax * 4 * sizeof(double), n18 = (size_t)Nmax * PTK_ROW_COLS * sizeof(double);
     const size_t nd = (size_t)Nmax * sizeof(double), ni = (size_t)Nmax * sizeof(int32_t);
 
-    // frames per chunk: ~2048 problems, at most 32 full chunks.  The first chunks are smaller
-    // (1/8, 1/4, 1/2 of a full one): the very first host-to-device copy is the one transfer no
-    // kernel can hide, so it is kept short and the pipeline ramps up behind it.
+    // frames per chunk: ~2048 problems, at most 32 full chunks.  PTK_HOST_RAMP=1 makes the first
+    // chunks smaller (1/8, 1/4, 1/2 of a full one) so that the first host-to-device copy -- the one
+    // transfer no kernel can hide -- is short.  Measured (profiles/README.md): no gain, the call is
+    // bound by the device-to-host copy of the rows (43 MB per 8 000 problems over PCIe), so it is off.
     const char* ce = getenv("PTK_HOST_CHUNK");  // tuning knob (problems per chunk)
     const int want = ce ? atoi(ce) : 2048;
     int fchunk = ((want > 0 ? want : 2048) + C - 1) / C;
@@ -1138,8 +1139,8 @@ PTK_API int ptk_reconstruct_host(ptk_ctx* c, const ptk_rig* rig, int F, int C, i
     const long long pchunk = (long long)fchunk * C;
     int chunk_f0[40], nchunks = 0;
     {
-        const char* re = getenv("PTK_HOST_RAMP");  // 0 disables the ramp (A/B)
-        int f = 0, step = (re && atoi(re) == 0) ? fchunk : (fchunk + 7) / 8;
+        const char* re = getenv("PTK_HOST_RAMP");
+        int f = 0, step = (re && atoi(re) == 1) ? (fchunk + 7) / 8 : fchunk;
         while (f < F) {
             chunk_f0[nchunks++] = f;
             f += step;
@@ -1183,6 +1184,12 @@ PTK_API int ptk_reconstruct_host(ptk_ctx* c, const ptk_rig* rig, int F, int C, i
         }
     }
 
+    // The host issues ~10 API calls per chunk and a small chunk's kernels are shorter than that, so
+    // only the two large streams are chunked: detections in, rows out.  The rod counts go in once,
+    // up front (4 bytes per problem); the small per-problem results come back once, after the last
+    // chunk, under the tracking kernels.
+    CK(cudaMemcpyAsync(c->n1.as<int32_t>(), n1, P * sizeof(int32_t), cudaMemcpyHostToDevice, c->s_in));
+    CK(cudaMemcpyAsync(c->n2.as<int32_t>(), n2, P * sizeof(int32_t), cudaMemcpyHostToDevice, c->s_in));
     for (int k = 0; k < nchunks; k++) {
         const int f0 = chunk_f0[k];
         const int fn = chunk_f0[k + 1] - f0;
@@ -1190,8 +1197,6 @@ PTK_API int ptk_reconstruct_host(ptk_ctx* c, const ptk_rig* rig, int F, int C, i
         // H2D
         CK(cudaMemcpyAsync(c->cam1.as<char>() + p0 * n4, (const char*)cam1 + p0 * n4, np * n4, cudaMemcpyHostToDevice, c->s_in));
         CK(cudaMemcpyAsync(c->cam2.as<char>() + p0 * n4, (const char*)cam2 + p0 * n4, np * n4, cudaMemcpyHostToDevice, c->s_in));
-        CK(cudaMemcpyAsync(c->n1.as<int32_t>() + p0, n1 + p0, np * sizeof(int32_t), cudaMemcpyHostToDevice, c->s_in));
-        CK(cudaMemcpyAsync(c->n2.as<int32_t>() + p0, n2 + p0, np * sizeof(int32_t), cudaMemcpyHostToDevice, c->s_in));
         CK(cudaEventRecord(c->ev_in[k], c->s_in));
         // compute
         CK(cudaStreamWaitEvent(c->s_comp, c->ev_in[k], 0));
@@ -1212,13 +1217,14 @@ PTK_API int ptk_reconstruct_host(ptk_ctx* c, const ptk_rig* rig, int F, int C, i
         // D2H
         CK(cudaStreamWaitEvent(c->s_out, c->ev_comp[k], 0));
         CK(cudaMemcpyAsync((char*)rows + p0 * n18, c->rows.as<char>() + p0 * n18, np * n18, cudaMemcpyDeviceToHost, c->s_out));
-        if (match_cost) CK(cudaMemcpyAsync((char*)match_cost + p0 * nd, c->mc.as<char>() + p0 * nd, np * nd, cudaMemcpyDeviceToHost, c->s_out));
-        if (row_ind) CK(cudaMemcpyAsync((char*)row_ind + p0 * ni, c->row.as<char>() + p0 * ni, np * ni, cudaMemcpyDeviceToHost, c->s_out));
-        if (col_ind) CK(cudaMemcpyAsync((char*)col_ind + p0 * ni, c->col.as<char>() + p0 * ni, np * ni, cudaMemcpyDeviceToHost, c->s_out));
-        CK(cudaMemcpyAsync(n_out + p0, c->nout.as<int32_t>() + p0, np * sizeof(int32_t), cudaMemcpyDeviceToHost, c->s_out));
-        CK(cudaMemcpyAsync(status + p0, c->status.as<int32_t>() + p0, np * sizeof(int32_t), cudaMemcpyDeviceToHost, c->s_out));
-        if (keep_mask) CK(cudaMemcpyAsync(keep_mask + p0 * Nmax, c->keep.as<uint8_t>() + p0 * Nmax, np * Nmax, cudaMemcpyDeviceToHost, c->s_out));
     }
+    // s_out has waited for the last chunk's kernels: everything of the matching stage is final
+    if (match_cost) CK(cudaMemcpyAsync(match_cost, c->mc.p, P * nd, cudaMemcpyDeviceToHost, c->s_out));
+    if (row_ind) CK(cudaMemcpyAsync(row_ind, c->row.p, P * ni, cudaMemcpyDeviceToHost, c->s_out));
+    if (col_ind) CK(cudaMemcpyAsync(col_ind, c->col.p, P * ni, cudaMemcpyDeviceToHost, c->s_out));
+    CK(cudaMemcpyAsync(n_out, c->nout.p, P * sizeof(int32_t), cudaMemcpyDeviceToHost, c->s_out));
+    CK(cudaMemcpyAsync(status, c->status.p, P * sizeof(int32_t), cudaMemcpyDeviceToHost, c->s_out));
+    if (keep_mask) CK(cudaMemcpyAsync(keep_mask, c->keep.p, (size_t)P * Nmax, cudaMemcpyDeviceToHost, c->s_out));
     if (do_track && Q > 0) {
         rc = ptk_track_batch(C, F, N, c->ends.as<double>(), nullptr, c->tcol.as<int32_t>(), c->ttot.as<double>(),
                              c->tstatus.as<int32_t>(), c->tws.p, c->tws.cap, c->s_comp);
