@@ -1130,8 +1130,9 @@ PTK_API int ptk_reconstruct_host(ptk_ctx* c, const ptk_rig* rig, int F, int C, i
 
     // frames per chunk: ~2048 problems, at most 32 full chunks.  PTK_HOST_RAMP=1 makes the first
     // chunks smaller (1/8, 1/4, 1/2 of a full one) so that the first host-to-device copy -- the one
-    // transfer no kernel can hide -- is short.  Measured (profiles/README.md): no gain, the call is
-    // bound by the device-to-host copy of the rows (43 MB per 8 000 problems over PCIe), so it is off.
+    // transfer no kernel can hide -- is short.  Measured (profiles/README.md): slower (527 k vs 546 k
+    // frames/s): the small chunks' launches fill the GPU badly and every extra chunk adds kernel
+    // tails, which costs more than the 60 us of copy it hides.  Off by default.
     const char* ce = getenv("PTK_HOST_CHUNK");  // tuning knob (problems per chunk)
     const int want = ce ? atoi(ce) : 2048;
     int fchunk = ((want > 0 ? want : 2048) + C - 1) / C;

@@ -51,13 +51,17 @@ def main():
             out[name] = e0.elapsed_time(e1) / 10
         m = r[0]
         rows, col = m.rows.cpu().numpy(), m.col_ind.cpu().numpy()
+        tcol, ttot = r[1].cpu().numpy(), r[2].cpu().numpy()
         if ref is None:
-            ref = (rows, col)
+            ref = (rows, col, tcol, ttot)
             out["vs_first"] = "reference"
         else:
             same = bool((col == ref[1]).all())
+            tsame = bool((tcol == ref[2]).all())
+            terr = float(np.max(np.abs(ttot - ref[3]) / np.abs(ref[3])))
             err = float(np.nanmax(np.abs(rows[..., :10] - ref[0][..., :10])) / max(np.nanmax(np.abs(ref[0][..., :10])), 1))
-            out["vs_first"] = f"assignments identical={same}, rows max rel diff={err:.2e}"
+            out["vs_first"] = (f"assignments identical={same}, rows max rel diff={err:.2e}, tracking col_ind identical={tsame}, "
+                               f"total_cost max rel diff={terr:.1e}")
         print(json.dumps({"lib": os.path.basename(path), **out}), flush=True)
 
 

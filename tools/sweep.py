@@ -17,7 +17,7 @@ import torch
 
 from particletracking_b200 import engine, rig as rigmod, synthetic as syn
 
-FLOP_PER_PAIR = 8840.0
+FLOP_PER_PAIR = 2400.0  # K1 as built (bench.py); the reference-algorithm model is 8840
 
 
 def main():
@@ -55,6 +55,7 @@ def main():
             "rods": N, "frames": F, "colours": C, "ms_per_step": ms, "frames_per_s": F / (ms * 1e-3),
             "k_cost_ms": k1, "k_cost_tflops": flops / (k1 * 1e-3) / 1e12, "fp64_peak_tflops": peak / 1e12,
             "k_cost_frac": flops / (k1 * 1e-3) / peak,
+            "k_cost_frac_reference_algorithm": flops * (8840.0 / FLOP_PER_PAIR) / (k1 * 1e-3) / peak,
             "kernel_ms": {k: v[0] / K for k, v in tm.items() if v[1]},
         }), flush=True)
         del c1, c2, n1, n2, out
