@@ -155,16 +155,36 @@ def run_reference(args):
 # clocks
 # ------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region.  NVML is read in-process every 10 ms
+    (microseconds per call); the `nvidia-smi -lms` child used before held the driver's lock for
+    milliseconds per poll, which stalled rank 0's CUDA calls and made short multi-GPU steps
+    host-bound in some runs (5.8 vs 1.7 ms per step at 2 GPUs).  nvidia-smi remains the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NVML_REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, gpu_index: int):
         self.idx = gpu_index
-        self.lines = []
+        self.lines = []    # nvidia-smi fallback: (t, csv line)
+        self.samples = []  # NVML: (t, sm_mhz, reasons bitmask)
         self.proc = None
+        self.nvml = None
+        self.max_mhz = None
+        self._stop = threading.Event()
 
     def start(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            threading.Thread(target=self._poll, daemon=True).start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.idx)],
@@ -173,11 +193,35 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop.is_set():
+            try:
+                self.samples.append((time.perf_counter(), float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)),
+                                     int(reasons(self.handle))))
+            except Exception:
+                pass
+            time.sleep(0.01)
+
     def _read(self):
         for ln in self.proc.stdout:
             self.lines.append((time.perf_counter(), ln.strip()))
 
     def stop(self, t0=None, t1=None):
+        if self.nvml is not None:
+            time.sleep(0.03)
+            self._stop.set()
+            sm, reasons = [], set()
+            for ts, mhz, bits in self.samples:
+                if t0 is not None and not (t0 - 0.02 <= ts <= t1 + 0.03):
+                    continue
+                sm.append(mhz)
+                for bit, name in self.NVML_REASONS:
+                    if bits & bit:
+                        reasons.add(name)
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(reasons),
+                    "samples": len(sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -198,7 +242,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------
@@ -259,7 +303,7 @@ def run_b200(args):
     # host enqueues a step in well under the time the GPUs need for it (i.e. the run is not
     # host-bound); at most 400 extra steps / 4 s.  The timed region below is still exactly K steps.
     extra, hist, t_settle0 = 0, [], time.perf_counter()
-    while extra < 400 and time.perf_counter() - t_settle0 < 4.0:
+    while True:
         t_s = time.perf_counter()
         out = step(W + extra)
         if sharded is not None:
@@ -269,12 +313,16 @@ def run_b200(args):
         t_all = time.perf_counter() - t_s
         hist.append(t_all)
         extra += 1
-        stable = len(hist) >= 3 and max(hist[-3:]) <= 1.10 * min(hist[-3:]) and t_host <= 0.5 * t_all
+        stable = len(hist) >= 3 and max(hist[-3:]) <= 1.10 * min(hist[-3:]) and t_host <= 0.6 * t_all
+        timed_out = extra >= 400 or time.perf_counter() - t_settle0 >= 4.0
         if world > 1:
-            flag = torch.tensor([1.0 if stable else 0.0], device=dev)
+            # both decisions are collective: a rank-local clock deciding when to leave this loop would
+            # leave the other ranks inside a collective (seen once: a 2-GPU run hung here)
+            flag = torch.tensor([1.0 if stable else 0.0, 0.0 if timed_out else 1.0], device=dev)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-            stable = bool(flag.item() == 1.0)
-        if stable and extra >= 5:
+            flag = flag.tolist()
+            stable, timed_out = flag[0] == 1.0, flag[1] == 0.0
+        if (stable and extra >= 5) or timed_out:
             break
     W_total = W + extra
     if sharded is not None:
@@ -287,6 +335,12 @@ def run_b200(args):
     if rank == 0:  # one sampler per job: nvidia-smi polling from every rank perturbs the driver
         clocks.start()
     time.sleep(0.3)
+    if sharded is not None and getattr(sharded, "_prof", None) is not None:
+        if rank == 0:
+            print("step() host profile, warm-up + settle, ms per step: " +
+                  json.dumps({k: round(v / max(sharded._step_idx, 1) * 1e3, 3) for k, v in sharded._prof.items()}), file=sys.stderr)
+        sharded._prof.clear()
+        prof_step0 = sharded._step_idx
     engine.kernel_timing(True)
     engine.kernel_timing_read(reset=True)
     engine.launch_count(reset=True)
@@ -371,6 +425,9 @@ def run_b200(args):
         "traffic": traffic,
     }
 
+    if sharded is not None and getattr(sharded, "_prof", None) and rank == 0:
+        print("step() host profile, timed region (+ e2e steps), ms per step: " +
+              json.dumps({k: round(v / max(sharded._step_idx - prof_step0, 1) * 1e3, 3) for k, v in sharded._prof.items()}), file=sys.stderr)
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W, "warmup_settle_steps": extra,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -103,6 +103,10 @@ class ShardedReconstructor:
         self._tid_all0 = self._tid_all1 = None
         self._pending = [None, None]
         self._step_idx = 0
+        # host-side time per segment of step() (seconds, summed), filled when PTK_STEP_PROFILE=1
+        import os as _os
+
+        self._prof = {} if _os.environ.get("PTK_STEP_PROFILE") == "1" else None
 
     # -- exchanges ------------------------------------------------------------------------
     def _halo(self, first_frame_ends: torch.Tensor) -> Optional[torch.Tensor]:
@@ -149,7 +153,21 @@ class ShardedReconstructor:
         """cam1/cam2 [F*C,Nmax,2,2] (problem = f*C+c), n1/n2 [F*C] for this rank's frames.
         Returns a dict; on rank 0 ``rows_all`` / ``track_id_all`` hold every rank's shard."""
         F, C, N = self.F, self.C, self.N
+        prof = self._prof
+        if prof is not None:
+            import time as _t
+
+            t_last = [_t.perf_counter()]
+
+            def mark(name):
+                now = _t.perf_counter()
+                prof[name] = prof.get(name, 0.0) + (now - t_last[0])
+                t_last[0] = now
+        else:
+            def mark(name):
+                pass
         rows, col_m, status = self.ops.match(cam1, cam2, n1, n2)
+        mark("match")
         rows_all = rows_work = None
         slot = self._step_idx % 2
         self._step_idx += 1
@@ -157,12 +175,18 @@ class ShardedReconstructor:
             self._wait(slot)  # this slot's receive buffers are free again
             # the big gather (rows) starts as soon as matching is enqueued and overlaps tracking
             rows_all, rows_work = self._gather(rows.view(F, C, -1, rows.shape[-1]), f"_rows_all{slot}", 0, async_op=True)
+        mark("wait+gather_rows")
         ends = self.ops.rows_to_ends(rows, F, C)  # [C,F,N,2,3]
+        mark("rows_to_ends")
         halo = self._halo(ends[:, 0].contiguous())
+        mark("halo")
         if halo is not None:
             ends = torch.cat([ends, halo[:, None]], dim=1)  # boundary pair solved here
+        mark("cat")
         col, total, tstatus = self.ops.track(ends)
+        mark("track")
         local = self.ops.chain(col)  # ids relative to this rank's first frame
+        mark("chain")
         if self.world > 1:
             if halo is not None:
                 my_map = local[:, -1].contiguous()
@@ -178,6 +202,7 @@ class ShardedReconstructor:
                 track_id = self.ops.chain(col, start)[:, :F].contiguous()
         else:
             track_id = local
+        mark("maps+rebase")
         out = dict(rows=rows, col_ind=col_m, status=status, track_col=col, track_total=total,
                    track_status=tstatus, track_id=track_id)
         if self.gather_to_root:
@@ -185,6 +210,7 @@ class ShardedReconstructor:
             self._pending[slot] = [w for w in (rows_work, tid_work) if w is not None]
             out["rows_all"] = rows_all        # [F,C,Nmax,18] per rank   } valid after finish()
             out["track_id_all"] = tid_all     # [C,F,N] per rank         } (or the next-but-one step)
+        mark("gather_tid")
         return out
 
     def _wait(self, slot: int):
