@@ -299,32 +299,35 @@ def run_b200(args):
     fp64_peak = engine.measure_fp64_peak(20000)  # also warms the clocks
     for i in range(W):
         out = step(i)
-    # Settling: on a fresh box the first process that brings up NCCL keeps paying host-side costs
-    # for a while (measured: 7-14 ms/step of host enqueue time instead of 0.9, for dozens of steps).
-    # Keep stepping, untimed, until three consecutive synchronised steps agree within 10 % AND the
-    # host enqueues a step in well under the time the GPUs need for it (i.e. the run is not
-    # host-bound); at most 400 extra steps / 4 s.  The timed region below is still exactly K steps.
+    # Settling.  The timed region enqueues K steps without synchronising, so several steps' worth of
+    # output tensors and asynchronous result gathers are in flight at once; until torch's caching
+    # allocator has grown its pool to that depth, a step now and then pays for a cudaMalloc (and on a
+    # fresh box NCCL keeps paying host-side set-up costs for dozens of steps).  Measured at 2 and 4
+    # GPUs: the same build gave 1.74 or 3.05-5.77 ms per step depending on whether that happened
+    # inside the timed region.  So the warm-up runs in the timed region's own pattern -- untimed
+    # bursts of K unsynchronised steps -- until two consecutive bursts agree within 10 % and the last
+    # one is within 10 % of the best seen; at most 6 s.  The exit decision is collective (a rank-local
+    # clock would leave the other ranks inside a collective: one 2-GPU run hung that way).  The timed
+    # region below is still exactly K steps.
     extra, hist, t_settle0 = 0, [], time.perf_counter()
+    burst = max(K, 10)
     while True:
         t_s = time.perf_counter()
-        out = step(W + extra)
+        for j in range(burst):
+            out = step(W + extra + j)
         if sharded is not None:
             sharded.finish()
-        t_host = time.perf_counter() - t_s
         torch.cuda.synchronize()
-        t_all = time.perf_counter() - t_s
-        hist.append(t_all)
-        extra += 1
-        stable = len(hist) >= 3 and max(hist[-3:]) <= 1.10 * min(hist[-3:]) and t_host <= 0.6 * t_all
-        timed_out = extra >= 400 or time.perf_counter() - t_settle0 >= 4.0
+        hist.append(time.perf_counter() - t_s)
+        extra += burst
+        stable = len(hist) >= 2 and max(hist[-2:]) <= 1.10 * min(hist[-2:]) and hist[-1] <= 1.10 * min(hist)
+        timed_out = time.perf_counter() - t_settle0 >= 6.0
         if world > 1:
-            # both decisions are collective: a rank-local clock deciding when to leave this loop would
-            # leave the other ranks inside a collective (seen once: a 2-GPU run hung here)
             flag = torch.tensor([1.0 if stable else 0.0, 0.0 if timed_out else 1.0], device=dev)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
             flag = flag.tolist()
             stable, timed_out = flag[0] == 1.0, flag[1] == 0.0
-        if (stable and extra >= 5) or timed_out:
+        if stable or timed_out:
             break
     W_total = W + extra
     if sharded is not None:
@@ -348,6 +351,7 @@ def run_b200(args):
     engine.launch_count(reset=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    seg0 = torch.cuda.memory_stats(dev).get("segment.all.allocated", 0)
     t_wall0 = time.perf_counter()
     e0.record()
     for i in range(K):
@@ -359,6 +363,7 @@ def run_b200(args):
     barrier()
     t_wall1 = time.perf_counter()
     ms = e0.elapsed_time(e1)
+    seg_added = torch.cuda.memory_stats(dev).get("segment.all.allocated", 0) - seg0  # cudaMallocs inside the timed region
     launches = engine.launch_count()
     timing = engine.kernel_timing_read(reset=True)
     k1_ms, k1_n = timing["cost"]
@@ -474,6 +479,7 @@ def run_b200(args):
         "kernel_ms_per_step": {k: v[0] / K for k, v in timing.items() if v[1]},
         "wall_s": t_wall1 - t_wall0,
         "host_enqueue_ms_per_step": t_enq / K * 1e3,
+        "cuda_mallocs_in_timed_region": int(seg_added),
     }
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
