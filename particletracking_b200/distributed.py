@@ -53,9 +53,15 @@ class _CudaOps:
 
         self.e = engine
         self.rig = rig
+        self._out = {}
 
-    def match(self, cam1, cam2, n1, n2):
-        m = self.e.match_batch(self.rig, cam1, cam2, n1, n2)
+    def match(self, cam1, cam2, n1, n2, slot=None):
+        # the rows of step k are still being gathered while step k+1 computes: two fixed sets of
+        # output tensors (one per gather slot) instead of a fresh 37 MB allocation per step
+        prev = self._out.get(slot) if slot is not None else None
+        m = self.e.match_batch(self.rig, cam1, cam2, n1, n2, out=prev)
+        if slot is not None:
+            self._out[slot] = m
         return m.rows, m.col_ind, m.status
 
     def rows_to_ends(self, rows, F, C):
@@ -151,7 +157,9 @@ class ShardedReconstructor:
     # -- one pass over this rank's frames ----------------------------------------------------
     def step(self, cam1, cam2, n1, n2):
         """cam1/cam2 [F*C,Nmax,2,2] (problem = f*C+c), n1/n2 [F*C] for this rank's frames.
-        Returns a dict; on rank 0 ``rows_all`` / ``track_id_all`` hold every rank's shard."""
+        Returns a dict; on rank 0 ``rows_all`` / ``track_id_all`` hold every rank's shard.  With
+        ``gather_to_root`` the matching outputs (``rows``, ``col_ind``, ``status``) live in two alternating
+        sets of buffers: they are overwritten by the step after next -- copy what must outlive that."""
         F, C, N = self.F, self.C, self.N
         prof = self._prof
         if prof is not None:
@@ -166,13 +174,17 @@ class ShardedReconstructor:
         else:
             def mark(name):
                 pass
-        rows, col_m, status = self.ops.match(cam1, cam2, n1, n2)
-        mark("match")
         rows_all = rows_work = None
         slot = self._step_idx % 2
         self._step_idx += 1
         if self.gather_to_root:
-            self._wait(slot)  # this slot's receive buffers are free again
+            self._wait(slot)  # this slot's send and receive buffers are free again
+        if isinstance(self.ops, _CudaOps):
+            rows, col_m, status = self.ops.match(cam1, cam2, n1, n2, slot=slot if self.gather_to_root else None)
+        else:
+            rows, col_m, status = self.ops.match(cam1, cam2, n1, n2)
+        mark("match")
+        if self.gather_to_root:
             # the big gather (rows) starts as soon as matching is enqueued and overlaps tracking
             rows_all, rows_work = self._gather(rows.view(F, C, -1, rows.shape[-1]), f"_rows_all{slot}", 0, async_op=True)
         mark("wait+gather_rows")

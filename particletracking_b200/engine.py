@@ -129,8 +129,11 @@ def lsap_batch(cost: torch.Tensor, nr: Optional[torch.Tensor] = None, nc: Option
     return row, col, n_out, status
 
 
-def match_batch(rig: PtkRig, cam1, cam2, n1, n2, want_cost=False, max_repr_err: Optional[float] = None) -> MatchResult:
-    """K0..K3: the whole ``match_frame`` body (match2D.py:843-983) for P problems."""
+def match_batch(rig: PtkRig, cam1, cam2, n1, n2, want_cost=False, max_repr_err: Optional[float] = None,
+                out: Optional[MatchResult] = None) -> MatchResult:
+    """K0..K3: the whole ``match_frame`` body (match2D.py:843-983) for P problems.  ``out``: a result of
+    an earlier call with the same shapes and options whose tensors are overwritten instead of allocating
+    new ones (callers that keep several steps in flight reuse a fixed set of buffers this way)."""
     _require_cuda()
     cam1, cam2 = _chk(cam1, _f64, "cam1"), _chk(cam2, _f64, "cam2")
     n1, n2 = _chk(n1, _i32, "n1"), _chk(n2, _i32, "n2")
@@ -138,15 +141,20 @@ def match_batch(rig: PtkRig, cam1, cam2, n1, n2, want_cost=False, max_repr_err: 
     if cam2.shape[:2] != (P, Nmax) or n1.numel() != P or n2.numel() != P:
         raise ValueError("cam1/cam2 must be [P,Nmax,2,2] with n1/n2 [P]")
     dev = cam1.device
-    rows = torch.empty((P, Nmax, nat.ROW_COLS), dtype=_f64, device=dev)
-    mc = torch.empty((P, Nmax), dtype=_f64, device=dev)
-    row = torch.empty((P, Nmax), dtype=_i32, device=dev)
-    col = torch.empty((P, Nmax), dtype=_i32, device=dev)
-    n_out = torch.empty((P,), dtype=_i32, device=dev)
-    status = torch.empty((P,), dtype=_i32, device=dev)
-    cost = torch.full((P, Nmax, Nmax), float("nan"), dtype=_f64, device=dev) if want_cost else None
-    choice = torch.zeros((P, Nmax, Nmax), dtype=_u8, device=dev) if want_cost else None
-    keep = torch.empty((P, Nmax), dtype=_u8, device=dev) if max_repr_err is not None else None
+    if out is not None and not want_cost and tuple(out.rows.shape) == (P, Nmax, nat.ROW_COLS) and out.rows.device == dev \
+            and (out.keep is not None) == (max_repr_err is not None):
+        rows, mc, row, col, n_out, status, cost, choice, keep = (out.rows, out.match_cost, out.row_ind, out.col_ind,
+                                                                 out.n_out, out.status, None, None, out.keep)
+    else:
+        rows = torch.empty((P, Nmax, nat.ROW_COLS), dtype=_f64, device=dev)
+        mc = torch.empty((P, Nmax), dtype=_f64, device=dev)
+        row = torch.empty((P, Nmax), dtype=_i32, device=dev)
+        col = torch.empty((P, Nmax), dtype=_i32, device=dev)
+        n_out = torch.empty((P,), dtype=_i32, device=dev)
+        status = torch.empty((P,), dtype=_i32, device=dev)
+        cost = torch.full((P, Nmax, Nmax), float("nan"), dtype=_f64, device=dev) if want_cost else None
+        choice = torch.zeros((P, Nmax, Nmax), dtype=_u8, device=dev) if want_cost else None
+        keep = torch.empty((P, Nmax), dtype=_u8, device=dev) if max_repr_err is not None else None
     nb = nat.lib().ptk_workspace_bytes(nat.WS_MATCH, P, Nmax)
     ws = _ws.get(nb, dev)
     thr = float("inf") if max_repr_err is None else float(max_repr_err)
