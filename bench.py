@@ -309,6 +309,14 @@ def run_b200(args):
     # one is within 10 % of the best seen; at most 6 s.  The exit decision is collective (a rank-local
     # clock would leave the other ranks inside a collective: one 2-GPU run hung that way).  The timed
     # region below is still exactly K steps.
+    # Python's cyclic collector stays out of the measured regions: a generation-2 pass over this
+    # process's heap (torch + numpy + pandas) is tens of milliseconds, the timed region of 20 steps
+    # is 35 ms, and with N ranks coupled by a halo exchange per step one rank's pause is everyone's.
+    import gc
+
+    gc.collect()
+    gc.freeze()
+    gc.disable()
     extra, hist, t_settle0 = 0, [], time.perf_counter()
     burst = max(K, 10)
     while True:
@@ -460,6 +468,7 @@ def run_b200(args):
     if sharded is not None and getattr(sharded, "_prof", None) and rank == 0:
         print("step() host profile, timed region (+ e2e steps), ms per step: " +
               json.dumps({k: round(v / max(sharded._step_idx - prof_step0, 1) * 1e3, 3) for k, v in sharded._prof.items()}), file=sys.stderr)
+    gc.enable()
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W, "warmup_settle_steps": extra,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
