@@ -345,7 +345,8 @@ def run_b200(args):
     assert int((st != 0).sum().item()) == 0, "matching reported invalid problems"
 
     clocks = ClockSampler(local)
-    if rank == 0:  # one sampler per job: nvidia-smi polling from every rank perturbs the driver
+    dbg = os.environ.get("PTK_BENCH_DEBUG", "")  # experiment switches: "nosampler", "notiming", "noe2e"
+    if rank == 0 and "nosampler" not in dbg:  # one sampler per job: nvidia-smi polling from every rank perturbs the driver
         clocks.start()
     time.sleep(0.3)
     if sharded is not None and getattr(sharded, "_prof", None) is not None:
@@ -354,7 +355,13 @@ def run_b200(args):
                   json.dumps({k: round(v / max(sharded._step_idx, 1) * 1e3, 3) for k, v in sharded._prof.items()}), file=sys.stderr)
         sharded._prof.clear()
         prof_step0 = sharded._step_idx
-    engine.kernel_timing(True)
+    # Per-kernel CUDA events inside the timed region only at N = 1 (one library call per step).  At
+    # N > 1 the step is ~25 launches + collectives issued from Python, and event pairs around every
+    # launch together with the NVML sampler made rank 0's host 5x slower in half of the 4-GPU runs
+    # (3 of 6 bad with both on, 0 of 6 with either one off): there the kernel breakdown comes from a
+    # second, untimed pass of K steps right after the timed region.
+    timing_in_region = world == 1 and "notiming" not in dbg
+    engine.kernel_timing(timing_in_region)
     engine.kernel_timing_read(reset=True)
     engine.launch_count(reset=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -373,10 +380,18 @@ def run_b200(args):
     ms = e0.elapsed_time(e1)
     seg_added = torch.cuda.memory_stats(dev).get("segment.all.allocated", 0) - seg0  # cudaMallocs inside the timed region
     launches = engine.launch_count()
+    clk = clocks.stop(t_wall0, t_wall1)
+    if not timing_in_region and "notiming" not in dbg:
+        engine.kernel_timing(True)
+        engine.kernel_timing_read(reset=True)
+        for i in range(K):
+            step(W_total + K + i)
+        if sharded is not None:
+            sharded.finish()
+        barrier()
     timing = engine.kernel_timing_read(reset=True)
     k1_ms, k1_n = timing["cost"]
     engine.kernel_timing(False)
-    clk = clocks.stop(t_wall0, t_wall1)
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -388,7 +403,7 @@ def run_b200(args):
     for i in range(2):
         pipe.reconstruct(rig, *host_batches[i % 2], track=True)
     barrier()
-    Ke = max(3, min(K, 10))
+    Ke = 1 if "noe2e" in dbg else max(3, min(K, 10))
     t0 = time.perf_counter()
     for i in range(Ke):
         pipe.reconstruct(rig, *host_batches[i % 2], track=True)
@@ -489,6 +504,9 @@ def run_b200(args):
         "wall_s": t_wall1 - t_wall0,
         "host_enqueue_ms_per_step": t_enq / K * 1e3,
         "cuda_mallocs_in_timed_region": int(seg_added),
+        "kernel_timing": "CUDA events around every launch inside the timed region" if timing_in_region
+                         else "separate untimed pass of K steps after the timed region",
+
     }
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
