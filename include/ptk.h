@@ -211,8 +211,10 @@ int ptk_project_points(const ptk_rig* rig, long long n, const double* X, int fro
  *   status[B]               PTK_AP3_OK: proven optimal (bound - value within rounding);
  *                           PTK_AP3_GAP: work limits hit, sol is the best found and bound its bound;
  *                           PTK_AP3_INVALID: NaN/inf weights or sizes out of range; PTK_AP3_EMPTY
- *   stats[B,4] (optional)   dual-descent steps, search nodes, candidate triples, step that proved it
- * max_steps / node_limit <= 0 select the defaults (60 / 20e6).
+ *   stats[B,4] (optional)   bounding steps (dual descent + subgradient iterations), search nodes,
+ *                           candidate triples, step that proved it (-1: the search did, or nothing)
+ * max_steps (dual-descent steps before the subgradient phase, which adds up to 1200 iterations) and
+ * node_limit (reduced-cost search) <= 0 select the defaults (60 / 2e6).
  * workspace: ptk_workspace_bytes(PTK_WS_AP3, B, 0). */
 #define PTK_AP3_OK 0
 #define PTK_AP3_GAP 1
