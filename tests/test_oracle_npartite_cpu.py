@@ -69,3 +69,25 @@ def test_bookkeeping_fill_in_and_unbalanced_error():
     np.testing.assert_array_equal(out[1, 10:14], r1[1].ravel())
     np.testing.assert_array_equal(out[1, 14:], r2[0].ravel())
     np.testing.assert_array_equal(c, costs[[2, 1, 0], [1, 0, 2]])
+
+
+def test_bounding_loop_prototype_reaches_stored_optima():
+    """tools/ap3_proto.py is the CPU model of k_ap3's bounding loop (dual descent, then deflected
+    subgradient) that its constants were chosen with.  On cubes from frames with dummy / dropped
+    detections it must close the bound at the stored HiGHS optimum (tests/golden/ap3_rod_optima.json)."""
+    import json
+    import os
+
+    from conftest import GOLDEN
+    from tools.ap3_check import rod_weights
+    from tools.ap3_proto import run
+
+    with open(os.path.join(GOLDEN, "ap3_rod_optima.json")) as f:
+        table = json.load(f)
+    for name in ("d16_1", "drop16_0", "e24_3"):
+        w = rod_weights(**table[name]["args"])
+        how, it, st = run(w)
+        opt = table[name]["milp"]
+        assert how != "gap", (name, how, it)
+        assert abs(st["best"] - opt) <= 1e-9 * abs(opt), (name, st["best"] - opt)
+        assert st["ub"] >= opt * (1 - 1e-12)
