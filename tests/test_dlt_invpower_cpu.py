@@ -69,7 +69,8 @@ def test_matches_cv2_on_all_rod_pairs(harness, kw):
 
 def test_convergence_flag_selects_the_fallback_by_singular_value_ratio(harness):
     """Near-degenerate geometry (baseline shrunk x1000): the flag must be exactly 'sigma_4/sigma_3
-    below ~0.39', and converged points must still agree with cv2."""
+    below ~0.62' (three squarings, one more where the first test fails), and converged points must
+    still agree with cv2."""
     sys.path.insert(0, ROOT)
     from particletracking_b200 import synthetic as syn
 
@@ -84,8 +85,9 @@ def test_convergence_flag_selects_the_fallback_by_singular_value_ratio(harness):
                   pts[:, 2, None] * P2[2] - P2[0], pts[:, 3, None] * P2[2] - P2[1]], axis=1)
     sv = np.linalg.svd(A, compute_uv=False)
     ratio = sv[:, 3] / sv[:, 2]
-    assert 0.2 < (~conv).mean() < 0.7  # a large share falls back here
-    assert ratio[conv].max() < 0.39 and ratio[~conv].min() > 0.38
+    assert 0.03 < (~conv).mean() < 0.5  # a sizeable share falls back here
+    assert ratio[conv].max() < 0.63 and ratio[~conv].min() > 0.61
+    assert (conv & (ratio > 0.40)).sum() > 100  # ... and many points needed the extra squaring
     ref = _cv2(P1, P2, pts)
     err = np.abs(X - ref).max(axis=1) / np.abs(ref).max(axis=1)
     assert err[conv].max() < 1e-10

@@ -575,9 +575,10 @@ def test_random_rigs_vs_c_oracle(eng, seed):
 @pytest.mark.parametrize("scale", [2e-3, 1e-3])
 def test_near_degenerate_rig_takes_jacobi_fallback(eng, scale):
     """A stereo rig whose baseline is shrunk to (almost) nothing: sigma_4/sigma_3 of the DLT matrices
-    is above 0.39 for 15 % (scale 2e-3) or 44 % (1e-3) of the end-point combinations, so K1's inverse
-    power iteration reports "not converged" there and the one-sided Jacobi (OpenCV's algorithm) takes
-    over per thread.  Mixed warps must give what the C oracle (OpenCV's Jacobi for every point) gives;
+    is above 0.39 for 15 % (scale 2e-3) or 44 % (1e-3) of the end-point combinations: K1's inverse
+    power iteration takes its extra squaring there, and above 0.62 (9 % at 1e-3) reports "not
+    converged", where the one-sided Jacobi (OpenCV's algorithm) takes over per thread.  Mixed
+    warps must give what the C oracle (OpenCV's Jacobi for every point) gives;
     profiles/experiments/dlt_invpower.py counts the fallbacks for this geometry on the CPU."""
     from oracle import c_oracle as co
     from particletracking_b200 import rig as rigmod
