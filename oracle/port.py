@@ -304,12 +304,14 @@ def tracking_arrays(p1: np.ndarray, p2: np.ndarray):
 
 def chain_tracks(col_ind: np.ndarray) -> np.ndarray:
     """Chain-pass extension (no reference counterpart):
-    ``ids[0] = arange(N)``, ``ids[f+1][col_ind[f][a]] = ids[f][a]``."""
+    ``ids[0] = arange(N)``, ``ids[f+1][col_ind[f][a]] = ids[f][a]``; entries outside ``0..N-1``
+    (a failed assignment) break the chain: unreached positions get -1 and -1 propagates."""
     Fm1, N = col_ind.shape
-    ids = np.zeros((Fm1 + 1, N), dtype=np.int64)
+    ids = np.full((Fm1 + 1, N), -1, dtype=np.int64)
     ids[0] = np.arange(N)
     for f in range(Fm1):
-        ids[f + 1, col_ind[f]] = ids[f]
+        ok = (col_ind[f] >= 0) & (col_ind[f] < N)
+        ids[f + 1, col_ind[f][ok]] = ids[f][ok]
     return ids
 
 

@@ -487,7 +487,10 @@ PTKO_API int ptko_track_batch(int C, int F, int N, const double* ends, double* c
     return 0;
 }
 
-/* D.3 chain pass (extension): ids[0] = ids_in or arange, ids[f+1][col[f][a]] = ids[f][a]. */
+/* D.3 chain pass (extension): ids[0] = ids_in or arange, ids[f+1][col[f][a]] = ids[f][a].
+ * A frame pair whose assignment failed (col < 0 or >= N: the LSAP reported INVALID / INFEASIBLE,
+ * e.g. NaN end points of a ragged frame) breaks the chain: positions that no valid entry maps
+ * to get id -1, and -1 propagates along the frames. */
 PTKO_API void ptko_chain_tracks(int C, int F, int N, const int32_t* col_ind,
                                 const int32_t* ids_in, int32_t* track_id)
 {
@@ -496,7 +499,9 @@ PTKO_API void ptko_chain_tracks(int C, int F, int N, const int32_t* col_ind,
         for (int a = 0; a < N; a++) ids[a] = ids_in ? ids_in[(size_t)c * N + a] : a;
         for (int f = 0; f + 1 < F; f++) {
             const int32_t* col = col_ind + ((size_t)c * (F - 1) + f) * N;
-            for (int a = 0; a < N; a++) ids[(size_t)(f + 1) * N + col[a]] = ids[(size_t)f * N + a];
+            for (int a = 0; a < N; a++) ids[(size_t)(f + 1) * N + a] = -1;
+            for (int a = 0; a < N; a++)
+                if (col[a] >= 0 && col[a] < N) ids[(size_t)(f + 1) * N + col[a]] = ids[(size_t)f * N + a];
         }
     }
 }

@@ -299,6 +299,13 @@ int launch_rows(const DevRig& rig, long long P, int Nmax, const double* cam1, co
 
 bool bad_n(int Nmax) { return Nmax <= 0 || Nmax > PTK_MAX_RODS; }
 
+// NULL, or a camera model the kernels do not implement: cv2's tilted-sensor coefficients tauX, tauY
+// (dist[12], dist[13]) -- rejected rather than silently computed with a different model.
+bool bad_rig(const ptk_rig* r)
+{
+    return !r || r->dist1[12] != 0.0 || r->dist1[13] != 0.0 || r->dist2[12] != 0.0 || r->dist2[13] != 0.0;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------ library
@@ -387,7 +394,7 @@ PTK_API size_t ptk_workspace_bytes(int kind, long long n_problems, int Nmax)
 PTK_API int ptk_undistort_batch(const ptk_rig* rig, int P, int Nmax, const double* cam1, const double* cam2,
                                 const int32_t* n1, const int32_t* n2, double* und1, double* und2, void* stream)
 {
-    if (!rig || P < 0 || bad_n(Nmax) || !cam1 || !cam2 || !n1 || !n2 || !und1 || !und2) return PTK_ERR_INVALID_ARG;
+    if (bad_rig(rig) || P < 0 || bad_n(Nmax) || !cam1 || !cam2 || !n1 || !n2 || !und1 || !und2) return PTK_ERR_INVALID_ARG;
     if (P == 0) return PTK_OK;
     return launch_undistort(make_devrig(rig), P, Nmax, cam1, cam2, n1, n2, und1, und2, (cudaStream_t)stream);
 }
@@ -397,7 +404,7 @@ PTK_API int ptk_cost_batch(const ptk_rig* rig, int P, int Nmax, const double* ca
                            const int32_t* n1, const int32_t* n2, double* cost, uint8_t* choice, double* p_world,
                            double* rep_errs, void* workspace, size_t workspace_bytes, void* stream)
 {
-    if (!rig || P < 0 || bad_n(Nmax) || !cam1 || !cam2 || !n1 || !n2 || !cost) return PTK_ERR_INVALID_ARG;
+    if (bad_rig(rig) || P < 0 || bad_n(Nmax) || !cam1 || !cam2 || !n1 || !n2 || !cost) return PTK_ERR_INVALID_ARG;
     if (P == 0) return PTK_OK;
     if (!workspace || workspace_bytes < ptk_workspace_bytes(PTK_WS_COST, P, Nmax)) return PTK_ERR_WORKSPACE;
     const DevRig d = make_devrig(rig);
@@ -431,7 +438,7 @@ PTK_API int ptk_match_batch(const ptk_rig* rig, int P, int Nmax, const double* c
                             double max_repr_err, uint8_t* keep_mask, void* workspace, size_t workspace_bytes,
                             void* stream)
 {
-    if (!rig || P < 0 || bad_n(Nmax) || !cam1 || !cam2 || !n1 || !n2 || !row_ind || !col_ind || !n_out || !status ||
+    if (bad_rig(rig) || P < 0 || bad_n(Nmax) || !cam1 || !cam2 || !n1 || !n2 || !row_ind || !col_ind || !n_out || !status ||
         !rows || !match_cost)
         return PTK_ERR_INVALID_ARG;
     if (P == 0) return PTK_OK;
@@ -472,7 +479,7 @@ PTK_API int ptk_rows_batch(const ptk_rig* rig, int P, int Nmax, const double* ca
                            const int32_t* n1, const int32_t* n2, const int32_t* col_ind, const int32_t* n_out,
                            double* rows, double* pair_cost, void* workspace, size_t workspace_bytes, void* stream)
 {
-    if (!rig || P < 0 || bad_n(Nmax) || !cam1 || !cam2 || !n1 || !n2 || !col_ind || !n_out || !rows)
+    if (bad_rig(rig) || P < 0 || bad_n(Nmax) || !cam1 || !cam2 || !n1 || !n2 || !col_ind || !n_out || !rows)
         return PTK_ERR_INVALID_ARG;
     if (P == 0) return PTK_OK;
     if (!workspace || workspace_bytes < ptk_workspace_bytes(PTK_WS_COST, P, Nmax)) return PTK_ERR_WORKSPACE;
@@ -598,7 +605,7 @@ PTK_API int ptk_chain_rebase(int W, int C, int F, int N, int rank, const int32_t
     const int threads = N < 32 ? 32 : ((N + 31) / 32 * 32);
     {
         LaunchTimer lt(K_CHAIN, st);
-        k_chain_compose<<<C, threads, 2 * (size_t)N * sizeof(int32_t), st>>>(W, C, N, rank, maps, start);
+        k_chain_compose<<<C, threads, 2 * (size_t)N * sizeof(int32_t), st>>>(W, C, N, rank, maps, (size_t)C * N, start);
         LAUNCHED("k_chain_compose");
         const long long total = (long long)C * F * N;
         if (total > 0) {
@@ -640,7 +647,7 @@ PTK_API int ptk_reconstruct_device(const ptk_rig* rig, int F, int C, int Nmax, c
                                    double* track_total, int32_t* track_id, int32_t* track_status, void* workspace,
                                    size_t workspace_bytes, void* stream)
 {
-    if (!rig || F < 0 || C < 0 || bad_n(Nmax)) return PTK_ERR_INVALID_ARG;
+    if (bad_rig(rig) || F < 0 || C < 0 || bad_n(Nmax)) return PTK_ERR_INVALID_ARG;
     if (do_track && (!track_col || !track_total || F < 1)) return PTK_ERR_INVALID_ARG;
     const long long P = (long long)F * C;
     if (P == 0) return PTK_OK;
@@ -768,7 +775,7 @@ PTK_API int ptk_matchnd_sequence(const ptk_rig* rig, int F, int C, int Nmax, con
                                  int32_t* status, int32_t* solver_stats, void* workspace, size_t workspace_bytes,
                                  void* stream)
 {
-    if (!rig || F < 0 || C < 0 || Nmax <= 0 || Nmax > AP3_MAXN || !cam1 || !cam2 || !n1 || !n2 || !rows || !costs ||
+    if (bad_rig(rig) || F < 0 || C < 0 || Nmax <= 0 || Nmax > AP3_MAXN || !cam1 || !cam2 || !n1 || !n2 || !rows || !costs ||
         !n_rows || !status)
         return PTK_ERR_INVALID_ARG;
     if (F == 0 || C == 0) return PTK_OK;
@@ -866,7 +873,7 @@ PTK_API int ptk_reorder_endpoints(int C, int F, int N, const double* ends, const
 PTK_API int ptk_triangulate_points(const ptk_rig* rig, long long n, const double* p1, const double* p2, int to_world,
                                    double* out, void* stream)
 {
-    if (!rig || n < 0 || !p1 || !p2 || !out) return PTK_ERR_INVALID_ARG;
+    if (bad_rig(rig) || n < 0 || !p1 || !p2 || !out) return PTK_ERR_INVALID_ARG;
     if (n == 0) return PTK_OK;
     k_triangulate_points<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(make_devrig(rig), n, to_world, p1, p2, out);
     LAUNCHED("k_triangulate_points");
@@ -876,7 +883,7 @@ PTK_API int ptk_triangulate_points(const ptk_rig* rig, long long n, const double
 PTK_API int ptk_project_points(const ptk_rig* rig, long long n, const double* X, int from_world, double* uv1, double* uv2,
                                void* stream)
 {
-    if (!rig || n < 0 || !X || !uv1 || !uv2) return PTK_ERR_INVALID_ARG;
+    if (bad_rig(rig) || n < 0 || !X || !uv1 || !uv2) return PTK_ERR_INVALID_ARG;
     if (n == 0) return PTK_OK;
     k_project_points<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(make_devrig(rig), n, from_world, X, uv1, uv2);
     LAUNCHED("k_project_points");
@@ -1118,7 +1125,7 @@ PTK_API int ptk_reconstruct_host(ptk_ctx* c, const ptk_rig* rig, int F, int C, i
                                  int32_t* status, double max_repr_err, uint8_t* keep_mask, int do_track,
                                  int32_t* track_col, double* track_total, int32_t* track_id, int32_t* track_status)
 {
-    if (!c || !rig || F < 0 || C < 0 || bad_n(Nmax) || !cam1 || !cam2 || !n1 || !n2 || !rows || !n_out || !status)
+    if (!c || bad_rig(rig) || F < 0 || C < 0 || bad_n(Nmax) || !cam1 || !cam2 || !n1 || !n2 || !rows || !n_out || !status)
         return PTK_ERR_INVALID_ARG;
     if (do_track && (!track_col || !track_total || F < 1)) return PTK_ERR_INVALID_ARG;
     const long long P = (long long)F * C;

@@ -436,7 +436,9 @@ PTK_HD bool dlt_null_invpower(const double* __restrict__ Q1, const double* __res
         const double tr = (b00 + b11) + (b22 + b33);                                                              \
         const double od = fma(b23, b23, fma(b13, b13, fma(b12, b12, fma(b03, b03, fma(b02, b02, b01 * b01)))));    \
         const double fr = fma(2.0, od, fma(b33, b33, fma(b22, b22, fma(b11, b11, b00 * b00))));                   \
-        okvar = fr >= (1.0 - PTK_INVPOWER_TOL) * (tr * tr);                                                       \
+        /* fr - (1 - tol) tr^2 >= 0, written so that Inf - Inf (a Gram-Schmidt norm that underflowed) is */         \
+        /* NaN and therefore NOT converged: the caller then takes the Jacobi fallback                    */         \
+        okvar = fma(-(1.0 - PTK_INVPOWER_TOL), tr * tr, fr) >= 0.0;                                               \
     }
     PTK_SQUARE_B PTK_SQUARE_B PTK_SQUARE_B
     bool ok;

@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(128) k_undistort(const __grid_constant__ DevRi
     const int camsel = blockIdx.z;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = camsel ? n2[p] : n1[p];
-    if (n <= 0 || j >= 2 * n) return;
+    if (n <= 0 || n > Nmax || j >= 2 * n) return;  // n > Nmax: the problem is reported INVALID by K2
     const double* in = (camsel ? cam2 : cam1) + (size_t)p * Nmax * 4;
     double* out = (camsel ? und2 : und1) + (size_t)p * Nmax * 4;
     const double* cm = camsel ? rig.CM2 : rig.CM1;
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(128, PTK_KCOST_MINBLOCKS) k_cost(const __grid_
     const int tile = (int)(blk - (long long)p * a.tiles);
     const int N1 = a.n1[p], N2 = a.n2[p];
     const int npairs = N1 * N2;
-    if (N1 <= 0 || N2 <= 0 || tile * 32 >= npairs) return;
+    if (N1 <= 0 || N2 <= 0 || N1 > a.Nmax || N2 > a.Nmax || tile * 32 >= npairs) return;
     int q = tile * 32 + (threadIdx.x >> 2);
     const bool active = q < npairs;
     if (!active) q = npairs - 1;  // keep the quad shuffles convergent; results are discarded
@@ -266,6 +266,7 @@ __global__ void __launch_bounds__(32) k_lsap(const __grid_constant__ LsapArgs a)
     int st = PTK_PROBLEM_OK;
     int n = 0;
     if (nr0 <= 0 || nc0 <= 0) st = PTK_PROBLEM_EMPTY;
+    else if (nr0 > a.ld_rows || nc0 > a.ld_cols) st = PTK_PROBLEM_INVALID;  // counts beyond the padded shape
     const bool tr = nc0 < nr0;  // tall matrices are solved transposed, as SciPy does
     const int nr = tr ? nc0 : nr0, nc = tr ? nr0 : nc0;
     const bool staged = a.stage != 0;
@@ -612,8 +613,19 @@ __global__ void __launch_bounds__(256) k_track_cost(int N, int F, long long q0, 
 //  pass B (one block per colour): start[0] = ids_in | identity, start[s+1][x] = start[s][map_s[x]].
 //  pass C (elementwise): track_id[f][x] = start[f / kChainSeg][ L[f][x] ].
 // The same three steps give the multi-GPU version: a rank is a super-segment and pass B runs
-// over the all-gathered per-rank maps (particletracking_b200/distributed.py).
+// over the gathered per-rank maps (particletracking_b200/distributed.py).
+//
+// Broken chains.  A frame pair whose LSAP failed (status INVALID / INFEASIBLE: NaN end points of a
+// ragged frame) has col = -1 for every rod; a caller may also pass arbitrary garbage.  Any entry
+// outside 0..N-1 is ignored, positions no valid entry maps to get id -1, and -1 propagates through
+// every later composition (all gathers below are guarded) -- the same rule as the oracle's
+// chain_tracks.  No index derived from col / ids is ever used unchecked.
 constexpr int kChainSeg = 32;
+
+__device__ __forceinline__ int32_t chain_pick(const int32_t* __restrict__ tab, int32_t idx, int N)
+{
+    return ((unsigned)idx < (unsigned)N) ? tab[idx] : -1;
+}
 
 __global__ void k_chain_local(int F, int N, int nseg, const int32_t* __restrict__ col_ind,
                               int32_t* __restrict__ track_id, int32_t* __restrict__ seg_map)
@@ -634,18 +646,23 @@ __global__ void k_chain_local(int F, int N, int nseg, const int32_t* __restrict_
     for (int k = threadIdx.x; k < (f_end - f0) * N; k += blockDim.x) cols[k] = g[k];
     for (int a = threadIdx.x; a < N; a += blockDim.x) {
         cur[a] = a;
+        nxt[a] = -1;
         tid[(size_t)f0 * N + a] = a;
     }
     __syncthreads();
     for (int f = f0; f < f_end; f++) {
         const int32_t* col = cols + (size_t)(f - f0) * N;
-        for (int a = threadIdx.x; a < N; a += blockDim.x) nxt[col[a]] = cur[a];
+        for (int a = threadIdx.x; a < N; a += blockDim.x) {
+            const int32_t j = col[a];
+            if ((unsigned)j < (unsigned)N) nxt[j] = cur[a];
+        }
         __syncthreads();
         if (f < fl) {
             for (int a = threadIdx.x; a < N; a += blockDim.x) tid[(size_t)(f + 1) * N + a] = nxt[a];
         } else {
             for (int a = threadIdx.x; a < N; a += blockDim.x) seg_map[((size_t)c * nseg + s) * N + a] = nxt[a];
         }
+        for (int a = threadIdx.x; a < N; a += blockDim.x) cur[a] = -1;  // becomes the next frame's target
         int32_t* t = cur; cur = nxt; nxt = t;
         __syncthreads();
     }
@@ -672,7 +689,7 @@ __global__ void k_chain_scan(int N, int nseg, const int32_t* __restrict__ ids_in
             for (int a = threadIdx.x; a < N; a += blockDim.x) seg_start[((size_t)c * nseg + s0 + s) * N + a] = cur[a];
             if (s0 + s + 1 == nseg) break;
             const int32_t* mp = maps + (size_t)s * N;
-            for (int a = threadIdx.x; a < N; a += blockDim.x) nxt[a] = cur[mp[a]];
+            for (int a = threadIdx.x; a < N; a += blockDim.x) nxt[a] = chain_pick(cur, mp[a], N);
             __syncthreads();
             int32_t* t = cur; cur = nxt; nxt = t;
         }
@@ -689,13 +706,13 @@ __global__ void k_chain_apply(int F, int N, int nseg, const int32_t* __restrict_
     const int f = (int)(r % F);
     const int c = (int)(r / F);
     const int s = f / kChainSeg;
-    track_id[t] = seg_start[((size_t)c * nseg + s) * N + track_id[t]];
+    track_id[t] = chain_pick(seg_start + ((size_t)c * nseg + s) * N, track_id[t], N);
 }
 
-// Multi-GPU chain pass: compose the all-gathered per-rank boundary maps up to `rank`
+// Multi-GPU chain pass: compose the gathered per-rank boundary maps up to `rank`
 // (start[c][x] = global track id of local id x on this rank) and re-base the local ids.
-// maps[W,C,N]: position x in rank r+1's first frame -> local id on rank r.
-__global__ void k_chain_compose(int W, int C, int N, int rank, const int32_t* __restrict__ maps,
+// maps[W,C,N] (rank stride map_stride ints): position x in rank r+1's first frame -> local id on rank r.
+__global__ void k_chain_compose(int W, int C, int N, int rank, const int32_t* __restrict__ maps, size_t map_stride,
                                 int32_t* __restrict__ start)
 {
     extern __shared__ int32_t sh[];
@@ -705,10 +722,11 @@ __global__ void k_chain_compose(int W, int C, int N, int rank, const int32_t* __
     for (int a = threadIdx.x; a < N; a += blockDim.x) cur[a] = a;
     __syncthreads();
     for (int r = 0; r < rank && r < W; r++) {
-        const int32_t* mp = maps + ((size_t)r * C + c) * N;
-        for (int a = threadIdx.x; a < N; a += blockDim.x) nxt[a] = cur[mp[a]];
+        const int32_t* mp = maps + (size_t)r * map_stride + (size_t)c * N;
+        for (int a = threadIdx.x; a < N; a += blockDim.x) nxt[a] = chain_pick(cur, mp[a], N);
         __syncthreads();
         int32_t* t = cur; cur = nxt; nxt = t;
+        __syncthreads();
     }
     for (int a = threadIdx.x; a < N; a += blockDim.x) start[(size_t)c * N + a] = cur[a];
 }
@@ -719,7 +737,7 @@ __global__ void k_chain_rebase(int F, int N, const int32_t* __restrict__ start, 
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total) return;
     const int c = (int)(t / ((long long)F * N));
-    track_id[t] = start[(size_t)c * N + track_id[t]];
+    track_id[t] = chain_pick(start + (size_t)c * N, track_id[t], N);
 }
 
 // ------------------------------------------------------------------------------------- K6

@@ -42,7 +42,11 @@ def _chk(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
 
 
 class _Workspace:
-    """Per-thread, per-device scratch (the callers run one worker per colour)."""
+    """Scratch per (thread, device, CUDA stream).  The callers run one worker per colour
+    and a worker may use several torch streams: kernels enqueued on different streams must never
+    share scratch, so the stream is part of the key.  A buffer that is replaced by a larger one is
+    handed back to the caching allocator only after ``record_stream`` -- the kernels that still read
+    it were enqueued on that stream, which need not be the one the tensor was allocated under."""
 
     def __init__(self):
         import threading
@@ -50,11 +54,18 @@ class _Workspace:
         self._tls = threading.local()
 
     def get(self, nbytes: int, device) -> torch.Tensor:
-        key = f"ws_{device}"
-        buf = getattr(self._tls, key, None)
+        stream = torch.cuda.current_stream(device)
+        bufs = getattr(self._tls, "bufs", None)
+        if bufs is None:
+            bufs = self._tls.bufs = {}
+        key = (str(device), stream.cuda_stream)
+        buf = bufs.get(key)
         if buf is None or buf.numel() < nbytes:
-            buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
-            setattr(self._tls, key, buf)
+            if buf is not None:
+                buf.record_stream(stream)
+            with torch.cuda.stream(stream):
+                buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+            bufs[key] = buf
         return buf
 
 
@@ -241,8 +252,22 @@ class DevicePipeline:
         nb = nat.lib().ptk_reconstruct_device_workspace_bytes(F, C, Nmax, 1 if track else 0)
         self.ws = torch.empty(nb, dtype=_u8, device=dev)
 
+    def _check_inputs(self, cam1, cam2, n1, n2):
+        P = self.F * self.C
+        for t, dt, name, shape in ((cam1, _f64, "cam1", (P, self.N, 2, 2)), (cam2, _f64, "cam2", (P, self.N, 2, 2)),
+                                   (n1, _i32, "n1", (P,)), (n2, _i32, "n2", (P,))):
+            if not isinstance(t, torch.Tensor) or not t.is_cuda or t.device != self.device:
+                raise ValueError(f"{name} must be a CUDA tensor on {self.device}")
+            if t.dtype != dt:
+                raise ValueError(f"{name} must be {dt}, got {t.dtype}")
+            if tuple(t.shape) != shape:
+                raise ValueError(f"{name} must have shape {shape}, got {tuple(t.shape)}")
+            if not t.is_contiguous():
+                raise ValueError(f"{name} must be contiguous")
+
     def run(self, cam1, cam2, n1, n2):
         """Enqueue one pass on the current stream; results are in the pipeline's tensors."""
+        self._check_inputs(cam1, cam2, n1, n2)
         with torch.cuda.device(self.device):
             nat.check(nat.lib().ptk_reconstruct_device(
                 ctypes.byref(self.rig), self.F, self.C, self.N, _ptr(cam1), _ptr(cam2), _ptr(n1), _ptr(n2),

@@ -11,7 +11,7 @@ import torch
 
 from .. import engine
 from ..rig import make_rig
-from ..synthetic import projection_matrices
+from ..rig import projection_matrices
 
 
 def _rig(calibration: dict, transforms):

@@ -53,6 +53,18 @@ def _rotation_matrix(r, name):
     raise ValueError(f"{name}: expected a 3x3 matrix or a rotation vector")
 
 
+def projection_matrices(calibration: Dict[str, np.ndarray]):
+    """P1 = CM1 [I|0], P2 = CM2 [R|T] and the (r, t) pairs the reference's
+    drivers derive (``match2D.py:584-592``)."""
+    r1 = np.eye(3)
+    t1 = np.zeros((3, 1))
+    r2 = np.asarray(calibration["R"], dtype=np.float64)
+    t2 = np.asarray(calibration["T"], dtype=np.float64).reshape(3, 1)
+    P1 = np.asarray(calibration["CM1"], dtype=np.float64) @ np.hstack([r1, t1])
+    P2 = np.asarray(calibration["CM2"], dtype=np.float64) @ np.hstack([r2, t2])
+    return P1, P2, r1, r2, t1, t2
+
+
 def make_rig(calibration: Dict[str, np.ndarray], P1, P2, rot, trans, r1, r2, t1, t2,
              agg_sum: bool = False) -> PtkRig:
     rig = PtkRig()
@@ -62,6 +74,10 @@ def make_rig(calibration: Dict[str, np.ndarray], P1, P2, rot, trans, r1, r2, t1,
         raise ValueError("camera matrices must be 3x3")
     _fill(rig.dist1, calibration["dist1"], 14, "dist1")
     _fill(rig.dist2, calibration["dist2"], 14, "dist2")
+    if rig.dist1[12] != 0.0 or rig.dist1[13] != 0.0 or rig.dist2[12] != 0.0 or rig.dist2[13] != 0.0:
+        # cv2's tilted-sensor terms (tauX, tauY) are not implemented by the kernels; computing with a
+        # different camera model than the reference's cv2 calls would be silent garbage
+        raise ValueError("distortion coefficients 13 and 14 (tauX, tauY: tilted sensor model) are not supported")
     _fill(rig.R1, _rotation_matrix(r1, "r1"), 9, "r1")
     _fill(rig.R2, _rotation_matrix(r2, "r2"), 9, "r2")
     _fill(rig.t1, t1, 3, "t1")
@@ -84,8 +100,6 @@ def rig_from_dicts(calibration: Dict[str, np.ndarray], transformation: Dict[str,
     """Rig the way ``match_complex`` / ``match_csv_complex`` derive it
     (match2D.py:584-596, 689-710)."""
     from scipy.spatial.transform import Rotation
-
-    from .synthetic import projection_matrices
 
     P1, P2, r1, r2, t1, t2 = projection_matrices(calibration)
     if "translation" in transformation:

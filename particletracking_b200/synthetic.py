@@ -51,16 +51,7 @@ def synthetic_transformation() -> Dict[str, np.ndarray]:
     }
 
 
-def projection_matrices(calibration: Dict[str, np.ndarray]):
-    """P1 = CM1 [I|0], P2 = CM2 [R|T] and the (r, t) pairs the reference's
-    drivers derive (``match2D.py:584-592``)."""
-    r1 = np.eye(3)
-    t1 = np.zeros((3, 1))
-    r2 = np.asarray(calibration["R"], dtype=np.float64)
-    t2 = np.asarray(calibration["T"], dtype=np.float64).reshape(3, 1)
-    P1 = np.asarray(calibration["CM1"], dtype=np.float64) @ np.hstack([r1, t1])
-    P2 = np.asarray(calibration["CM2"], dtype=np.float64) @ np.hstack([r2, t2])
-    return P1, P2, r1, r2, t1, t2
+from .rig import projection_matrices  # noqa: E402,F401  (lives with the rig; re-exported for the tests / tools)
 
 
 def project(X: np.ndarray, Rm: np.ndarray, t: np.ndarray, CM: np.ndarray, dist: np.ndarray) -> np.ndarray:

@@ -104,3 +104,136 @@ def test_host_pipeline_reports_invalid_like_scipy(env):
     st = out["status"].numpy()
     assert st[2, 1] == nat.PROBLEM_INVALID and (np.delete(st.ravel(), 5) == 0).all()
     pipe.close()
+
+
+def _ragged(F=70, C=3, N=10, seed=11):
+    """Frames with dropped detections (n_out < Nmax -> NaN rows -> the tracking LSAP of the pairs
+    touching them is INVALID) and one partially-NaN rod: the case ADVICE r1 flagged."""
+    from particletracking_b200 import synthetic as syn
+
+    data = syn.make_stereo(F, C, N, seed=seed, p_drop=0.02)
+    cam1 = data.cam1.copy()
+    cam1[40, 1, 0, 0, 0] = np.nan
+    return data, cam1
+
+
+def test_chain_tolerates_failed_assignments_device(env):
+    """track=True on ragged / NaN input must not fault: failed pairs have col = -1, the chain pass
+    ignores them, marks unreached positions -1 and propagates (same rule as the oracle)."""
+    import torch
+    from oracle import c_oracle as co
+
+    engine, nat, crig = env
+    data, cam1 = _ragged()
+    F, C, N = cam1.shape[:3]
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    c1, c2 = t(cam1.reshape(F * C, N, 2, 2)), t(data.cam2.reshape(F * C, N, 2, 2))
+    n1, n2 = t(data.n1.reshape(-1)), t(data.n2.reshape(-1))
+    pipe = engine.DevicePipeline(crig, F, C, N, track=True)
+    pipe.run(c1, c2, n1, n2)
+    torch.cuda.synchronize()
+    col = pipe.track_col.cpu().numpy()
+    tst = pipe.track_status.cpu().numpy()
+    assert (tst != 0).any() and (tst == 0).any()
+    assert (col[tst != 0] == -1).all()
+    tid = pipe.track_id.cpu().numpy()
+    np.testing.assert_array_equal(tid, co.chain_tracks(col))
+    assert (tid == -1).any() and tid.min() == -1 and tid.max() < N
+    # the generic entry points agree
+    m, col2, tot2, tid2, st2 = engine.reconstruct_device(crig, c1, c2, n1, n2, F, C, track=True)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(col2.cpu().numpy(), col)
+    np.testing.assert_array_equal(tid2.cpu().numpy(), tid)
+    # garbage maps straight into the chain kernels: nothing is dereferenced unchecked
+    rng = np.random.default_rng(0)
+    junk = rng.integers(-5, N + 5, size=(C, F - 1, N)).astype(np.int32)
+    got = engine.chain_tracks(t(junk)).cpu().numpy()
+    assert got.min() >= -1 and got.max() < N
+    # (duplicates make the result order dependent; compare on a permutation-or-invalid input)
+    perm = np.stack([[rng.permutation(N) for _ in range(F - 1)] for _ in range(C)]).astype(np.int32)
+    perm[:, 13] = -1
+    perm[1, 50, 3] = N + 2
+    np.testing.assert_array_equal(engine.chain_tracks(t(perm)).cpu().numpy(), co.chain_tracks(perm))
+
+
+def test_chain_tolerates_failed_assignments_host_and_sharded(env):
+    import torch
+    from oracle import c_oracle as co
+    from particletracking_b200 import distributed as pdist
+
+    engine, nat, crig = env
+    data, cam1 = _ragged(seed=12)
+    F, C, N = cam1.shape[:3]
+    pipe = engine.HostPipeline(0)
+    with pytest.raises(ValueError, match="invalid numeric entries"):
+        pipe.reconstruct(crig, cam1, data.cam2, data.n1, data.n2, track=True)
+    out = pipe.reconstruct(crig, cam1, data.cam2, data.n1, data.n2, track=True, raise_on_invalid=False)
+    col = out["track_col"].numpy().copy()
+    tid = out["track_id"].numpy().copy()
+    np.testing.assert_array_equal(tid, co.chain_tracks(col))
+    assert (tid == -1).any()
+    pipe.close()
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    rec = pdist.ShardedReconstructor(crig, F, C, N, torch.device("cuda", 0))
+    o = rec.step(t(cam1.reshape(F * C, N, 2, 2)), t(data.cam2.reshape(F * C, N, 2, 2)), t(data.n1.reshape(-1)),
+                 t(data.n2.reshape(-1)))
+    rec.finish()
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(o["track_id"].cpu().numpy(), tid)
+
+
+def test_counts_beyond_nmax_and_tilt_are_rejected(env):
+    import torch
+
+    engine, nat, crig = env
+    from particletracking_b200 import rig as rigmod, synthetic as syn
+
+    data = syn.make_stereo(3, 2, 6, seed=5)
+    c1, c2, n1, n2 = (torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in data.problems())
+    n1 = n1.clone()
+    n1[2] = 7  # > Nmax
+    r = engine.match_batch(crig, c1, c2, n1, n2)
+    st = r.status.cpu().numpy()
+    assert st[2] == nat.PROBLEM_INVALID and (np.delete(st, 2) == 0).all()
+    cal = dict(data.calibration)
+    cal["dist1"] = np.concatenate([np.asarray(cal["dist1"], dtype=float).ravel(), np.zeros(14)])[:14]
+    cal["dist1"][12] = 0.01
+    with pytest.raises(ValueError, match="tauX"):
+        rigmod.rig_from_dicts(cal, data.transformation)
+    bad = rigmod.PtkRig.from_buffer_copy(bytes(crig))
+    bad.dist2[13] = 1e-3
+    ws = torch.empty(1 << 20, dtype=torch.uint8, device="cuda")
+    p = lambda x: ctypes.c_void_p(x.data_ptr())
+    rc = nat.lib().ptk_undistort_batch(ctypes.byref(bad), 6, 6, p(c1), p(c2), p(n1), p(n2), p(ws), p(ws), None)
+    assert rc == -1
+    pipe = engine.DevicePipeline(crig, 3, 2, 6, track=True)
+    with pytest.raises(ValueError, match="float64"):
+        pipe.run(c1.float(), c2, n1, n2)
+    with pytest.raises(ValueError, match="shape"):
+        pipe.run(c1[:4], c2, n1, n2)
+
+
+def test_workspace_is_per_stream(env):
+    """Two streams of one thread must not share scratch: interleaved calls on two
+    streams give the serial results."""
+    import torch
+    from particletracking_b200 import synthetic as syn
+
+    engine, nat, crig = env
+    d1 = syn.make_stereo(200, 4, 24, seed=21)
+    d2 = syn.make_stereo(200, 4, 24, seed=22)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    a1 = tuple(t(x) for x in d1.problems())
+    a2 = tuple(t(x) for x in d2.problems())
+    r1 = engine.match_batch(crig, *a1)
+    r2 = engine.match_batch(crig, *a2)
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(4):
+        with torch.cuda.stream(s1):
+            q1 = engine.match_batch(crig, *a1)
+        with torch.cuda.stream(s2):
+            q2 = engine.match_batch(crig, *a2)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(q1.rows.cpu().numpy(), r1.rows.cpu().numpy())
+    np.testing.assert_array_equal(q2.rows.cpu().numpy(), r2.rows.cpu().numpy())

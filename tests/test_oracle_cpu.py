@@ -311,3 +311,25 @@ def test_c_oracle_vs_cv2_on_random_rigs(seed):
     np.testing.assert_array_equal(o["choice"], ref["choice"])
     d = np.abs(o["p_world"] - ref["p_world"]).max(axis=-1) / np.maximum(np.abs(ref["p_world"]).max(axis=-1), 1.0)
     assert d.max() < TOL
+
+
+def test_chain_broken_maps_port_vs_c():
+    """Failed assignments (col = -1 / out of range) break the chain: -1 from there on, in both
+    restatements of the chain-pass extension."""
+    from oracle import c_oracle as co
+    from oracle import port
+
+    rng = np.random.default_rng(4)
+    F, N = 40, 7
+    col = np.stack([rng.permutation(N) for _ in range(F - 1)]).astype(np.int32)
+    col[9] = -1
+    col[20, 2] = N + 3
+    a = port.chain_tracks(col)
+    b = co.chain_tracks(col[None])[0]
+    np.testing.assert_array_equal(a, b)
+    assert (a[:10] >= 0).all() and (a[10:] == -1).all()
+    col = np.stack([rng.permutation(N) for _ in range(F - 1)]).astype(np.int32)
+    col[20, 2] = N + 3
+    a = port.chain_tracks(col)
+    np.testing.assert_array_equal(a, co.chain_tracks(col[None])[0])
+    assert (a[21:] == -1).sum(axis=1).tolist() == [1] * (F - 21)
