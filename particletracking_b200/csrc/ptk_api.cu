@@ -16,6 +16,7 @@
 #include "ptk_csv.cuh"
 #include "ptk_csv_reader.h"
 #include "ptk_kernels.cuh"
+#include "ptk_lsap_trk.cuh"
 #include "ptk_ap3.cuh"
 
 using namespace ptk;
@@ -238,16 +239,13 @@ int launch_lsap(long long P, LsapArgs a, cudaStream_t st)
 {
     const int M = a.ld_rows > a.ld_cols ? a.ld_rows : a.ld_cols;
     const size_t bytes = (size_t)a.ld_rows * a.ld_cols * sizeof(double);
-    const bool trk = a.trk_ends != nullptr;
-    a.stage = (!trk && bytes <= (size_t)kLsapStageBytes) ? 1 : 0;
-    const size_t smem = ((lsap_row_state_bytes(M) + 15) / 16) * 16 +
-                        (trk ? (size_t)14 * M * sizeof(double) : (a.stage ? bytes : 0));
+    a.stage = (bytes <= (size_t)kLsapStageBytes) ? 1 : 0;
+    const size_t smem = ((lsap_row_state_bytes(M) + 15) / 16) * 16 + (a.stage ? bytes : 0);
     const long long max_p = 1ll << 30;
     for (long long p0 = 0; p0 < P; p0 += max_p) {
         const long long np = (P - p0) < max_p ? (P - p0) : max_p;
         LsapArgs b = a;
         if (a.cost) b.cost = a.cost + (size_t)p0 * a.cost_stride;
-        if (trk && p0 != 0) return PTK_ERR_INVALID_ARG;  // TRK launches index frames by the launch-local problem id
         if (a.nr) b.nr = a.nr + p0;
         if (a.nc) b.nc = a.nc + p0;
         if (a.row_ind) b.row_ind = a.row_ind + (size_t)p0 * a.out_ld;
@@ -259,11 +257,7 @@ int launch_lsap(long long P, LsapArgs a, cudaStream_t st)
         if (a.keep) b.keep = a.keep + (size_t)p0 * a.out_ld;
         {
             LaunchTimer lt(a.total ? K_LSAP_TRACK : K_LSAP_MATCH, st);
-            if (trk) {
-                if (M <= 64) k_lsap<2, true><<<(unsigned)np, 32, smem, st>>>(b);
-                else if (M <= 128) k_lsap<4, true><<<(unsigned)np, 32, smem, st>>>(b);
-                else k_lsap<8, true><<<(unsigned)np, 32, smem, st>>>(b);
-            } else if (M <= 32) k_lsap<1><<<(unsigned)np, 32, smem, st>>>(b);
+            if (M <= 32) k_lsap<1><<<(unsigned)np, 32, smem, st>>>(b);
             else if (M <= 64) k_lsap<2><<<(unsigned)np, 32, smem, st>>>(b);
             else if (M <= 128) k_lsap<4><<<(unsigned)np, 32, smem, st>>>(b);
             else k_lsap<8><<<(unsigned)np, 32, smem, st>>>(b);
@@ -271,6 +265,67 @@ int launch_lsap(long long P, LsapArgs a, cudaStream_t st)
         LAUNCHED("k_lsap");
     }
     return PTK_OK;
+}
+
+// K2T: the tracking assignment straight from the end points (ptk_lsap_trk.cuh): k_trk_prepare writes the
+// separable norms and the exception list of every problem into `scratch`, k_lsap_trk solves, WARPS
+// problems per CTA.
+template <int CPL, int WARPS, int MINB, bool MASKED>
+int launch_lsap_trk_m(const TrkArgs& a, void* scratch, cudaStream_t st)
+{
+    const size_t smem = (size_t)WARPS * trk_warp_bytes<CPL>(a.N);
+    if (smem > 48 * 1024) {
+        static std::once_flag once;  // per instantiation
+        static cudaError_t attr_rc = cudaSuccess;
+        std::call_once(once, [&] {
+            attr_rc = cudaFuncSetAttribute(k_lsap_trk<CPL, WARPS, MINB, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)((size_t)WARPS * trk_warp_bytes<CPL>(32 * CPL)));
+        });
+        if (attr_rc != cudaSuccess) return cuda_fail(attr_rc, "cudaFuncSetAttribute(k_lsap_trk)");
+    }
+    const long long blocks = (a.Q + WARPS - 1) / WARPS;
+    {
+        LaunchTimer lt(K_LSAP_TRACK, st);
+        k_lsap_trk<CPL, WARPS, MINB, MASKED><<<(unsigned)blocks, 32 * WARPS, smem, st>>>(a, scratch);
+    }
+    LAUNCHED("k_lsap_trk");
+    return PTK_OK;
+}
+
+// Every problem is solved by exactly one of the two launches (k_trk_prepare's flag decides): the
+// common case by the lean loop, problems with more than one exception per column by the one that can
+// re-evaluate masked entries.  Where no problem is masked the second launch is ~2 us of early exits.
+template <int CPL, int WARPS, int MINB>
+int launch_lsap_trk_t(const TrkArgs& a, void* scratch, cudaStream_t st)
+{
+    int rc = launch_lsap_trk_m<CPL, WARPS, MINB, false>(a, scratch, st);
+    if (rc) return rc;
+    return launch_lsap_trk_m<CPL, WARPS, MINB, true>(a, scratch, st);
+}
+
+int launch_lsap_trk(const TrkArgs& a, void* scratch, cudaStream_t st)
+{
+    if (a.Q >= (1ll << 31)) return PTK_ERR_INVALID_ARG;
+    {
+        const size_t smem = (size_t)kTrkPrepWarps * 14 * a.N * sizeof(double);  // <= 112 KB at N = 256
+        if (smem > 48 * 1024) {
+            static std::once_flag once;
+            static cudaError_t attr_rc = cudaSuccess;
+            std::call_once(once, [&] {
+                attr_rc = cudaFuncSetAttribute(k_trk_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)((size_t)kTrkPrepWarps * 14 * PTK_MAX_RODS * sizeof(double)));
+            });
+            if (attr_rc != cudaSuccess) return cuda_fail(attr_rc, "cudaFuncSetAttribute(k_trk_prepare)");
+        }
+        LaunchTimer lt(K_TRACK_COST, st);
+        k_trk_prepare<<<(unsigned)((a.Q + kTrkPrepWarps - 1) / kTrkPrepWarps), 32 * kTrkPrepWarps, smem, st>>>(a, scratch);
+    }
+    LAUNCHED("k_trk_prepare");
+    // occupancy of the solver is set by registers: 40 / 24 / 20 / 12 warps per SM
+    if (a.N <= 32) return launch_lsap_trk_t<1, 4, 10>(a, scratch, st);
+    if (a.N <= 64) return launch_lsap_trk_t<2, 4, 6>(a, scratch, st);
+    if (a.N <= 128) return launch_lsap_trk_t<4, 4, 5>(a, scratch, st);
+    return launch_lsap_trk_t<8, 4, 3>(a, scratch, st);
 }
 
 int launch_rows(const DevRig& rig, long long P, int Nmax, const double* cam1, const double* cam2, const double* und1,
@@ -380,7 +435,7 @@ PTK_API size_t ptk_workspace_bytes(int kind, long long n_problems, int Nmax)
         }
         case PTK_WS_TRACK: {
             if (bad_n(Nmax)) return 0;
-            return align_up((size_t)match_chunk(n_problems, Nmax) * Nmax * Nmax * sizeof(double)) + 256;
+            return align_up((size_t)n_problems * trk_prep_bytes(Nmax)) + 256;  // k_trk_prepare's records
         }
         case PTK_WS_WEIGHTS:
             return align_up((size_t)((n_problems + 255) / 256) * sizeof(double)) + 256;
@@ -512,28 +567,23 @@ PTK_API int ptk_track_batch(int C, int F, int N, const double* ends, double* cos
     if (C < 0 || F < 1 || bad_n(N) || !ends || !col_ind || !total_cost) return PTK_ERR_INVALID_ARG;
     const long long Q = (long long)C * (F - 1);
     if (Q == 0) return PTK_OK;
-    if (!cost && (!workspace || workspace_bytes < ptk_workspace_bytes(PTK_WS_TRACK, Q, N))) return PTK_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t NN = (size_t)N * N;
-    if (!cost && N > 64) {
-        // large N: solve straight from the end points (k_lsap<CPL, true>), no cost matrix in HBM at
-        // all.  Measured (profiles/README.md): N=128 96 -> 81 ms, N=256 382 -> 239 ms per 16000 /
-        // 4000 problems; at N=64 the matrix path is as fast (8.6 vs 8.9 ms), below it is faster.
-        LsapArgs a{};
-        a.ld_rows = N; a.ld_cols = N; a.cost_stride = 0; a.cost = nullptr;
-        a.out_ld = N;
-        a.col_ind = col_ind;
-        a.status = status;
-        a.total = total_cost;
-        a.max_err = INFINITY;
-        a.trk_ends = ends; a.trk_F = F;
-        return launch_lsap(Q, a, st);
+    if (!cost) {
+        // no matrix wanted: solve straight from the end points (k_trk_prepare + k_lsap_trk) -- no
+        // N^2 matrix in HBM or shared memory for any N; the workspace holds 32..60 N bytes per problem
+        if (!workspace || workspace_bytes < ptk_workspace_bytes(PTK_WS_TRACK, Q, N)) return PTK_ERR_WORKSPACE;
+        TrkArgs a{};
+        a.N = N; a.F = F; a.Q = Q;
+        a.ends = ends; a.col_ind = col_ind; a.total = total_cost; a.status = status;
+        return launch_lsap_trk(a, (void*)align_up((size_t)workspace), st);
     }
-    long long chunk = cost ? Q : match_chunk(Q, N);
-    double* wcost = cost ? cost : reinterpret_cast<double*>(align_up((size_t)workspace));
+    // the caller wants the matrix (tests, diagnostics): K4 writes it, the generic K2 solves it
+    (void)workspace; (void)workspace_bytes;
+    const long long chunk = Q;
     for (long long q0 = 0; q0 < Q; q0 += chunk) {
         const long long nq = (Q - q0) < chunk ? (Q - q0) : chunk;
-        double* cchunk = cost ? cost + (size_t)q0 * NN : wcost;
+        double* cchunk = cost + (size_t)q0 * NN;
         {
             LaunchTimer lt(K_TRACK_COST, st);
             k_track_cost<<<(unsigned)nq, 256, (size_t)14 * N * sizeof(double), st>>>(N, F, q0, ends, cchunk);

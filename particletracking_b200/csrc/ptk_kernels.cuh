@@ -148,10 +148,6 @@ struct LsapArgs {
     uint8_t* keep;           // optional [P,out_ld]: assigned <= max_err
     double max_err;
     int stage;               // set by the launcher: cost matrix fits the shared-memory staging budget
-    // TRK mode (k_lsap<CPL, true>): no cost matrix; the tracking cost (tracking.py:100-121) is
-    // evaluated on the fly from the two frames' end points: ends[C,F,N,2,3], problem p = c*(F-1)+f
-    const double* trk_ends;
-    int trk_F;
 };
 
 __device__ __forceinline__ double warp_min(double x)
@@ -166,29 +162,6 @@ __device__ __forceinline__ double warp_sum(double x)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(kFull, x, o);
     return x;
-}
-
-__device__ __forceinline__ double norm3(double ax, double ay, double az, double bx, double by, double bz);
-
-// Tracking cost entry (a, b) of one frame pair, evaluated from shared memory: cur/nxt hold the
-// two frames' rods ([N][2][3]), n1[a] = |q1[a]-p1[a]|, n2[b] = |q2[b]-p2[b]| (k_track_cost's
-// separable term).  Bit-identical to k_track_cost: the cross term d1 is only skipped when a cheap
-// lower bound (largest coordinate difference of each of its two norms) already exceeds d0 by more
-// than any rounding could bridge, in which case min(d0, d1) == d0 exactly.
-__device__ __forceinline__ double trk_cost_entry(const double* __restrict__ cur, const double* __restrict__ nxt,
-                                                 const double* __restrict__ n1, const double* __restrict__ n2, int a, int b)
-{
-    const double d0 = n1[a] + n2[b];
-    const double* p1a = cur + 6 * a;
-    const double* p2b = cur + 6 * b + 3;
-    const double* q1a = nxt + 6 * a;
-    const double* q2b = nxt + 6 * b + 3;
-    const double la = fmax(fmax(fabs(p1a[0] - q2b[0]), fabs(p1a[1] - q2b[1])), fabs(p1a[2] - q2b[2]));
-    const double lb = fmax(fmax(fabs(p2b[0] - q1a[0]), fabs(p2b[1] - q1a[1])), fabs(p2b[2] - q1a[2]));
-    if ((la + lb) * 0.99999999999999 > d0) return d0;
-    const double d1 = norm3(p1a[0], p1a[1], p1a[2], q2b[0], q2b[1], q2b[2]) +
-                      norm3(p2b[0], p2b[1], p2b[2], q1a[0], q1a[1], q1a[2]);
-    return (d0 != d0) ? d0 : ((d1 != d1) ? d1 : (d1 < d0 ? d1 : d0));
 }
 
 // order-preserving map double -> unsigned 64 (for REDUX-based min / equality)
@@ -234,11 +207,8 @@ __host__ __device__ inline size_t lsap_row_state_bytes(int M) { return (size_t)M
 // which is all the tie rule needs; removal = "the column at the last position takes the freed
 // one").  Row duals u and col4row sit in shared memory (one read per Dijkstra step).  A step is
 // ~60 warp instructions + ~25 per owned column; the kernel is issue bound, not latency bound.
-// TRK = true: the tracking variant for matrices too large to stage (N > 45).  The 8 N^2-byte cost
-// matrix is never materialised; entries come from trk_cost_entry out of 112 N bytes of shared
-// memory, which removes k_track_cost's write and, more importantly, one L2/HBM round trip from
-// every one of the n(n+1)/2 dependent Dijkstra steps of the degenerate tracking problems.
-template <int CPL, bool TRK = false>
+// (The tracking assignment has its own kernel without a cost matrix: ptk_lsap_trk.cuh.)
+template <int CPL>
 __global__ void __launch_bounds__(32) k_lsap(const __grid_constant__ LsapArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -246,11 +216,6 @@ __global__ void __launch_bounds__(32) k_lsap(const __grid_constant__ LsapArgs a)
     double* u = reinterpret_cast<double*>(smem_raw);
     int32_t* c4r = reinterpret_cast<int32_t*>(u + M);
     double* sm = reinterpret_cast<double*>(smem_raw + ((lsap_row_state_bytes(M) + 15) / 16) * 16);
-    // TRK: sm = cur[6N] | nxt[6N] | n1[N] | n2[N]
-    const double* tcur = sm;
-    const double* tnxt = sm + 6 * M;
-    double* tn1 = sm + 12 * M;
-    double* tn2 = tn1 + M;
     const int lane = threadIdx.x;
     const long long p = blockIdx.x;
     const int nr0 = a.nr ? a.nr[p] : a.ld_rows;
@@ -274,25 +239,7 @@ __global__ void __launch_bounds__(32) k_lsap(const __grid_constant__ LsapArgs a)
     if (st == PTK_PROBLEM_OK) {
         // validate (SciPy: "matrix contains invalid numeric entries") and stage in solver orientation
         bool bad = false;
-        if (TRK) {
-            const int cc = (int)(p / (a.trk_F - 1)), ff = (int)(p - (long long)cc * (a.trk_F - 1));
-            const double* g = a.trk_ends + ((size_t)cc * a.trk_F + ff) * nr0 * 6;
-            for (int k = lane; k < 12 * nr0; k += 32) sm[(k < 6 * nr0) ? k : (6 * M + k - 6 * nr0)] = g[k];
-            __syncwarp();
-            for (int k = lane; k < 2 * nr0; k += 32) {
-                const int r = k >> 1, e = (k & 1) * 3;
-                const double vv = norm3(tnxt[6 * r + e], tnxt[6 * r + e + 1], tnxt[6 * r + e + 2],
-                                        tcur[6 * r + e], tcur[6 * r + e + 1], tcur[6 * r + e + 2]);
-                if (k & 1) tn2[r] = vv; else tn1[r] = vv;
-            }
-            __syncwarp();
-            const int tot = nr0 * nc0;
-            for (int idx = lane; idx < tot; idx += 32) {
-                const int i = idx / nc0, j = idx - i * nc0;
-                const double c = trk_cost_entry(tcur, tnxt, tn1, tn2, i, j);
-                bad |= (c != c) || (c == -INFINITY);
-            }
-        } else {
+        {
             const int tot = nr0 * nc0;
             for (int idx = lane; idx < tot; idx += 32) {
                 const int i = idx / nc0, j = idx - i * nc0;
@@ -331,8 +278,7 @@ __global__ void __launch_bounds__(32) k_lsap(const __grid_constant__ LsapArgs a)
                     key[s] = ~0ull;
                     if (pos[s] >= 0) {
                         const int j = lane + 32 * s;
-                        const double c = TRK ? trk_cost_entry(tcur, tnxt, tn1, tn2, i, j)
-                                             : (staged ? sm[i * nc + j] : (tr ? C[(size_t)j * ldc + i] : C[(size_t)i * ldc + j]));
+                        const double c = staged ? sm[i * nc + j] : (tr ? C[(size_t)j * ldc + i] : C[(size_t)i * ldc + j]);
                         const double r = ((minVal + c) - ui) - v[s];
                         if (r < spc[s]) { spc[s] = r; path[s] = i; }
                         key[s] = ordered_key(spc[s]);
@@ -409,7 +355,7 @@ __global__ void __launch_bounds__(32) k_lsap(const __grid_constant__ LsapArgs a)
         if (!tr) {
             for (int r = lane; r < nr; r += 32) {
                 const int cj = c4r[r];
-                const double cst = TRK ? trk_cost_entry(tcur, tnxt, tn1, tn2, r, cj) : C[(size_t)r * ldc + cj];
+                const double cst = C[(size_t)r * ldc + cj];
                 if (orow) orow[r] = r;
                 ocol[r] = cj;
                 if (oasg) oasg[r] = cst;

@@ -624,3 +624,48 @@ def test_tracking_on_the_fly_large_n(eng, C, F, N):
     _, _, st_b, _ = eng.track_batch(dev(bad))
     st_b = st_b.cpu().numpy()
     assert st_b[0, 0] == 1 and (F < 3 or st_b[0, 1] == 1) and (st_b[0, 2:] == 0).all()
+
+
+@pytest.mark.parametrize("C,F,N,crowd", [(2, 6, 5, 0), (3, 12, 12, 0), (4, 30, 32, 0), (2, 9, 33, 0), (2, 9, 64, 0),
+                                          (2, 8, 12, 1), (3, 20, 32, 1), (2, 6, 48, 1), (1, 4, 150, 1), (1, 3, 256, 1)])
+def test_tracking_without_matrix_exceptions_and_masked(eng, C, F, N, crowd):
+    """k_trk_prepare + k_lsap_trk (no cost matrix): the separable cost is formed in registers, the
+    entries where the cross term wins are exceptions.  `crowd = 0`: flipped rods (one exception per
+    column, register path); `crowd = 1`: all rods inside a ball the size of one frame's motion, so that
+    the cross term wins all over the matrix (several exceptions per column: the masked instantiation).
+    Assignments must equal the oracle's SciPy-exact LSAP on the full matrix bit for bit."""
+    from oracle import c_oracle as co
+
+    rng = np.random.default_rng(17 * N + F + crowd)
+    if crowd:
+        base = rng.normal(size=(C, 1, N, 2, 3)) * 0.3
+        ends = base + np.cumsum(rng.normal(size=(C, F, N, 2, 3)) * 0.3, axis=1)
+    else:
+        base = rng.normal(size=(C, 1, N, 2, 3)) * 30
+        ends = base + np.cumsum(rng.normal(size=(C, F, N, 2, 3)) * 0.2, axis=1)
+        flip = rng.random((C, F, N)) < 0.3
+        ends[flip] = ends[flip][:, ::-1]
+    o = co.track_batch(ends, want_cost=True)
+    d0 = (np.linalg.norm(ends[:, 1:, :, 0] - ends[:, :-1, :, 0], axis=-1)[..., :, None]
+          + np.linalg.norm(ends[:, 1:, :, 1] - ends[:, :-1, :, 1], axis=-1)[..., None, :])
+    exc = (o["cost"] != d0).sum(axis=2)  # exceptions per column
+    assert exc.max() >= (2 if crowd else 1), "the test data does not exercise the intended path"
+    col, tot, st, _ = eng.track_batch(dev(ends))
+    assert (st.cpu().numpy() == 0).all()
+    np.testing.assert_array_equal(col.cpu().numpy(), o["col_ind"])
+    assert rel_err(tot.cpu().numpy(), o["total_cost"]) < 1e-13
+    # identical rods (exact ties all over: SciPy's tie rule decides) and an infinite coordinate
+    tie = ends.copy()
+    tie[:, :, 1:] = tie[:, :, :1]
+    ot = co.track_batch(tie)
+    ct, _, stt, _ = eng.track_batch(dev(tie))
+    np.testing.assert_array_equal(ct.cpu().numpy(), ot["col_ind"])
+    inf = ends.copy()
+    inf[0, 1, 0, 0, 0] = np.inf
+    oi = co.track_batch(inf)
+    ci, _, sti, _ = eng.track_batch(dev(inf))
+    np.testing.assert_array_equal(sti.cpu().numpy(), oi["status"])
+    assert (oi["status"] == 2).any()  # a row of +inf costs: SciPy's "cost matrix is infeasible"
+    ok = oi["status"] == 0
+    np.testing.assert_array_equal(ci.cpu().numpy()[ok], oi["col_ind"][ok])
+    assert (ci.cpu().numpy()[~ok] == -1).all()
