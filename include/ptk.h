@@ -160,7 +160,8 @@ int ptk_track_batch(int C, int F, int N, const double* ends,
 
 /* ---- K5: chain pass (extension; SURVEY.md App. D.3, no reference counterpart) --------
  * ids[c,0] = ids_in[c] (or arange(N) if ids_in is NULL); ids[c,f+1][col_ind[c,f][a]] = ids[c,f][a].
- * col_ind[C,F-1,N] -> track_id[C,F,N]; last_ids[C,N] (optional) = track_id[c,F-1]. */
+ * col_ind[C,F-1,N] -> track_id[C,F,N].  Entries of col_ind outside 0..N-1 (a failed assignment:
+ * ptk_track_batch writes -1) break the chain: unreached positions get id -1 and -1 propagates. */
 int ptk_chain_tracks(int C, int F, int N, const int32_t* col_ind, const int32_t* ids_in,
                      int32_t* track_id, void* stream);
 
@@ -318,6 +319,35 @@ int ptk_reconstruct_device(const ptk_rig* rig, int F, int C, int Nmax,
                            int do_track, int32_t* track_col, double* track_total,
                            int32_t* track_id, int32_t* track_status,
                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- one rank's frame range of a sharded run, one call ------------------------
+ * As ptk_reconstruct_device with tracking, for F own frames followed by n_halo (0 or 1) frames that
+ * belong to the next rank: cam1/cam2/n1/n2 and rows/match_cost/row_ind/col_ind/n_out/status hold
+ * F + n_halo frames.  The halo frame is matched again here (the matching is a pure function of its
+ * inputs: same bits as on its owner), so the boundary pair (F-1, F) is tracked locally and no halo
+ * exchange is needed (the "recompute" option of SURVEY.md 8e; replaces the per-step send/recv).
+ * track_col[C,F+n_halo-1,N], track_total / track_status[C,F+n_halo-1]; track_id[C,F,N] are LOCAL ids
+ * (relative to this rank's first frame); halo_map[C,N] (required if n_halo) = local id of every position
+ * of the halo frame, i.e. the map from the next rank's local ids to this rank's.  Kernel launches
+ * only: capturable in a CUDA graph.  workspace: ptk_reconstruct_shard_workspace_bytes(F, n_halo, C, Nmax). */
+size_t ptk_reconstruct_shard_workspace_bytes(int F, int n_halo, int C, int Nmax);
+int ptk_reconstruct_shard(const ptk_rig* rig, int F, int n_halo, int C, int Nmax,
+                          const double* cam1, const double* cam2, const int32_t* n1, const int32_t* n2,
+                          double* rows, double* match_cost, int32_t* row_ind, int32_t* col_ind,
+                          int32_t* n_out, int32_t* status, double max_repr_err, uint8_t* keep_mask,
+                          int32_t* track_col, double* track_total, int32_t* track_status,
+                          int32_t* track_id, int32_t* halo_map,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* Root side of the sharded chain pass, after the final gather: block r (r = 0..W-1) starts at
+ * blocks + r*block_stride bytes and holds rank r's local ids track_id[C,frames_per_rank[r],N] at byte
+ * offset tid_off and its halo_map[C,N] at map_off.  Composes the maps (start_r = start_{r-1} o map_{r-1},
+ * start_0 = identity) and re-bases every rank's ids in place; ids of a broken chain stay -1.
+ * frames_per_rank is a HOST array; start_scratch[C,N] device scratch. */
+int ptk_chain_rebase_gathered(int W, int C, int N, const int32_t* frames_per_rank, void* blocks,
+                              size_t block_stride, size_t tid_off, size_t map_off,
+                              int32_t* start_scratch, void* stream);
+
 
 /* ---- host-buffer pipeline (what bench.py's `e2e` and match_csv_complex call) ----------
  * A ptk_ctx owns a device, streams, pinned staging and device buffers sized on demand. */

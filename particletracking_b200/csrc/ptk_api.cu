@@ -13,6 +13,8 @@
 #include <utility>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX 3: ranges cost nothing unless a profiler injects itself
+
 #include "ptk_csv.cuh"
 #include "ptk_csv_reader.h"
 #include "ptk_kernels.cuh"
@@ -73,6 +75,12 @@ struct LaunchTimer {
         std::lock_guard<std::mutex> lk(g_timing_mu);
         g_timed.push_back({kind, t0, t1});
     }
+};
+
+// NVTX range around a stage of the pipeline (visible in Nsight Systems / ncu --nvtx)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
 };
 
 inline int cuda_fail(cudaError_t e, const char* what)
@@ -604,22 +612,25 @@ PTK_API int ptk_track_batch(int C, int F, int N, const double* ends, double* cos
 
 // ------------------------------------------------------------------------------------ K5
 namespace {
-int chain_impl(int C, int F, int N, const int32_t* col_ind, const int32_t* ids_in, int32_t* track_id, int32_t* scratch,
-               cudaStream_t st)
+// F frames are chained; the first F_out of them are stored in track_id[C,F_out,N], frame F_out (if
+// F_out < F: the halo frame of a shard) in halo_map[C,N].  scratch: chain_scratch_ints(C, F, N).
+int chain_impl(int C, int F, int N, const int32_t* col_ind, const int32_t* ids_in, int F_out, int32_t* track_id,
+               int32_t* halo_map, int32_t* scratch, cudaStream_t st)
 {
     const int nseg = (F + kChainSeg - 1) / kChainSeg;
     int32_t* seg_map = scratch;
     int32_t* seg_start = scratch + (size_t)C * nseg * N;
+    int32_t* loc = seg_start + (size_t)C * nseg * N;
     const int threads = N < 128 ? 128 : ((N + 31) / 32 * 32);
     const size_t smem = (2 + (size_t)kChainSeg) * N * sizeof(int32_t);
     const long long total = (long long)C * F * N;
     {
         LaunchTimer lt(K_CHAIN, st);
-        k_chain_local<<<dim3(nseg, C), threads, smem, st>>>(F, N, nseg, col_ind, track_id, seg_map);
+        k_chain_local<<<dim3(nseg, C), threads, smem, st>>>(F, N, nseg, col_ind, loc, seg_map);
         LAUNCHED("k_chain_local");
         k_chain_scan<<<C, threads, smem, st>>>(N, nseg, ids_in, seg_map, seg_start);
         LAUNCHED("k_chain_scan");
-        k_chain_apply<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(F, N, nseg, seg_start, track_id, total);
+        k_chain_apply<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(F, N, nseg, seg_start, loc, F_out, track_id, halo_map, total);
         LAUNCHED("k_chain_apply");
     }
     return PTK_OK;
@@ -627,7 +638,7 @@ int chain_impl(int C, int F, int N, const int32_t* col_ind, const int32_t* ids_i
 size_t chain_scratch_ints(int C, int F, int N)
 {
     const int nseg = (F + kChainSeg - 1) / kChainSeg;
-    return 2 * (size_t)C * nseg * N;
+    return 2 * (size_t)C * nseg * N + (size_t)C * F * N;
 }
 }  // namespace
 
@@ -640,7 +651,7 @@ PTK_API int ptk_chain_tracks(int C, int F, int N, const int32_t* col_ind, const 
     // segment maps are tiny (2*C*ceil(F/32)*N ints); stream-ordered allocation keeps the ABI simple
     int32_t* scratch = nullptr;
     CK(cudaMallocAsync((void**)&scratch, chain_scratch_ints(C, F, N) * sizeof(int32_t) + 16, st));
-    int rc = chain_impl(C, F, N, col_ind, ids_in, track_id, scratch, st);
+    int rc = chain_impl(C, F, N, col_ind, ids_in, F, track_id, nullptr, scratch, st);
     cudaFreeAsync(scratch, st);
     return rc;
 }
@@ -690,6 +701,53 @@ PTK_API size_t ptk_reconstruct_device_workspace_bytes(int F, int C, int Nmax, in
     return device_ws(F, C, Nmax, do_track).total;
 }
 
+PTK_API size_t ptk_reconstruct_shard_workspace_bytes(int F, int n_halo, int C, int Nmax)
+{
+    if (F < 0 || n_halo < 0 || n_halo > 1 || C < 0 || bad_n(Nmax)) return 0;
+    return device_ws(F + n_halo, C, Nmax, 1).total;
+}
+
+// One rank's frame range of a sharded run: F own frames followed by n_halo (0 or 1) frames that belong
+// to the next rank and are re-computed here, so that the boundary pair is tracked locally -- the
+// matching is a pure function of its inputs, so the re-computed frame has the bits the owner gets.
+PTK_API int ptk_reconstruct_shard(const ptk_rig* rig, int F, int n_halo, int C, int Nmax, const double* cam1,
+                                  const double* cam2, const int32_t* n1, const int32_t* n2, double* rows, double* match_cost,
+                                  int32_t* row_ind, int32_t* col_ind, int32_t* n_out, int32_t* status, double max_repr_err,
+                                  uint8_t* keep_mask, int32_t* track_col, double* track_total, int32_t* track_status,
+                                  int32_t* track_id, int32_t* halo_map, void* workspace, size_t workspace_bytes, void* stream)
+{
+    if (bad_rig(rig) || F < 1 || n_halo < 0 || n_halo > 1 || C < 0 || bad_n(Nmax)) return PTK_ERR_INVALID_ARG;
+    if (!track_col || !track_total || !track_id || (n_halo && !halo_map)) return PTK_ERR_INVALID_ARG;
+    const int Ft = F + n_halo;
+    const long long P = (long long)Ft * C;
+    if (P == 0) return PTK_OK;
+    const DevWs w = device_ws(Ft, C, Nmax, 1);
+    if (!workspace || workspace_bytes < w.total) return PTK_ERR_WORKSPACE;
+    char* base = (char*)align_up((size_t)workspace);
+    NvtxRange nv("ptk_reconstruct_shard");
+    int rc;
+    {
+        NvtxRange nv1("match");
+        rc = ptk_match_batch(rig, (int)P, Nmax, cam1, cam2, n1, n2, nullptr, nullptr, row_ind, col_ind, n_out, status, rows,
+                             match_cost, max_repr_err, keep_mask, base, w.match, stream);
+        if (rc) return rc;
+    }
+    double* ends = reinterpret_cast<double*>(base + w.match);
+    {
+        NvtxRange nv2("track");
+        rc = ptk_rows_to_ends(Ft, C, Nmax, Nmax, rows, ends, stream);
+        if (rc) return rc;
+        if (Ft > 1) {
+            rc = ptk_track_batch(C, Ft, Nmax, ends, nullptr, track_col, track_total, track_status, base + w.match + w.ends, w.track,
+                                 stream);
+            if (rc) return rc;
+        }
+    }
+    NvtxRange nv3("chain");
+    return chain_impl(C, Ft, Nmax, track_col, nullptr, F, track_id, halo_map,
+                      reinterpret_cast<int32_t*>(base + w.match + w.ends + w.track), (cudaStream_t)stream);
+}
+
 PTK_API int ptk_reconstruct_device(const ptk_rig* rig, int F, int C, int Nmax, const double* cam1, const double* cam2,
                                    const int32_t* n1, const int32_t* n2, double* rows, double* match_cost,
                                    int32_t* row_ind, int32_t* col_ind, int32_t* n_out, int32_t* status,
@@ -704,21 +762,60 @@ PTK_API int ptk_reconstruct_device(const ptk_rig* rig, int F, int C, int Nmax, c
     const DevWs w = device_ws(F, C, Nmax, do_track);
     if (!workspace || workspace_bytes < w.total) return PTK_ERR_WORKSPACE;
     char* base = (char*)align_up((size_t)workspace);
-    int rc = ptk_match_batch(rig, (int)P, Nmax, cam1, cam2, n1, n2, nullptr, nullptr, row_ind, col_ind, n_out, status, rows,
+    NvtxRange nv("ptk_reconstruct_device");
+    int rc;
+    {
+        NvtxRange nv1("match");
+        rc = ptk_match_batch(rig, (int)P, Nmax, cam1, cam2, n1, n2, nullptr, nullptr, row_ind, col_ind, n_out, status, rows,
                              match_cost, max_repr_err, keep_mask, base, w.match, stream);
+    }
     if (rc || !do_track) return rc;
     double* ends = reinterpret_cast<double*>(base + w.match);
-    rc = ptk_rows_to_ends(F, C, Nmax, Nmax, rows, ends, stream);
-    if (rc) return rc;
-    if (F > 1) {
-        rc = ptk_track_batch(C, F, Nmax, ends, nullptr, track_col, track_total, track_status, base + w.match + w.ends, w.track,
-                             stream);
+    {
+        NvtxRange nv2("track");
+        rc = ptk_rows_to_ends(F, C, Nmax, Nmax, rows, ends, stream);
         if (rc) return rc;
+        if (F > 1) {
+            rc = ptk_track_batch(C, F, Nmax, ends, nullptr, track_col, track_total, track_status, base + w.match + w.ends, w.track,
+                                 stream);
+            if (rc) return rc;
+        }
     }
-    if (track_id)
-        rc = chain_impl(C, F, Nmax, track_col, nullptr, track_id, reinterpret_cast<int32_t*>(base + w.match + w.ends + w.track),
-                        (cudaStream_t)stream);
+    if (track_id) {
+        NvtxRange nv3("chain");
+        rc = chain_impl(C, F, Nmax, track_col, nullptr, F, track_id, nullptr,
+                        reinterpret_cast<int32_t*>(base + w.match + w.ends + w.track), (cudaStream_t)stream);
+    }
     return rc;
+}
+
+// Root side of the sharded chain pass: blocks[W] are the gathered per-rank result blocks (block r at
+// blocks + r * block_stride bytes) holding local ids track_id[C,F_r,N] at tid_off and the rank's halo map
+// [C,N] at map_off.  Composes the maps up to every rank and re-bases that rank's ids in place.
+PTK_API int ptk_chain_rebase_gathered(int W, int C, int N, const int32_t* frames_per_rank, void* blocks, size_t block_stride,
+                                      size_t tid_off, size_t map_off, int32_t* start_scratch, void* stream)
+{
+    if (W < 1 || C < 0 || bad_n(N) || !frames_per_rank || !blocks || !start_scratch || (block_stride % 4) || (tid_off % 4) ||
+        (map_off % 4))
+        return PTK_ERR_INVALID_ARG;
+    if (C == 0) return PTK_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int threads = N < 32 ? 32 : ((N + 31) / 32 * 32);
+    char* b = static_cast<char*>(blocks);
+    const int32_t* maps = reinterpret_cast<const int32_t*>(b + map_off);
+    for (int r = 1; r < W; r++) {
+        if (frames_per_rank[r] < 0) return PTK_ERR_INVALID_ARG;
+        LaunchTimer lt(K_CHAIN, st);
+        k_chain_compose<<<C, threads, 2 * (size_t)N * sizeof(int32_t), st>>>(W, C, N, r, maps, block_stride / 4, start_scratch);
+        LAUNCHED("k_chain_compose");
+        const long long total = (long long)C * frames_per_rank[r] * N;
+        if (total > 0) {
+            k_chain_rebase<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+                frames_per_rank[r], N, start_scratch, reinterpret_cast<int32_t*>(b + (size_t)r * block_stride + tid_off), total);
+            LAUNCHED("k_chain_rebase");
+        }
+    }
+    return PTK_OK;
 }
 
 // ------------------------------------------------------------------------------------ K6
@@ -1181,6 +1278,7 @@ PTK_API int ptk_reconstruct_host(ptk_ctx* c, const ptk_rig* rig, int F, int C, i
     const long long P = (long long)F * C;
     if (P == 0) return PTK_OK;
     CK(cudaSetDevice(c->device));
+    NvtxRange nv("ptk_reconstruct_host");
     const DevRig d = make_devrig(rig);
     const size_t n4 = (size_t)Nmax * 4 * sizeof(double), n18 = (size_t)Nmax * PTK_ROW_COLS * sizeof(double);
     const size_t nd = (size_t)Nmax * sizeof(double), ni = (size_t)Nmax * sizeof(int32_t);
@@ -1249,6 +1347,7 @@ PTK_API int ptk_reconstruct_host(ptk_ctx* c, const ptk_rig* rig, int F, int C, i
     CK(cudaMemcpyAsync(c->n1.as<int32_t>(), n1, P * sizeof(int32_t), cudaMemcpyHostToDevice, c->s_in));
     CK(cudaMemcpyAsync(c->n2.as<int32_t>(), n2, P * sizeof(int32_t), cudaMemcpyHostToDevice, c->s_in));
     for (int k = 0; k < nchunks; k++) {
+        NvtxRange nvc("chunk: H2D + match + D2H");
         const int f0 = chunk_f0[k];
         const int fn = chunk_f0[k + 1] - f0;
         const long long p0 = (long long)f0 * C, np = (long long)fn * C;
@@ -1284,11 +1383,12 @@ PTK_API int ptk_reconstruct_host(ptk_ctx* c, const ptk_rig* rig, int F, int C, i
     CK(cudaMemcpyAsync(status, c->status.p, P * sizeof(int32_t), cudaMemcpyDeviceToHost, c->s_out));
     if (keep_mask) CK(cudaMemcpyAsync(keep_mask, c->keep.p, (size_t)P * Nmax, cudaMemcpyDeviceToHost, c->s_out));
     if (do_track && Q > 0) {
+        NvtxRange nvt("track + chain + D2H");
         rc = ptk_track_batch(C, F, N, c->ends.as<double>(), nullptr, c->tcol.as<int32_t>(), c->ttot.as<double>(),
                              c->tstatus.as<int32_t>(), c->tws.p, c->tws.cap, c->s_comp);
         if (rc) return rc;
         if (track_id) {
-            rc = chain_impl(C, F, N, c->tcol.as<int32_t>(), nullptr, c->tid.as<int32_t>(), c->tscratch.as<int32_t>(), c->s_comp);
+            rc = chain_impl(C, F, N, c->tcol.as<int32_t>(), nullptr, F, c->tid.as<int32_t>(), nullptr, c->tscratch.as<int32_t>(), c->s_comp);
             if (rc) return rc;
         }
         CK(cudaEventRecord(c->ev_track, c->s_comp));

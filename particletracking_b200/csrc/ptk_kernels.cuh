@@ -643,16 +643,21 @@ __global__ void k_chain_scan(int N, int nseg, const int32_t* __restrict__ ids_in
     }
 }
 
-__global__ void k_chain_apply(int F, int N, int nseg, const int32_t* __restrict__ seg_start,
-                              int32_t* __restrict__ track_id, long long total)
+// loc[C,F,N]: local ids of pass A.  Frames f < F_out go to track_id[C,F_out,N]; frame F_out (the halo
+// frame of a shard, if F_out < F) goes to halo_map[C,N].
+__global__ void k_chain_apply(int F, int N, int nseg, const int32_t* __restrict__ seg_start, const int32_t* __restrict__ loc,
+                              int F_out, int32_t* __restrict__ track_id, int32_t* __restrict__ halo_map, long long total)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total) return;
+    const int a = (int)(t % N);
     const long long r = t / N;
     const int f = (int)(r % F);
     const int c = (int)(r / F);
     const int s = f / kChainSeg;
-    track_id[t] = chain_pick(seg_start + ((size_t)c * nseg + s) * N, track_id[t], N);
+    const int32_t id = chain_pick(seg_start + ((size_t)c * nseg + s) * N, loc[t], N);
+    if (f < F_out) track_id[((size_t)c * F_out + f) * N + a] = id;
+    else if (f == F_out && halo_map) halo_map[(size_t)c * N + a] = id;
 }
 
 // Multi-GPU chain pass: compose the gathered per-rank boundary maps up to `rank`

@@ -1,27 +1,35 @@
 """Frame sharding across the GPUs of one box.
 
 One process per GPU (``torch.distributed``, backend ``nccl``; ``gloo`` in the CPU tests).
-The path shards naturally:
+The path shards naturally, and a step of one rank is ONE library call plus ONE collective:
 
-* matching: every (frame, colour) problem is independent -> contiguous frame ranges per
-  rank, no exchange;
-* tracking: the pair (f, f+1) needs only those two frames' rows -> same partition plus a
-  1-frame halo: rank r receives the first frame's end points of rank r+1 (``[C,N,2,3]``,
-  a few KB) and solves the boundary pair itself;
+* matching: every (frame, colour) problem is independent -> contiguous frame ranges per rank;
+* tracking: the pair (f, f+1) needs only those two frames' rows -> same partition plus a 1-frame
+  halo.  The halo is RE-COMPUTED, not exchanged: rank r is handed the detections of its own F
+  frames plus the first frame of rank r+1 and matches that frame again (the matching is a pure
+  function of its inputs: identical bits on both ranks), so the boundary pair is tracked locally
+  and there is no send/recv on the critical path (``ptk_reconstruct_shard``);
 * chain pass: permutation composition is associative -> every rank chains locally from the
-  identity, the per-rank boundary maps (``[C,N]`` int32) are all-gathered, composed
-  (``compose_rank_maps``), and the local ids are re-based with the rank's start ids;
-* final collective: gather of the 18-column rows and track ids to rank 0.
+  identity and emits, besides its local ids, its boundary map (the local id of every position of
+  the halo frame);
+* final collective: every rank's result block -- rows, costs, local track ids, boundary map, status
+  words, one contiguous buffer -- is gathered to rank 0 by ONE NCCL gather per step, issued on a
+  side stream so that it overlaps the next step's kernels; rank 0 then composes the boundary maps
+  and re-bases the gathered ids in place (``ptk_chain_rebase_gathered``), also on the side stream.
 
-There is no data-path collective inside matching or the per-pair assignment; NCCL carries
-only the halo, the boundary maps and the final gather.
+There is no data-path collective inside matching or the per-pair assignment; NCCL carries only the
+final gather (the north star's "NCCL only for the final gather of 3D rods and track IDs").  Nothing
+in step k+1 depends on the gather of step k except the reuse of its buffers two steps later, which
+is ordered by CUDA events, never by the host.
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from typing import Dict, Optional, Tuple
 
 import torch
 import torch.distributed as dist
+
+ROW_COLS = 18
 
 
 def shard_frames(n_frames: int, world: int, rank: int) -> Tuple[int, int]:
@@ -31,208 +39,238 @@ def shard_frames(n_frames: int, world: int, rank: int) -> Tuple[int, int]:
     return f0, f0 + base + (1 if rank < rem else 0)
 
 
+def shard_input_range(n_frames: int, world: int, rank: int) -> Tuple[int, int]:
+    """Frames whose detections ``rank`` must be given: its own range plus the 1-frame halo."""
+    f0, f1 = shard_frames(n_frames, world, rank)
+    return f0, min(f1 + 1, n_frames) if rank < world - 1 else f1
+
+
+def _pick(table: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """table[c, idx[c, x]] with -1 for idx outside 0..N-1 (a broken chain stays broken)."""
+    N = table.shape[-1]
+    ok = (idx >= 0) & (idx < N)
+    out = torch.gather(table, -1, idx.clamp(0, N - 1).long())
+    return torch.where(ok, out, torch.full_like(out, -1))
+
+
 def compose_rank_maps(maps: torch.Tensor) -> torch.Tensor:
     """maps[W,C,N]: for rank r, position x in rank r+1's first frame -> local id (position in
     rank r's first frame).  Returns starts[W,C,N]: global track id of local id x on rank r:
-    starts[0] = arange(N), starts[r+1][c][x] = starts[r][c][maps[r][c][x]]."""
+    starts[0] = arange(N), starts[r+1][c][x] = starts[r][c][maps[r][c][x]] (-1 where the chain broke)."""
     W, C, N = maps.shape
     starts = torch.empty_like(maps)
     cur = torch.arange(N, dtype=maps.dtype, device=maps.device).expand(C, N).contiguous()
     for r in range(W):
         starts[r] = cur
         if r + 1 < W:
-            cur = torch.gather(cur, 1, maps[r].long())
+            cur = _pick(cur, maps[r])
     return starts
 
 
-class _CudaOps:
-    """The product's compute: libptk.so kernels through particletracking_b200.engine."""
+class _BlockLayout:
+    """Byte layout of one rank's result block (every region 256-byte aligned):
+    ``track_id | halo_map | status | n_out | track_status | track_total | match_cost | rows``.
+    ``rows`` is last and has room for the halo frame; only ``send_bytes`` (everything up to the rows of
+    ``Fmax`` own frames) travel."""
 
-    def __init__(self, rig):
-        from . import engine
+    def __init__(self, Fmax: int, C: int, N: int):
+        self.Fmax, self.C, self.N = Fmax, C, N
+        self.off: Dict[str, int] = {}
+        o = 0
+        for name, nbytes in (("track_id", C * Fmax * N * 4), ("halo_map", C * N * 4), ("status", (Fmax + 1) * C * 4),
+                             ("n_out", (Fmax + 1) * C * 4), ("track_status", C * Fmax * 4), ("track_total", C * Fmax * 8),
+                             ("match_cost", (Fmax + 1) * C * N * 8), ("rows", (Fmax + 1) * C * N * ROW_COLS * 8)):
+            self.off[name] = o
+            o += (nbytes + 255) // 256 * 256
+        self.capacity = o
+        self.send_bytes = self.off["rows"] + Fmax * C * N * ROW_COLS * 8
 
-        self.e = engine
-        self.rig = rig
-        self._out = {}
+    def views(self, block: torch.Tensor, F: int, h: int, own_only: bool = False) -> Dict[str, torch.Tensor]:
+        """Typed views of ``block`` (uint8) for a rank with F own frames and h halo frames.  ``own_only``:
+        the per-problem arrays cover the F own frames only (a received block is ``send_bytes`` long: the
+        halo frame's rows did not travel); the per-pair arrays keep their [C, F+h-1] shape."""
+        C, N = self.C, self.N
+        f64, i32 = torch.float64, torch.int32
 
-    def match(self, cam1, cam2, n1, n2, slot=None):
-        # the rows of step k are still being gathered while step k+1 computes: two fixed sets of
-        # output tensors (one per gather slot) instead of a fresh 37 MB allocation per step
-        prev = self._out.get(slot) if slot is not None else None
-        m = self.e.match_batch(self.rig, cam1, cam2, n1, n2, out=prev)
-        if slot is not None:
-            self._out[slot] = m
-        return m.rows, m.col_ind, m.status
+        def v(name, dtype, shape):
+            n = 1
+            for d in shape:
+                n *= d
+            nb = n * (8 if dtype == f64 else 4)
+            return block[self.off[name]: self.off[name] + nb].view(dtype).view(shape)
 
-    def rows_to_ends(self, rows, F, C):
-        return self.e.rows_to_ends(rows, F, C)
-
-    def track(self, ends):
-        col, tot, st, _ = self.e.track_batch(ends)
-        return col, tot, st
-
-    def chain(self, col, ids_in=None):
-        return self.e.chain_tracks(col, ids_in)
-
-    def rebase(self, maps, rank, local):
-        """compose the gathered boundary maps and re-base ``local`` [C,F',N] in place"""
-        self.e.chain_rebase(maps, rank, local)
-        return local
+        Fp = F if own_only else F + h
+        return dict(track_id=v("track_id", i32, (C, F, N)), halo_map=v("halo_map", i32, (C, N)),
+                    status=v("status", i32, (Fp * C,)), n_out=v("n_out", i32, (Fp * C,)),
+                    track_status=v("track_status", i32, (C, F + h - 1)), track_total=v("track_total", f64, (C, F + h - 1)),
+                    match_cost=v("match_cost", f64, (Fp * C, N)), rows=v("rows", f64, (Fp * C, N, ROW_COLS)))
 
 
 class ShardedReconstructor:
-    """match -> track -> chain for one rank's frame range, with the halo / boundary-map /
-    gather exchanges described in the module docstring.
+    """match -> track -> chain for one rank's frame range; see the module docstring.
 
-    ``ops`` is the compute back end (default: the CUDA kernels).  The CPU tests inject an
-    oracle-backed one to exercise the exchange logic under ``gloo`` -- test infrastructure,
-    not a fallback: the default never touches it.
+    ``step`` takes the detections of ``F + n_halo`` frames (``n_halo`` = 1 on every rank but the last:
+    ``shard_input_range``) and returns views of the rank's result block; on rank 0 ``rows_all`` /
+    ``track_id_all`` (global ids) / ``match_cost_all`` / ``status_all`` hold every rank's shard once the
+    gather has completed (``finish()`` orders the current stream after it).  Results live in two
+    alternating sets of buffers: they are overwritten by the step after next.
+
+    ``ops`` is the compute back end (default: the CUDA kernels through ``engine.ShardPipeline``).  The
+    CPU tests inject an oracle-backed one to exercise the exchange logic under ``gloo`` -- test
+    infrastructure, not a fallback: the default never touches it.
     """
 
     def __init__(self, rig, n_frames_local: int, n_colors: int, n_rods: int, device, ops=None,
-                 gather_to_root: bool = True, group=None, n_frames_total: Optional[int] = None):
+                 gather_to_root: bool = True, group=None, n_frames_total: Optional[int] = None,
+                 max_repr_err: Optional[float] = None, use_graph: bool = True):
         self.F, self.C, self.N = n_frames_local, n_colors, n_rods
-        self.device = device
-        self.ops = ops if ops is not None else _CudaOps(rig)
+        self.device = torch.device(device)
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self.gather_to_root = gather_to_root
-        # frames held by every rank (shards may differ by one frame; gathers are padded to the max)
+        self.gather_to_root = gather_to_root and self.world > 1
+        self.use_graph = use_graph
         total = n_frames_total if n_frames_total is not None else n_frames_local * self.world
         self.shard_sizes = [b - a for a, b in (shard_frames(total, self.world, r) for r in range(self.world))]
         if self.shard_sizes[self.rank] != n_frames_local:
             raise ValueError("n_frames_local does not match shard_frames(n_frames_total, world, rank)")
-        # final-gather pipelining: two sets of receive buffers; the gather of step k runs on
-        # NCCL's stream while step k+1 computes, and is waited for before its buffers are reused
-        self._rows_all0 = self._rows_all1 = None
-        self._tid_all0 = self._tid_all1 = None
-        self._pending = [None, None]
+        self.h = 1 if self.rank < self.world - 1 else 0
+        self.layout = _BlockLayout(max(self.shard_sizes), n_colors, n_rods)
+        self.cuda = self.device.type == "cuda"
+        self.ops = ops
+        if ops is None and not self.cuda:
+            raise RuntimeError("ShardedReconstructor: the product path needs a CUDA device (there is no CPU fallback)")
+        u8 = torch.uint8
+        self.blocks = [torch.zeros(self.layout.capacity, dtype=u8, device=self.device) for _ in range(2)]
+        self.views = [self.layout.views(b, self.F, self.h) for b in self.blocks]
+        self.recv = [None, None]
+        if self.gather_to_root and self.rank == 0:
+            self.recv = [torch.zeros((self.world, self.layout.send_bytes), dtype=u8, device=self.device) for _ in range(2)]
         self._step_idx = 0
-        # host-side time per segment of step() (seconds, summed), filled when PTK_STEP_PROFILE=1
-        import os as _os
+        if self.cuda:
+            from . import engine
 
-        self._prof = {} if _os.environ.get("PTK_STEP_PROFILE") == "1" else None
+            self._engine = engine
+            ws = None
+            self.pipes = []
+            for s in range(2):
+                if ops is None:
+                    p = engine.ShardPipeline(rig, self.F, self.h, self.C, self.N, self.device, out=self.views[s],
+                                             max_repr_err=max_repr_err, workspace=ws)
+                    ws = p.ws  # both slots run on the same stream, in order: one workspace
+                    self.pipes.append(p)
+            self.side = torch.cuda.Stream(self.device)
+            self.ev_comp = [torch.cuda.Event() for _ in range(2)]
+            self.ev_done = [torch.cuda.Event() for _ in range(2)]
+            self._done_recorded = [False, False]
+            self._scratch = torch.empty((self.C, self.N), dtype=torch.int32, device=self.device)
+            self._maps_all = torch.empty((self.world, self.C, self.N), dtype=torch.int32, device=self.device)
 
-    # -- exchanges ------------------------------------------------------------------------
-    def _halo(self, first_frame_ends: torch.Tensor) -> Optional[torch.Tensor]:
-        """Send my first frame's ends to rank-1, receive rank+1's.  Returns None on the last rank."""
-        if self.world == 1:
-            return None
-        ops = []
-        recv = None
-        if self.rank > 0:
-            ops.append(dist.P2POp(dist.isend, first_frame_ends, self.rank - 1, self.group))
-        if self.rank < self.world - 1:
-            recv = torch.empty_like(first_frame_ends)
-            ops.append(dist.P2POp(dist.irecv, recv, self.rank + 1, self.group))
-        for w in dist.batch_isend_irecv(ops):
-            w.wait()
-        return recv
-
-    def _gather(self, t: torch.Tensor, cache_name: str, frame_dim: int, async_op: bool = False):
-        """Gather ``t`` (frames along ``frame_dim``) to rank 0; returns the list of per-rank
-        shards there, None elsewhere.  Shards of unequal length are padded for the collective.
-        With ``async_op`` returns ``(result, work)``: the collective runs on NCCL's stream while
-        the caller keeps enqueueing compute; ``work.wait()`` orders the current stream after it."""
-        if self.world == 1:
-            return ([t], None) if async_op else [t]
-        fmax = max(self.shard_sizes)
-        if t.shape[frame_dim] < fmax:
-            pad_shape = list(t.shape)
-            pad_shape[frame_dim] = fmax - t.shape[frame_dim]
-            t = torch.cat([t, t.new_zeros(pad_shape)], dim=frame_dim)
-        t = t.contiguous()
-        if self.rank == 0:
-            buf = getattr(self, cache_name)
-            if buf is None or buf[0].shape != t.shape:
-                buf = [torch.empty_like(t) for _ in range(self.world)]
-                setattr(self, cache_name, buf)
-            work = dist.gather(t, buf, dst=0, group=self.group, async_op=async_op)
-            res = [b.narrow(frame_dim, 0, n) for b, n in zip(buf, self.shard_sizes)]
-            return (res, work) if async_op else res
-        work = dist.gather(t, None, dst=0, group=self.group, async_op=async_op)
-        return (None, work) if async_op else None
-
-    # -- one pass over this rank's frames ----------------------------------------------------
-    def step(self, cam1, cam2, n1, n2):
-        """cam1/cam2 [F*C,Nmax,2,2] (problem = f*C+c), n1/n2 [F*C] for this rank's frames.
-        Returns a dict; on rank 0 ``rows_all`` / ``track_id_all`` hold every rank's shard.  With
-        ``gather_to_root`` the matching outputs (``rows``, ``col_ind``, ``status``) live in two alternating
-        sets of buffers: they are overwritten by the step after next -- copy what must outlive that."""
-        F, C, N = self.F, self.C, self.N
-        prof = self._prof
-        if prof is not None:
-            import time as _t
-
-            t_last = [_t.perf_counter()]
-
-            def mark(name):
-                now = _t.perf_counter()
-                prof[name] = prof.get(name, 0.0) + (now - t_last[0])
-                t_last[0] = now
+    # -- compute ----------------------------------------------------------------------------------
+    def _compute_with_ops(self, v, cam1, cam2, n1, n2):
+        """Generic back end (tests): same outputs as ptk_reconstruct_shard, written into the block views."""
+        F, h, C = self.F, self.h, self.C
+        rows, col_m, status = self.ops.match(cam1, cam2, n1, n2)
+        v["rows"].copy_(rows.view(v["rows"].shape))
+        v["status"].copy_(status.view(-1))
+        ends = self.ops.rows_to_ends(v["rows"], F + h, C)  # [C,F+h,N,2,3]
+        if F + h > 1:
+            col, total, tstatus = self.ops.track(ends)
+            v["track_total"].copy_(total)
+            v["track_status"].copy_(tstatus)
         else:
-            def mark(name):
-                pass
-        rows_all = rows_work = None
+            col = torch.empty((C, 0, self.N), dtype=torch.int32)
+        loc = self.ops.chain(col)  # ids relative to this rank's first frame, [C,F+h,N]
+        v["track_id"].copy_(loc[:, :F])
+        if h:
+            v["halo_map"].copy_(loc[:, F])
+        return col
+
+    # -- one pass over this rank's frames -----------------------------------------------------------
+    def step(self, cam1, cam2, n1, n2):
+        """cam1/cam2 [(F+n_halo)*C,Nmax,2,2] (problem = f*C+c), n1/n2 [(F+n_halo)*C]: this rank's frames
+        followed by the next rank's first frame (not on the last rank)."""
         slot = self._step_idx % 2
         self._step_idx += 1
-        if self.gather_to_root:
-            self._wait(slot)  # this slot's send and receive buffers are free again
-        if isinstance(self.ops, _CudaOps):
-            rows, col_m, status = self.ops.match(cam1, cam2, n1, n2, slot=slot if self.gather_to_root else None)
-        else:
-            rows, col_m, status = self.ops.match(cam1, cam2, n1, n2)
-        mark("match")
-        if self.gather_to_root:
-            # the big gather (rows) starts as soon as matching is enqueued and overlaps tracking
-            rows_all, rows_work = self._gather(rows.view(F, C, -1, rows.shape[-1]), f"_rows_all{slot}", 0, async_op=True)
-        mark("wait+gather_rows")
-        ends = self.ops.rows_to_ends(rows, F, C)  # [C,F,N,2,3]
-        mark("rows_to_ends")
-        halo = self._halo(ends[:, 0].contiguous())
-        mark("halo")
-        if halo is not None:
-            ends = torch.cat([ends, halo[:, None]], dim=1)  # boundary pair solved here
-        mark("cat")
-        col, total, tstatus = self.ops.track(ends)
-        mark("track")
-        local = self.ops.chain(col)  # ids relative to this rank's first frame
-        mark("chain")
-        if self.world > 1:
-            if halo is not None:
-                my_map = local[:, -1].contiguous()
+        v = self.views[slot]
+        F, C = self.F, self.C
+        out = dict(rows=v["rows"][: F * C].view(F, C, self.N, ROW_COLS), match_cost=v["match_cost"][: F * C],
+                   status=v["status"][: F * C], n_out=v["n_out"][: F * C], track_total=v["track_total"],
+                   track_status=v["track_status"], track_id=v["track_id"], halo_map=v["halo_map"] if self.h else None)
+        if self.cuda:
+            main = torch.cuda.current_stream(self.device)
+            if self._done_recorded[slot]:
+                main.wait_event(self.ev_done[slot])  # the slot's block has been sent (two steps ago)
+            if self.ops is None:
+                p = self.pipes[slot]
+                (p.run_graph if self.use_graph else p.run)(cam1, cam2, n1, n2)
+                out["track_col"], out["col_ind"] = p.track_col, p.col_ind
             else:
-                my_map = torch.arange(N, dtype=local.dtype, device=local.device).expand(C, N).contiguous()
-            maps = torch.empty((self.world * C, N), dtype=local.dtype, device=local.device)
-            dist.all_gather_into_tensor(maps, my_map, group=self.group)
-            maps = maps.view(self.world, C, N)
-            if hasattr(self.ops, "rebase"):
-                track_id = self.ops.rebase(maps, self.rank, local)[:, :F].contiguous()
-            else:  # back ends without a fused kernel: same composition with torch ops
-                start = compose_rank_maps(maps)[self.rank].contiguous()
-                track_id = self.ops.chain(col, start)[:, :F].contiguous()
+                out["track_col"] = self._compute_with_ops(v, cam1, cam2, n1, n2)
+            if self.world > 1:
+                self.ev_comp[slot].record(main)
+                with torch.cuda.stream(self.side):
+                    self.side.wait_event(self.ev_comp[slot])
+                    self._exchange(slot, out)
+                    self.ev_done[slot].record(self.side)
+                self._done_recorded[slot] = True
         else:
-            track_id = local
-        mark("maps+rebase")
-        out = dict(rows=rows, col_ind=col_m, status=status, track_col=col, track_total=total,
-                   track_status=tstatus, track_id=track_id)
-        if self.gather_to_root:
-            tid_all, tid_work = self._gather(track_id, f"_tid_all{slot}", 1, async_op=True)
-            self._pending[slot] = [w for w in (rows_work, tid_work) if w is not None]
-            out["rows_all"] = rows_all        # [F,C,Nmax,18] per rank   } valid after finish()
-            out["track_id_all"] = tid_all     # [C,F,N] per rank         } (or the next-but-one step)
-        mark("gather_tid")
+            out["track_col"] = self._compute_with_ops(v, cam1, cam2, n1, n2)
+            if self.world > 1:
+                self._exchange(slot, out)
+        if self.world == 1:
+            out["track_id_global"] = out["track_id"]
         return out
 
-    def _wait(self, slot: int):
-        if self._pending[slot]:
-            for w in self._pending[slot]:
-                w.wait()
-        self._pending[slot] = None
+    def _exchange(self, slot: int, out: dict):
+        """The step's only collective (+ the re-base).  Runs on the side stream on CUDA."""
+        L, W = self.layout, self.world
+        send = self.blocks[slot][: L.send_bytes]
+        if self.gather_to_root:
+            if self.rank == 0:
+                recv = self.recv[slot]
+                dist.gather(send, [recv[r] for r in range(W)], dst=0, group=self.group)
+                if self.cuda and self.ops is None:
+                    self._engine.chain_rebase_gathered(recv, self.shard_sizes, self.C, self.N, L.off["track_id"],
+                                                       L.off["halo_map"], self._scratch)
+                    per = [L.views(recv[r], self.shard_sizes[r], 1 if r < W - 1 else 0, own_only=True) for r in range(W)]
+                else:
+                    per = [L.views(recv[r], self.shard_sizes[r], 1 if r < W - 1 else 0, own_only=True) for r in range(W)]
+                    maps = torch.stack([p["halo_map"] for p in per])
+                    starts = compose_rank_maps(maps)
+                    for r in range(1, W):
+                        per[r]["track_id"].copy_(_pick(starts[r][:, None, :].expand_as(per[r]["track_id"]), per[r]["track_id"]))
+                Fs = self.shard_sizes
+                out["rows_all"] = [per[r]["rows"].view(Fs[r], self.C, self.N, ROW_COLS) for r in range(W)]
+                out["track_id_all"] = [per[r]["track_id"] for r in range(W)]
+                out["match_cost_all"] = [per[r]["match_cost"] for r in range(W)]
+                out["status_all"] = [per[r]["status"] for r in range(W)]
+                out["track_total_all"] = [per[r]["track_total"] for r in range(W)]
+                out["track_status_all"] = [per[r]["track_status"] for r in range(W)]
+                out["track_id_global"] = per[0]["track_id"]
+            else:
+                dist.gather(send, None, dst=0, group=self.group)
+                out["rows_all"] = out["track_id_all"] = None
+        else:
+            # every rank wants its own global ids: all-gather the boundary maps (a few KB), re-base locally
+            v = self.views[slot]
+            my_map = v["halo_map"] if self.h else torch.arange(self.N, dtype=torch.int32, device=self.device).expand(
+                self.C, self.N).contiguous()
+            maps = self._maps_all if self.cuda else torch.empty((W, self.C, self.N), dtype=torch.int32)
+            dist.all_gather_into_tensor(maps.view(W * self.C, self.N), my_map.contiguous(), group=self.group)
+            if self.cuda and self.ops is None:
+                gid = v["track_id"].clone()
+                self._engine.chain_rebase(maps, self.rank, gid)
+            else:
+                start = compose_rank_maps(maps)[self.rank]
+                gid = _pick(start[:, None, :].expand_as(v["track_id"]), v["track_id"])
+            out["track_id_global"] = gid
 
     def finish(self):
-        """Order the current stream after every outstanding gather (call before reading
-        ``rows_all`` / ``track_id_all`` of the latest steps)."""
-        self._wait(0)
-        self._wait(1)
+        """Order the current stream after every outstanding gather / re-base (call before reading
+        ``rows_all`` / ``track_id_all`` / ``track_id_global`` of the latest steps)."""
+        if self.cuda and self.world > 1:
+            main = torch.cuda.current_stream(self.device)
+            for s in range(2):
+                if self._done_recorded[s]:
+                    main.wait_event(self.ev_done[s])

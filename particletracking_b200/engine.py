@@ -278,6 +278,121 @@ class DevicePipeline:
         return self
 
 
+class ShardPipeline:
+    """One rank's frame range of a sharded run through ONE library call per step
+    (``ptk_reconstruct_shard``): ``F`` own frames followed by ``n_halo`` (0 or 1) frames of the next rank
+    that are re-computed locally, so that no halo exchange is needed.  Outputs are caller-provided
+    tensors (``out``: the views of the rank's gather block, see ``distributed.ShardedReconstructor``) or
+    allocated here.  ``run`` is eager; ``run_graph`` replays a CUDA graph of the same call captured the
+    second time a set of input tensors is seen (the step is then a single ``cudaGraphLaunch``)."""
+
+    OUT_SPEC = (  # name, dtype, shape as a function of (F, h, C, N)
+        ("rows", _f64, lambda F, h, C, N: ((F + h) * C, N, nat.ROW_COLS)),
+        ("match_cost", _f64, lambda F, h, C, N: ((F + h) * C, N)),
+        ("n_out", _i32, lambda F, h, C, N: ((F + h) * C,)),
+        ("status", _i32, lambda F, h, C, N: ((F + h) * C,)),
+        ("track_total", _f64, lambda F, h, C, N: (C, F + h - 1)),
+        ("track_status", _i32, lambda F, h, C, N: (C, F + h - 1)),
+        ("track_id", _i32, lambda F, h, C, N: (C, F, N)),
+        ("halo_map", _i32, lambda F, h, C, N: (C, N)),
+    )
+
+    def __init__(self, rig: PtkRig, F: int, n_halo: int, C: int, Nmax: int, device=None, out=None,
+                 max_repr_err: Optional[float] = None, workspace: Optional[torch.Tensor] = None):
+        _require_cuda()
+        if n_halo not in (0, 1) or F < 1:
+            raise ValueError("ShardPipeline: F >= 1 and n_halo in (0, 1)")
+        self.rig, self.F, self.h, self.C, self.N = rig, F, n_halo, C, Nmax
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.device = dev
+        out = {} if out is None else out
+        for name, dt, shp in self.OUT_SPEC:
+            shape = shp(F, n_halo, C, Nmax)
+            t = out.get(name)
+            if t is None:
+                t = torch.empty(shape, dtype=dt, device=dev)
+            elif tuple(t.shape) != tuple(shape) or t.dtype != dt or t.device != dev or not t.is_contiguous():
+                raise ValueError(f"ShardPipeline: out[{name!r}] must be a contiguous {dt} tensor of shape {shape} on {dev}")
+            setattr(self, name, t)
+        P = (F + n_halo) * C
+        self.row_ind = torch.empty((P, Nmax), dtype=_i32, device=dev)
+        self.col_ind = torch.empty((P, Nmax), dtype=_i32, device=dev)
+        self.track_col = torch.empty((C, F + n_halo - 1, Nmax), dtype=_i32, device=dev)
+        self.keep = torch.empty((P, Nmax), dtype=_u8, device=dev) if max_repr_err is not None else None
+        self.thr = float("inf") if max_repr_err is None else float(max_repr_err)
+        nb = nat.lib().ptk_reconstruct_shard_workspace_bytes(F, n_halo, C, Nmax)
+        if workspace is not None and (workspace.numel() < nb or workspace.device != dev):
+            raise ValueError("ShardPipeline: workspace too small")
+        self.ws = workspace if workspace is not None else torch.empty(nb, dtype=_u8, device=dev)
+        self._seen, self._graphs, self._keep = {}, {}, []
+
+    def _check_inputs(self, cam1, cam2, n1, n2):
+        P = (self.F + self.h) * self.C
+        for t, dt, name, shape in ((cam1, _f64, "cam1", (P, self.N, 2, 2)), (cam2, _f64, "cam2", (P, self.N, 2, 2)),
+                                   (n1, _i32, "n1", (P,)), (n2, _i32, "n2", (P,))):
+            if not isinstance(t, torch.Tensor) or not t.is_cuda or t.device != self.device:
+                raise ValueError(f"{name} must be a CUDA tensor on {self.device}")
+            if t.dtype != dt or tuple(t.shape) != shape or not t.is_contiguous():
+                raise ValueError(f"{name} must be a contiguous {dt} tensor of shape {shape} (F + n_halo frames), "
+                                 f"got {t.dtype} {tuple(t.shape)}")
+
+    def _enqueue(self, cam1, cam2, n1, n2):
+        nat.check(nat.lib().ptk_reconstruct_shard(
+            ctypes.byref(self.rig), self.F, self.h, self.C, self.N, _ptr(cam1), _ptr(cam2), _ptr(n1), _ptr(n2),
+            _ptr(self.rows), _ptr(self.match_cost), _ptr(self.row_ind), _ptr(self.col_ind), _ptr(self.n_out),
+            _ptr(self.status), self.thr, _ptr(self.keep), _ptr(self.track_col), _ptr(self.track_total),
+            _ptr(self.track_status), _ptr(self.track_id), _ptr(self.halo_map) if self.h else None, _ptr(self.ws),
+            self.ws.numel(), _stream()), "ptk_reconstruct_shard")
+
+    def run(self, cam1, cam2, n1, n2):
+        """Enqueue one pass on the current stream (eager launches)."""
+        self._check_inputs(cam1, cam2, n1, n2)
+        with torch.cuda.device(self.device):
+            self._enqueue(cam1, cam2, n1, n2)
+        return self
+
+    def run_graph(self, cam1, cam2, n1, n2):
+        """As ``run``; from the second call with the same input tensors on, one CUDA-graph launch."""
+        key = (cam1.data_ptr(), cam2.data_ptr(), n1.data_ptr(), n2.data_ptr())
+        g = self._graphs.get(key)
+        if g is not None:
+            g.replay()
+            return self
+        n = self._seen.get(key, 0)
+        self._seen[key] = n + 1
+        if n == 0 or _timing_on:  # first sight (one-time attribute set-up runs eagerly) / event timing on
+            return self.run(cam1, cam2, n1, n2)
+        self._check_inputs(cam1, cam2, n1, n2)
+        g = torch.cuda.CUDAGraph()
+        cur = torch.cuda.current_stream(self.device)
+        cap = torch.cuda.Stream(self.device)
+        cap.wait_stream(cur)
+        with torch.cuda.device(self.device), torch.cuda.graph(g, stream=cap):
+            self._enqueue(cam1, cam2, n1, n2)
+        cur.wait_stream(cap)
+        self._graphs[key] = g
+        self._keep.append((cam1, cam2, n1, n2))  # the graph holds raw pointers: keep the tensors alive
+        g.replay()
+        return self
+
+
+def chain_rebase_gathered(blocks: torch.Tensor, frames_per_rank, C: int, N: int, tid_off: int, map_off: int,
+                          scratch: Optional[torch.Tensor] = None):
+    """Root side of the sharded chain pass: ``blocks[W, block_bytes]`` uint8 (the gathered result blocks);
+    re-bases every rank's local ids in place (``ptk_chain_rebase_gathered``)."""
+    _require_cuda()
+    if blocks.dtype != _u8 or blocks.dim() != 2 or not blocks.is_contiguous() or not blocks.is_cuda:
+        raise ValueError("blocks must be a contiguous CUDA uint8 tensor [W, block_bytes]")
+    W = blocks.shape[0]
+    fr = (ctypes.c_int32 * W)(*[int(x) for x in frames_per_rank])
+    if scratch is None:
+        scratch = torch.empty((C, N), dtype=_i32, device=blocks.device)
+    with torch.cuda.device(blocks.device):
+        nat.check(nat.lib().ptk_chain_rebase_gathered(W, C, N, fr, _ptr(blocks), blocks.stride(0), int(tid_off), int(map_off),
+                                                      _ptr(scratch), _stream()), "ptk_chain_rebase_gathered")
+    return blocks
+
+
 def track_batch(ends: torch.Tensor, want_cost=False):
     """K4+K2: ``tracking_global_assignment`` (tracking.py:97-123,136-137) for C colours.
     ends[C,F,N,2,3] -> col_ind[C,F-1,N], total_cost[C,F-1], status[C,F-1] (, cost[C,F-1,N,N])."""
@@ -456,8 +571,14 @@ def measure_fp64_peak(iters: int = 20000) -> float:
     return out.value
 
 
+_timing_on = False
+
+
 def kernel_timing(enable: bool) -> None:
-    """Switch CUDA-event timing of the dominant kernel (K1) on or off."""
+    """Switch CUDA-event timing around every kernel launch on or off (graph replays are not timed:
+    ``ShardPipeline.run_graph`` launches eagerly while it is on)."""
+    global _timing_on
+    _timing_on = bool(enable)
     nat.lib().ptk_timing_enable(1 if enable else 0)
 
 

@@ -65,7 +65,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, F, C, N, out_path):
+def _worker(rank, world, port, F, C, N, out_path, to_root):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from particletracking_b200 import rig as rigmod
@@ -74,29 +74,32 @@ def _worker(rank, world, port, F, C, N, out_path):
     data = syn.make_stereo(F, C, N, seed=5)
     rig = rigmod.rig_from_dicts(data.calibration, data.transformation)
     f0, f1 = pdist.shard_frames(F, world, rank)
-    sl = slice(f0, f1)
-    Fl = f1 - f0
+    i0, i1 = pdist.shard_input_range(F, world, rank)  # own frames + the re-computed halo frame
+    assert (i0, i1) == (f0, f1 + (1 if rank < world - 1 else 0))
+    sl = slice(i0, i1)
+    Fin = i1 - i0
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
-    rec = pdist.ShardedReconstructor(rig, Fl, C, N, "cpu", ops=OracleOps(rig), n_frames_total=F)
-    out = rec.step(t(data.cam1[sl].reshape(Fl * C, N, 2, 2)), t(data.cam2[sl].reshape(Fl * C, N, 2, 2)),
-                   t(data.n1[sl].reshape(-1)), t(data.n2[sl].reshape(-1)))
+    rec = pdist.ShardedReconstructor(rig, f1 - f0, C, N, "cpu", ops=OracleOps(rig), n_frames_total=F, gather_to_root=to_root)
+    args = (t(data.cam1[sl].reshape(Fin * C, N, 2, 2)), t(data.cam2[sl].reshape(Fin * C, N, 2, 2)),
+            t(data.n1[sl].reshape(-1)), t(data.n2[sl].reshape(-1)))
+    for _ in range(3):  # both buffer slots, and a slot's reuse
+        out = rec.step(*args)
     rec.finish()
-    if rank == 0:
-        rows = torch.cat(list(out["rows_all"]), dim=0).numpy()
-        tid = torch.cat(list(out["track_id_all"]), dim=1).numpy()
-        np.savez(out_path, rows=rows, tid=tid)
+    if to_root:
+        if rank == 0:
+            rows = torch.cat(list(out["rows_all"]), dim=0).numpy()
+            tid = torch.cat(list(out["track_id_all"]), dim=1).numpy()
+            tot = torch.cat(list(out["track_total_all"]), dim=1).numpy()
+            assert all(int((s != 0).sum()) == 0 for s in out["status_all"])
+            np.savez(out_path, rows=rows, tid=tid, tot=tot)
+        else:
+            assert out["rows_all"] is None
     else:
-        assert out["rows_all"] is None
+        np.savez(out_path + f".{rank}.npz", tid=out["track_id_global"].numpy(), f0=f0, f1=f1)
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,F", [(2, 11), (3, 10)])
-def test_sharded_equals_single_rank(tmp_path, world, F):
-    C, N = 2, 6
-    out_path = str(tmp_path / "out.npz")
-    mp.spawn(_worker, args=(world, _free_port(), F, C, N, out_path), nprocs=world, join=True)
-    got = np.load(out_path)
-    # single-rank oracle over the whole range
+def _single_rank_oracle(F, C, N):
     from oracle import c_oracle as co
     from particletracking_b200 import rig as rigmod
     from particletracking_b200 import synthetic as syn
@@ -106,7 +109,46 @@ def test_sharded_equals_single_rank(tmp_path, world, F):
     c1, c2, n1, n2 = data.problems()
     o = co.match_batch(rig, c1, c2, n1, n2)
     rows = o["rows"].reshape(F, C, N, 18)
-    np.testing.assert_array_equal(got["rows"], rows)
     ends = rows[..., :6].reshape(F, C, N, 2, 3).transpose(1, 0, 2, 3, 4).copy()
-    tid = co.chain_tracks(co.track_batch(ends)["col_ind"])
+    tr = co.track_batch(ends)
+    return rows, co.chain_tracks(tr["col_ind"]), tr["total_cost"]
+
+
+@pytest.mark.parametrize("world,F", [(2, 11), (3, 10)])
+def test_sharded_equals_single_rank(tmp_path, world, F):
+    """One gather of the result blocks + root-side re-base == a single-rank run over the whole range
+    (halo frame re-computed on the rank before it, no send/recv)."""
+    C, N = 2, 6
+    out_path = str(tmp_path / "out.npz")
+    mp.spawn(_worker, args=(world, _free_port(), F, C, N, out_path, True), nprocs=world, join=True)
+    got = np.load(out_path)
+    rows, tid, tot = _single_rank_oracle(F, C, N)
+    np.testing.assert_array_equal(got["rows"], rows)
     np.testing.assert_array_equal(got["tid"], tid)
+    np.testing.assert_array_equal(got["tot"], tot)  # every pair tracked exactly once, boundary pairs included
+
+
+def test_sharded_global_ids_on_every_rank(tmp_path):
+    """gather_to_root=False: the boundary maps are all-gathered and every rank re-bases its own ids."""
+    world, F, C, N = 3, 10, 2, 6
+    out_path = str(tmp_path / "out")
+    mp.spawn(_worker, args=(world, _free_port(), F, C, N, out_path, False), nprocs=world, join=True)
+    _, tid, _ = _single_rank_oracle(F, C, N)
+    for r in range(world):
+        g = np.load(out_path + f".{r}.npz")
+        np.testing.assert_array_equal(g["tid"], tid[:, int(g["f0"]):int(g["f1"])])
+
+
+def test_block_layout_and_broken_maps():
+    L = pdist._BlockLayout(7, 3, 5)
+    assert all(o % 256 == 0 for o in L.off.values()) and L.send_bytes <= L.capacity
+    blk = torch.zeros(L.capacity, dtype=torch.uint8)
+    v = L.views(blk, 6, 1)
+    assert v["rows"].shape == (7 * 3, 5, 18) and v["track_id"].shape == (3, 6, 5) and v["track_total"].shape == (3, 6)
+    v["rows"].fill_(1.5)
+    assert float(L.views(blk, 7, 0)["rows"].sum()) == 1.5 * 7 * 3 * 5 * 18
+    w = L.views(blk[: L.send_bytes], 6, 1, own_only=True)
+    assert w["rows"].shape == (6 * 3, 5, 18) and w["track_total"].shape == (3, 6)
+    maps = torch.tensor([[[1, 0, -1]], [[2, 1, 0]], [[0, 1, 2]]], dtype=torch.int32)  # W=3, C=1, N=3
+    st = pdist.compose_rank_maps(maps)
+    assert st[1].tolist() == [[1, 0, -1]] and st[2].tolist() == [[-1, 0, 1]]
