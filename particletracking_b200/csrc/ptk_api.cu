@@ -278,42 +278,33 @@ int launch_lsap(long long P, LsapArgs a, cudaStream_t st)
 // K2T: the tracking assignment straight from the end points (ptk_lsap_trk.cuh): k_trk_prepare writes the
 // separable norms and the exception list of every problem into `scratch`, k_lsap_trk solves, WARPS
 // problems per CTA.
-template <int CPL, int WARPS, int MINB, bool MASKED>
-int launch_lsap_trk_m(const TrkArgs& a, void* scratch, cudaStream_t st)
+template <int CPL, int WARPS, int MINB>
+int launch_lsap_trk_t(const TrkArgs& a, void* scratch, cudaStream_t st)
 {
     const size_t smem = (size_t)WARPS * trk_warp_bytes<CPL>(a.N);
     if (smem > 48 * 1024) {
         static std::once_flag once;  // per instantiation
         static cudaError_t attr_rc = cudaSuccess;
         std::call_once(once, [&] {
-            attr_rc = cudaFuncSetAttribute(k_lsap_trk<CPL, WARPS, MINB, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            attr_rc = cudaFuncSetAttribute(k_lsap_trk<CPL, WARPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)((size_t)WARPS * trk_warp_bytes<CPL>(32 * CPL)));
         });
         if (attr_rc != cudaSuccess) return cuda_fail(attr_rc, "cudaFuncSetAttribute(k_lsap_trk)");
     }
-    const long long blocks = (a.Q + WARPS - 1) / WARPS;
+    // first half of the grid: problems with exceptions (k_trk_prepare's flag), second half: the rest
+    const long long blocks = 2 * ((a.Q + WARPS - 1) / WARPS);
+    if (blocks >= (1ll << 31)) return PTK_ERR_INVALID_ARG;
     {
         LaunchTimer lt(K_LSAP_TRACK, st);
-        k_lsap_trk<CPL, WARPS, MINB, MASKED><<<(unsigned)blocks, 32 * WARPS, smem, st>>>(a, scratch);
+        k_lsap_trk<CPL, WARPS, MINB><<<(unsigned)blocks, 32 * WARPS, smem, st>>>(a, scratch);
     }
     LAUNCHED("k_lsap_trk");
     return PTK_OK;
 }
 
-// Every problem is solved by exactly one of the two launches (k_trk_prepare's flag decides): the
-// common case by the lean loop, problems with more than one exception per column by the one that can
-// re-evaluate masked entries.  Where no problem is masked the second launch is ~2 us of early exits.
-template <int CPL, int WARPS, int MINB>
-int launch_lsap_trk_t(const TrkArgs& a, void* scratch, cudaStream_t st)
-{
-    int rc = launch_lsap_trk_m<CPL, WARPS, MINB, false>(a, scratch, st);
-    if (rc) return rc;
-    return launch_lsap_trk_m<CPL, WARPS, MINB, true>(a, scratch, st);
-}
-
 int launch_lsap_trk(const TrkArgs& a, void* scratch, cudaStream_t st)
 {
-    if (a.Q >= (1ll << 31)) return PTK_ERR_INVALID_ARG;
+    if (a.Q >= (1ll << 30)) return PTK_ERR_INVALID_ARG;
     {
         const size_t smem = (size_t)kTrkPrepWarps * 14 * a.N * sizeof(double);  // <= 112 KB at N = 256
         if (smem > 48 * 1024) {
@@ -330,7 +321,15 @@ int launch_lsap_trk(const TrkArgs& a, void* scratch, cudaStream_t st)
     }
     LAUNCHED("k_trk_prepare");
     // occupancy of the solver is set by registers: 40 / 24 / 20 / 12 warps per SM
-    if (a.N <= 32) return launch_lsap_trk_t<1, 4, 10>(a, scratch, st);
+    if (a.N <= 32) {
+        static const int cfg = getenv("PTK_TRK_CFG") ? atoi(getenv("PTK_TRK_CFG")) : 0;  // tuning knob (tools/trk_ab.py)
+        if (cfg == 1) return launch_lsap_trk_t<1, 4, 7>(a, scratch, st);
+        if (cfg == 2) return launch_lsap_trk_t<1, 2, 16>(a, scratch, st);
+        if (cfg == 3) return launch_lsap_trk_t<1, 1, 32>(a, scratch, st);
+        if (cfg == 4) return launch_lsap_trk_t<1, 4, 12>(a, scratch, st);
+        if (cfg == 5) return launch_lsap_trk_t<1, 8, 5>(a, scratch, st);
+        return launch_lsap_trk_t<1, 4, 10>(a, scratch, st);
+    }
     if (a.N <= 64) return launch_lsap_trk_t<2, 4, 6>(a, scratch, st);
     if (a.N <= 128) return launch_lsap_trk_t<4, 4, 5>(a, scratch, st);
     return launch_lsap_trk_t<8, 4, 3>(a, scratch, st);

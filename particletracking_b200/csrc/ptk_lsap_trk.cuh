@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(32 * kTrkPrepWarps) k_trk_prepare(const __grid
         if (k & 1) { Bs[r] = v; t.B[r] = v; } else { As[r] = v; t.A[r] = v; }
     }
     __syncwarp();
-    bool bad = false, masked = false;
+    bool bad = false, masked = false, anyexc = false;
     for (int s = 0; s < W; s++) {
         const int j = lane + 32 * s;
         const bool own = j < N;
@@ -175,9 +175,10 @@ __global__ void __launch_bounds__(32 * kTrkPrepWarps) k_trk_prepare(const __grid
             if (lane == 0) t.xm[(size_t)i * W + s] = w;
         }
         if (own) { t.xrow[j] = xrow; t.xval[j] = xval; }
+        anyexc |= __any_sync(kFull, own && xrow >= 0);
     }
     const bool anybad = __any_sync(kFull, bad);
-    if (lane == 0) t.bad[0] = (anybad ? 1 : 0) | (masked ? 2 : 0);
+    if (lane == 0) t.bad[0] = (anybad ? 1 : 0) | (anyexc ? 2 : 0) | (masked ? 4 : 0);
 }
 
 template <int CPL>
@@ -193,65 +194,84 @@ __host__ __device__ inline size_t trk_warp_bytes(int N)
     return (((size_t)N * (sizeof(TrkRow<CPL>) + sizeof(int32_t))) + 15) / 16 * 16;
 }
 
-// WARPS problems per CTA, one warp each; no block-level synchronisation anywhere.
-// MASKED = false: problems without masked exceptions (at most one exception per column: all of them in
-// practice); the others return at once and are solved by the MASKED = true instantiation, whose loop
-// carries the out-of-line call -- and the spills around it -- that the common case must not pay for.
-template <int CPL, int WARPS, int MINB, bool MASKED>
-__global__ void __launch_bounds__(32 * WARPS, MINB) k_lsap_trk(const __grid_constant__ TrkArgs a, const void* scratch)
+// ---- the solver: one warp per problem, WARPS problems per CTA, no block-level synchronisation.
+//
+// EXC = false: problems whose matrix is purely separable (no exception at all: every problem of a
+// run without end-point flips).  EXC = true: the loop also checks the column's register exception and
+// can re-evaluate masked entries through an out-of-line call.  Both live in ONE kernel (the first half
+// of the grid takes the EXC problems, the second half the others; a warp whose problem belongs to the
+// other half returns after one 4-byte load), so that the few slow EXC problems start first and overlap
+// the bulk instead of forming a serial tail.
+//
+// The Dijkstra step is bound by the ALU pipe (16 lanes per scheduler: every integer / select / compare
+// instruction costs two issue cycles; ncu r2a: ALU 81 % busy at 36 such instructions per step), so the
+// step is written to keep integer work off it:
+//  * keys are the RAW bits of the shortest-path cost: for non-negative doubles the signed integer
+//    order of the bits is the value order, so the key costs nothing to form and the minimum nothing to
+//    convert back.  One unsigned compare on the first REDUX result (>= 0x7ff00000) detects both rare
+//    cases -- every remaining column at +inf (infeasible) and a negative candidate (possible through
+//    rounding only) -- and the latter is redone with the order-preserving transform;
+//  * a visited column's high word becomes that of +NaN (its real high word moves to `seen_hi`):
+//    `r < NaN` is false (no update), NaN's bits are above +inf's (never the minimum), NaN == min is
+//    false (never the winner) -- no "live" predicate anywhere in the loop.  Lanes beyond N start as NaN;
+//  * the winner test is DSETP.EQ on the FP64 pipe (which also makes -0.0 tie with +0.0 as in SciPy);
+//  * the next row is not decoded from the REDUX result: every assigned column keeps the shared-memory
+//    address of its row in a register (0 = unassigned) and the winner's is fetched with one SHFL, as
+//    is its position in SciPy's `remaining` list.
+template <int CPL, bool EXC>
+__device__ __forceinline__ void trk_solve(const TrkArgs& a, const void* scratch, long long p, int lane, unsigned char* base)
 {
-    extern __shared__ __align__(16) unsigned char trk_smem[];
     typedef TrkRow<CPL> Row;
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const long long p = (long long)blockIdx.x * WARPS + warp;
-    if (p >= a.Q) return;
     const int N = a.N;
-    unsigned char* base = trk_smem + (size_t)warp * trk_warp_bytes<CPL>(N);
     Row* rows = reinterpret_cast<Row*>(base);
     int32_t* c4r = reinterpret_cast<int32_t*>(rows + N);
+    const unsigned rows_addr = (unsigned)__cvta_generic_to_shared(rows);
 
-    // ---- k_trk_prepare's record: A and the mask words go to shared memory beside u, the column side
+    // ---- k_trk_prepare's record: A (and the mask words) go to shared memory beside u, the column side
     // (B, the first exception of the column) into registers
     int st;
     double Bj[CPL], xval[CPL];
-    int xrow[CPL];
+    unsigned xrow_addr[CPL];
     {
-    const TrkPrep t = trk_prep_at(const_cast<void*>(scratch), p, N);
-    const int W = trk_mask_words(N);
-    for (int r = lane; r < N; r += 32) {
-        Row& R = rows[r];
-        R.u = 0.0;
-        R.A = t.A[r];
+        const TrkPrep t = trk_prep_at(const_cast<void*>(scratch), p, N);
+        const int flags = t.bad[0];  // bit 0: invalid entries, bit 1: exceptions present, bit 2: masked ones too
+        if (((flags >> 1) & 1) != (EXC ? 1 : 0)) return;  // warp-uniform: the other half's problem
+        st = (flags & 1) ? PTK_PROBLEM_INVALID : PTK_PROBLEM_OK;
+        const int W = trk_mask_words(N);
+        for (int r = lane; r < N; r += 32) {
+            Row& R = rows[r];
+            R.u = 0.0;
+            R.A = t.A[r];
 #pragma unroll
-        for (int s = 0; s < CPL; s++) R.xm[s] = (MASKED && s < W) ? t.xm[(size_t)r * W + s] : 0u;
-        c4r[r] = -1;
-    }
+            for (int s = 0; s < CPL; s++) R.xm[s] = (EXC && s < W) ? t.xm[(size_t)r * W + s] : 0u;
+            c4r[r] = -1;
+        }
 #pragma unroll
-    for (int s = 0; s < CPL; s++) {
-        const int j = lane + 32 * s;
-        const int jj = j < N ? j : N - 1;
-        Bj[s] = t.B[jj];
-        xrow[s] = j < N ? t.xrow[jj] : -1;
-        xval[s] = t.xval[jj];
-    }
-    const int flags = t.bad[0];  // bit 0: invalid entries, bit 1: masked exceptions present
-    if (((flags >> 1) & 1) != (MASKED ? 1 : 0)) return;  // warp-uniform
-    st = (flags & 1) ? PTK_PROBLEM_INVALID : PTK_PROBLEM_OK;
+        for (int s = 0; s < CPL; s++) {
+            const int j = lane + 32 * s;
+            const int jj = j < N ? j : N - 1;
+            Bj[s] = t.B[jj];
+            const int xr = (EXC && j < N) ? t.xrow[jj] : -1;
+            xrow_addr[s] = xr >= 0 ? rows_addr + (unsigned)xr * (unsigned)sizeof(Row) : 0u;
+            xval[s] = EXC ? t.xval[jj] : 0.0;
+        }
     }
     __syncwarp();
 
-    double v[CPL], spc[CPL];
-    int path[CPL], r4c[CPL], pos[CPL];
-    unsigned ka[CPL], kb[CPL];  // tie-rule candidate = ka * pos + kb (see below)
+    const int kDeadHi = 0x7ff80000;  // high word of +NaN: a visited (or absent) column
+    double v[CPL];
+    int spc_hi[CPL], spc_lo[CPL], seen_hi[CPL];  // shortest-path cost as two words (see above)
+    unsigned path[CPL];                          // shared-memory address of the row the cost came from
+    unsigned r4c_addr[CPL];                      // ... of the row the column is assigned to, 0 = unassigned
+    int pos[CPL];
+    unsigned ka[CPL], kb[CPL];                   // tie-rule candidate = ka * pos + kb (see below)
 #pragma unroll
     for (int s = 0; s < CPL; s++) {
-        v[s] = 0.0; spc[s] = 0.0; path[s] = -1; r4c[s] = -1; pos[s] = -1;
+        v[s] = 0.0; spc_hi[s] = kDeadHi; spc_lo[s] = 0; seen_hi[s] = kDeadHi; path[s] = 0u; r4c_addr[s] = 0u; pos[s] = -1;
         // unassigned column: rank = 511 - pos, so that the LARGEST list position wins a tie
-        ka[s] = 0u - (1u << 18);
-        kb[s] = (511u << 18) | (unsigned)(lane + 32 * s);
+        ka[s] = 0u - (1u << 9);
+        kb[s] = (511u << 9) | (unsigned)(lane + 32 * s);
     }
-    const int kInfHi = 0x7ff00000;
 
     if (st == PTK_PROBLEM_OK) {
 #pragma unroll 1
@@ -259,68 +279,97 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) k_lsap_trk(const __grid_cons
 #pragma unroll
             for (int s = 0; s < CPL; s++) {
                 const int j = lane + 32 * s;
-                spc[s] = INFINITY;
+                spc_hi[s] = (j < N) ? 0x7ff00000 : kDeadHi;  // +inf
+                spc_lo[s] = 0;
+                seen_hi[s] = kDeadHi;                 // NaN = not visited in this row
                 pos[s] = (j < N) ? (N - 1 - j) : -1;  // remaining[it] = nc-1-it  <=>  pos[j] = nc-1-j
             }
             double minVal = 0.0;
-            int i = curRow, num_rem = N, sink = -1;
+            unsigned iaddr = rows_addr + (unsigned)curRow * (unsigned)sizeof(Row);
+            int num_rem = N, sink = -1;
             bool infeasible = false;
 #pragma unroll 1
             while (sink == -1) {
-                const Row& R = rows[i];
-                const double ui = R.u, Ai = R.A;
-                int khi[CPL], mhi;
-                unsigned klo[CPL], mlo;
+                double ui, Ai;
+                unsigned xmw[CPL];
+                {
+                    unsigned long long w0, w1;
+                    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "r"(iaddr));
+                    ui = __longlong_as_double((long long)w0);
+                    Ai = __longlong_as_double((long long)w1);
+                    if (EXC) {
+#pragma unroll
+                        for (int s = 0; s < CPL; s++) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(xmw[s]) : "r"(iaddr + 16u + 4u * s));
+                    }
+                }
+                int mhi;
+                unsigned mlo;
 #pragma unroll
                 for (int s = 0; s < CPL; s++) {
-                    // branch-free: every lane evaluates, only columns still in `remaining` update
-                    const bool live = pos[s] >= 0;
                     double c = Ai + Bj[s];
-                    if (i == xrow[s]) c = xval[s];
-                    if (MASKED && live && ((R.xm[s] >> lane) & 1u)) c = trk_cross_min_q(a, p, c, i, lane + 32 * s);
+                    if (EXC) {
+                        if (iaddr == xrow_addr[s]) c = xval[s];
+                        if ((xmw[s] >> lane) & 1u)
+                            c = trk_cross_min_q(a, p, c, (int)((iaddr - rows_addr) / (unsigned)sizeof(Row)), lane + 32 * s);
+                    }
                     const double r = ((minVal + c) - ui) - v[s];
-                    if (live && r < spc[s]) { spc[s] = r; path[s] = i; }
-                    int h;
-                    unsigned l;
-                    skey(spc[s], h, l);
-                    khi[s] = live ? h : 0x7fffffff;
-                    klo[s] = live ? l : 0xffffffffu;
-                    if (s == 0) { mhi = khi[0]; mlo = klo[0]; }
-                    else if (khi[s] < mhi || (khi[s] == mhi && klo[s] < mlo)) { mhi = khi[s]; mlo = klo[s]; }
+                    if (r < __hiloint2double(spc_hi[s], spc_lo[s])) {  // false for a visited column (NaN)
+                        spc_hi[s] = __double2hiint(r);
+                        spc_lo[s] = __double2loint(r);
+                        path[s] = iaddr;
+                    }
+                    const int h = spc_hi[s];
+                    const unsigned l = (unsigned)spc_lo[s];
+                    if (s == 0 || h < mhi || (h == mhi && l < mlo)) { mhi = h; mlo = l; }
                 }
-                // warp argmin with SciPy's tie rule in three REDUX ops: (1) high and (2) low word of
-                // the order-preserving key, then (3) one packed integer whose order is the tie rule
-                // -- unassigned columns first (largest list position wins), then assigned ones
-                // (smallest position wins) -- and whose low bits carry row4col+1 and the column.
+                // warp argmin with SciPy's tie rule in three REDUX ops: (1) high and (2) low word of the
+                // cost's bits, then (3) one packed integer whose order is the tie rule -- unassigned
+                // columns first (largest list position wins), then assigned ones (smallest position wins).
                 const int mh = __reduce_min_sync(kFull, mhi);
-                const unsigned ml = __reduce_min_sync(kFull, mhi == mh ? mlo : 0xffffffffu);
-                // all remaining columns at +inf (spc is never NaN: a NaN candidate fails r < spc)
-                if (mh >= kInfHi) { infeasible = true; break; }
+                if ((unsigned)mh >= 0x7ff00000u) {  // rare: +inf everywhere, or a negative candidate
+                    if (mh >= 0) { infeasible = true; break; }
+                    int h2 = 0x7fffffff;
+                    unsigned l2 = 0xffffffffu;
+#pragma unroll
+                    for (int s = 0; s < CPL; s++) {
+                        int h;
+                        unsigned l;
+                        skey(__hiloint2double(spc_hi[s], spc_lo[s]), h, l);
+                        if (h < h2 || (h == h2 && l < l2)) { h2 = h; l2 = l; }
+                    }
+                    const int mh2 = __reduce_min_sync(kFull, h2);
+                    const unsigned ml2 = __reduce_min_sync(kFull, h2 == mh2 ? l2 : 0xffffffffu);
+                    minVal = skey_value(mh2, ml2);
+                } else {
+                    const unsigned ml = __reduce_min_sync(kFull, mhi == mh ? mlo : 0xffffffffu);
+                    minVal = __hiloint2double(mh, (int)ml);
+                }
                 unsigned key3 = 0xffffffffu;
 #pragma unroll
                 for (int s = 0; s < CPL; s++) {
-                    const bool win = (khi[s] == mh) & (klo[s] == ml);
                     const unsigned cand = ka[s] * (unsigned)pos[s] + kb[s];
-                    key3 = min(key3, win ? cand : 0xffffffffu);
+                    key3 = min(key3, (__hiloint2double(spc_hi[s], spc_lo[s]) == minVal) ? cand : 0xffffffffu);
                 }
                 key3 = __reduce_min_sync(kFull, key3);
                 const int jsel = (int)(key3 & 511u);
-                const int r4p1 = (int)((key3 >> 9) & 511u);  // row4col + 1
+                // the winner's row address (0: unassigned -> sink) and list position, straight from its lane
+                unsigned naddr;
                 int index;
-                if (CPL == 1) {
+                if (CPL == 1) {  // jsel < 32: the winner's lane
+                    naddr = __shfl_sync(kFull, r4c_addr[0], jsel);
                     index = __shfl_sync(kFull, pos[0], jsel);
                 } else {
-                    const unsigned rank = key3 >> 18;
-                    index = rank < 512u ? (int)(511u - rank) : (int)(rank - 512u);
+                    naddr = lane_array_get<CPL>(r4c_addr, jsel);
+                    index = lane_array_get<CPL>(pos, jsel);
                 }
-                minVal = skey_value(mh, ml);
-                if (r4p1 == 0) sink = jsel; else i = r4p1 - 1;
-                // remaining[index] = remaining[--num_remaining]; -2 marks "visited" (SC)
+                if (naddr == 0u) sink = jsel; else iaddr = naddr;
+                // remaining[index] = remaining[--num_remaining]: the column at the last position takes
+                // the freed one; the selected column becomes visited (SC): its high word moves to `seen_hi`
                 num_rem--;
 #pragma unroll
                 for (int s = 0; s < CPL; s++) {
-                    const int ps = pos[s];
-                    pos[s] = (ps == index) ? -2 : ((ps == num_rem) ? index : ps);
+                    if (lane + 32 * s == jsel) { seen_hi[s] = spc_hi[s]; spc_hi[s] = kDeadHi; }
+                    else if (pos[s] == num_rem) pos[s] = index;
                 }
             }
             if (infeasible) { st = PTK_PROBLEM_INFEASIBLE; break; }
@@ -328,9 +377,12 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) k_lsap_trk(const __grid_cons
             if (lane == 0) rows[curRow].u += minVal;
 #pragma unroll
             for (int s = 0; s < CPL; s++) {
-                if (pos[s] == -2) {
-                    const double d = minVal - spc[s];
-                    if (r4c[s] >= 0) rows[r4c[s]].u += d;
+                if (seen_hi[s] != kDeadHi) {  // visited in this row
+                    const double d = minVal - __hiloint2double(seen_hi[s], spc_lo[s]);
+                    if (r4c_addr[s] != 0u) {
+                        Row* R = rows + (r4c_addr[s] - rows_addr) / (unsigned)sizeof(Row);
+                        R->u += d;
+                    }
                     v[s] -= d;
                 }
             }
@@ -338,14 +390,15 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) k_lsap_trk(const __grid_cons
             // augment along the path
             int j = sink;
             while (true) {
-                const int r = lane_array_get<CPL>(path, j);
+                const unsigned raddr = lane_array_get<CPL>(path, j);
+                const int r = (int)((raddr - rows_addr) / (unsigned)sizeof(Row));
 #pragma unroll
                 for (int s = 0; s < CPL; s++)
                     if (lane == (j & 31) && s == (j >> 5)) {
-                        r4c[s] = r;
+                        r4c_addr[s] = raddr;
                         // assigned column: rank = 512 + pos, the SMALLEST list position wins a tie
-                        ka[s] = 1u << 18;
-                        kb[s] = (512u << 18) | ((unsigned)(r + 1) << 9) | (unsigned)j;
+                        ka[s] = 1u << 9;
+                        kb[s] = (512u << 9) | (unsigned)j;
                     }
                 const int t = c4r[r];
                 __syncwarp();
@@ -379,6 +432,22 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) k_lsap_trk(const __grid_cons
         }
         if (lane == 0 && a.status) a.status[p] = st;
     }
+}
+
+// grid = 2 * ceil(Q / WARPS): the first half solves the problems with exceptions, the second the rest
+template <int CPL, int WARPS, int MINB>
+__global__ void __launch_bounds__(32 * WARPS, MINB) k_lsap_trk(const __grid_constant__ TrkArgs a, const void* scratch)
+{
+    extern __shared__ __align__(16) unsigned char trk_smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const unsigned half = gridDim.x >> 1;
+    const bool exc = blockIdx.x < half;
+    const long long p = (long long)(exc ? blockIdx.x : blockIdx.x - half) * WARPS + warp;
+    if (p >= a.Q) return;
+    unsigned char* base = trk_smem + (size_t)warp * trk_warp_bytes<CPL>(a.N);
+    if (exc) trk_solve<CPL, true>(a, scratch, p, lane, base);
+    else trk_solve<CPL, false>(a, scratch, p, lane, base);
 }
 
 }  // namespace ptk
