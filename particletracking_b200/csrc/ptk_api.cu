@@ -155,6 +155,22 @@ DevRig make_devrig(const ptk_rig* r)
         for (int k : {2, 3, 8, 9, 10, 11}) tg = tg || (ks[c][k] != 0.0);
         d.tangential[c] = tg ? 1 : 0;
     }
+    {
+        // rig class: what the reference's drivers build (match2D.py:584-592) is canonical and, with the
+        // calibrations it ships, simple; anything else runs the general instantiation
+        const double fx = r->CM1[0], fy = r->CM1[4], cx = r->CM1[2], cy = r->CM1[5];
+        const double canonP1[12] = {fx, 0, cx, 0, 0, fy, cy, 0, 0, 0, 1, 0};
+        bool canon = d.ext_identity[0] != 0 && r->CM1[1] == 0.0 && r->CM1[3] == 0.0 && r->CM1[6] == 0.0 && r->CM1[7] == 0.0 &&
+                     r->CM1[8] == 1.0 && fx > 0.0 && fy > 0.0;
+        for (int k = 0; k < 12; k++) canon = canon && (r->P1[k] == canonP1[k]);
+        bool simple = !d.tangential[0] && !d.tangential[1];
+        for (int c = 0; c < 2; c++)
+            for (int k : {5, 6, 7}) simple = simple && (ks[c][k] == 0.0);
+        d.canon = canon ? 1 : 0;
+        d.simple = simple ? 1 : 0;
+        d.fx2 = fx * fx;
+        if (getenv("PTK_RIG_GENERAL")) d.canon = d.simple = 0;  // A/B switch: force the general instantiation
+    }
     return d;
 }
 
@@ -223,8 +239,8 @@ int launch_cost(const DevRig& rig, long long P, int Nmax, const double* cam1, co
     CostArgs a;
     a.Nmax = Nmax;
     a.tiles = (Nmax * Nmax + 31) / 32;
-    // 1-D grids hold 2^31-1 blocks; slice anyway to stay far below
-    const long long max_p = (long long)(1u << 30) / a.tiles;
+    // grid = (tiles, problems): gridDim.y holds 65535
+    const long long max_p = 65535;
     for (long long p0 = 0; p0 < P; p0 += max_p) {
         const long long np = (P - p0) < max_p ? (P - p0) : max_p;
         const size_t o4 = (size_t)p0 * Nmax * 4, o2 = (size_t)p0 * Nmax * Nmax;
@@ -234,9 +250,14 @@ int launch_cost(const DevRig& rig, long long P, int Nmax, const double* cam1, co
         a.choice = choice ? choice + o2 : nullptr;
         a.p_world = p_world ? p_world + o2 * 12 : nullptr;
         a.rep_errs = rep_errs ? rep_errs + o2 * 8 : nullptr;
+        const dim3 grid((unsigned)a.tiles, (unsigned)np);
         {
             LaunchTimer lt(K_COST, st);
-            k_cost<<<(unsigned)(np * a.tiles), 128, 0, st>>>(rig, a);
+            // the rig class picks the instantiation (same bits from every one of them, see eval_combo)
+            if (rig.canon && rig.simple) k_cost<true, true><<<grid, 128, 0, st>>>(rig, a);
+            else if (rig.canon) k_cost<true, false><<<grid, 128, 0, st>>>(rig, a);
+            else if (rig.simple) k_cost<false, true><<<grid, 128, 0, st>>>(rig, a);
+            else k_cost<false, false><<<grid, 128, 0, st>>>(rig, a);
         }
         LAUNCHED("k_cost");
     }
@@ -352,7 +373,10 @@ int launch_rows(const DevRig& rig, long long P, int Nmax, const double* cam1, co
         dim3 grid((Nmax + 31) / 32, np);
         {
             LaunchTimer lt(K_ROWS, st);
-            k_rows<<<grid, 128, 0, st>>>(rig, a);
+            if (rig.canon && rig.simple) k_rows<true, true><<<grid, 128, 0, st>>>(rig, a);
+            else if (rig.canon) k_rows<true, false><<<grid, 128, 0, st>>>(rig, a);
+            else if (rig.simple) k_rows<false, true><<<grid, 128, 0, st>>>(rig, a);
+            else k_rows<false, false><<<grid, 128, 0, st>>>(rig, a);
         }
         LAUNCHED("k_rows");
     }

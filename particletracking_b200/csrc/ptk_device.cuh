@@ -32,6 +32,10 @@ struct DevRig {
     // rig-constant shortcuts for the projection (set by make_devrig; warp-uniform branches):
     int ext_identity[2];  // camera k has R = I, t = 0 (camera 1 of a stereo rig)
     int tangential[2];    // camera k has any of p1, p2, s1..s4 non-zero
+    // rig class, selects the kernel instantiation (make_devrig):
+    int canon;            // P1 == CM1 [I|0] exactly, zero skew, and camera 1 has identity extrinsics
+    int simple;           // both cameras: radial k1, k2, k3 only (no rational, tangential, thin-prism terms)
+    double fx2;           // CM1 fx * fx (canon)
 };
 
 // ---------------------------------------------------------------------------------------
@@ -361,37 +365,13 @@ static inline double ptk_pow2_inv(double x)
 #define PTK_HD __host__ __device__ inline
 #endif
 
-// P1o, P2o: 3x4 row-major projection matrices in the caller's column order.  v: the null vector
-// (any scale).  Returns whether the power iteration has converged.
-PTK_HD bool dlt_null_invpower(const double* __restrict__ Q1, const double* __restrict__ Q2, double x1, double y1,
-                              double x2, double y2, double (&v)[4])
+// Everything after the QR: T = R~^-1, B = T diag(w) T^T, NSQ symmetric squarings, the convergence
+// check and the final product with the largest-diagonal column.  r_kj: the unit upper-triangular
+// factor's entries, w_k = 1 / |q_k|^2.  Returns whether the power iteration has converged.
+template <int NSQ>
+PTK_HD bool dlt_invpower_tail(double r01, double r02, double r03, double r12, double r13, double r23, double w0, double w1,
+                              double w2, double w3, double (&v)[4])
 {
-    double a0[4], a1[4], a2[4], a3[4];
-#define PTK_COL(Ak, k)                      \
-    Ak[0] = fma(x1, Q1[8 + k], -Q1[0 + k]); \
-    Ak[1] = fma(y1, Q1[8 + k], -Q1[4 + k]); \
-    Ak[2] = fma(x2, Q2[8 + k], -Q2[0 + k]); \
-    Ak[3] = fma(y2, Q2[8 + k], -Q2[4 + k]);
-    PTK_COL(a0, 0) PTK_COL(a1, 1) PTK_COL(a2, 2) PTK_COL(a3, 3)
-#undef PTK_COL
-#define PTK_DOT(x, y) fma(x[3], y[3], fma(x[2], y[2], fma(x[1], y[1], x[0] * y[0])))
-#define PTK_AXPY(y, r, q) { y[0] = fma(-r, q[0], y[0]); y[1] = fma(-r, q[1], y[1]); y[2] = fma(-r, q[2], y[2]); y[3] = fma(-r, q[3], y[3]); }
-    // modified Gram-Schmidt WITHOUT normalising: q_k = a_k^(k) (orthogonal, |q_k|^2 = n_k),
-    // A = Q~ R~ with R~ unit upper triangular, r~_kj = (q_k . a_j) / n_k.  Then
-    // (A^T A)^-1 = T diag(1/n_k) T^T with T = R~^-1 (unit upper triangular): no square root anywhere,
-    // four reciprocals w_k = 1/n_k.
-    const double w0 = ptk_rcp(PTK_DOT(a0, a0));
-    const double r01 = PTK_DOT(a0, a1) * w0, r02 = PTK_DOT(a0, a2) * w0, r03 = PTK_DOT(a0, a3) * w0;
-    PTK_AXPY(a1, r01, a0) PTK_AXPY(a2, r02, a0) PTK_AXPY(a3, r03, a0)
-    const double w1 = ptk_rcp(PTK_DOT(a1, a1));
-    const double r12 = PTK_DOT(a1, a2) * w1, r13 = PTK_DOT(a1, a3) * w1;
-    PTK_AXPY(a2, r12, a1) PTK_AXPY(a3, r13, a1)
-    const double w2 = ptk_rcp(PTK_DOT(a2, a2));
-    const double r23 = PTK_DOT(a2, a3) * w2;
-    PTK_AXPY(a3, r23, a2)
-    const double w3 = ptk_rcp(PTK_DOT(a3, a3));
-#undef PTK_DOT
-#undef PTK_AXPY
     // T = R~^-1: t01 = -r01, t12 = -r12, t23 = -r23 and
     const double t02 = fma(r01, r12, -r02);                  // -(r02 + r01 t12)
     const double t13 = fma(r12, r23, -r13);                  // -(r13 + r12 t23)
@@ -430,28 +410,18 @@ PTK_HD bool dlt_null_invpower(const double* __restrict__ Q1, const double* __res
         b00 = c00; b01 = c01; b02 = c02; b03 = c03; b11 = c11;                           \
         b12 = c12; b13 = c13; b22 = c22; b23 = c23; b33 = c33;                           \
     }
-    // converged?  |B^k|_F^2 >= (1 - tol) tr(B^k)^2
-#define PTK_CONVERGED(okvar)                                                                                      \
-    {                                                                                                             \
-        const double tr = (b00 + b11) + (b22 + b33);                                                              \
-        const double od = fma(b23, b23, fma(b13, b13, fma(b12, b12, fma(b03, b03, fma(b02, b02, b01 * b01)))));    \
-        const double fr = fma(2.0, od, fma(b33, b33, fma(b22, b22, fma(b11, b11, b00 * b00))));                   \
-        /* fr - (1 - tol) tr^2 >= 0, written so that Inf - Inf (a Gram-Schmidt norm that underflowed) is */         \
-        /* NaN and therefore NOT converged: the caller then takes the Jacobi fallback                    */         \
-        okvar = fma(-(1.0 - PTK_INVPOWER_TOL), tr * tr, fr) >= 0.0;                                               \
-    }
     PTK_SQUARE_B PTK_SQUARE_B PTK_SQUARE_B
-    bool ok;
-    PTK_CONVERGED(ok)
-    if (!ok) {
-        // sigma_4/sigma_3 between 0.39 and 0.62 (geometry unlike a rod experiment's): one more squaring,
-        // B^16 and B^32 e_j below, is still 15 x cheaper than the Jacobi.  tr(B^8) is within
-        // 2^-32 .. 2^16, so its square neither overflows nor underflows.
-        PTK_SQUARE_B
-        PTK_CONVERGED(ok)
-    }
+    // sigma_4/sigma_3 between 0.39 and 0.62 (geometry unlike a rod experiment's): one more squaring, B^16
+    // and B^32 e_j below.  tr(B^8) is within 2^-32 .. 2^16, so its square neither overflows nor underflows.
+    if (NSQ > 3) PTK_SQUARE_B
 #undef PTK_SQUARE_B
-#undef PTK_CONVERGED
+    // converged?  |B^k|_F^2 >= (1 - tol) tr(B^k)^2, written as fr - (1 - tol) tr^2 >= 0 so that Inf - Inf
+    // (a Gram-Schmidt norm that underflowed) is NaN and therefore NOT converged: the caller then takes
+    // the Jacobi fallback
+    const double tr = (b00 + b11) + (b22 + b33);
+    const double od = fma(b23, b23, fma(b13, b13, fma(b12, b12, fma(b03, b03, fma(b02, b02, b01 * b01)))));
+    const double fr = fma(2.0, od, fma(b33, b33, fma(b22, b22, fma(b11, b11, b00 * b00))));
+    const bool ok = fma(-(1.0 - PTK_INVPOWER_TOL), tr * tr, fr) >= 0.0;
     // v = B^k (column of B^k with the largest diagonal entry: |v_4[j]|^2 >= 1/4 there)
     double u0 = b00, u1 = b01, u2 = b02, u3 = b03, dm = b00;
     if (b11 > dm) { dm = b11; u0 = b01; u1 = b11; u2 = b12; u3 = b13; }
@@ -464,11 +434,106 @@ PTK_HD bool dlt_null_invpower(const double* __restrict__ Q1, const double* __res
     return ok;
 }
 
-// The Jacobi as an out-of-line call: only points whose inverse power iteration did not converge
-// get here, so its 80 registers must not set the register budget of the callers.
+#define PTK_DOT(x, y) fma(x[3], y[3], fma(x[2], y[2], fma(x[1], y[1], x[0] * y[0])))
+#define PTK_AXPY(y, r, q) { y[0] = fma(-r, q[0], y[0]); y[1] = fma(-r, q[1], y[1]); y[2] = fma(-r, q[2], y[2]); y[3] = fma(-r, q[3], y[3]); }
+
+// P1o, P2o: 3x4 row-major projection matrices in the caller's column order.  v: the null vector
+// (any scale).  NSQ = 3 or 4 squarings.  Returns whether the power iteration has converged.
+template <int NSQ>
+PTK_HD bool dlt_null_invpower_n(const double* __restrict__ Q1, const double* __restrict__ Q2, double x1, double y1,
+                                double x2, double y2, double (&v)[4])
+{
+    double a0[4], a1[4], a2[4], a3[4];
+#define PTK_COL(Ak, k)                      \
+    Ak[0] = fma(x1, Q1[8 + k], -Q1[0 + k]); \
+    Ak[1] = fma(y1, Q1[8 + k], -Q1[4 + k]); \
+    Ak[2] = fma(x2, Q2[8 + k], -Q2[0 + k]); \
+    Ak[3] = fma(y2, Q2[8 + k], -Q2[4 + k]);
+    PTK_COL(a0, 0) PTK_COL(a1, 1) PTK_COL(a2, 2) PTK_COL(a3, 3)
+#undef PTK_COL
+    // modified Gram-Schmidt WITHOUT normalising: q_k = a_k^(k) (orthogonal, |q_k|^2 = n_k),
+    // A = Q~ R~ with R~ unit upper triangular, r~_kj = (q_k . a_j) / n_k.  Then
+    // (A^T A)^-1 = T diag(1/n_k) T^T with T = R~^-1 (unit upper triangular): no square root anywhere,
+    // four reciprocals w_k = 1/n_k.
+    const double w0 = ptk_rcp(PTK_DOT(a0, a0));
+    const double r01 = PTK_DOT(a0, a1) * w0, r02 = PTK_DOT(a0, a2) * w0, r03 = PTK_DOT(a0, a3) * w0;
+    PTK_AXPY(a1, r01, a0) PTK_AXPY(a2, r02, a0) PTK_AXPY(a3, r03, a0)
+    const double w1 = ptk_rcp(PTK_DOT(a1, a1));
+    const double r12 = PTK_DOT(a1, a2) * w1, r13 = PTK_DOT(a1, a3) * w1;
+    PTK_AXPY(a2, r12, a1) PTK_AXPY(a3, r13, a1)
+    const double w2 = ptk_rcp(PTK_DOT(a2, a2));
+    const double r23 = PTK_DOT(a2, a3) * w2;
+    PTK_AXPY(a3, r23, a2)
+    const double w3 = ptk_rcp(PTK_DOT(a3, a3));
+    return dlt_invpower_tail<NSQ>(r01, r02, r03, r12, r13, r23, w0, w1, w2, w3, v);
+}
+
+// The same for a canonical first camera, P1 = CM1 [I|0] with zero skew (what match2D.py:584-586 builds):
+// the DLT columns are a0 = (-fx, 0, p0, q0), a1 = (0, -fy, p1, q1), a2 = (x1-cx, y1-cy, p2, q2),
+// a3 = (0, 0, p3, q3), and the operations on the exact zeros are left out.  Leaving them out does not
+// change a bit (x*0 = 0, fma(x, 0, c) = c on finite data): tests/test_dlt_invpower_cpu.py compares the two
+// functions for bit-identity.  16 FP64 instructions and 12 constant loads fewer per point.
+// cm1 = (fx, fy, cx, cy), fx2 = fx*fx (rounded once, as the device product would be).
+PTK_HD bool dlt_null_invpower_canon(const double* __restrict__ cm1, double fx2, const double* __restrict__ Q2, double x1,
+                                    double y1, double x2, double y2, double (&v)[4])
+{
+    const double fx = cm1[0], fy = cm1[1];
+    const double gx = x1 - cm1[2], gy = y1 - cm1[3];
+    const double p0 = fma(x2, Q2[8], -Q2[0]), q0 = fma(y2, Q2[8], -Q2[4]);
+    const double p1 = fma(x2, Q2[9], -Q2[1]), q1 = fma(y2, Q2[9], -Q2[5]);
+    const double p2 = fma(x2, Q2[10], -Q2[2]), q2 = fma(y2, Q2[10], -Q2[6]);
+    const double p3 = fma(x2, Q2[11], -Q2[3]), q3 = fma(y2, Q2[11], -Q2[7]);
+    // column 0 = (-fx, 0, p0, q0)
+    const double w0 = ptk_rcp(fma(q0, q0, fma(p0, p0, fx2)));
+    const double r01 = fma(q0, q1, p0 * p1) * w0;
+    const double r02 = fma(q0, q2, fma(p0, p2, -fx * gx)) * w0;
+    const double r03 = fma(q0, q3, p0 * p3) * w0;
+    double a1[4], a2[4], a3[4];
+    a1[0] = r01 * fx;              a1[1] = -fy; a1[2] = fma(-r01, p0, p1); a1[3] = fma(-r01, q0, q1);
+    a2[0] = fma(-r02, -fx, gx);    a2[1] = gy;  a2[2] = fma(-r02, p0, p2); a2[3] = fma(-r02, q0, q2);
+    a3[0] = r03 * fx;              /* a3[1] = 0 */ a3[2] = fma(-r03, p0, p3); a3[3] = fma(-r03, q0, q3);
+    const double w1 = ptk_rcp(PTK_DOT(a1, a1));
+    const double r12 = PTK_DOT(a1, a2) * w1;
+    const double r13 = fma(a1[3], a3[3], fma(a1[2], a3[2], a1[0] * a3[0])) * w1;
+    PTK_AXPY(a2, r12, a1)
+    a3[0] = fma(-r13, a1[0], a3[0]); a3[1] = r13 * fy; a3[2] = fma(-r13, a1[2], a3[2]); a3[3] = fma(-r13, a1[3], a3[3]);
+    const double w2 = ptk_rcp(PTK_DOT(a2, a2));
+    const double r23 = PTK_DOT(a2, a3) * w2;
+    PTK_AXPY(a3, r23, a2)
+    const double w3 = ptk_rcp(PTK_DOT(a3, a3));
+    return dlt_invpower_tail<3>(r01, r02, r03, r12, r13, r23, w0, w1, w2, w3, v);
+}
+#undef PTK_DOT
+#undef PTK_AXPY
+
+// Three squarings, and one more where that has not converged (the harness' and K8's entry point).
+PTK_HD bool dlt_null_invpower(const double* __restrict__ Q1, const double* __restrict__ Q2, double x1, double y1,
+                              double x2, double y2, double (&v)[4])
+{
+    if (dlt_null_invpower_n<3>(Q1, Q2, x1, y1, x2, y2, v)) return true;
+    return dlt_null_invpower_n<4>(Q1, Q2, x1, y1, x2, y2, v);
+}
+
+// Out of line: only points whose three-squaring power iteration did not converge get here (none on rod
+// data), so neither the fourth squaring nor the Jacobi's 80 registers weigh on the callers' main path.
+// Two separate functions: inlined into one, their combined register need made ptxas spill in the CALLERS'
+// main path (44 bytes per thread) to keep the kernels at 80 registers.
+__device__ __noinline__ bool dlt_invpower4_outofline(const DevRig& rig, double x1, double y1, double x2, double y2,
+                                                     double* __restrict__ xyz)
+{
+    double v[4];
+    const bool ok = dlt_null_invpower_n<4>(rig.P1o, rig.P2o, x1, y1, x2, y2, v);
+    const double rw = fast_rcp(v[3]);
+    xyz[0] = v[0] * rw;
+    xyz[1] = v[1] * rw;
+    xyz[2] = v[2] * rw;
+    return ok;
+}
+
 __device__ __noinline__ void dlt_triangulate_fallback(const DevRig& rig, double x1, double y1, double x2, double y2,
                                                       double* __restrict__ xyz)
 {
+    if (dlt_invpower4_outofline(rig, x1, y1, x2, y2, xyz)) return;
     double X, Y, Z;
     dlt_triangulate_jacobi(rig, x1, y1, x2, y2, X, Y, Z);
     xyz[0] = X;
@@ -477,14 +542,18 @@ __device__ __noinline__ void dlt_triangulate_fallback(const DevRig& rig, double 
 }
 
 // cv2.triangulatePoints for one point (match2D.py:889) + p[0:3]/p[3] (match2D.py:895).
-__device__ __forceinline__ void dlt_triangulate(const DevRig& rig, double x1, double y1, double x2, double y2,
-                                                double& X, double& Y, double& Z)
+// CANON: the rig's first camera is canonical (DevRig::canon, see make_devrig).
+template <bool CANON>
+__device__ __forceinline__ void dlt_triangulate_t(const DevRig& rig, double x1, double y1, double x2, double y2,
+                                                  double& X, double& Y, double& Z)
 {
 #ifdef PTK_DLT_JACOBI  // A/B switch (tools/ab_bench.py): the one-sided Jacobi for every point
     dlt_triangulate_jacobi(rig, x1, y1, x2, y2, X, Y, Z);
 #else
     double v[4];
-    if (dlt_null_invpower(rig.P1o, rig.P2o, x1, y1, x2, y2, v)) {
+    const bool ok = CANON ? dlt_null_invpower_canon(rig.CM1, rig.fx2, rig.P2o, x1, y1, x2, y2, v)
+                          : dlt_null_invpower_n<3>(rig.P1o, rig.P2o, x1, y1, x2, y2, v);
+    if (ok) {
         const double rw = fast_rcp(v[3]);
         X = v[0] * rw;
         Y = v[1] * rw;
@@ -499,11 +568,20 @@ __device__ __forceinline__ void dlt_triangulate(const DevRig& rig, double x1, do
 #endif
 }
 
-// cv2.projectPoints for one point (match2D.py:898-903)
-__device__ __forceinline__ void project_point(const double* __restrict__ R, const double* __restrict__ t,
-                                              const double* __restrict__ cm, const double* __restrict__ k,
-                                              double X, double Y, double Z, double& u, double& v,
-                                              bool ext_identity = false, bool tangential = true)
+__device__ __forceinline__ void dlt_triangulate(const DevRig& rig, double x1, double y1, double x2, double y2,
+                                                double& X, double& Y, double& Z)
+{
+    dlt_triangulate_t<false>(rig, x1, y1, x2, y2, X, Y, Z);
+}
+
+// cv2.projectPoints for one point (match2D.py:898-903).  SIMPLE (compile time): the
+// camera has radial terms k1, k2, k3 only -- the rational, tangential and thin-prism blocks do not exist
+// in the code; otherwise they are warp-uniform branches on rig constants.
+template <bool SIMPLE>
+__device__ __forceinline__ void project_point_t(const double* __restrict__ R, const double* __restrict__ t,
+                                                const double* __restrict__ cm, const double* __restrict__ k,
+                                                double X, double Y, double Z, double& u, double& v,
+                                                bool ext_identity, bool tangential)
 {
     double x = X, y = Y, z = Z;
     if (!ext_identity) {
@@ -517,10 +595,10 @@ __device__ __forceinline__ void project_point(const double* __restrict__ R, cons
     const double r2 = fma(x, x, y * y), r4 = r2 * r2, r6 = r4 * r2;
     const double cdist = fma(k[4], r6, fma(k[1], r4, fma(k[0], r2, 1.0)));
     double rad = cdist;
-    if (k[5] != 0.0 || k[6] != 0.0 || k[7] != 0.0)  // rational model (k4..k6); warp-uniform branch on rig constants
+    if (!SIMPLE && (k[5] != 0.0 || k[6] != 0.0 || k[7] != 0.0))  // rational model (k4..k6)
         rad = cdist * fast_rcp(fma(k[7], r6, fma(k[6], r4, fma(k[5], r2, 1.0))));
     double xd = x * rad, yd = y * rad;
-    if (tangential) {  // p1, p2 and thin-prism s1..s4
+    if (!SIMPLE && tangential) {  // p1, p2 and thin-prism s1..s4
         const double a1 = 2 * x * y, a2 = fma(2 * x, x, r2), a3 = fma(2 * y, y, r2);
         xd = fma(k[9], r4, fma(k[8], r2, fma(k[3], a2, fma(k[2], a1, xd))));
         yd = fma(k[11], r4, fma(k[10], r2, fma(k[3], a1, fma(k[2], a3, yd))));
@@ -529,14 +607,23 @@ __device__ __forceinline__ void project_point(const double* __restrict__ R, cons
     v = fma(yd, cm[1], cm[3]);
 }
 
+__device__ __forceinline__ void project_point(const double* __restrict__ R, const double* __restrict__ t,
+                                              const double* __restrict__ cm, const double* __restrict__ k,
+                                              double X, double Y, double Z, double& u, double& v,
+                                              bool ext_identity = false, bool tangential = true)
+{
+    project_point_t<false>(R, t, cm, k, X, Y, Z, u, v, ext_identity, tangential);
+}
+
 // ... and the distance of the reprojection to the original (distorted) detection (match2D.py:905-910)
+template <bool SIMPLE>
 __device__ __forceinline__ double reproject_dist(const double* __restrict__ R, const double* __restrict__ t,
                                                  const double* __restrict__ cm, const double* __restrict__ k,
                                                  double X, double Y, double Z, double ou, double ov,
                                                  bool ext_identity, bool tangential)
 {
     double u, v;
-    project_point(R, t, cm, k, X, Y, Z, u, v, ext_identity, tangential);
+    project_point_t<SIMPLE>(R, t, cm, k, X, Y, Z, u, v, ext_identity, tangential);
     const double ex = ou - u;
     const double ey = ov - v;
     const double q = fma(ex, ex, ey * ey);
@@ -547,13 +634,19 @@ __device__ __forceinline__ double reproject_dist(const double* __restrict__ R, c
 
 // One end-point combination (match2D.py:889-913): triangulate the undistorted pair, reproject
 // into both cameras, per-camera distances d1, d2, and the point in camera-1 coordinates.
+// CANON / SIMPLE: the rig's class (DevRig::canon / ::simple), fixed at compile time so that K1 and K3 -- which
+// must produce the same bits for the same rod pair -- run the same straight-line code.  The class only
+// removes operations on exact zeros and branches never taken: every class gives the same bits.
+template <bool CANON, bool SIMPLE>
 __device__ __forceinline__ void eval_combo(const DevRig& rig, double u1x, double u1y, double u2x, double u2y,
                                            double o1x, double o1y, double o2x, double o2y,
                                            double& d1, double& d2, double& X, double& Y, double& Z)
 {
-    dlt_triangulate(rig, u1x, u1y, u2x, u2y, X, Y, Z);
-    d1 = reproject_dist(rig.R1, rig.t1, rig.CM1, rig.k1, X, Y, Z, o1x, o1y, rig.ext_identity[0] != 0, rig.tangential[0] != 0);
-    d2 = reproject_dist(rig.R2, rig.t2, rig.CM2, rig.k2, X, Y, Z, o2x, o2y, rig.ext_identity[1] != 0, rig.tangential[1] != 0);
+    dlt_triangulate_t<CANON>(rig, u1x, u1y, u2x, u2y, X, Y, Z);
+    d1 = reproject_dist<SIMPLE>(rig.R1, rig.t1, rig.CM1, rig.k1, X, Y, Z, o1x, o1y, CANON || rig.ext_identity[0] != 0,
+                                rig.tangential[0] != 0);
+    d2 = reproject_dist<SIMPLE>(rig.R2, rig.t2, rig.CM2, rig.k2, X, Y, Z, o2x, o2y, rig.ext_identity[1] != 0,
+                                rig.tangential[1] != 0);
 }
 
 // match2D.py:913: X_w = rot.apply(X) + trans

@@ -51,10 +51,15 @@ __global__ void __launch_bounds__(128) k_undistort(const __grid_constant__ DevRi
 // ------------------------------------------------------------------------------------- K1
 // One thread per end-point combination; lanes 4q..4q+3 of a warp hold combos
 // (e1,e2) = (0,0),(0,1),(1,0),(1,1) of one rod pair.  A block of 128 threads covers 32
-// consecutive pairs (row-major i*N2+j) of one problem; grid = n_problems * tiles.
+// consecutive pairs (row-major i*N2+j) of one problem; grid = (tiles, problems).
 // Inputs are 16-byte vector loads through the read-only path: 8 consecutive cam2 rods of a
 // warp are one 256-byte segment, the cam1 rod is a broadcast -- no shared-memory staging is
 // needed for coalescing, and bytes are ~0.1 % of the kernel's time (profiles/).
+// The kernel is co-limited by the FP64 pipe and by issue slots (every FP64 instruction blocks
+// the pipe for two cycles; the other instructions have to fit in the cycles between), so the
+// non-FP64 work is kept minimal: the problem index is blockIdx.y (no division), the pair's row
+// comes from one float reciprocal instead of an integer division (exact for q < 2^16,
+// N2 <= 256, see pair_row), the rig class is a template parameter (no rig-constant branches).
 struct CostArgs {
     int Nmax;
     int tiles;  // tiles per problem = ceil(Nmax*Nmax/32)
@@ -72,17 +77,26 @@ struct CostArgs {
 
 __device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
 
-// 6 CTAs x 4 warps per SM (80 registers; the Jacobi state is 16 + 4 doubles since V is no longer
-// accumulated) measured fastest: 2.67 / 2.57 / 2.53 / 2.55 / 2.54 ms at 4 / 5 / 6 / 7 / 8 CTAs
-// (tools/ab_bench.py, profiles/README.md).
+// q / n for 0 <= q < 65536, 1 <= n <= 256 without an integer division: (q + 0.5) / n is at least
+// 0.5 / n away from every integer, and its float evaluation with the hardware reciprocal (MUFU.RCP,
+// relative error 2^-22) is off by less than 65536.5 / n * 2^-20 < 0.07 / n.
+__device__ __forceinline__ int pair_row(int q, int n)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"((float)n));
+    return __float2int_rz(((float)q + 0.5f) * r);
+}
+
+// 6 CTAs x 4 warps per SM (80 registers) measured fastest: 2.67 / 2.57 / 2.53 / 2.55 / 2.54 ms at
+// 4 / 5 / 6 / 7 / 8 CTAs (Jacobi era, tools/ab_bench.py, profiles/README.md).
 #ifndef PTK_KCOST_MINBLOCKS
 #define PTK_KCOST_MINBLOCKS 6
 #endif
+template <bool CANON, bool SIMPLE>
 __global__ void __launch_bounds__(128, PTK_KCOST_MINBLOCKS) k_cost(const __grid_constant__ DevRig rig, const __grid_constant__ CostArgs a)
 {
-    const long long blk = blockIdx.x;
-    const int p = (int)(blk / a.tiles);
-    const int tile = (int)(blk - (long long)p * a.tiles);
+    const int p = blockIdx.y;
+    const int tile = blockIdx.x;
     const int N1 = a.n1[p], N2 = a.n2[p];
     const int npairs = N1 * N2;
     if (N1 <= 0 || N2 <= 0 || N1 > a.Nmax || N2 > a.Nmax || tile * 32 >= npairs) return;
@@ -91,14 +105,14 @@ __global__ void __launch_bounds__(128, PTK_KCOST_MINBLOCKS) k_cost(const __grid_
     if (!active) q = npairs - 1;  // keep the quad shuffles convergent; results are discarded
     const int c = threadIdx.x & 3;
     const int e1 = c >> 1, e2 = c & 1;
-    const int i = q / N2, j = q - i * N2;
+    const int i = pair_row(q, N2), j = q - i * N2;
     const size_t base = (size_t)p * a.Nmax;
     const double2 u1 = ldg2(a.und1 + (base + i) * 4 + 2 * e1);
     const double2 u2 = ldg2(a.und2 + (base + j) * 4 + 2 * e2);
     const double2 o1 = ldg2(a.cam1 + (base + i) * 4 + 2 * e1);
     const double2 o2 = ldg2(a.cam2 + (base + j) * 4 + 2 * e2);
     double d1, d2, X, Y, Z;
-    eval_combo(rig, u1.x, u1.y, u2.x, u2.y, o1.x, o1.y, o2.x, o2.y, d1, d2, X, Y, Z);
+    eval_combo<CANON, SIMPLE>(rig, u1.x, u1.y, u2.x, u2.y, o1.x, o1.y, o2.x, o2.y, d1, d2, X, Y, Z);
     // match2D.py:910 np.mean over the two cameras; matchND.py:525 np.sum
     const double e = rig.agg_sum ? (d1 + d2) : (d1 + d2) / 2.0;
     // e0+e3 (straight) lives in lanes 0,3 of the quad, e1+e2 (crossed) in lanes 1,2
@@ -420,6 +434,7 @@ struct RowsArgs {
     double* pair_cost;       // optional [P,Nmax]: min(e0+e3, e1+e2) of the evaluated pair (m, col_ind[m])
 };
 
+template <bool CANON, bool SIMPLE>
 __global__ void __launch_bounds__(128) k_rows(const __grid_constant__ DevRig rig, const __grid_constant__ RowsArgs a)
 {
     const int p = blockIdx.y;
@@ -445,7 +460,7 @@ __global__ void __launch_bounds__(128) k_rows(const __grid_constant__ DevRig rig
     const double2 o1 = ldg2(a.cam1 + (base + mm) * 4 + 2 * e1);
     const double2 o2 = ldg2(a.cam2 + (base + i2) * 4 + 2 * e2);
     double d1, d2, X, Y, Z;
-    eval_combo(rig, u1.x, u1.y, u2.x, u2.y, o1.x, o1.y, o2.x, o2.y, d1, d2, X, Y, Z);
+    eval_combo<CANON, SIMPLE>(rig, u1.x, u1.y, u2.x, u2.y, o1.x, o1.y, o2.x, o2.y, d1, d2, X, Y, Z);
     const double e = rig.agg_sum ? (d1 + d2) : (d1 + d2) / 2.0;
     const double s_mine = e + __shfl_xor_sync(kFull, e, 3);
     const double s_other = __shfl_xor_sync(kFull, s_mine, 1);

@@ -91,3 +91,26 @@ def test_convergence_flag_selects_the_fallback_by_singular_value_ratio(harness):
     ref = _cv2(P1, P2, pts)
     err = np.abs(X - ref).max(axis=1) / np.abs(ref).max(axis=1)
     assert err[conv].max() < 1e-10
+
+
+def test_canonical_first_camera_variant_is_bit_identical(harness):
+    """K1's `canon` instantiation leaves out the operations on the exact zeros of P1 = CM1 [I|0]; that must
+    not change a bit of the null vector (K1 / K3 / K8 may run different instantiations on the same rig)."""
+    sys.path.insert(0, ROOT)
+    from particletracking_b200 import synthetic as syn
+
+    for seed, sig in ((2, 0.25), (9, 0.0), (11, 3.0)):
+        s = syn.make_stereo(2, 1, 40, seed, sigma_px=sig, p_dummy=0.05)
+        cal = s.calibration
+        P1, P2 = syn.projection_matrices(cal)[:2]
+        CM1 = np.asarray(cal["CM1"], dtype=np.float64)
+        assert np.array_equal(P1, CM1 @ np.hstack([np.eye(3), np.zeros((3, 1))]))
+        cm1 = np.array([CM1[0, 0], CM1[1, 1], CM1[0, 2], CM1[1, 2]])
+        pts = _combos(s.cam1[0, 0], s.cam2[0, 0])
+        M = len(pts)
+        va, vb = np.empty((M, 4)), np.empty((M, 4))
+        conv = np.empty((M, 2), np.int32)
+        p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        harness.tri_invpower_canon_host(p(cm1), p(np.ascontiguousarray(P2)), ctypes.c_longlong(M), p(pts), p(va), p(vb), p(conv))
+        assert np.array_equal(va.view(np.int64), vb.view(np.int64))
+        assert np.array_equal(conv[:, 0], conv[:, 1])
