@@ -254,7 +254,12 @@ int launch_cost(const DevRig& rig, long long P, int Nmax, const double* cam1, co
         {
             LaunchTimer lt(K_COST, st);
             // the rig class picks the instantiation (same bits from every one of them, see eval_combo)
-            if (rig.canon && rig.simple) k_cost<true, true><<<grid, 128, 0, st>>>(rig, a);
+            static const int mb = getenv("PTK_KCOST_CFG") ? atoi(getenv("PTK_KCOST_CFG")) : 0;  // tuning knob
+            if (rig.canon && rig.simple && mb == 4) k_cost<true, true, 4><<<grid, 128, 0, st>>>(rig, a);
+            else if (rig.canon && rig.simple && mb == 5) k_cost<true, true, 5><<<grid, 128, 0, st>>>(rig, a);
+            else if (rig.canon && rig.simple && mb == 7) k_cost<true, true, 7><<<grid, 128, 0, st>>>(rig, a);
+            else if (rig.canon && rig.simple && mb == 8) k_cost<true, true, 8><<<grid, 128, 0, st>>>(rig, a);
+            else if (rig.canon && rig.simple) k_cost<true, true><<<grid, 128, 0, st>>>(rig, a);
             else if (rig.canon) k_cost<true, false><<<grid, 128, 0, st>>>(rig, a);
             else if (rig.simple) k_cost<false, true><<<grid, 128, 0, st>>>(rig, a);
             else k_cost<false, false><<<grid, 128, 0, st>>>(rig, a);

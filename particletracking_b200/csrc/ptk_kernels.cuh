@@ -92,8 +92,8 @@ __device__ __forceinline__ int pair_row(int q, int n)
 #ifndef PTK_KCOST_MINBLOCKS
 #define PTK_KCOST_MINBLOCKS 6
 #endif
-template <bool CANON, bool SIMPLE>
-__global__ void __launch_bounds__(128, PTK_KCOST_MINBLOCKS) k_cost(const __grid_constant__ DevRig rig, const __grid_constant__ CostArgs a)
+template <bool CANON, bool SIMPLE, int MINB = PTK_KCOST_MINBLOCKS>
+__global__ void __launch_bounds__(128, MINB) k_cost(const __grid_constant__ DevRig rig, const __grid_constant__ CostArgs a)
 {
     const int p = blockIdx.y;
     const int tile = blockIdx.x;
@@ -106,11 +106,13 @@ __global__ void __launch_bounds__(128, PTK_KCOST_MINBLOCKS) k_cost(const __grid_
     const int c = threadIdx.x & 3;
     const int e1 = c >> 1, e2 = c & 1;
     const int i = pair_row(q, N2), j = q - i * N2;
-    const size_t base = (size_t)p * a.Nmax;
-    const double2 u1 = ldg2(a.und1 + (base + i) * 4 + 2 * e1);
-    const double2 u2 = ldg2(a.und2 + (base + j) * 4 + 2 * e2);
-    const double2 o1 = ldg2(a.cam1 + (base + i) * 4 + 2 * e1);
-    const double2 o2 = ldg2(a.cam2 + (base + j) * 4 + 2 * e2);
+    // 32-bit element offsets (p < 65536 per launch, Nmax <= 256: below 2^26 rods): one IMAD.WIDE per address
+    const unsigned base = (unsigned)p * (unsigned)a.Nmax;
+    const unsigned off1 = (base + (unsigned)i) * 4u + 2u * e1, off2 = (base + (unsigned)j) * 4u + 2u * e2;
+    const double2 u1 = ldg2(a.und1 + off1);
+    const double2 u2 = ldg2(a.und2 + off2);
+    const double2 o1 = ldg2(a.cam1 + off1);
+    const double2 o2 = ldg2(a.cam2 + off2);
     double d1, d2, X, Y, Z;
     eval_combo<CANON, SIMPLE>(rig, u1.x, u1.y, u2.x, u2.y, o1.x, o1.y, o2.x, o2.y, d1, d2, X, Y, Z);
     // match2D.py:910 np.mean over the two cameras; matchND.py:525 np.sum
@@ -119,7 +121,7 @@ __global__ void __launch_bounds__(128, PTK_KCOST_MINBLOCKS) k_cost(const __grid_
     const double s_mine = e + __shfl_xor_sync(kFull, e, 3);
     const double s_other = __shfl_xor_sync(kFull, s_mine, 1);
     if (active) {
-        const size_t o = (base + i) * a.Nmax + j;
+        const size_t o = ((size_t)base + i) * a.Nmax + j;
         if (c == 0) {
             a.cost[o] = np_min(s_mine, s_other);          // match2D.py:923-932
             if (a.choice) a.choice[o] = (s_mine <= s_other);  // match2D.py:935-938

@@ -426,14 +426,36 @@ def test_config3_ragged_all_frames_vs_oracle(eng, crig):
     np.testing.assert_array_equal(keep.astype(bool), np.nan_to_num(mc, nan=np.inf) <= 5.0)
     o = co.match_batch(crig, c1, c2, n1, n2, nthreads=0)
     np.testing.assert_array_equal(n_out, o["n_out"])
-    np.testing.assert_array_equal(col, o["col_ind"])
-    np.testing.assert_array_equal(row, o["row_ind"])
-    valid = o["row_ind"] >= 0
+    # Assignments: identical, except where the optimum itself is degenerate.  Dummy detections (-1,-1,-1,-1)
+    # are bit-identical rods: swapping the partners of two of them (or leaving the other one unmatched when
+    # N1 > N2) costs exactly the same, and which of the equal optima SciPy's tie rule lands on is steered by
+    # the last bit of the duals, i.e. of a DLT that differs from the oracle's (and from cv2's) in the 15th
+    # digit.  Measured: 1 of 80 000 problems.
+    differs = np.where((col != o["col_ind"]).any(axis=1) | (row != o["row_ind"]).any(axis=1))[0]
+    assert len(differs) <= 8, f"{len(differs)} problems differ from the oracle"
+    for p in differs:
+        k = n_out[p]
+        oc = co.match_batch(crig, c1[p:p + 1], c2[p:p + 1], n1[p:p + 1], n2[p:p + 1], want_cost=True)["cost"][0]
+        t_o = oc[o["row_ind"][p, :k], o["col_ind"][p, :k]].sum()
+        t_g = oc[row[p, :k], col[p, :k]].sum()
+        assert abs(t_o - t_g) <= 1e-12 * abs(t_o), "a different assignment must be an equally optimal one"
+        assert len(set(col[p, :k])) == k and len(set(row[p, :k])) == k
+        pairs_o = set(zip(o["row_ind"][p, :k].tolist(), o["col_ind"][p, :k].tolist()))
+        r1 = c1[p, :n1[p]].reshape(n1[p], -1)
+        r2 = c2[p, :n2[p]].reshape(n2[p], -1)
+        for a, b in zip(row[p, :k].tolist(), col[p, :k].tolist()):
+            if (a, b) in pairs_o:
+                continue
+            # the rods involved are exact duplicates of another rod (in camera 1 or in camera 2)
+            assert (r1 == r1[a]).all(axis=1).sum() > 1 or (r2 == r2[b]).all(axis=1).sum() > 1
+    same = np.ones(len(n1), dtype=bool)
+    same[differs] = False
+    valid = (o["row_ind"] >= 0) & same[:, None]
     assert rel_err(np.where(valid, mc, 0.0), np.where(valid, o["match_cost"], 0.0)) < TOL
     v3 = valid[..., None]
     assert rel_err(np.where(v3, rows[..., :10], 0.0), np.where(v3, o["rows"][..., :10], 0.0)) < TOL
     np.testing.assert_array_equal(np.where(v3, rows[..., 10:], 0.0), np.where(v3, o["rows"][..., 10:], 0.0))
-    assert np.isnan(rows[~valid]).all()  # the padding is defined (NaN), as documented
+    assert np.isnan(rows[o["row_ind"] < 0]).all()  # the padding is defined (NaN), as documented
 
 
 # ------------------------------------------------------------------ BASELINE config 4 shape (8 colours x 64 rods, match + track), 2 000 frames
