@@ -589,7 +589,7 @@ __device__ __forceinline__ void project_point_t(const double* __restrict__ R, co
         y = fma(R[5], Z, fma(R[4], Y, R[3] * X)) + t[1];
         z = fma(R[8], Z, fma(R[7], Y, R[6] * X)) + t[2];
     }
-    z = (z != 0.0) ? fast_rcp(z) : 1.0;
+    z = ((__double2hiint(z) & 0x7fffffff) | __double2loint(z)) != 0 ? fast_rcp(z) : 1.0;  // z != 0.0, tested on the ALU pipe
     x *= z;
     y *= z;
     const double r2 = fma(x, x, y * y), r4 = r2 * r2, r6 = r4 * r2;
@@ -628,8 +628,11 @@ __device__ __forceinline__ double reproject_dist(const double* __restrict__ R, c
     const double ey = ov - v;
     const double q = fma(ex, ex, ey * ey);
     // sqrt as q * rsqrt(q) (seed + one third-order step: an ulp or two, 7 instructions instead of
-    // the ~14 of the IEEE sequence); zero, denormal, infinite and NaN arguments take the library path
-    return (q > 1e-300 && q < 1e300) ? q * rsqrt_refine(q, rsqrt_seed(q)) : sqrt(q);
+    // the ~14 of the IEEE sequence); zero, denormal, huge, infinite and NaN arguments take the library
+    // path.  The range test is on the exponent bits (ALU pipe, idle here) instead of two DSETPs on the
+    // FP64 pipe that bounds the kernel: biased exponent in [27, 2019], i.e. 2^-996 <= q < 2^997 (q >= 0).
+    const unsigned ex11 = ((unsigned)__double2hiint(q) >> 20) - 27u;
+    return (ex11 < 1993u) ? q * rsqrt_refine(q, rsqrt_seed(q)) : sqrt(q);
 }
 
 // One end-point combination (match2D.py:889-913): triangulate the undistorted pair, reproject
