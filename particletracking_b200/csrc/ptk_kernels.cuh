@@ -432,8 +432,13 @@ struct RowsArgs {
     const double* und2;
     const int32_t* col_ind;  // [P,Nmax]
     const int32_t* n_out;    // [P]
-    double* rows;            // [P,Nmax,18]
+    double* rows;            // optional [P,Nmax,18]
     double* pair_cost;       // optional [P,Nmax]: min(e0+e3, e1+e2) of the evaluated pair (m, col_ind[m])
+    // compact output (ptk_reconstruct_host_compact): the six computed coordinates and the straight /
+    // crossed verdict; the other 12 columns are functions of these, of col_ind and of the caller's own
+    // input arrays (ptk_expand_rows_host)
+    double* ends6;           // optional [P,Nmax,6]
+    uint8_t* straight;       // optional [P,Nmax]
 };
 
 template <bool CANON, bool SIMPLE>
@@ -447,9 +452,18 @@ __global__ void __launch_bounds__(128) k_rows(const __grid_constant__ DevRig rig
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     if (blockIdx.x * 32 >= n) {  // whole block past the matches: NaN fill
         if (m < a.Nmax) {
-            double* o = a.rows + (base + m) * PTK_ROW_COLS;
-            for (int k = c; k < PTK_ROW_COLS; k += 4) o[k] = qnan;
-            if (a.pair_cost && c == 0) a.pair_cost[base + m] = qnan;
+            if (a.rows) {
+                double* o = a.rows + (base + m) * PTK_ROW_COLS;
+                for (int k = c; k < PTK_ROW_COLS; k += 4) o[k] = qnan;
+            }
+            if (a.ends6) {
+                double* o = a.ends6 + (base + m) * 6;
+                for (int k = c; k < 6; k += 4) o[k] = qnan;
+            }
+            if (c == 0) {
+                if (a.pair_cost) a.pair_cost[base + m] = qnan;
+                if (a.straight) a.straight[base + m] = 0;
+            }
         }
         return;
     }
@@ -478,35 +492,49 @@ __global__ void __launch_bounds__(128) k_rows(const __grid_constant__ DevRig rig
     const double bx = __shfl_sync(kFull, wx, s2), by = __shfl_sync(kFull, wy, s2), bz = __shfl_sync(kFull, wz, s2);
     if (c == 0) {
         if (a.pair_cost && m < a.Nmax) a.pair_cost[base + m] = active ? np_min(s_mine, s_other) : qnan;
+        if (a.straight && m < a.Nmax) a.straight[base + m] = (active && straight) ? 1 : 0;
         if (active) {
-            double* o = a.rows + (base + m) * PTK_ROW_COLS;
-            o[0] = ax; o[1] = ay; o[2] = az;
-            o[3] = bx; o[4] = by; o[5] = bz;
-            o[6] = (ax + bx) / 2; o[7] = (ay + by) / 2; o[8] = (az + bz) / 2;  // match2D.py:969
-            const double dx = bx - ax, dy = by - ay, dz = bz - az;
-            o[9] = sqrt(dx * dx + dy * dy + dz * dz);                           // match2D.py:970-972
-            const double* r1 = a.cam1 + (base + m) * 4;
-            const double* r2 = a.cam2 + (base + i2) * 4;
-            if (straight) {  // match2D.py:973-974
-                o[10] = r1[0]; o[11] = r1[1]; o[12] = r1[2]; o[13] = r1[3];
-                o[14] = r2[0]; o[15] = r2[1]; o[16] = r2[2]; o[17] = r2[3];
-            } else {         // match2D.py:982-983: both cameras' end points reversed
-                o[10] = r1[2]; o[11] = r1[3]; o[12] = r1[0]; o[13] = r1[1];
-                o[14] = r2[2]; o[15] = r2[3]; o[16] = r2[0]; o[17] = r2[1];
+            if (a.ends6) {
+                double* o = a.ends6 + (base + m) * 6;
+                o[0] = ax; o[1] = ay; o[2] = az;
+                o[3] = bx; o[4] = by; o[5] = bz;
+            }
+            if (a.rows) {
+                double* o = a.rows + (base + m) * PTK_ROW_COLS;
+                o[0] = ax; o[1] = ay; o[2] = az;
+                o[3] = bx; o[4] = by; o[5] = bz;
+                o[6] = (ax + bx) / 2; o[7] = (ay + by) / 2; o[8] = (az + bz) / 2;  // match2D.py:969
+                const double dx = bx - ax, dy = by - ay, dz = bz - az;
+                o[9] = sqrt(dx * dx + dy * dy + dz * dz);                           // match2D.py:970-972
+                const double* r1 = a.cam1 + (base + m) * 4;
+                const double* r2 = a.cam2 + (base + i2) * 4;
+                if (straight) {  // match2D.py:973-974
+                    o[10] = r1[0]; o[11] = r1[1]; o[12] = r1[2]; o[13] = r1[3];
+                    o[14] = r2[0]; o[15] = r2[1]; o[16] = r2[2]; o[17] = r2[3];
+                } else {         // match2D.py:982-983: both cameras' end points reversed
+                    o[10] = r1[2]; o[11] = r1[3]; o[12] = r1[0]; o[13] = r1[1];
+                    o[14] = r2[2]; o[15] = r2[3]; o[16] = r2[0]; o[17] = r2[1];
+                }
             }
         } else if (m < a.Nmax) {
-            double* o = a.rows + (base + m) * PTK_ROW_COLS;
-            for (int k = 0; k < PTK_ROW_COLS; k++) o[k] = qnan;
+            if (a.rows) {
+                double* o = a.rows + (base + m) * PTK_ROW_COLS;
+                for (int k = 0; k < PTK_ROW_COLS; k++) o[k] = qnan;
+            }
+            if (a.ends6) {
+                double* o = a.ends6 + (base + m) * 6;
+                for (int k = 0; k < 6; k++) o[k] = qnan;
+            }
         }
     }
 }
 
 // gather (x1..z2) of every output row into the tracking layout ends[C,F,N,2,3]
 // (what tracking.py:97-98 extracts from the DataFrame), problem index = f*C + c.
-__global__ void k_rows_to_ends(int F0, int Fn, int F, int C, int N, int Nmax, const double* __restrict__ rows,
+__global__ void k_rows_to_ends(int F0, int Fn, int F, int C, int N, int Nmax, int row_cols, const double* __restrict__ rows,
                                double* __restrict__ ends)
 {
-    // rows: [Fn*C, Nmax, 18] for frames F0..F0+Fn-1; ends: [C, F, N, 6]
+    // rows: [Fn*C, Nmax, row_cols] (18-column rows, or the compact 6-column ends) for frames F0..F0+Fn-1; ends: [C, F, N, 6]
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long tot = (long long)Fn * C * N * 6;
     if (t >= tot) return;
@@ -515,7 +543,7 @@ __global__ void k_rows_to_ends(int F0, int Fn, int F, int C, int N, int Nmax, co
     const int m = (int)(r % N); r /= N;
     const int c = (int)(r % C);
     const int f = (int)(r / C);
-    ends[(((size_t)c * F + (F0 + f)) * N + m) * 6 + k] = rows[(((size_t)f * C + c) * Nmax + m) * PTK_ROW_COLS + k];
+    ends[(((size_t)c * F + (F0 + f)) * N + m) * 6 + k] = rows[(((size_t)f * C + c) * Nmax + m) * row_cols + k];
 }
 
 // ------------------------------------------------------------------------------------- K4

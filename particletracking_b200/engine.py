@@ -631,14 +631,24 @@ class HostPipeline:
         return t
 
     def reconstruct(self, rig: PtkRig, cam1, cam2, n1, n2, track: bool = False, max_repr_err: Optional[float] = None,
-                    raise_on_invalid: bool = True):
+                    raise_on_invalid: bool = True, compact: bool = False):
         """cam1, cam2: [F,C,Nmax,2,2] float64 host (numpy or CPU torch, ideally pinned);
         n1, n2: [F,C] int32.  Returns a dict of pinned CPU torch tensors (views reused by the
-        next call -- copy what you keep)."""
+        next call -- copy what you keep).
+
+        ``compact``: instead of ``rows[F,C,Nmax,18]`` the result carries ``ends[F,C,Nmax,6]`` (x1..z2) and
+        ``straight[F,C,Nmax]``: 12.5 MB come back instead of 36.9 MB per 8000 x 32 problems, which is what
+        bounds this path on a multi-GPU host.  ``expand_rows(result, cam1, cam2)`` rebuilds the 18 columns
+        bit for bit (``ptk_reconstruct_host_compact`` / ``ptk_expand_rows_host``)."""
         c1, c2 = _as_host(cam1, _f64), _as_host(cam2, _f64)
         m1, m2 = _as_host(n1, _i32), _as_host(n2, _i32)
         F, C, Nmax = c1.shape[:3]
-        rows = self._buf("rows", (F, C, Nmax, nat.ROW_COLS), _f64)
+        rows = ends = straight = None
+        if compact:
+            ends = self._buf("ends", (F, C, Nmax, 6), _f64)
+            straight = self._buf("straight", (F, C, Nmax), _u8)
+        else:
+            rows = self._buf("rows", (F, C, Nmax, nat.ROW_COLS), _f64)
         mc = self._buf("mc", (F, C, Nmax), _f64)
         row = self._buf("row", (F, C, Nmax), _i32)
         col = self._buf("col", (F, C, Nmax), _i32)
@@ -652,17 +662,35 @@ class HostPipeline:
             tid = self._buf("tid", (C, F, Nmax), _i32)
             tst = self._buf("tst", (C, max(F - 1, 0)), _i32)
         thr = float("inf") if max_repr_err is None else float(max_repr_err)
-        rc = nat.lib().ptk_reconstruct_host(self._ctx, ctypes.byref(rig), F, C, Nmax, _ptr(c1), _ptr(c2), _ptr(m1), _ptr(m2),
-                                            _ptr(rows), _ptr(mc), _ptr(row), _ptr(col), _ptr(n_out), _ptr(status), thr,
-                                            _ptr(keep), 1 if track else 0, _ptr(tcol), _ptr(ttot), _ptr(tid), _ptr(tst))
+        tail = (_ptr(mc), _ptr(row), _ptr(col), _ptr(n_out), _ptr(status), thr, _ptr(keep), 1 if track else 0, _ptr(tcol),
+                _ptr(ttot), _ptr(tid), _ptr(tst))
+        head = (self._ctx, ctypes.byref(rig), F, C, Nmax, _ptr(c1), _ptr(c2), _ptr(m1), _ptr(m2))
+        if compact:
+            rc = nat.lib().ptk_reconstruct_host_compact(*head, _ptr(ends), _ptr(straight), *tail)
+        else:
+            rc = nat.lib().ptk_reconstruct_host(*head, _ptr(rows), *tail)
         if rc == nat.PTK_ERR_NUMERIC:
             if raise_on_invalid:
                 # scipy raises ValueError from linear_sum_assignment (match2D.py:933, tracking.py:122)
                 raise ValueError("matrix contains invalid numeric entries")
         else:
             nat.check(rc, "ptk_reconstruct_host")
-        return dict(rows=rows, match_cost=mc, row_ind=row, col_ind=col, n_out=n_out, status=status, keep=keep,
-                    track_col=tcol, track_total=ttot, track_id=tid, track_status=tst)
+        return dict(rows=rows, ends=ends, straight=straight, match_cost=mc, row_ind=row, col_ind=col, n_out=n_out, status=status,
+                    keep=keep, track_col=tcol, track_total=ttot, track_id=tid, track_status=tst)
+
+
+def expand_rows(result: dict, cam1, cam2, out: Optional[torch.Tensor] = None, n_threads: int = 0) -> torch.Tensor:
+    """The 18-column rows ``[F,C,Nmax,18]`` of a ``compact`` result (host arrays; ``ptk_expand_rows_host``)."""
+    c1, c2 = _as_host(cam1, _f64), _as_host(cam2, _f64)
+    ends, straight, col, n_out = result["ends"], result["straight"], result["col_ind"], result["n_out"]
+    F, C, Nmax = c1.shape[:3]
+    if out is None:
+        out = torch.empty((F, C, Nmax, nat.ROW_COLS), dtype=_f64)
+    elif tuple(out.shape) != (F, C, Nmax, nat.ROW_COLS) or out.dtype != _f64 or not out.is_contiguous() or out.is_cuda:
+        raise ValueError("expand_rows: out must be a contiguous float64 host tensor [F,C,Nmax,18]")
+    nat.check(nat.lib().ptk_expand_rows_host(F * C, Nmax, _ptr(c1), _ptr(c2), _ptr(ends), _ptr(straight), _ptr(col), _ptr(n_out),
+                                            _ptr(out), int(n_threads)), "ptk_expand_rows_host")
+    return out
 
 
 def _as_host(a, dtype) -> torch.Tensor:

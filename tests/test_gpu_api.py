@@ -271,3 +271,29 @@ def test_project_and_reproject_points_api(api, rig):
     assert rel_err(pw, g["p3d_w"]) < TOL
     # reference test_calibrate_cameras.py: shapes
     assert a.shape == (64, 2) and b.shape == (64, 2)
+
+
+def test_host_pipeline_compact_result_expands_to_the_full_rows(env_api=None):
+    """ptk_reconstruct_host_compact + ptk_expand_rows_host == ptk_reconstruct_host, bit for bit (rows, costs,
+    assignments, tracking), on ragged data with a threshold and on the benchmark's shape."""
+    import torch
+    from particletracking_b200 import engine, rig as rigmod, synthetic as syn
+
+    for (F, C, N, kw) in ((300, 4, 16, dict(p_drop=0.05, p_dummy=0.02)), (260, 8, 32, {})):
+        data = syn.make_stereo(F, C, N, seed=41, **kw)
+        crig = rigmod.rig_from_dicts(data.calibration, data.transformation)
+        track = not kw
+        pipe = engine.HostPipeline(0)
+        full = pipe.reconstruct(crig, data.cam1, data.cam2, data.n1, data.n2, track=track, max_repr_err=4.0)
+        full = {k: (v.clone() if v is not None else None) for k, v in full.items()}
+        comp = pipe.reconstruct(crig, data.cam1, data.cam2, data.n1, data.n2, track=track, max_repr_err=4.0, compact=True)
+        assert comp["rows"] is None and full["ends"] is None
+        rows = engine.expand_rows(comp, data.cam1, data.cam2)
+        a, b = rows.numpy(), full["rows"].numpy()
+        assert np.array_equal(np.isnan(a), np.isnan(b))
+        assert np.array_equal(np.nan_to_num(a).view(np.int64), np.nan_to_num(b).view(np.int64))
+        for k in ("match_cost", "row_ind", "col_ind", "n_out", "status", "keep", "track_col", "track_id", "track_total"):
+            if full[k] is not None:
+                x, y = comp[k].numpy(), full[k].numpy()
+                assert np.array_equal(np.nan_to_num(x), np.nan_to_num(y)), k
+        pipe.close()

@@ -333,3 +333,47 @@ def test_chain_broken_maps_port_vs_c():
     a = port.chain_tracks(col)
     np.testing.assert_array_equal(a, co.chain_tracks(col[None])[0])
     assert (a[21:] == -1).sum(axis=1).tolist() == [1] * (F - 21)
+
+
+def test_expand_rows_host_rebuilds_the_oracle_rows_bit_for_bit():
+    """ptk_expand_rows_host (host code of libptk.so, no GPU needed): from the six computed coordinates,
+    the straight / crossed verdict and col_ind it must rebuild the reference-shaped 18 columns exactly --
+    checked against the C oracle's rows on ragged data (N1 != N2, dummies)."""
+    import ctypes
+
+    from oracle import c_oracle as co
+    from particletracking_b200 import _native as nat
+    from particletracking_b200 import rig as rigmod
+    from particletracking_b200 import synthetic as syn
+
+    data = syn.make_stereo(40, 3, 17, seed=8, p_drop=0.08, p_dummy=0.03)
+    crig = rigmod.rig_from_dicts(data.calibration, data.transformation)
+    c1, c2, n1, n2 = data.problems()
+    o = co.match_batch(crig, c1, c2, n1, n2)
+    P, N = c1.shape[:2]
+    rows = o["rows"]
+    ends = np.ascontiguousarray(rows[..., :6])
+    k = np.arange(N)[None, :] < o["n_out"][:, None]
+    # straight <=> both cameras' end points are in input order (crossed rows carry both reversed); a dummy
+    # rod (-1,-1,-1,-1) reads the same both ways, hence both cameras are consulted
+    m = np.broadcast_to(np.arange(N), (P, N))
+    pi = np.arange(P)[:, None]
+    r1 = c1.reshape(P, N, 4)[pi, m]
+    r2 = c2.reshape(P, N, 4)[pi, np.where(k, o["col_ind"], 0)]
+    straight = (rows[..., 10:14] == r1).all(axis=-1) & (rows[..., 14:18] == r2).all(axis=-1)
+    rev = (rows[..., 10:14] == r1[..., [2, 3, 0, 1]]).all(axis=-1) & (rows[..., 14:18] == r2[..., [2, 3, 0, 1]]).all(axis=-1)
+    assert (straight | rev)[k].all()
+    straight = np.ascontiguousarray((straight & k).astype(np.uint8))
+    col = np.ascontiguousarray(np.where(k, o["col_ind"], -1).astype(np.int32))
+    out = np.full((P, N, 18), 7.0)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    c1c, c2c = np.ascontiguousarray(c1), np.ascontiguousarray(c2)
+    n_out = np.ascontiguousarray(o["n_out"].astype(np.int32))
+    for nt in (1, 3):
+        rc = nat.lib().ptk_expand_rows_host(P, N, p(c1c), p(c2c), p(ends), p(straight), p(col), p(n_out), p(out), nt)
+        assert rc == 0
+        assert np.array_equal(out[k].view(np.int64), rows[k].view(np.int64))  # bit for bit, incl. centre and length
+        assert np.isnan(out[~k]).all()
+    bad = col.copy()
+    bad[0, 0] = N + 1
+    assert nat.lib().ptk_expand_rows_host(P, N, p(c1c), p(c2c), p(ends), p(straight), p(bad), p(n_out), p(out), 1) == -1
