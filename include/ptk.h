@@ -342,11 +342,11 @@ int ptk_reconstruct_shard(const ptk_rig* rig, int F, int n_halo, int C, int Nmax
 /* Root side of the sharded chain pass, after the final gather: block r (r = 0..W-1) starts at
  * blocks + r*block_stride bytes and holds rank r's local ids track_id[C,frames_per_rank[r],N] at byte
  * offset tid_off and its halo_map[C,N] at map_off.  Composes the maps (start_r = start_{r-1} o map_{r-1},
- * start_0 = identity) and re-bases every rank's ids in place; ids of a broken chain stay -1.
- * frames_per_rank is a HOST array; start_scratch[C,N] device scratch. */
+ * start_0 = identity) and re-bases every rank's ids in place, one kernel launch for all ranks; ids of a
+ * broken chain stay -1.  frames_per_rank is a HOST array; frames_dev[W] device scratch for its copy. */
 int ptk_chain_rebase_gathered(int W, int C, int N, const int32_t* frames_per_rank, void* blocks,
                               size_t block_stride, size_t tid_off, size_t map_off,
-                              int32_t* start_scratch, void* stream);
+                              int32_t* frames_dev, void* stream);
 
 
 /* ---- host-buffer pipeline (what bench.py's `e2e` and match_csv_complex call) ----------

@@ -840,28 +840,24 @@ PTK_API int ptk_reconstruct_device(const ptk_rig* rig, int F, int C, int Nmax, c
 // blocks + r * block_stride bytes) holding local ids track_id[C,F_r,N] at tid_off and the rank's halo map
 // [C,N] at map_off.  Composes the maps up to every rank and re-bases that rank's ids in place.
 PTK_API int ptk_chain_rebase_gathered(int W, int C, int N, const int32_t* frames_per_rank, void* blocks, size_t block_stride,
-                                      size_t tid_off, size_t map_off, int32_t* start_scratch, void* stream)
+                                      size_t tid_off, size_t map_off, int32_t* frames_dev, void* stream)
 {
-    if (W < 1 || C < 0 || bad_n(N) || !frames_per_rank || !blocks || !start_scratch || (block_stride % 4) || (tid_off % 4) ||
-        (map_off % 4))
+    if (W < 1 || W > 1024 || C < 0 || bad_n(N) || !frames_per_rank || !blocks || !frames_dev || (block_stride % 4) ||
+        (tid_off % 4) || (map_off % 4))
         return PTK_ERR_INVALID_ARG;
-    if (C == 0) return PTK_OK;
-    cudaStream_t st = (cudaStream_t)stream;
-    const int threads = N < 32 ? 32 : ((N + 31) / 32 * 32);
-    char* b = static_cast<char*>(blocks);
-    const int32_t* maps = reinterpret_cast<const int32_t*>(b + map_off);
-    for (int r = 1; r < W; r++) {
+    if (C == 0 || W == 1) return PTK_OK;
+    for (int r = 0; r < W; r++)
         if (frames_per_rank[r] < 0) return PTK_ERR_INVALID_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    // the shard sizes are launch parameters of one kernel for all ranks: 4 W bytes through frames_dev
+    // (a pageable-to-device copy of a few bytes is staged by the driver before the call returns)
+    CK(cudaMemcpyAsync(frames_dev, frames_per_rank, (size_t)W * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    {
         LaunchTimer lt(K_CHAIN, st);
-        k_chain_compose<<<C, threads, 2 * (size_t)N * sizeof(int32_t), st>>>(W, C, N, r, maps, block_stride / 4, start_scratch);
-        LAUNCHED("k_chain_compose");
-        const long long total = (long long)C * frames_per_rank[r] * N;
-        if (total > 0) {
-            k_chain_rebase<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-                frames_per_rank[r], N, start_scratch, reinterpret_cast<int32_t*>(b + (size_t)r * block_stride + tid_off), total);
-            LAUNCHED("k_chain_rebase");
-        }
+        k_chain_rebase_gathered<<<dim3(C, W - 1), 256, 2 * (size_t)N * sizeof(int32_t), st>>>(
+            C, N, frames_dev, static_cast<int32_t*>(blocks), block_stride / 4, tid_off / 4, map_off / 4);
     }
+    LAUNCHED("k_chain_rebase_gathered");
     return PTK_OK;
 }
 

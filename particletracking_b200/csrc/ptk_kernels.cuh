@@ -727,6 +727,30 @@ __global__ void k_chain_compose(int W, int C, int N, int rank, const int32_t* __
     for (int a = threadIdx.x; a < N; a += blockDim.x) start[(size_t)c * N + a] = cur[a];
 }
 
+// The root side of the sharded chain pass in one launch: block (c, r - 1) composes the boundary maps of
+// ranks 0..r-1 for colour c (start = global id of every local id of rank r) and re-bases rank r's ids in
+// place.  blocks: the gathered result blocks, rank stride `stride` ints; ids at tid_off, maps at map_off (ints).
+__global__ void k_chain_rebase_gathered(int C, int N, const int32_t* __restrict__ frames, int32_t* __restrict__ blocks,
+                                        size_t stride, size_t tid_off, size_t map_off)
+{
+    extern __shared__ int32_t sh[];
+    int32_t* cur = sh;
+    int32_t* nxt = sh + N;
+    const int c = blockIdx.x, r = blockIdx.y + 1;
+    for (int a = threadIdx.x; a < N; a += blockDim.x) cur[a] = a;
+    __syncthreads();
+    for (int q = 0; q < r; q++) {
+        const int32_t* mp = blocks + (size_t)q * stride + map_off + (size_t)c * N;
+        for (int a = threadIdx.x; a < N; a += blockDim.x) nxt[a] = chain_pick(cur, mp[a], N);
+        __syncthreads();
+        int32_t* t = cur; cur = nxt; nxt = t;
+        __syncthreads();
+    }
+    const int F = frames[r];
+    int32_t* tid = blocks + (size_t)r * stride + tid_off + (size_t)c * F * N;
+    for (int e = threadIdx.x; e < F * N; e += blockDim.x) tid[e] = chain_pick(cur, tid[e], N);
+}
+
 __global__ void k_chain_rebase(int F, int N, const int32_t* __restrict__ start, int32_t* __restrict__ track_id,
                                long long total)
 {

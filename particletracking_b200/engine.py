@@ -385,8 +385,8 @@ def chain_rebase_gathered(blocks: torch.Tensor, frames_per_rank, C: int, N: int,
         raise ValueError("blocks must be a contiguous CUDA uint8 tensor [W, block_bytes]")
     W = blocks.shape[0]
     fr = (ctypes.c_int32 * W)(*[int(x) for x in frames_per_rank])
-    if scratch is None:
-        scratch = torch.empty((C, N), dtype=_i32, device=blocks.device)
+    if scratch is None or scratch.numel() < W:
+        scratch = torch.empty((max(W, 1),), dtype=_i32, device=blocks.device)
     with torch.cuda.device(blocks.device):
         nat.check(nat.lib().ptk_chain_rebase_gathered(W, C, N, fr, _ptr(blocks), blocks.stride(0), int(tid_off), int(map_off),
                                                       _ptr(scratch), _stream()), "ptk_chain_rebase_gathered")
