@@ -420,3 +420,31 @@ def reproject_points(points, calibration, transforms=None):
     a = cv2.projectPoints(points, r1, t1, calibration["CM1"], calibration["dist1"])[0].squeeze()
     b = cv2.projectPoints(points, r2, t2, calibration["CM2"], calibration["dist2"])[0].squeeze()
     return a, b
+
+
+def reproject_data(data, cam_ids, calibration, position_scaling=1.0, transformation=None):
+    """RodTracker/src/RodTracker/backend/reconstruction.py:373-469 (``Plotter.reproject_data``), restated on
+    the ``reproject_points`` port above.  Parity unpinned for this wrapper: the module imports PyQt5, which is
+    not installed; its arithmetic is ``reproject_points`` (pinned by tests/golden/project.npz)."""
+    if calibration is None:
+        return None
+    id1, id2 = cam_ids
+    cols = ["x1", "y1", "z1", "x2", "y2", "z2", "x", "y", "z", "l",
+            f"x1_{id1}", f"y1_{id1}", f"x2_{id1}", f"y2_{id1}", f"x1_{id2}", f"y1_{id2}", f"x2_{id2}", f"y2_{id2}"]
+    d = data[cols]
+    e1_3d = d.iloc[:, 0:3].to_numpy(dtype=float) * position_scaling
+    e2_3d = d.iloc[:, 3:6].to_numpy(dtype=float) * position_scaling
+    e1_2d_c1 = d.iloc[:, 10:12].to_numpy(dtype=float) * position_scaling
+    e2_2d_c1 = d.iloc[:, 12:14].to_numpy(dtype=float) * position_scaling
+    e1_2d_c2 = d.iloc[:, 14:16].to_numpy(dtype=float) * position_scaling
+    e2_2d_c2 = d.iloc[:, 16:18].to_numpy(dtype=float) * position_scaling
+    drop1 = np.isnan(e1_3d).all(axis=1)
+    drop2 = np.isnan(e2_3d).all(axis=1)
+    e1_3d, e1_2d_c1, e1_2d_c2 = e1_3d[~drop1], e1_2d_c1[~drop1], e1_2d_c2[~drop1]
+    e2_3d, e2_2d_c1, e2_2d_c2 = e2_3d[~drop2], e2_2d_c1[~drop2], e2_2d_c2[~drop2]
+    if not len(e1_3d) or not len(e2_3d):
+        return None
+    a1, a2 = reproject_points(e1_3d, calibration, transformation)
+    b1, b2 = reproject_points(e2_3d, calibration, transformation)
+    errs = [np.abs(a1 - e1_2d_c1), np.abs(a2 - e1_2d_c2), np.abs(b1 - e2_2d_c1), np.abs(b2 - e2_2d_c2)]
+    return np.sum(np.asarray(errs), axis=-1)

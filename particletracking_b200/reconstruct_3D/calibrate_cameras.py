@@ -52,3 +52,31 @@ def reproject_points(points: np.ndarray, calibration: dict, transforms: Union[di
     uv1, uv2 = engine.project_points(_rig(calibration, transforms), torch.from_numpy(np.ascontiguousarray(pts)).to(dev),
                                      from_world=transforms is not None)
     return uv1.cpu().numpy().squeeze(), uv2.cpu().numpy().squeeze()
+
+
+def reproject_data(data, cam_ids, calibration: dict, position_scaling: float = 1.0, transformation: Union[dict, None] = None):
+    """Absolute reprojection errors of every row of a rod DataFrame -- RodTracker's
+    ``Plotter.reproject_data`` (``RodTracker/backend/reconstruction.py:373-469``, the numeric body behind
+    its reprojection-error histogram; the Qt plumbing around it is out of scope): both 3D end points are
+    projected into both cameras (K9, one launch for all of them) and compared with the stored 2D end points.
+    Returns ``None`` without a calibration or without reconstructable rows, else an array ``[4, n]``:
+    end 1 in camera 1, end 1 in camera 2, end 2 in camera 1, end 2 in camera 2 (sum of |dx| + |dy|)."""
+    if calibration is None:
+        return None
+    id1, id2 = cam_ids[0], cam_ids[1]
+    cols = ["x1", "y1", "z1", "x2", "y2", "z2", "x", "y", "z", "l",
+            f"x1_{id1:s}", f"y1_{id1:s}", f"x2_{id1:s}", f"y2_{id1:s}",
+            f"x1_{id2:s}", f"y1_{id2:s}", f"x2_{id2:s}", f"y2_{id2:s}"]
+    a = data[cols].to_numpy(dtype=float) * position_scaling
+    e1_3d, e2_3d = a[:, 0:3], a[:, 3:6]
+    keep1 = ~np.isnan(e1_3d).all(axis=1)
+    keep2 = ~np.isnan(e2_3d).all(axis=1)
+    e1_3d, e1_c1, e1_c2 = e1_3d[keep1], a[keep1, 10:12], a[keep1, 14:16]
+    e2_3d, e2_c1, e2_c2 = e2_3d[keep2], a[keep2, 12:14], a[keep2, 16:18]
+    if not len(e1_3d) or not len(e2_3d):
+        return None
+    n1 = len(e1_3d)
+    uv1, uv2 = reproject_points(np.concatenate([e1_3d, e2_3d]), calibration, transformation)
+    uv1, uv2 = np.atleast_2d(uv1), np.atleast_2d(uv2)
+    errs = [np.abs(uv1[:n1] - e1_c1), np.abs(uv2[:n1] - e1_c2), np.abs(uv1[n1:] - e2_c1), np.abs(uv2[n1:] - e2_c2)]
+    return np.sum(np.asarray(errs), axis=-1)

@@ -297,3 +297,29 @@ def test_host_pipeline_compact_result_expands_to_the_full_rows(env_api=None):
                 x, y = comp[k].numpy(), full[k].numpy()
                 assert np.array_equal(np.nan_to_num(x), np.nan_to_num(y)), k
         pipe.close()
+
+
+def test_reproject_data_vs_port(api, rig):
+    """Plotter.reproject_data (RodTracker backend/reconstruction.py:373-469): our K9-based function against
+    the cv2 restatement, on a matched frame (world coordinates) incl. NaN rows and position scaling."""
+    import pandas as pd
+    from oracle import port
+    from particletracking_b200 import synthetic as syn
+    from particletracking_b200.reconstruct_3D import calibrate_cameras as cc
+    from particletracking_b200.reconstruct_3D import match2D
+
+    data = syn.make_stereo(3, 1, 14, seed=6)
+    df = syn.to_dataframes(data)["black"]
+    cal, trf = rig["calibration"], rig["transformation"]
+    out, _, _ = match2D.match_complex(df, [int(f) for f in data.frames], "black", cal, trf)
+    out = out.copy()
+    out.loc[out.index[2], ["x1", "y1", "z1"]] = np.nan
+    for scale in (1.0, 0.5):
+        got = cc.reproject_data(out, ["gp1", "gp2"], cal, scale, trf)
+        want = port.reproject_data(out, ["gp1", "gp2"], cal, scale, trf)
+        assert got.shape == want.shape and got.shape[0] == 4
+        assert rel_err(got, want) < 1e-9
+    assert cc.reproject_data(out, ["gp1", "gp2"], None) is None
+    empty = out.copy()
+    empty[["x1", "y1", "z1"]] = np.nan
+    assert cc.reproject_data(empty, ["gp1", "gp2"], cal, 1.0, trf) is None
