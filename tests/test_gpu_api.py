@@ -313,7 +313,7 @@ def test_reproject_data_vs_port(api, rig):
     cal, trf = rig["calibration"], rig["transformation"]
     out, _, _ = match2D.match_complex(df, [int(f) for f in data.frames], "black", cal, trf)
     out = out.copy()
-    out.loc[out.index[2], ["x1", "y1", "z1"]] = np.nan
+    out.loc[out.index[2], ["x1", "y1", "z1", "x2", "y2", "z2"]] = np.nan
     for scale in (1.0, 0.5):
         got = cc.reproject_data(out, ["gp1", "gp2"], cal, scale, trf)
         want = port.reproject_data(out, ["gp1", "gp2"], cal, scale, trf)
@@ -323,3 +323,9 @@ def test_reproject_data_vs_port(api, rig):
     empty = out.copy()
     empty[["x1", "y1", "z1"]] = np.nan
     assert cc.reproject_data(empty, ["gp1", "gp2"], cal, 1.0, trf) is None
+    ragged = out.copy()  # end 1 missing in one row only: the reference's np.asarray of unequal lists raises, so do we
+    ragged.loc[ragged.index[5], ["x1", "y1", "z1"]] = np.nan
+    with pytest.raises(ValueError):
+        port.reproject_data(ragged, ["gp1", "gp2"], cal, 1.0, trf)
+    with pytest.raises(ValueError):
+        cc.reproject_data(ragged, ["gp1", "gp2"], cal, 1.0, trf)
