@@ -408,6 +408,12 @@ int ptk_measure_fp64_peak(int iters, double* flops, void* stream);
  * kinds: 0 undistort, 1 cost (K1), 2 lsap (matching), 3 rows, 4 rows_to_ends, 5 track_cost,
  *        6 lsap (tracking), 7 chain (3 launches), 8 create_weights, 9 npartite3 */
 #define PTK_TIMING_KINDS 10
+/* Bounds-checked debug build (make -C particletracking_b200/csrc debug -> libptk_dbg.so, selected with
+ * PTK_LIB=<path>): every data-derived index is checked on the device; violations are counted, not trapped.
+ * enabled = 1 only in that build; count / first_* describe the log (site: see ptk_bounds.cuh call sites). */
+int ptk_bounds_report(int* enabled, long long* count, int* first_site, long long* first_idx,
+                      long long* first_bound, int reset);
+
 void ptk_timing_enable(int on);
 int ptk_timing_read(double* ms_by_kind, long long* launches_by_kind, int reset);
 

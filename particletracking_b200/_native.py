@@ -12,7 +12,8 @@ import os
 from .rig import PtkRig
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libptk.so")
+# PTK_LIB selects another build of the same ABI (the bounds-checked libptk_dbg.so); default: the release library
+LIB_PATH = os.environ.get("PTK_LIB") or os.path.join(_HERE, "libptk.so")
 
 PTK_OK = 0
 PTK_ERR_NUMERIC = -5
@@ -35,7 +36,7 @@ SYMBOLS = [
     "ptk_ctx_create", "ptk_ctx_destroy", "ptk_reconstruct_host", "ptk_reconstruct_host_compact", "ptk_expand_rows_host",
     "ptk_reconstruct_device", "ptk_reconstruct_device_workspace_bytes",
     "ptk_reconstruct_shard", "ptk_reconstruct_shard_workspace_bytes", "ptk_chain_rebase_gathered",
-    "ptk_measure_fp64_peak", "ptk_launch_count", "ptk_timing_enable", "ptk_timing_read",
+    "ptk_measure_fp64_peak", "ptk_launch_count", "ptk_bounds_report", "ptk_timing_enable", "ptk_timing_read",
 ]
 
 
@@ -125,6 +126,8 @@ def lib() -> ctypes.CDLL:
     L.ptk_reconstruct_host.argtypes = [vp, rigp, i32, i32, i32] + [vp] * 10 + [dbl, vp, i32] + [vp] * 4
     L.ptk_reconstruct_host_compact.argtypes = [vp, rigp, i32, i32, i32] + [vp] * 11 + [dbl, vp, i32] + [vp] * 4
     L.ptk_expand_rows_host.argtypes = [ll, i32] + [vp] * 7 + [i32]
+    L.ptk_bounds_report.argtypes = [ctypes.POINTER(i32), ctypes.POINTER(ll), ctypes.POINTER(i32), ctypes.POINTER(ll),
+                                    ctypes.POINTER(ll), i32]
     L.ptk_timing_enable.argtypes = [i32]
     L.ptk_timing_enable.restype = None
     L.ptk_timing_read.argtypes = [vp, vp, i32]

@@ -432,6 +432,34 @@ PTK_API int ptk_device_count(void)
     return ok;
 }
 
+// Debug build (-DPTK_BOUNDS_CHECK, libptk_dbg.so): the device-side log of index violations.  Release: enabled = 0.
+PTK_API int ptk_bounds_report(int* enabled, long long* count, int* first_site, long long* first_idx, long long* first_bound,
+                              int reset)
+{
+    if (enabled) *enabled = 0;
+    if (count) *count = 0;
+    if (first_site) *first_site = 0;
+    if (first_idx) *first_idx = 0;
+    if (first_bound) *first_bound = 0;
+#ifdef PTK_BOUNDS_CHECK
+    BoundsLog h;
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpyFromSymbol(&h, g_bounds_log, sizeof(h)));
+    if (enabled) *enabled = 1;
+    if (count) *count = (long long)h.count;
+    if (first_site) *first_site = h.first_site;
+    if (first_idx) *first_idx = h.first_idx;
+    if (first_bound) *first_bound = h.first_bound;
+    if (reset) {
+        BoundsLog z = {0ull, 0ll, 0ll, 0, 1};
+        CK(cudaMemcpyToSymbol(g_bounds_log, &z, sizeof(z)));
+    }
+#else
+    (void)reset;
+#endif
+    return PTK_OK;
+}
+
 PTK_API long long ptk_launch_count(int reset)
 {
     return reset ? g_launches.exchange(0) : g_launches.load();

@@ -16,6 +16,7 @@
 #include <stdint.h>
 
 #include "../../include/ptk.h"
+#include "ptk_bounds.cuh"
 
 namespace ptk {
 

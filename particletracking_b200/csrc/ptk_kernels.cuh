@@ -37,14 +37,14 @@ __global__ void __launch_bounds__(128) k_undistort(const __grid_constant__ DevRi
     double ou, ov;
     if (n == 1) {
         // 2x2 input is read row-wise by OpenCV (proper points); the write-back transposes.
-        undistort_point(cm, k, in[2 * j], in[2 * j + 1], ou, ov);
-        out[j] = ou;
-        out[j + 2] = ov;
+        undistort_point(cm, k, PTK_AT(in, 2 * j, 4 * Nmax, 1), PTK_AT(in, 2 * j + 1, 4 * Nmax, 2), ou, ov);
+        PTK_AT(out, j, 4 * Nmax, 3) = ou;
+        PTK_AT(out, j + 2, 4 * Nmax, 4) = ov;
     } else {
         // rods.reshape(2,-1): pseudo-point j = (flat[j], flat[j+2n])
-        undistort_point(cm, k, in[j], in[j + 2 * n], ou, ov);
-        out[j] = ou;
-        out[j + 2 * n] = ov;
+        undistort_point(cm, k, PTK_AT(in, j, 4 * Nmax, 5), PTK_AT(in, j + 2 * n, 4 * Nmax, 6), ou, ov);
+        PTK_AT(out, j, 4 * Nmax, 7) = ou;
+        PTK_AT(out, j + 2 * n, 4 * Nmax, 8) = ov;
     }
 }
 
@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(128, MINB) k_cost(const __grid_constant__ DevR
     const int c = threadIdx.x & 3;
     const int e1 = c >> 1, e2 = c & 1;
     const int i = pair_row(q, N2), j = q - i * N2;
+    if (!PTK_OK_IDX(i, N1, 10) || !PTK_OK_IDX(j, N2, 11)) return;  // (debug build) the reciprocal-based row index
     // 32-bit element offsets (p < 65536 per launch, Nmax <= 256: below 2^26 rods): one IMAD.WIDE per address
     const unsigned base = (unsigned)p * (unsigned)a.Nmax;
     const unsigned off1 = (base + (unsigned)i) * 4u + 2u * e1, off2 = (base + (unsigned)j) * 4u + 2u * e2;
@@ -261,7 +262,7 @@ __global__ void __launch_bounds__(32) k_lsap(const __grid_constant__ LsapArgs a)
                 const int i = idx / nc0, j = idx - i * nc0;
                 const double c = C[(size_t)i * ldc + j];
                 bad |= (c != c) || (c == -INFINITY);
-                if (staged) sm[tr ? (j * nc + i) : (i * nc + j)] = c;
+                if (staged) PTK_AT(sm, tr ? (j * nc + i) : (i * nc + j), nr * nc, 20) = c;
             }
         }
         if (__any_sync(kFull, bad)) st = PTK_PROBLEM_INVALID;
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(32) k_lsap(const __grid_constant__ LsapArgs a)
             double minVal = 0.0;
             int i = cur, num_rem = nc, sink = -1;
             while (sink == -1) {
-                const double ui = u[i];
+                const double ui = PTK_AT(u, i, nr, 21);
                 unsigned long long kmin = ~0ull;
                 unsigned long long key[CPL];
 #pragma unroll
@@ -294,7 +295,8 @@ __global__ void __launch_bounds__(32) k_lsap(const __grid_constant__ LsapArgs a)
                     key[s] = ~0ull;
                     if (pos[s] >= 0) {
                         const int j = lane + 32 * s;
-                        const double c = staged ? sm[i * nc + j] : (tr ? C[(size_t)j * ldc + i] : C[(size_t)i * ldc + j]);
+                        const double c = staged ? PTK_AT(sm, i * nc + j, nr * nc, 22)
+                                                : (tr ? C[(size_t)j * ldc + i] : C[(size_t)i * ldc + j]);
                         const double r = ((minVal + c) - ui) - v[s];
                         if (r < spc[s]) { spc[s] = r; path[s] = i; }
                         key[s] = ordered_key(spc[s]);
@@ -354,6 +356,7 @@ __global__ void __launch_bounds__(32) k_lsap(const __grid_constant__ LsapArgs a)
             while (true) {
                 const int r = lane_array_get<CPL>(path, j);
                 lane_array_set<CPL>(r4c, j, r, lane);
+                if (!PTK_OK_IDX(r, nr, 23) || !PTK_OK_IDX(j, nc, 24)) break;  // (debug build) a corrupt augmenting path
                 const int t = c4r[r];
                 __syncwarp();
                 if (lane == 0) c4r[r] = j;
@@ -371,7 +374,7 @@ __global__ void __launch_bounds__(32) k_lsap(const __grid_constant__ LsapArgs a)
         if (!tr) {
             for (int r = lane; r < nr; r += 32) {
                 const int cj = c4r[r];
-                const double cst = C[(size_t)r * ldc + cj];
+                const double cst = PTK_OK_IDX(cj, nc, 25) ? C[(size_t)r * ldc + cj] : qnan;
                 if (orow) orow[r] = r;
                 ocol[r] = cj;
                 if (oasg) oasg[r] = cst;
@@ -469,7 +472,8 @@ __global__ void __launch_bounds__(128) k_rows(const __grid_constant__ DevRig rig
     }
     const bool active = m < n;
     const int mm = active ? m : n - 1;
-    const int i2 = a.col_ind[base + mm];
+    int i2 = a.col_ind[base + mm];
+    if (!PTK_OK_IDX(i2, a.Nmax, 30)) i2 = 0;  // (debug build) an assignment outside the padded problem
     const int e1 = c >> 1, e2 = c & 1;
     const double2 u1 = ldg2(a.und1 + (base + mm) * 4 + 2 * e1);
     const double2 u2 = ldg2(a.und2 + (base + i2) * 4 + 2 * e2);

@@ -292,6 +292,12 @@ __device__ __forceinline__ void trk_solve(const TrkArgs& a, const void* scratch,
             while (sink == -1) {
                 double ui, Ai;
                 unsigned xmw[CPL];
+                // (debug build) the row address comes out of a SHFL of per-column state: it must be a record of this problem
+                if (!PTK_OK_IDX((long long)iaddr - (long long)rows_addr, (long long)N * (long long)sizeof(Row), 40) ||
+                    !PTK_OK_IDX(((long long)iaddr - (long long)rows_addr) % (long long)sizeof(Row), 1, 41)) {
+                    infeasible = true;
+                    break;
+                }
                 {
                     unsigned long long w0, w1;
                     asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "r"(iaddr));
@@ -392,6 +398,7 @@ __device__ __forceinline__ void trk_solve(const TrkArgs& a, const void* scratch,
             while (true) {
                 const unsigned raddr = lane_array_get<CPL>(path, j);
                 const int r = (int)((raddr - rows_addr) / (unsigned)sizeof(Row));
+                if (!PTK_OK_IDX(r, N, 42) || !PTK_OK_IDX(j, N, 43)) break;  // (debug build) a corrupt augmenting path
 #pragma unroll
                 for (int s = 0; s < CPL; s++)
                     if (lane == (j & 31) && s == (j >> 5)) {
@@ -422,6 +429,7 @@ __device__ __forceinline__ void trk_solve(const TrkArgs& a, const void* scratch,
             for (int r = lane; r < N; r += 32) {
                 const int cj = c4r[r];
                 ocol[r] = cj;
+                if (!PTK_OK_IDX(cj, N, 44)) continue;
                 tsum += trk_entry(cur, nxt, rows[r].A + t.B[cj], r, cj);
             }
             tsum = warp_sum(tsum);

@@ -42,3 +42,29 @@ def rel_err(a, b):
     if a.size == 0:
         return 0.0
     return float(np.max(np.abs(a - b)) / max(float(np.max(np.abs(b))), 1.0))
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Bounds-checked debug build (PTK_LIB=.../libptk_dbg.so, ptk_bounds.cuh): the device-side log of index
+    violations must be empty after the whole suite, except for what test_bounds_log_* provoked and reset."""
+    import ctypes
+
+    try:
+        import torch
+
+        if not torch.cuda.is_available():
+            return
+        from particletracking_b200 import _native as nat
+
+        if nat._lib is None:
+            return
+        en, cnt, site = ctypes.c_int(0), ctypes.c_longlong(0), ctypes.c_int(0)
+        idx, bnd = ctypes.c_longlong(0), ctypes.c_longlong(0)
+        nat.lib().ptk_bounds_report(ctypes.byref(en), ctypes.byref(cnt), ctypes.byref(site), ctypes.byref(idx), ctypes.byref(bnd), 0)
+        if en.value:
+            msg = f"bounds-checked build: {cnt.value} violations (first: site {site.value}, index {idx.value}, bound {bnd.value})"
+            print("\n" + msg)
+            if cnt.value:
+                session.exitstatus = 1
+    except Exception as e:  # pragma: no cover
+        print(f"\nbounds report unavailable: {e}")

@@ -237,3 +237,32 @@ def test_workspace_is_per_stream(env):
     torch.cuda.synchronize()
     np.testing.assert_array_equal(q1.rows.cpu().numpy(), r1.rows.cpu().numpy())
     np.testing.assert_array_equal(q2.rows.cpu().numpy(), r2.rows.cpu().numpy())
+
+
+def test_bounds_log_counts_a_provoked_violation(env):
+    """The debug build's checker itself: an assignment outside the padded problem handed to ptk_rows_batch
+    must be counted (and not dereferenced); the release build reports enabled = 0."""
+    import torch
+    from particletracking_b200 import synthetic as syn
+
+    engine, nat, crig = env
+    L = nat.lib()
+    en, cnt, site = ctypes.c_int(0), ctypes.c_longlong(0), ctypes.c_int(0)
+    idx, bnd = ctypes.c_longlong(0), ctypes.c_longlong(0)
+    rep = lambda reset: L.ptk_bounds_report(ctypes.byref(en), ctypes.byref(cnt), ctypes.byref(site), ctypes.byref(idx),
+                                            ctypes.byref(bnd), reset)
+    assert rep(0) == 0
+    if not en.value:
+        assert cnt.value == 0
+        return
+    before = cnt.value
+    assert before == 0, f"violations before this test: {before} (site {site.value})"
+    data = syn.make_stereo(2, 1, 6, seed=1)
+    c1, c2, n1, n2 = (torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in data.problems())
+    col = torch.full((2, 6), 9, dtype=torch.int32, device="cuda")  # 9 >= Nmax = 6
+    n_out = torch.full((2,), 6, dtype=torch.int32, device="cuda")
+    engine.rows_batch(crig, c1, c2, n1, n2, col, n_out)
+    torch.cuda.synchronize()
+    assert rep(1) == 0
+    assert cnt.value > 0 and site.value == 30 and idx.value == 9 and bnd.value == 6
+    assert rep(0) == 0 and cnt.value == 0  # reset: the session-end check sees only real violations
