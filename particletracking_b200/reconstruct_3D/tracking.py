@@ -1,7 +1,7 @@
 """``tracking.tracking_global_assignment`` of the reference (``reconstruct_3D/tracking.py``
-:70-138) on the B200: the cost tensor over all consecutive frame pairs (K4) and one LSAP per
-pair (K2) run in ``libptk.so``; the DataFrame glue mirrors the reference, including its
-positional ``particle`` rewrite.
+:70-138) on the B200: the assignments of all consecutive frame pairs are solved in ``libptk.so``
+straight from the end points (K2T: no cost matrix; its separable part lives in registers); the
+DataFrame glue mirrors the reference, including its positional ``particle`` rewrite.
 
 ``tracking_trackpy`` is a thin wrapper over the third-party ``trackpy`` and is out of scope.
 """
@@ -37,14 +37,10 @@ def _track(ends: np.ndarray):
     return col, tot
 
 
-def tracking_global_assignment(data: pd.DataFrame) -> Tuple[pd.DataFrame, np.ndarray]:
-    """Tracks rods (one colour) over multiple frames with optimal assignment (reference
-    tracking.py:70-138).  Returns the data with the reference's ``particle`` numbers (frame 1
-    keeps its ids, later frames get their row position -- that is what tracking.py:130-133
-    does) sorted by (frame, particle), and the assignment cost per frame pair.
-
-    Deviation: two frames (one pair) work here; the reference raises IndexError there because
-    of a ``squeeze`` (tracking.py:123)."""
+def _assign(data: pd.DataFrame):
+    """The body shared by both entry points: one pass of the tracking kernels.  Returns the
+    reference-shaped DataFrame, the per-pair costs and the device tensor col_ind[1,F-1,N] (None for
+    fewer than two frames)."""
     frames, ends = _ends(data)
     F, N = ends.shape[:2]
     out = data.copy()
@@ -53,26 +49,36 @@ def tracking_global_assignment(data: pd.DataFrame) -> Tuple[pd.DataFrame, np.nda
         first = (out.frame == frames[0]).to_numpy()
         out.loc[first, "particle"] = np.arange(int(first.sum()))
     if F < 2:
-        return out.sort_values(by=["frame", "particle"]).reset_index(drop=True), np.zeros(0)
-    _, tot = _track(ends)
+        return out.sort_values(by=["frame", "particle"]).reset_index(drop=True), np.zeros(0), None, N
+    col, tot = _track(ends)
     later = (out.frame != frames[0]).to_numpy()
     pos_in_frame = out.groupby("frame", sort=False).cumcount().to_numpy()
     part = out["particle"].to_numpy().copy()
     part[later] = pos_in_frame[later]
     out["particle"] = part
     out = out.sort_values(by=["frame", "particle"]).reset_index(drop=True)
-    return out, tot.cpu().numpy()[0]
+    return out, tot.cpu().numpy()[0], col, N
+
+
+def tracking_global_assignment(data: pd.DataFrame) -> Tuple[pd.DataFrame, np.ndarray]:
+    """Tracks rods (one colour) over multiple frames with optimal assignment (reference
+    tracking.py:70-138).  Returns the data with the reference's ``particle`` numbers (frame 1
+    keeps its ids, later frames get their row position -- that is what tracking.py:130-133
+    does) sorted by (frame, particle), and the assignment cost per frame pair.
+
+    Deviation: two frames (one pair) work here; the reference raises IndexError there because
+    of a ``squeeze`` (tracking.py:123)."""
+    out, total, _, _ = _assign(data)
+    return out, total
 
 
 def tracking_global_assignment_chained(data: pd.DataFrame):
     """Extension (north star "chain pass"; no reference counterpart):
     like ``tracking_global_assignment`` but also returns ``col_ind[F-1,N]`` and
-    ``track_id[F,N]`` with ids[0] = arange(N), ids[f+1][col_ind[f][a]] = ids[f][a]."""
-    frames, ends = _ends(data)
-    out, total = tracking_global_assignment(data)
-    if len(frames) < 2:
-        N = ends.shape[1]
+    ``track_id[F,N]`` with ids[0] = arange(N), ids[f+1][col_ind[f][a]] = ids[f][a].  One pass of the
+    tracking kernels serves both results."""
+    out, total, col, N = _assign(data)
+    if col is None:
         return out, total, np.zeros((0, N), dtype=np.int32), np.arange(N, dtype=np.int32)[None]
-    col, _ = _track(ends)
     tid = engine.chain_tracks(col)
     return out, total, col.cpu().numpy()[0], tid.cpu().numpy()[0]
