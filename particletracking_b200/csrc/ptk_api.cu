@@ -199,8 +199,14 @@ long long match_chunk(long long P, int Nmax)
 
 struct MatchWs {
     double *und1, *und2, *cost;
+    double2* rec2;  // k_prep2's planes (canonical rigs): kCanon2RecPlanes x [chunk * Nmax * 2] double2
     size_t bytes;
 };
+
+inline size_t rec2_bytes(long long chunk, int Nmax)
+{
+    return (size_t)kCanon2RecPlanes * (size_t)chunk * Nmax * 2 * sizeof(double2);
+}
 
 MatchWs carve_match(void* ws, long long chunk, int Nmax, bool need_cost)
 {
@@ -210,6 +216,7 @@ MatchWs carve_match(void* ws, long long chunk, int Nmax, bool need_cost)
     const size_t und = align_up((size_t)chunk * Nmax * 4 * sizeof(double));
     m.und1 = reinterpret_cast<double*>(b + o); o += und;
     m.und2 = reinterpret_cast<double*>(b + o); o += und;
+    m.rec2 = reinterpret_cast<double2*>(b + o); o += align_up(rec2_bytes(chunk, Nmax));
     m.cost = reinterpret_cast<double*>(b + o);
     if (need_cost) o += align_up((size_t)chunk * Nmax * Nmax * sizeof(double));
     m.bytes = o;
@@ -233,21 +240,33 @@ int launch_undistort(const DevRig& rig, long long P, int Nmax, const double* cam
     return PTK_OK;
 }
 
+// rec2: workspace for k_prep2's planes, rec2_bytes(P, Nmax) (used by canonical rigs only)
 int launch_cost(const DevRig& rig, long long P, int Nmax, const double* cam1, const double* cam2, const double* und1,
-                const double* und2, const int32_t* n1, const int32_t* n2, double* cost, uint8_t* choice,
+                const double* und2, double2* rec2, const int32_t* n1, const int32_t* n2, double* cost, uint8_t* choice,
                 double* p_world, double* rep_errs, cudaStream_t st)
 {
     CostArgs a;
     a.Nmax = Nmax;
     a.tiles = (Nmax * Nmax + 31) / 32;
+    a.rec_stride = (unsigned)((size_t)P * Nmax * 2);
+    if (rig.canon && !rec2) return PTK_ERR_INVALID_ARG;
     // grid = (tiles, problems): gridDim.y holds 65535
     const long long max_p = 65535;
     for (long long p0 = 0; p0 < P; p0 += max_p) {
         const long long np = (P - p0) < max_p ? (P - p0) : max_p;
         const size_t o4 = (size_t)p0 * Nmax * 4, o2 = (size_t)p0 * Nmax * Nmax;
         a.cam1 = cam1 + o4; a.cam2 = cam2 + o4; a.und1 = und1 + o4; a.und2 = und2 + o4;
+        a.rec2 = rec2 ? rec2 + (size_t)p0 * Nmax * 2 : nullptr;
         a.n1 = n1 + p0; a.n2 = n2 + p0;
         a.cost = cost + o2;
+        if (rig.canon) {  // K0b: the camera-2 share of the DLT, once per end point (ptk_device.cuh: canon_prep2)
+            const dim3 pgrid((2 * Nmax + 127) / 128, (unsigned)np);
+            {
+                LaunchTimer lt(K_UNDISTORT, st);
+                k_prep2<<<pgrid, 128, 0, st>>>(rig, Nmax, a.und2, a.n2, const_cast<double2*>(a.rec2), a.rec_stride);
+            }
+            LAUNCHED("k_prep2");
+        }
         a.choice = choice ? choice + o2 : nullptr;
         a.p_world = p_world ? p_world + o2 * 12 : nullptr;
         a.rep_errs = rep_errs ? rep_errs + o2 * 8 : nullptr;
@@ -534,7 +553,7 @@ PTK_API int ptk_cost_batch(const ptk_rig* rig, int P, int Nmax, const double* ca
     MatchWs w = carve_match((void*)align_up((size_t)workspace), P, Nmax, false);
     int rc = launch_undistort(d, P, Nmax, cam1, cam2, n1, n2, w.und1, w.und2, st);
     if (rc) return rc;
-    return launch_cost(d, P, Nmax, cam1, cam2, w.und1, w.und2, n1, n2, cost, choice, p_world, rep_errs, st);
+    return launch_cost(d, P, Nmax, cam1, cam2, w.und1, w.und2, w.rec2, n1, n2, cost, choice, p_world, rep_errs, st);
 }
 
 // ------------------------------------------------------------------------------------ K2
@@ -578,7 +597,7 @@ int match_batch_impl(const ptk_rig* rig, int P, int Nmax, const double* cam1, co
         double* cchunk = cost ? cost + (size_t)p0 * NN : w.cost;
         int rc = launch_undistort(d, np, Nmax, cam1 + o4, cam2 + o4, n1 + p0, n2 + p0, w.und1, w.und2, st);
         if (rc) return rc;
-        rc = launch_cost(d, np, Nmax, cam1 + o4, cam2 + o4, w.und1, w.und2, n1 + p0, n2 + p0, cchunk,
+        rc = launch_cost(d, np, Nmax, cam1 + o4, cam2 + o4, w.und1, w.und2, w.rec2, n1 + p0, n2 + p0, cchunk,
                          choice ? choice + (size_t)p0 * NN : nullptr, nullptr, nullptr, st);
         if (rc) return rc;
         LsapArgs a{};
@@ -943,6 +962,7 @@ PTK_API int ptk_npartite3_batch(int B, int D0, int D1, int D2, const double* wei
 namespace {
 struct NdWs {
     double *und1, *und2, *cost, *pw, *re, *w, *value, *bound;
+    double2* rec2;
     uint8_t* choices;
     unsigned long long* wkey;
     int32_t *sol, *n_sol, *ap3_status, *stats, *row_ind, *col_ind;
@@ -960,6 +980,7 @@ NdWs carve_nd(void* base, int F, int C, int D)
     const size_t CD = (size_t)C * D, CDD = CD * D, CDDD = CDD * D;
     w.und1 = (double*)take(CD * 4 * sizeof(double));
     w.und2 = (double*)take(CD * 4 * sizeof(double));
+    w.rec2 = (double2*)take(rec2_bytes(C, D));
     w.cost = (double*)take(CDD * sizeof(double));
     w.pw = (double*)take(CDD * 12 * sizeof(double));
     w.re = (double*)take(CDD * 8 * sizeof(double));
@@ -1018,7 +1039,7 @@ PTK_API int ptk_matchnd_sequence(const ptk_rig* rig, int F, int C, int Nmax, con
         const int32_t* m2 = n2 + (size_t)f * C;
         rc = launch_undistort(dsum, C, D, c1, c2, m1, m2, w.und1, w.und2, st);
         if (rc) return rc;
-        rc = launch_cost(dsum, C, D, c1, c2, w.und1, w.und2, m1, m2, w.cost, nullptr, w.pw, w.re, st);
+        rc = launch_cost(dsum, C, D, c1, c2, w.und1, w.und2, w.rec2, m1, m2, w.cost, nullptr, w.pw, w.re, st);
         if (rc) return rc;
         NdArgs a;
         a.D = D;

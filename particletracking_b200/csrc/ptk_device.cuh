@@ -366,31 +366,13 @@ static inline double ptk_pow2_inv(double x)
 #define PTK_HD __host__ __device__ inline
 #endif
 
-// Everything after the QR: T = R~^-1, B = T diag(w) T^T, NSQ symmetric squarings, the convergence
-// check and the final product with the largest-diagonal column.  r_kj: the unit upper-triangular
-// factor's entries, w_k = 1 / |q_k|^2.  Returns whether the power iteration has converged.
+// The power iteration on B = (A^T A)^-1 (symmetric, given by its upper triangle): scaling by a power of
+// two, NSQ symmetric squarings, the convergence check and the final product with the largest-diagonal
+// column.  Returns whether the iteration has converged.
 template <int NSQ>
-PTK_HD bool dlt_invpower_tail(double r01, double r02, double r03, double r12, double r13, double r23, double w0, double w1,
-                              double w2, double w3, double (&v)[4])
+PTK_HD bool dlt_invpower_core(double b00, double b01, double b02, double b03, double b11, double b12, double b13,
+                              double b22, double b23, double b33, double (&v)[4])
 {
-    // T = R~^-1: t01 = -r01, t12 = -r12, t23 = -r23 and
-    const double t02 = fma(r01, r12, -r02);                  // -(r02 + r01 t12)
-    const double t13 = fma(r12, r23, -r13);                  // -(r13 + r12 t23)
-    const double t03 = fma(r02, r23, -fma(r01, t13, r03));   // -(r03 + r01 t13 + r02 t23)
-    // B = T diag(w) T^T.  Columns of T scaled by w: c1 = w1 T[:,1], c2 = w2 T[:,2], c3 = w3 T[:,3]
-    const double c01 = -r01 * w1;
-    const double c02 = t02 * w2, c12 = -r12 * w2;
-    const double c03 = t03 * w3, c13 = t13 * w3, c23 = -r23 * w3;
-    double b00 = fma(t03, c03, fma(t02, c02, fma(-r01, c01, w0)));
-    double b01 = fma(t03, c13, fma(t02, c12, c01));
-    double b02 = fma(t03, c23, c02);
-    double b03 = c03;
-    double b11 = fma(t13, c13, fma(-r12, c12, w1));
-    double b12 = fma(t13, c23, c12);
-    double b13 = c13;
-    double b22 = fma(-r23, c23, w2);
-    double b23 = c23;
-    double b33 = w3;
     {
         const double sc = ptk_pow2_inv((b00 + b11) + (b22 + b33));
         b00 *= sc; b01 *= sc; b02 *= sc; b03 *= sc; b11 *= sc;
@@ -433,6 +415,29 @@ PTK_HD bool dlt_invpower_tail(double r01, double r02, double r03, double r12, do
     v[2] = fma(b23, u3, fma(b22, u2, fma(b12, u1, b02 * u0)));
     v[3] = fma(b33, u3, fma(b23, u2, fma(b13, u1, b03 * u0)));
     return ok;
+}
+
+// Everything after the QR: T = R~^-1, B = T diag(w) T^T, then the power iteration.  r_kj: the unit
+// upper-triangular factor's entries, w_k = 1 / |q_k|^2.  Returns whether the power iteration has converged.
+template <int NSQ>
+PTK_HD bool dlt_invpower_tail(double r01, double r02, double r03, double r12, double r13, double r23, double w0, double w1,
+                              double w2, double w3, double (&v)[4])
+{
+    // T = R~^-1: t01 = -r01, t12 = -r12, t23 = -r23 and
+    const double t02 = fma(r01, r12, -r02);                  // -(r02 + r01 t12)
+    const double t13 = fma(r12, r23, -r13);                  // -(r13 + r12 t23)
+    const double t03 = fma(r02, r23, -fma(r01, t13, r03));   // -(r03 + r01 t13 + r02 t23)
+    // B = T diag(w) T^T.  Columns of T scaled by w: c1 = w1 T[:,1], c2 = w2 T[:,2], c3 = w3 T[:,3]
+    const double c01 = -r01 * w1;
+    const double c02 = t02 * w2, c12 = -r12 * w2;
+    const double c03 = t03 * w3, c13 = t13 * w3, c23 = -r23 * w3;
+    const double b00 = fma(t03, c03, fma(t02, c02, fma(-r01, c01, w0)));
+    const double b01 = fma(t03, c13, fma(t02, c12, c01));
+    const double b02 = fma(t03, c23, c02);
+    const double b11 = fma(t13, c13, fma(-r12, c12, w1));
+    const double b12 = fma(t13, c23, c12);
+    const double b22 = fma(-r23, c23, w2);
+    return dlt_invpower_core<NSQ>(b00, b01, b02, c03, b11, b12, c13, b22, c23, w3, v);
 }
 
 #define PTK_DOT(x, y) fma(x[3], y[3], fma(x[2], y[2], fma(x[1], y[1], x[0] * y[0])))
@@ -504,6 +509,94 @@ PTK_HD bool dlt_null_invpower_canon(const double* __restrict__ cm1, double fx2, 
     const double w3 = ptk_rcp(PTK_DOT(a3, a3));
     return dlt_invpower_tail<3>(r01, r02, r03, r12, r13, r23, w0, w1, w2, w3, v);
 }
+
+// ---------------------------------------------------------------------------------------
+// Canonical first camera, with the work that depends on the camera-2 point alone taken out of the
+// per-combination path (round 2).  Of the four DLT columns above only a2 = (x1-cx, y1-cy, p2, q2) contains
+// the camera-1 point.  Orthogonalising in the order a0, a1, a3, a2 therefore makes the first three
+// Gram-Schmidt vectors, their reciprocal norms, the leading 3x3 block of T = R~^-1 and that block's share of
+// B = T diag(w) T^T functions of (x2, y2) only: `canon_prep2` computes them ONCE per camera-2 end point
+// (2 N2 per problem, kernel k_prep2) into a 22-double record, and a combination only projects its own column
+// a2 against the three stored vectors and adds the rank-one term of the last pivot:
+//     B = [B3 0; 0 0] + w2 z z^T,   z = (t03, t13, t23, 1)   (in the order 0, 1, 3, 2)
+// -- 46 FP64 instructions per combination instead of 103 for the QR and B.  The power iteration is the same;
+// the null vector comes back in the caller's column order.  Same accuracy against cv2.triangulatePoints as the
+// functions above (tests/test_dlt_invpower_cpu.py); the bits differ from theirs (another elimination order),
+// so K1 and K3 -- which must agree bit for bit -- both go through prep + finish, K1 with the record read from
+// memory and K3 with the record computed in place by the same function.
+// ---------------------------------------------------------------------------------------
+struct Canon2Rec {
+    double p0, q0, p2, q2;        // camera-2 halves of columns 0 and 2
+    double w0, g10, g12, g13;     // 1/|g0|^2; g1 = (g10, -fy, g12, g13)
+    double w1, g30, g31, g32;     // 1/|g1|^2; g3 = (g30, g31, g32, g33)
+    double g33, w3, r13, r03;     // 1/|g3|^2; R~ entries among the stored columns
+    double r01, B00, B01, B02;    // the stored columns' share of B (B22 = w3)
+    double B11, B12;
+};
+constexpr int kCanon2RecPlanes = 11;  // double2 planes of the record in memory (structure of arrays)
+
+PTK_HD void canon_prep2(const double* __restrict__ cm1, double fx2, const double* __restrict__ Q2, double x2, double y2,
+                        Canon2Rec& r)
+{
+    const double fx = cm1[0], fy = cm1[1];
+    const double p0 = fma(x2, Q2[8], -Q2[0]), q0 = fma(y2, Q2[8], -Q2[4]);
+    const double p1 = fma(x2, Q2[9], -Q2[1]), q1 = fma(y2, Q2[9], -Q2[5]);
+    const double p3 = fma(x2, Q2[11], -Q2[3]), q3 = fma(y2, Q2[11], -Q2[7]);
+    r.p0 = p0; r.q0 = q0;
+    r.p2 = fma(x2, Q2[10], -Q2[2]); r.q2 = fma(y2, Q2[10], -Q2[6]);
+    // g0 = a0 = (-fx, 0, p0, q0)
+    const double w0 = ptk_rcp(fma(q0, q0, fma(p0, p0, fx2)));
+    const double r01 = fma(q0, q1, p0 * p1) * w0;
+    const double r03 = fma(q0, q3, p0 * p3) * w0;
+    // g1 = a1 - r01 g0,  a3' = a3 - r03 g0
+    const double g10 = r01 * fx, g12 = fma(-r01, p0, p1), g13 = fma(-r01, q0, q1);
+    const double a30 = r03 * fx, a32 = fma(-r03, p0, p3), a33 = fma(-r03, q0, q3);
+    const double w1 = ptk_rcp(fma(g13, g13, fma(g12, g12, fma(fy, fy, g10 * g10))));
+    const double r13 = fma(g13, a33, fma(g12, a32, g10 * a30)) * w1;
+    // g3 = a3' - r13 g1
+    const double g30 = fma(-r13, g10, a30), g31 = r13 * fy, g32 = fma(-r13, g12, a32), g33 = fma(-r13, g13, a33);
+    const double w3 = ptk_rcp(fma(g33, g33, fma(g32, g32, fma(g31, g31, g30 * g30))));
+    r.w0 = w0; r.g10 = g10; r.g12 = g12; r.g13 = g13;
+    r.w1 = w1; r.g30 = g30; r.g31 = g31; r.g32 = g32;
+    r.g33 = g33; r.w3 = w3; r.r13 = r13; r.r03 = r03;
+    r.r01 = r01;
+    // leading block of T (order 0, 1, 3): t01 = -r01, t13' = -r13, t03' = r01 r13 - r03; B3 = T3 diag(w0, w1, w3) T3^T
+    const double t02 = fma(r01, r13, -r03);
+    const double c01 = -r01 * w1, c02 = t02 * w3, c12 = -r13 * w3;
+    r.B00 = fma(t02, c02, fma(-r01, c01, w0));
+    r.B01 = fma(t02, c12, c01);
+    r.B02 = c02;
+    r.B11 = fma(-r13, c12, w1);
+    r.B12 = c12;
+}
+
+// cm1 = (fx, fy, cx, cy); r = canon_prep2 of the camera-2 point; (x1, y1) the camera-1 point.
+PTK_HD bool dlt_null_invpower_canon_rec(const double* __restrict__ cm1, const Canon2Rec& r, double x1, double y1,
+                                        double (&v)[4])
+{
+    const double fx = cm1[0], fy = cm1[1];
+    const double gx = x1 - cm1[2], gy = y1 - cm1[3];
+    // a2 = (gx, gy, p2, q2) against g0 = (-fx, 0, p0, q0)
+    const double r02 = fma(r.q0, r.q2, fma(r.p0, r.p2, -fx * gx)) * r.w0;
+    double a[4];
+    a[0] = fma(r02, fx, gx); a[1] = gy; a[2] = fma(-r02, r.p0, r.p2); a[3] = fma(-r02, r.q0, r.q2);
+    // ... against g1 = (g10, -fy, g12, g13)
+    const double r12 = fma(r.g13, a[3], fma(r.g12, a[2], fma(-fy, a[1], r.g10 * a[0]))) * r.w1;
+    a[0] = fma(-r12, r.g10, a[0]); a[1] = fma(r12, fy, a[1]); a[2] = fma(-r12, r.g12, a[2]); a[3] = fma(-r12, r.g13, a[3]);
+    // ... against g3
+    const double r32 = fma(r.g33, a[3], fma(r.g32, a[2], fma(r.g31, a[1], r.g30 * a[0]))) * r.w3;
+    a[0] = fma(-r32, r.g30, a[0]); a[1] = fma(-r32, r.g31, a[1]); a[2] = fma(-r32, r.g32, a[2]); a[3] = fma(-r32, r.g33, a[3]);
+    const double w2 = ptk_rcp(PTK_DOT(a, a));
+    // last column of T (order 0, 1, 3, 2): t23 = -r32, t13 = r13 r32 - r12, t03 = r03 r32 - (r01 t13 + r02)
+    const double t13 = fma(r.r13, r32, -r12);
+    const double t03 = fma(r.r03, r32, -fma(r.r01, t13, r02));
+    const double c03 = t03 * w2, c13 = t13 * w2, c23 = -r32 * w2;
+    double u[4];
+    const bool ok = dlt_invpower_core<3>(fma(t03, c03, r.B00), fma(t03, c13, r.B01), fma(t03, c23, r.B02), c03,
+                                         fma(t13, c13, r.B11), fma(t13, c23, r.B12), c13, fma(-r32, c23, r.w3), c23, w2, u);
+    v[0] = u[0]; v[1] = u[1]; v[2] = u[3]; v[3] = u[2];
+    return ok;
+}
 #undef PTK_DOT
 #undef PTK_AXPY
 
@@ -542,19 +635,16 @@ __device__ __noinline__ void dlt_triangulate_fallback(const DevRig& rig, double 
     xyz[2] = Z;
 }
 
-// cv2.triangulatePoints for one point (match2D.py:889) + p[0:3]/p[3] (match2D.py:895).
-// CANON: the rig's first camera is canonical (DevRig::canon, see make_devrig).
-template <bool CANON>
-__device__ __forceinline__ void dlt_triangulate_t(const DevRig& rig, double x1, double y1, double x2, double y2,
-                                                  double& X, double& Y, double& Z)
+// cv2.triangulatePoints for one point (match2D.py:889) + p[0:3]/p[3] (match2D.py:895): the stand-alone
+// entry (K8) on the general function.
+__device__ __forceinline__ void dlt_triangulate(const DevRig& rig, double x1, double y1, double x2, double y2,
+                                                double& X, double& Y, double& Z)
 {
 #ifdef PTK_DLT_JACOBI  // A/B switch (tools/ab_bench.py): the one-sided Jacobi for every point
     dlt_triangulate_jacobi(rig, x1, y1, x2, y2, X, Y, Z);
 #else
     double v[4];
-    const bool ok = CANON ? dlt_null_invpower_canon(rig.CM1, rig.fx2, rig.P2o, x1, y1, x2, y2, v)
-                          : dlt_null_invpower_n<3>(rig.P1o, rig.P2o, x1, y1, x2, y2, v);
-    if (ok) {
+    if (dlt_null_invpower_n<3>(rig.P1o, rig.P2o, x1, y1, x2, y2, v)) {
         const double rw = fast_rcp(v[3]);
         X = v[0] * rw;
         Y = v[1] * rw;
@@ -569,30 +659,14 @@ __device__ __forceinline__ void dlt_triangulate_t(const DevRig& rig, double x1, 
 #endif
 }
 
-__device__ __forceinline__ void dlt_triangulate(const DevRig& rig, double x1, double y1, double x2, double y2,
-                                                double& X, double& Y, double& Z)
-{
-    dlt_triangulate_t<false>(rig, x1, y1, x2, y2, X, Y, Z);
-}
-
-// cv2.projectPoints for one point (match2D.py:898-903).  SIMPLE (compile time): the
-// camera has radial terms k1, k2, k3 only -- the rational, tangential and thin-prism blocks do not exist
-// in the code; otherwise they are warp-uniform branches on rig constants.
+// The distortion model and the camera matrix of cv2.projectPoints on a normalised point (x, y)
+// (SURVEY App. B.3).  SIMPLE (compile time): the camera has radial terms k1, k2, k3 only -- the rational,
+// tangential and thin-prism blocks do not exist in the code; otherwise they are warp-uniform branches on
+// rig constants.
 template <bool SIMPLE>
-__device__ __forceinline__ void project_point_t(const double* __restrict__ R, const double* __restrict__ t,
-                                                const double* __restrict__ cm, const double* __restrict__ k,
-                                                double X, double Y, double Z, double& u, double& v,
-                                                bool ext_identity, bool tangential)
+__device__ __forceinline__ void distort_to_pixel(const double* __restrict__ cm, const double* __restrict__ k, double x,
+                                                 double y, double& u, double& v, bool tangential)
 {
-    double x = X, y = Y, z = Z;
-    if (!ext_identity) {
-        x = fma(R[2], Z, fma(R[1], Y, R[0] * X)) + t[0];
-        y = fma(R[5], Z, fma(R[4], Y, R[3] * X)) + t[1];
-        z = fma(R[8], Z, fma(R[7], Y, R[6] * X)) + t[2];
-    }
-    z = ((__double2hiint(z) & 0x7fffffff) | __double2loint(z)) != 0 ? fast_rcp(z) : 1.0;  // z != 0.0, tested on the ALU pipe
-    x *= z;
-    y *= z;
     const double r2 = fma(x, x, y * y), r4 = r2 * r2, r6 = r4 * r2;
     const double cdist = fma(k[4], r6, fma(k[1], r4, fma(k[0], r2, 1.0)));
     double rad = cdist;
@@ -608,6 +682,23 @@ __device__ __forceinline__ void project_point_t(const double* __restrict__ R, co
     v = fma(yd, cm[1], cm[3]);
 }
 
+// cv2.projectPoints for one point (match2D.py:898-903, calibrate_cameras.py:202-262).
+template <bool SIMPLE>
+__device__ __forceinline__ void project_point_t(const double* __restrict__ R, const double* __restrict__ t,
+                                                const double* __restrict__ cm, const double* __restrict__ k,
+                                                double X, double Y, double Z, double& u, double& v,
+                                                bool ext_identity, bool tangential)
+{
+    double x = X, y = Y, z = Z;
+    if (!ext_identity) {
+        x = fma(R[2], Z, fma(R[1], Y, R[0] * X)) + t[0];
+        y = fma(R[5], Z, fma(R[4], Y, R[3] * X)) + t[1];
+        z = fma(R[8], Z, fma(R[7], Y, R[6] * X)) + t[2];
+    }
+    z = ((__double2hiint(z) & 0x7fffffff) | __double2loint(z)) != 0 ? fast_rcp(z) : 1.0;  // z != 0.0, tested on the ALU pipe
+    distort_to_pixel<SIMPLE>(cm, k, x * z, y * z, u, v, tangential);
+}
+
 __device__ __forceinline__ void project_point(const double* __restrict__ R, const double* __restrict__ t,
                                               const double* __restrict__ cm, const double* __restrict__ k,
                                               double X, double Y, double Z, double& u, double& v,
@@ -616,15 +707,28 @@ __device__ __forceinline__ void project_point(const double* __restrict__ R, cons
     project_point_t<false>(R, t, cm, k, X, Y, Z, u, v, ext_identity, tangential);
 }
 
-// ... and the distance of the reprojection to the original (distorted) detection (match2D.py:905-910)
+// Reprojection of the HOMOGENEOUS point h = (h0, h1, h2, h3) (the DLT null vector as it comes, in the
+// coordinates the projection matrices refer to) and its distance to the original (distorted) detection
+// (match2D.py:895-910).  The reference de-homogenises first (p[0:3] / p[3]) and cv2.projectPoints divides by the
+// depth afterwards; the two divisions cancel -- x / z = (R h[0:3] + t h3)_x / (R h[0:3] + t h3)_z -- so the
+// per-camera path is one reciprocal, not two, and the point itself is only formed where a caller wants it
+// (K3, K1's optional output).  cv2's "z == 0 -> leave x, y undivided" becomes "divide by h3 instead".
 template <bool SIMPLE>
-__device__ __forceinline__ double reproject_dist(const double* __restrict__ R, const double* __restrict__ t,
-                                                 const double* __restrict__ cm, const double* __restrict__ k,
-                                                 double X, double Y, double Z, double ou, double ov,
-                                                 bool ext_identity, bool tangential)
+__device__ __forceinline__ double reproject_dist_h(const double* __restrict__ R, const double* __restrict__ t,
+                                                   const double* __restrict__ cm, const double* __restrict__ k,
+                                                   const double (&h)[4], double ou, double ov, bool ext_identity,
+                                                   bool tangential)
 {
+    double x = h[0], y = h[1], z = h[2];
+    if (!ext_identity) {
+        x = fma(R[2], h[2], fma(R[1], h[1], fma(R[0], h[0], t[0] * h[3])));
+        y = fma(R[5], h[2], fma(R[4], h[1], fma(R[3], h[0], t[1] * h[3])));
+        z = fma(R[8], h[2], fma(R[7], h[1], fma(R[6], h[0], t[2] * h[3])));
+    }
+    const bool znz = ((__double2hiint(z) & 0x7fffffff) | __double2loint(z)) != 0;  // z != 0.0, tested on the ALU pipe
+    const double iz = fast_rcp(znz ? z : h[3]);
     double u, v;
-    project_point_t<SIMPLE>(R, t, cm, k, X, Y, Z, u, v, ext_identity, tangential);
+    distort_to_pixel<SIMPLE>(cm, k, x * iz, y * iz, u, v, tangential);
     const double ex = ou - u;
     const double ey = ov - v;
     const double q = fma(ex, ex, ey * ey);
@@ -636,21 +740,49 @@ __device__ __forceinline__ double reproject_dist(const double* __restrict__ R, c
     return (ex11 < 1993u) ? q * rsqrt_refine(q, rsqrt_seed(q)) : sqrt(q);
 }
 
-// One end-point combination (match2D.py:889-913): triangulate the undistorted pair, reproject
-// into both cameras, per-camera distances d1, d2, and the point in camera-1 coordinates.
+// One end-point combination (match2D.py:889-913): triangulate the undistorted pair, reproject into both
+// cameras, per-camera distances d1, d2, and the homogeneous point h (camera-1 coordinates; `dehomogenise`).
 // CANON / SIMPLE: the rig's class (DevRig::canon / ::simple), fixed at compile time so that K1 and K3 -- which
-// must produce the same bits for the same rod pair -- run the same straight-line code.  The class only
-// removes operations on exact zeros and branches never taken: every class gives the same bits.
+// must produce the same bits for the same rod pair -- run the same straight-line code.
+// CANON: `rec` is canon_prep2 of the camera-2 point (read from k_prep2's planes by K1, computed in place by K3:
+// the same function, the same bits) and u2 is only read if the power iteration has not converged; otherwise
+// rec is unused and u2 points at the undistorted camera-2 point.
 template <bool CANON, bool SIMPLE>
-__device__ __forceinline__ void eval_combo(const DevRig& rig, double u1x, double u1y, double u2x, double u2y,
-                                           double o1x, double o1y, double o2x, double o2y,
-                                           double& d1, double& d2, double& X, double& Y, double& Z)
+__device__ __forceinline__ void eval_combo(const DevRig& rig, double u1x, double u1y, const double* __restrict__ u2,
+                                           const Canon2Rec& rec, double o1x, double o1y, double o2x, double o2y,
+                                           double& d1, double& d2, double (&h)[4])
 {
-    dlt_triangulate_t<CANON>(rig, u1x, u1y, u2x, u2y, X, Y, Z);
-    d1 = reproject_dist<SIMPLE>(rig.R1, rig.t1, rig.CM1, rig.k1, X, Y, Z, o1x, o1y, CANON || rig.ext_identity[0] != 0,
-                                rig.tangential[0] != 0);
-    d2 = reproject_dist<SIMPLE>(rig.R2, rig.t2, rig.CM2, rig.k2, X, Y, Z, o2x, o2y, rig.ext_identity[1] != 0,
-                                rig.tangential[1] != 0);
+    bool ok;
+    double u2x = 0.0, u2y = 0.0;
+    if (CANON) {
+        ok = dlt_null_invpower_canon_rec(rig.CM1, rec, u1x, u1y, h);
+    } else {
+        const double2 q = __ldg(reinterpret_cast<const double2*>(u2));
+        u2x = q.x; u2y = q.y;
+        ok = dlt_null_invpower_n<3>(rig.P1o, rig.P2o, u1x, u1y, u2x, u2y, h);
+    }
+    if (!ok) {
+        if (CANON) {
+            const double2 q = __ldg(reinterpret_cast<const double2*>(u2));
+            u2x = q.x; u2y = q.y;
+        }
+        double xyz[3];
+        dlt_triangulate_fallback(rig, u1x, u1y, u2x, u2y, xyz);
+        h[0] = xyz[0]; h[1] = xyz[1]; h[2] = xyz[2]; h[3] = 1.0;
+    }
+    d1 = reproject_dist_h<SIMPLE>(rig.R1, rig.t1, rig.CM1, rig.k1, h, o1x, o1y, CANON || rig.ext_identity[0] != 0,
+                                  rig.tangential[0] != 0);
+    d2 = reproject_dist_h<SIMPLE>(rig.R2, rig.t2, rig.CM2, rig.k2, h, o2x, o2y, rig.ext_identity[1] != 0,
+                                  rig.tangential[1] != 0);
+}
+
+// match2D.py:895: p[0:3] / p[3]
+__device__ __forceinline__ void dehomogenise(const double (&h)[4], double& X, double& Y, double& Z)
+{
+    const double rw = fast_rcp(h[3]);
+    X = h[0] * rw;
+    Y = h[1] * rw;
+    Z = h[2] * rw;
 }
 
 // match2D.py:913: X_w = rot.apply(X) + trans

@@ -67,6 +67,8 @@ struct CostArgs {
     const double* cam2;
     const double* und1;
     const double* und2;
+    const double2* rec2;  // canonical rigs: k_prep2's record planes of the camera-2 end points (else unused)
+    unsigned rec_stride;  // double2 elements per plane
     const int32_t* n1;
     const int32_t* n2;
     double* cost;      // [P,Nmax,Nmax]
@@ -76,6 +78,49 @@ struct CostArgs {
 };
 
 __device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
+
+// The camera-2 record of the canonical-rig DLT (ptk_device.cuh: canon_prep2), kept in memory as
+// kCanon2RecPlanes planes of double2 indexed by end point e = (problem * Nmax + rod) * 2 + end -- the lanes of
+// a warp read 16 consecutive end points, i.e. two full 128-byte lines per plane.
+__device__ __forceinline__ void rec_store(double2* __restrict__ r, unsigned s, const Canon2Rec& c)
+{
+    r[0] = make_double2(c.p0, c.q0);         r[s] = make_double2(c.p2, c.q2);
+    r[2 * s] = make_double2(c.w0, c.g10);    r[3 * s] = make_double2(c.g12, c.g13);
+    r[4 * s] = make_double2(c.w1, c.g30);    r[5 * s] = make_double2(c.g31, c.g32);
+    r[6 * s] = make_double2(c.g33, c.w3);    r[7 * s] = make_double2(c.r13, c.r03);
+    r[8 * s] = make_double2(c.r01, c.B00);   r[9 * s] = make_double2(c.B01, c.B02);
+    r[10 * s] = make_double2(c.B11, c.B12);
+}
+__device__ __forceinline__ void rec_load(const double2* __restrict__ r, unsigned s, Canon2Rec& c)
+{
+    double2 t;
+    t = __ldg(r);          c.p0 = t.x;  c.q0 = t.y;
+    t = __ldg(r + s);      c.p2 = t.x;  c.q2 = t.y;
+    t = __ldg(r + 2 * s);  c.w0 = t.x;  c.g10 = t.y;
+    t = __ldg(r + 3 * s);  c.g12 = t.x; c.g13 = t.y;
+    t = __ldg(r + 4 * s);  c.w1 = t.x;  c.g30 = t.y;
+    t = __ldg(r + 5 * s);  c.g31 = t.x; c.g32 = t.y;
+    t = __ldg(r + 6 * s);  c.g33 = t.x; c.w3 = t.y;
+    t = __ldg(r + 7 * s);  c.r13 = t.x; c.r03 = t.y;
+    t = __ldg(r + 8 * s);  c.r01 = t.x; c.B00 = t.y;
+    t = __ldg(r + 9 * s);  c.B01 = t.x; c.B02 = t.y;
+    t = __ldg(r + 10 * s); c.B11 = t.x; c.B12 = t.y;
+}
+
+// K0b (canonical rigs): one thread per camera-2 end point, grid = (ceil(2*Nmax/128), P).
+__global__ void __launch_bounds__(128) k_prep2(const __grid_constant__ DevRig rig, int Nmax, const double* __restrict__ und2,
+                                               const int32_t* __restrict__ n2, double2* __restrict__ rec2, unsigned rec_stride)
+{
+    const int p = blockIdx.y;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;  // 2 * rod + end
+    const int n = n2[p];
+    if (n <= 0 || n > Nmax || e >= 2 * n) return;
+    const unsigned idx = (unsigned)p * (unsigned)Nmax * 2u + (unsigned)e;
+    const double2 u = ldg2(und2 + (size_t)idx * 2);
+    Canon2Rec c;
+    canon_prep2(rig.CM1, rig.fx2, rig.P2o, u.x, u.y, c);
+    rec_store(rec2 + idx, rec_stride, c);
+}
 
 // q / n for 0 <= q < 65536, 1 <= n <= 256 without an integer division: (q + 0.5) / n is at least
 // 0.5 / n away from every integer, and its float evaluation with the hardware reciprocal (MUFU.RCP,
@@ -111,11 +156,12 @@ __global__ void __launch_bounds__(128, MINB) k_cost(const __grid_constant__ DevR
     const unsigned base = (unsigned)p * (unsigned)a.Nmax;
     const unsigned off1 = (base + (unsigned)i) * 4u + 2u * e1, off2 = (base + (unsigned)j) * 4u + 2u * e2;
     const double2 u1 = ldg2(a.und1 + off1);
-    const double2 u2 = ldg2(a.und2 + off2);
+    Canon2Rec rec;
+    if (CANON) rec_load(a.rec2 + (off2 >> 1), a.rec_stride, rec);
     const double2 o1 = ldg2(a.cam1 + off1);
     const double2 o2 = ldg2(a.cam2 + off2);
-    double d1, d2, X, Y, Z;
-    eval_combo<CANON, SIMPLE>(rig, u1.x, u1.y, u2.x, u2.y, o1.x, o1.y, o2.x, o2.y, d1, d2, X, Y, Z);
+    double d1, d2, h[4];
+    eval_combo<CANON, SIMPLE>(rig, u1.x, u1.y, a.und2 + off2, rec, o1.x, o1.y, o2.x, o2.y, d1, d2, h);
     // match2D.py:910 np.mean over the two cameras; matchND.py:525 np.sum
     const double e = rig.agg_sum ? (d1 + d2) : (d1 + d2) / 2.0;
     // e0+e3 (straight) lives in lanes 0,3 of the quad, e1+e2 (crossed) in lanes 1,2
@@ -128,7 +174,8 @@ __global__ void __launch_bounds__(128, MINB) k_cost(const __grid_constant__ DevR
             if (a.choice) a.choice[o] = (s_mine <= s_other);  // match2D.py:935-938
         }
         if (a.p_world) {
-            double wx, wy, wz;
+            double X, Y, Z, wx, wy, wz;
+            dehomogenise(h, X, Y, Z);
             to_world(rig, X, Y, Z, wx, wy, wz);
             double* w = a.p_world + (o * 4 + c) * 3;
             w[0] = wx; w[1] = wy; w[2] = wz;
@@ -476,11 +523,17 @@ __global__ void __launch_bounds__(128) k_rows(const __grid_constant__ DevRig rig
     if (!PTK_OK_IDX(i2, a.Nmax, 30)) i2 = 0;  // (debug build) an assignment outside the padded problem
     const int e1 = c >> 1, e2 = c & 1;
     const double2 u1 = ldg2(a.und1 + (base + mm) * 4 + 2 * e1);
-    const double2 u2 = ldg2(a.und2 + (base + i2) * 4 + 2 * e2);
+    const double* u2p = a.und2 + (base + i2) * 4 + 2 * e2;
     const double2 o1 = ldg2(a.cam1 + (base + mm) * 4 + 2 * e1);
     const double2 o2 = ldg2(a.cam2 + (base + i2) * 4 + 2 * e2);
-    double d1, d2, X, Y, Z;
-    eval_combo<CANON, SIMPLE>(rig, u1.x, u1.y, u2.x, u2.y, o1.x, o1.y, o2.x, o2.y, d1, d2, X, Y, Z);
+    Canon2Rec rec;
+    if (CANON) {  // the record K1 read from k_prep2's planes, recomputed by the same function: the same bits
+        const double2 u2 = ldg2(u2p);
+        canon_prep2(rig.CM1, rig.fx2, rig.P2o, u2.x, u2.y, rec);
+    }
+    double d1, d2, h[4], X, Y, Z;
+    eval_combo<CANON, SIMPLE>(rig, u1.x, u1.y, u2p, rec, o1.x, o1.y, o2.x, o2.y, d1, d2, h);
+    dehomogenise(h, X, Y, Z);
     const double e = rig.agg_sum ? (d1 + d2) : (d1 + d2) / 2.0;
     const double s_mine = e + __shfl_xor_sync(kFull, e, 3);
     const double s_other = __shfl_xor_sync(kFull, s_mine, 1);

@@ -28,3 +28,18 @@ extern "C" void tri_invpower_canon_host(const double* cm1 /*fx fy cx cy*/, const
         for (int k = 0; k < 4; k++) { v_canon[4 * m + k] = a[k]; v_general[4 * m + k] = b[k]; }
     }
 }
+
+// Round 2: the canonical variant split into a per-camera-2-point record (canon_prep2) and the per-combination
+// finish (dlt_null_invpower_canon_rec): compared with cv2 and with the unsplit function by the CPU tests.
+extern "C" void tri_invpower_canon_rec_host(const double* cm1 /*fx fy cx cy*/, const double* P2, long long M, const double* pts,
+                                            double* v_rec /*[M,4]*/, int* conv /*[M]*/)
+{
+    const double fx2 = cm1[0] * cm1[0];
+    for (long long m = 0; m < M; m++) {
+        ptk::Canon2Rec r;
+        ptk::canon_prep2(cm1, fx2, P2, pts[4 * m + 2], pts[4 * m + 3], r);
+        double a[4];
+        conv[m] = ptk::dlt_null_invpower_canon_rec(cm1, r, pts[4 * m], pts[4 * m + 1], a) ? 1 : 0;
+        for (int k = 0; k < 4; k++) v_rec[4 * m + k] = a[k];
+    }
+}

@@ -114,3 +114,66 @@ def test_canonical_first_camera_variant_is_bit_identical(harness):
         harness.tri_invpower_canon_host(p(cm1), p(np.ascontiguousarray(P2)), ctypes.c_longlong(M), p(pts), p(va), p(vb), p(conv))
         assert np.array_equal(va.view(np.int64), vb.view(np.int64))
         assert np.array_equal(conv[:, 0], conv[:, 1])
+
+
+def test_canonical_record_variant_matches_cv2_and_the_unsplit_function(harness):
+    """Round 2: K1's canonical instantiation reads the camera-2 share of the DLT from a per-end-point record
+    (`canon_prep2`, computed once per camera-2 end point) and finishes per combination
+    (`dlt_null_invpower_canon_rec`; columns orthogonalised in the order 0, 1, 3, 2).  Another elimination order,
+    so not the unsplit function's bits -- but the same point to rounding accuracy, the same accuracy against
+    cv2.triangulatePoints, and the same convergence verdicts."""
+    sys.path.insert(0, ROOT)
+    from particletracking_b200 import synthetic as syn
+
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    for n, seed, sig, pd in ((32, 2, 0.25, 0.0), (32, 3, 0.0, 0.0), (40, 11, 3.0, 0.05), (64, 5, 0.5, 0.0)):
+        s = syn.make_stereo(2, 1, n, seed, sigma_px=sig, p_dummy=pd)
+        cal = s.calibration
+        P1, P2 = syn.projection_matrices(cal)[:2]
+        CM1 = np.asarray(cal["CM1"], dtype=np.float64)
+        cm1 = np.array([CM1[0, 0], CM1[1, 1], CM1[0, 2], CM1[1, 2]])
+        pts = _combos(s.cam1[0, 0], s.cam2[0, 0])
+        M = len(pts)
+        va, vb, vr = np.empty((M, 4)), np.empty((M, 4)), np.empty((M, 4))
+        conv = np.empty((M, 2), np.int32)
+        convr = np.empty(M, np.int32)
+        P2c = np.ascontiguousarray(P2)
+        harness.tri_invpower_canon_host(p(cm1), p(P2c), ctypes.c_longlong(M), p(pts), p(va), p(vb), p(conv))
+        harness.tri_invpower_canon_rec_host(p(cm1), p(P2c), ctypes.c_longlong(M), p(pts), p(vr), p(convr))
+        assert np.array_equal(convr, conv[:, 0]) and convr.all()
+        ref = _cv2(P1, P2, pts)
+        Xr, Xa = vr[:, :3] / vr[:, 3:], va[:, :3] / va[:, 3:]
+        scale = np.abs(ref).max(axis=1)
+        assert (np.abs(Xr - ref).max(axis=1) / scale).max() < 1e-13  # measured 1.5e-15
+        assert (np.abs(Xr - Xa).max(axis=1) / scale).max() < 1e-13
+
+
+def test_canonical_record_variant_flags_near_degenerate_points(harness):
+    """Baseline shrunk x1000: the record variant must hand the same points to the fallback as the general
+    function's three-squaring test does (the verdict depends on the spectrum, not on the elimination order)."""
+    sys.path.insert(0, ROOT)
+    from particletracking_b200 import synthetic as syn
+
+    s = syn.make_stereo(2, 1, 24, 77)
+    cal = dict(s.calibration)
+    cal["R"] = np.eye(3)
+    cal["T"] = np.asarray(cal["T"], dtype=np.float64) * 1e-3
+    P1, P2 = syn.projection_matrices(cal)[:2]
+    CM1 = np.asarray(cal["CM1"], dtype=np.float64)
+    cm1 = np.array([CM1[0, 0], CM1[1, 1], CM1[0, 2], CM1[1, 2]])
+    pts = _combos(s.cam1[0, 0], s.cam2[0, 0])
+    M = len(pts)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    va, vb, vr = np.empty((M, 4)), np.empty((M, 4)), np.empty((M, 4))
+    conv = np.empty((M, 2), np.int32)
+    convr = np.empty(M, np.int32)
+    P2c = np.ascontiguousarray(P2)
+    harness.tri_invpower_canon_host(p(cm1), p(P2c), ctypes.c_longlong(M), p(pts), p(va), p(vb), p(conv))
+    harness.tri_invpower_canon_rec_host(p(cm1), p(P2c), ctypes.c_longlong(M), p(pts), p(vr), p(convr))
+    assert 0.03 < (convr == 0).mean() < 0.9
+    assert (convr != conv[:, 0]).mean() < 0.01  # borderline points may flip with the rounding
+    ok = (convr == 1) & (conv[:, 0] == 1)
+    ref = _cv2(P1, P2, pts)
+    Xr = vr[:, :3] / vr[:, 3:]
+    err = np.abs(Xr - ref).max(axis=1) / np.abs(ref).max(axis=1)
+    assert err[ok].max() < 1e-9
