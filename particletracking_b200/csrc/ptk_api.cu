@@ -205,7 +205,8 @@ struct MatchWs {
 
 inline size_t rec2_bytes(long long chunk, int Nmax)
 {
-    return (size_t)kCanon2RecPlanes * (size_t)chunk * Nmax * 2 * sizeof(double2);
+    const size_t blocks = ((size_t)chunk * Nmax * 2 + kRecBlock - 1) / kRecBlock;  // see rec_index (ptk_kernels.cuh)
+    return blocks * kRecBlock * kCanon2RecPlanes * sizeof(double2);
 }
 
 MatchWs carve_match(void* ws, long long chunk, int Nmax, bool need_cost)
@@ -248,22 +249,22 @@ int launch_cost(const DevRig& rig, long long P, int Nmax, const double* cam1, co
     CostArgs a;
     a.Nmax = Nmax;
     a.tiles = (Nmax * Nmax + 31) / 32;
-    a.rec_stride = (unsigned)((size_t)P * Nmax * 2);
     if (rig.canon && !rec2) return PTK_ERR_INVALID_ARG;
-    // grid = (tiles, problems): gridDim.y holds 65535
-    const long long max_p = 65535;
+    // grid = (tiles, problems): gridDim.y holds 65535; slices start on a multiple of 8 problems so that a
+    // slice's end points start on a record block
+    const long long max_p = 65528;
     for (long long p0 = 0; p0 < P; p0 += max_p) {
         const long long np = (P - p0) < max_p ? (P - p0) : max_p;
         const size_t o4 = (size_t)p0 * Nmax * 4, o2 = (size_t)p0 * Nmax * Nmax;
         a.cam1 = cam1 + o4; a.cam2 = cam2 + o4; a.und1 = und1 + o4; a.und2 = und2 + o4;
-        a.rec2 = rec2 ? rec2 + (size_t)p0 * Nmax * 2 : nullptr;
+        a.rec2 = rec2 ? rec2 + rec_index((size_t)p0 * Nmax * 2) : nullptr;
         a.n1 = n1 + p0; a.n2 = n2 + p0;
         a.cost = cost + o2;
         if (rig.canon) {  // K0b: the camera-2 share of the DLT, once per end point (ptk_device.cuh: canon_prep2)
             const dim3 pgrid((2 * Nmax + 127) / 128, (unsigned)np);
             {
                 LaunchTimer lt(K_UNDISTORT, st);
-                k_prep2<<<pgrid, 128, 0, st>>>(rig, Nmax, a.und2, a.n2, const_cast<double2*>(a.rec2), a.rec_stride);
+                k_prep2<<<pgrid, 128, 0, st>>>(rig, Nmax, a.und2, a.n2, const_cast<double2*>(a.rec2));
             }
             LAUNCHED("k_prep2");
         }

@@ -369,7 +369,9 @@ static inline double ptk_pow2_inv(double x)
 // The power iteration on B = (A^T A)^-1 (symmetric, given by its upper triangle): scaling by a power of
 // two, NSQ symmetric squarings, the convergence check and the final product with the largest-diagonal
 // column.  Returns whether the iteration has converged.
-template <int NSQ>
+// LAST_FIRST: the caller expects the last diagonal entry to be the largest (the record variant, whose last
+// column carries the depth): that column is then taken on a branch without any select.
+template <int NSQ, bool LAST_FIRST = false>
 PTK_HD bool dlt_invpower_core(double b00, double b01, double b02, double b03, double b11, double b12, double b13,
                               double b22, double b23, double b33, double (&v)[4])
 {
@@ -406,6 +408,13 @@ PTK_HD bool dlt_invpower_core(double b00, double b01, double b02, double b03, do
     const double fr = fma(2.0, od, fma(b33, b33, fma(b22, b22, fma(b11, b11, b00 * b00))));
     const bool ok = fma(-(1.0 - PTK_INVPOWER_TOL), tr * tr, fr) >= 0.0;
     // v = B^k (column of B^k with the largest diagonal entry: |v_4[j]|^2 >= 1/4 there)
+    if (LAST_FIRST && b33 >= b00 && b33 >= b11 && b33 >= b22) {
+        v[0] = fma(b03, b33, fma(b02, b23, fma(b01, b13, b00 * b03)));
+        v[1] = fma(b13, b33, fma(b12, b23, fma(b11, b13, b01 * b03)));
+        v[2] = fma(b23, b33, fma(b22, b23, fma(b12, b13, b02 * b03)));
+        v[3] = fma(b33, b33, fma(b23, b23, fma(b13, b13, b03 * b03)));
+        return ok;
+    }
     double u0 = b00, u1 = b01, u2 = b02, u3 = b03, dm = b00;
     if (b11 > dm) { dm = b11; u0 = b01; u1 = b11; u2 = b12; u3 = b13; }
     if (b22 > dm) { dm = b22; u0 = b02; u1 = b12; u2 = b22; u3 = b23; }
@@ -592,7 +601,7 @@ PTK_HD bool dlt_null_invpower_canon_rec(const double* __restrict__ cm1, const Ca
     const double t03 = fma(r.r03, r32, -fma(r.r01, t13, r02));
     const double c03 = t03 * w2, c13 = t13 * w2, c23 = -r32 * w2;
     double u[4];
-    const bool ok = dlt_invpower_core<3>(fma(t03, c03, r.B00), fma(t03, c13, r.B01), fma(t03, c23, r.B02), c03,
+    const bool ok = dlt_invpower_core<3, true>(fma(t03, c03, r.B00), fma(t03, c13, r.B01), fma(t03, c23, r.B02), c03,
                                          fma(t13, c13, r.B11), fma(t13, c23, r.B12), c13, fma(-r32, c23, r.w3), c23, w2, u);
     v[0] = u[0]; v[1] = u[1]; v[2] = u[3]; v[3] = u[2];
     return ok;
@@ -737,7 +746,9 @@ __device__ __forceinline__ double reproject_dist_h(const double* __restrict__ R,
     // path.  The range test is on the exponent bits (ALU pipe, idle here) instead of two DSETPs on the
     // FP64 pipe that bounds the kernel: biased exponent in [27, 2019], i.e. 2^-996 <= q < 2^997 (q >= 0).
     const unsigned ex11 = ((unsigned)__double2hiint(q) >> 20) - 27u;
-    return (ex11 < 1993u) ? q * rsqrt_refine(q, rsqrt_seed(q)) : sqrt(q);
+    double d = q * rsqrt_refine(q, rsqrt_seed(q));
+    if (__builtin_expect(!(ex11 < 1993u), 0)) d = sqrt(q);
+    return d;
 }
 
 // One end-point combination (match2D.py:889-913): triangulate the undistorted pair, reproject into both

@@ -67,8 +67,7 @@ struct CostArgs {
     const double* cam2;
     const double* und1;
     const double* und2;
-    const double2* rec2;  // canonical rigs: k_prep2's record planes of the camera-2 end points (else unused)
-    unsigned rec_stride;  // double2 elements per plane
+    const double2* rec2;  // canonical rigs: k_prep2's records of the camera-2 end points (else unused)
     const int32_t* n1;
     const int32_t* n2;
     double* cost;      // [P,Nmax,Nmax]
@@ -79,37 +78,43 @@ struct CostArgs {
 
 __device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
 
-// The camera-2 record of the canonical-rig DLT (ptk_device.cuh: canon_prep2), kept in memory as
-// kCanon2RecPlanes planes of double2 indexed by end point e = (problem * Nmax + rod) * 2 + end -- the lanes of
-// a warp read 16 consecutive end points, i.e. two full 128-byte lines per plane.
-__device__ __forceinline__ void rec_store(double2* __restrict__ r, unsigned s, const Canon2Rec& c)
+// The camera-2 record of the canonical-rig DLT (ptk_device.cuh: canon_prep2) in memory: end points
+// e = (problem * Nmax + rod) * 2 + end are grouped in blocks of 16; a block holds kCanon2RecPlanes planes of
+// 16 double2 (256 bytes each).  A warp of K1 reads 16 consecutive end points, i.e. one or two full 256-byte
+// runs per plane, and a thread's eleven 16-byte loads share ONE address register (the plane is an immediate
+// offset) -- with separate plane arrays every load needed its own 64-bit address (five integer instructions
+// each on the half-rate ALU pipe, which undid half of the gain; profiles/README.md).
+constexpr unsigned kRecBlock = 16;
+__host__ __device__ inline size_t rec_index(size_t e) { return (e / kRecBlock) * (kRecBlock * kCanon2RecPlanes) + (e % kRecBlock); }
+
+__device__ __forceinline__ void rec_store(double2* __restrict__ r, const Canon2Rec& c)
 {
-    r[0] = make_double2(c.p0, c.q0);         r[s] = make_double2(c.p2, c.q2);
-    r[2 * s] = make_double2(c.w0, c.g10);    r[3 * s] = make_double2(c.g12, c.g13);
-    r[4 * s] = make_double2(c.w1, c.g30);    r[5 * s] = make_double2(c.g31, c.g32);
-    r[6 * s] = make_double2(c.g33, c.w3);    r[7 * s] = make_double2(c.r13, c.r03);
-    r[8 * s] = make_double2(c.r01, c.B00);   r[9 * s] = make_double2(c.B01, c.B02);
-    r[10 * s] = make_double2(c.B11, c.B12);
+    r[0 * kRecBlock] = make_double2(c.p0, c.q0);    r[1 * kRecBlock] = make_double2(c.p2, c.q2);
+    r[2 * kRecBlock] = make_double2(c.w0, c.g10);   r[3 * kRecBlock] = make_double2(c.g12, c.g13);
+    r[4 * kRecBlock] = make_double2(c.w1, c.g30);   r[5 * kRecBlock] = make_double2(c.g31, c.g32);
+    r[6 * kRecBlock] = make_double2(c.g33, c.w3);   r[7 * kRecBlock] = make_double2(c.r13, c.r03);
+    r[8 * kRecBlock] = make_double2(c.r01, c.B00);  r[9 * kRecBlock] = make_double2(c.B01, c.B02);
+    r[10 * kRecBlock] = make_double2(c.B11, c.B12);
 }
-__device__ __forceinline__ void rec_load(const double2* __restrict__ r, unsigned s, Canon2Rec& c)
+__device__ __forceinline__ void rec_load(const double2* __restrict__ r, Canon2Rec& c)
 {
     double2 t;
-    t = __ldg(r);          c.p0 = t.x;  c.q0 = t.y;
-    t = __ldg(r + s);      c.p2 = t.x;  c.q2 = t.y;
-    t = __ldg(r + 2 * s);  c.w0 = t.x;  c.g10 = t.y;
-    t = __ldg(r + 3 * s);  c.g12 = t.x; c.g13 = t.y;
-    t = __ldg(r + 4 * s);  c.w1 = t.x;  c.g30 = t.y;
-    t = __ldg(r + 5 * s);  c.g31 = t.x; c.g32 = t.y;
-    t = __ldg(r + 6 * s);  c.g33 = t.x; c.w3 = t.y;
-    t = __ldg(r + 7 * s);  c.r13 = t.x; c.r03 = t.y;
-    t = __ldg(r + 8 * s);  c.r01 = t.x; c.B00 = t.y;
-    t = __ldg(r + 9 * s);  c.B01 = t.x; c.B02 = t.y;
-    t = __ldg(r + 10 * s); c.B11 = t.x; c.B12 = t.y;
+    t = __ldg(r + 0 * kRecBlock);  c.p0 = t.x;  c.q0 = t.y;
+    t = __ldg(r + 1 * kRecBlock);  c.p2 = t.x;  c.q2 = t.y;
+    t = __ldg(r + 2 * kRecBlock);  c.w0 = t.x;  c.g10 = t.y;
+    t = __ldg(r + 3 * kRecBlock);  c.g12 = t.x; c.g13 = t.y;
+    t = __ldg(r + 4 * kRecBlock);  c.w1 = t.x;  c.g30 = t.y;
+    t = __ldg(r + 5 * kRecBlock);  c.g31 = t.x; c.g32 = t.y;
+    t = __ldg(r + 6 * kRecBlock);  c.g33 = t.x; c.w3 = t.y;
+    t = __ldg(r + 7 * kRecBlock);  c.r13 = t.x; c.r03 = t.y;
+    t = __ldg(r + 8 * kRecBlock);  c.r01 = t.x; c.B00 = t.y;
+    t = __ldg(r + 9 * kRecBlock);  c.B01 = t.x; c.B02 = t.y;
+    t = __ldg(r + 10 * kRecBlock); c.B11 = t.x; c.B12 = t.y;
 }
 
 // K0b (canonical rigs): one thread per camera-2 end point, grid = (ceil(2*Nmax/128), P).
 __global__ void __launch_bounds__(128) k_prep2(const __grid_constant__ DevRig rig, int Nmax, const double* __restrict__ und2,
-                                               const int32_t* __restrict__ n2, double2* __restrict__ rec2, unsigned rec_stride)
+                                               const int32_t* __restrict__ n2, double2* __restrict__ rec2)
 {
     const int p = blockIdx.y;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;  // 2 * rod + end
@@ -119,7 +124,7 @@ __global__ void __launch_bounds__(128) k_prep2(const __grid_constant__ DevRig ri
     const double2 u = ldg2(und2 + (size_t)idx * 2);
     Canon2Rec c;
     canon_prep2(rig.CM1, rig.fx2, rig.P2o, u.x, u.y, c);
-    rec_store(rec2 + idx, rec_stride, c);
+    rec_store(rec2 + (idx / kRecBlock) * (kRecBlock * kCanon2RecPlanes) + (idx % kRecBlock), c);
 }
 
 // q / n for 0 <= q < 65536, 1 <= n <= 256 without an integer division: (q + 0.5) / n is at least
@@ -157,7 +162,10 @@ __global__ void __launch_bounds__(128, MINB) k_cost(const __grid_constant__ DevR
     const unsigned off1 = (base + (unsigned)i) * 4u + 2u * e1, off2 = (base + (unsigned)j) * 4u + 2u * e2;
     const double2 u1 = ldg2(a.und1 + off1);
     Canon2Rec rec;
-    if (CANON) rec_load(a.rec2 + (off2 >> 1), a.rec_stride, rec);
+    if (CANON) {
+        const unsigned e = off2 >> 1;  // end point index (problem * Nmax + rod) * 2 + end
+        rec_load(a.rec2 + ((e / kRecBlock) * (kRecBlock * kCanon2RecPlanes) + (e % kRecBlock)), rec);
+    }
     const double2 o1 = ldg2(a.cam1 + off1);
     const double2 o2 = ldg2(a.cam2 + off2);
     double d1, d2, h[4];
