@@ -143,6 +143,7 @@ DevRig make_devrig(const ptk_rig* r)
     memcpy(d.Rw, r->Rw, sizeof(d.Rw));
     memcpy(d.tw, r->tw, sizeof(d.tw));
     d.agg_sum = r->agg_sum;
+    d.agg_scale = r->agg_sum ? 1.0 : 0.5;
     const double eye[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     const double* Rs[2] = {r->R1, r->R2};
     const double* ts[2] = {r->t1, r->t2};
@@ -276,7 +277,23 @@ int launch_cost(const DevRig& rig, long long P, int Nmax, const double* cam1, co
             LaunchTimer lt(K_COST, st);
             // the rig class picks the instantiation (same bits from every one of them, see eval_combo)
             static const int mb = getenv("PTK_KCOST_CFG") ? atoi(getenv("PTK_KCOST_CFG")) : 0;  // tuning knob
-            if (rig.canon && rig.simple && mb == 4) k_cost<true, true, 4><<<grid, 128, 0, st>>>(rig, a);
+            static const int rows_env = getenv("PTK_KCOST_ROWS") ? atoi(getenv("PTK_KCOST_ROWS")) : 16;  // 0: tile kernel
+            if (rig.canon && rows_env > 0 && (mb == 0 || mb >= 14)) {
+                RowsLoopArgs la;
+                la.rows_per = rows_env > kRowsMax ? kRowsMax : rows_env;
+                if (Nmax <= 32) {
+                    const dim3 g((unsigned)((Nmax + la.rows_per - 1) / la.rows_per), (unsigned)np, 1);
+                    if (rig.simple && mb == 15) k_cost_rows<true, 32, 5><<<g, 128, 0, st>>>(rig, a, la);
+                    else if (rig.simple && mb == 14) k_cost_rows<true, 32, 4><<<g, 128, 0, st>>>(rig, a, la);
+                    else if (rig.simple) k_cost_rows<true, 32, 6><<<g, 128, 0, st>>>(rig, a, la);
+                    else k_cost_rows<false, 32, 6><<<g, 128, 0, st>>>(rig, a, la);
+                } else {
+                    const dim3 g((unsigned)((Nmax + la.rows_per - 1) / la.rows_per), (unsigned)np, (unsigned)((Nmax + 63) / 64));
+                    if (rig.simple) k_cost_rows<true, 64, 6><<<g, 128, 0, st>>>(rig, a, la);
+                    else k_cost_rows<false, 64, 6><<<g, 128, 0, st>>>(rig, a, la);
+                }
+            }
+            else if (rig.canon && rig.simple && mb == 4) k_cost<true, true, 4><<<grid, 128, 0, st>>>(rig, a);
             else if (rig.canon && rig.simple && mb == 5) k_cost<true, true, 5><<<grid, 128, 0, st>>>(rig, a);
             else if (rig.canon && rig.simple && mb == 7) k_cost<true, true, 7><<<grid, 128, 0, st>>>(rig, a);
             else if (rig.canon && rig.simple && mb == 8) k_cost<true, true, 8><<<grid, 128, 0, st>>>(rig, a);

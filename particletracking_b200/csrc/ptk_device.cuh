@@ -30,6 +30,7 @@ struct DevRig {
     double k1[12], k2[12];  // k1 k2 p1 p2 k3 k4 k5 k6 s1 s2 s3 s4
     double Rw[9], tw[3];
     int agg_sum;
+    double agg_scale;     // 1 (agg_sum: matchND.py:525 np.sum) or 0.5 (match2D.py:910 np.mean; x * 0.5 == x / 2.0 exactly)
     // rig-constant shortcuts for the projection (set by make_devrig; warp-uniform branches):
     int ext_identity[2];  // camera k has R = I, t = 0 (camera 1 of a stereo rig)
     int tangential[2];    // camera k has any of p1, p2, s1..s4 non-zero
@@ -336,13 +337,13 @@ __device__ __forceinline__ void dlt_triangulate_jacobi(const DevRig& rig, double
 // (not of A^T A), so the vector is as accurate as the one-sided Jacobi's: max 1.8e-15 relative on
 // the triangulated point against cv2.triangulatePoints over 1.1 M combinations.
 //
-// Convergence is CHECKED, not assumed: with C = B^8 / tr(B^8), 1 - tr(C^2) ~ 2 rho^8.  A point
-// with rho^8 > 2.5e-7 (sigma_4/sigma_3 > 0.39) gets one more squaring and the same test on B^16
+// Convergence is CHECKED, not assumed: tr(B^8) / tr(B^4)^2 ~ 1 - 2 rho^4.  A point with rho^4 > 5e-4
+// (sigma_4/sigma_3 > 0.39) gets one more squaring and the same test on tr(B^16) / tr(B^8)^2
 // (good up to sigma_4/sigma_3 = 0.62); beyond that (near-degenerate geometry), or if R is singular
 // (NaN), the function reports false and the caller falls back to the Jacobi, which reproduces
 // OpenCV there.
 // ---------------------------------------------------------------------------------------
-#define PTK_INVPOWER_TOL 5e-7
+#define PTK_INVPOWER_TOL 1e-3
 
 #if defined(__CUDA_ARCH__)
 __device__ __forceinline__ double ptk_rsqrt(double x) { return rsqrt_refine(x, rsqrt_seed(x)); }
@@ -371,11 +372,14 @@ static inline double ptk_pow2_inv(double x)
 // column.  Returns whether the iteration has converged.
 // LAST_FIRST: the caller expects the last diagonal entry to be the largest (the record variant, whose last
 // column carries the depth): that column is then taken on a branch without any select.
-template <int NSQ, bool LAST_FIRST = false>
+// SCALE: B is first scaled by a power of two so that its trace is in [1, 2) (the record variant passes
+// B / w2 whose trace is 1 + |z|^2 + small and needs none; absurd magnitudes overflow to Inf / NaN, which the
+// convergence test reports as "not converged").
+template <int NSQ, bool LAST_FIRST = false, bool SCALE = true>
 PTK_HD bool dlt_invpower_core(double b00, double b01, double b02, double b03, double b11, double b12, double b13,
                               double b22, double b23, double b33, double (&v)[4])
 {
-    {
+    if (SCALE) {
         const double sc = ptk_pow2_inv((b00 + b11) + (b22 + b33));
         b00 *= sc; b01 *= sc; b02 *= sc; b03 *= sc; b11 *= sc;
         b12 *= sc; b13 *= sc; b22 *= sc; b23 *= sc; b33 *= sc;
@@ -395,18 +399,20 @@ PTK_HD bool dlt_invpower_core(double b00, double b01, double b02, double b03, do
         b00 = c00; b01 = c01; b02 = c02; b03 = c03; b11 = c11;                           \
         b12 = c12; b13 = c13; b22 = c22; b23 = c23; b33 = c33;                           \
     }
-    PTK_SQUARE_B PTK_SQUARE_B PTK_SQUARE_B
+    PTK_SQUARE_B PTK_SQUARE_B
     // sigma_4/sigma_3 between 0.39 and 0.62 (geometry unlike a rod experiment's): one more squaring, B^16
     // and B^32 e_j below.  tr(B^8) is within 2^-32 .. 2^16, so its square neither overflows nor underflows.
     if (NSQ > 3) PTK_SQUARE_B
+    const double trh = (b00 + b11) + (b22 + b33);  // tr(B^(k/2))
+    PTK_SQUARE_B
 #undef PTK_SQUARE_B
-    // converged?  |B^k|_F^2 >= (1 - tol) tr(B^k)^2, written as fr - (1 - tol) tr^2 >= 0 so that Inf - Inf
-    // (a Gram-Schmidt norm that underflowed) is NaN and therefore NOT converged: the caller then takes
-    // the Jacobi fallback
+    // converged?  With k = 2^NSQ: tr(B^k) = |B^(k/2)|_F^2 >= (1 - tol) tr(B^(k/2))^2, i.e. 2 rho^(k/2) <= tol, rho =
+    // (sigma_4/sigma_3)^2 -- the trace of the last square against the squared trace before it, six additions
+    // instead of a Frobenius norm.  Written as tr - (1 - tol) trh^2 >= 0 so that Inf - Inf (a Gram-Schmidt norm
+    // that underflowed, an overflow in the squarings) is NaN and therefore NOT converged: the caller then takes
+    // the Jacobi fallback.
     const double tr = (b00 + b11) + (b22 + b33);
-    const double od = fma(b23, b23, fma(b13, b13, fma(b12, b12, fma(b03, b03, fma(b02, b02, b01 * b01)))));
-    const double fr = fma(2.0, od, fma(b33, b33, fma(b22, b22, fma(b11, b11, b00 * b00))));
-    const bool ok = fma(-(1.0 - PTK_INVPOWER_TOL), tr * tr, fr) >= 0.0;
+    const bool ok = fma(-(1.0 - PTK_INVPOWER_TOL), trh * trh, tr) >= 0.0;
     // v = B^k (column of B^k with the largest diagonal entry: |v_4[j]|^2 >= 1/4 there)
     if (LAST_FIRST && b33 >= b00 && b33 >= b11 && b33 >= b22) {
         v[0] = fma(b03, b33, fma(b02, b23, fma(b01, b13, b00 * b03)));
@@ -522,27 +528,27 @@ PTK_HD bool dlt_null_invpower_canon(const double* __restrict__ cm1, double fx2, 
 // ---------------------------------------------------------------------------------------
 // Canonical first camera, with the work that depends on the camera-2 point alone taken out of the
 // per-combination path (round 2).  Of the four DLT columns above only a2 = (x1-cx, y1-cy, p2, q2) contains
-// the camera-1 point.  Orthogonalising in the order a0, a1, a3, a2 therefore makes the first three
-// Gram-Schmidt vectors, their reciprocal norms, the leading 3x3 block of T = R~^-1 and that block's share of
-// B = T diag(w) T^T functions of (x2, y2) only: `canon_prep2` computes them ONCE per camera-2 end point
-// (2 N2 per problem, kernel k_prep2) into a 22-double record, and a combination only projects its own column
-// a2 against the three stored vectors and adds the rank-one term of the last pivot:
-//     B = [B3 0; 0 0] + w2 z z^T,   z = (t03, t13, t23, 1)   (in the order 0, 1, 3, 2)
-// -- 46 FP64 instructions per combination instead of 103 for the QR and B.  The power iteration is the same;
-// the null vector comes back in the caller's column order.  Same accuracy against cv2.triangulatePoints as the
-// functions above (tests/test_dlt_invpower_cpu.py); the bits differ from theirs (another elimination order),
-// so K1 and K3 -- which must agree bit for bit -- both go through prep + finish, K1 with the record read from
-// memory and K3 with the record computed in place by the same function.
+// the camera-1 point, and it is AFFINE in it: a2 = gx e0 + gy e1 + d, d = (0, 0, p2, q2).  Orthogonalising in
+// the order a0, a1, a3, a2 makes the first three Gram-Schmidt vectors g0, g1, g3, their norms, the leading 3x3
+// block of T = R~^-1 and that block's share B3 of B = T diag(w) T^T functions of (x2, y2) only, and what
+// remains per combination is linear algebra on fixed operators applied to (gx, gy, 1):
+//     z = Zm (gx, gy, 1)      the last column of T (order 0, 1, 3, 2; its fourth entry is 1),
+//     a = Am (gx, gy, 1)      the residual of a2 after the three projections,  n2 = |a|^2,
+//     B / w2 = z z^T + n2 [B3 0; 0 0]                          (w2 = 1 / n2, the last pivot)
+// `canon_prep2` computes Zm (3x3), Am (4x3) and B3 (6) ONCE per camera-2 end point (2 N2 per problem, kernel
+// k_prep2) by running the Gram-Schmidt step on e0, e1 and d separately; a combination then costs 32 FP64
+// instructions up to B instead of 103, needs no reciprocal (B is used divided by w2: same eigenvectors) and no
+// power-of-two scaling (tr(B / w2) = 1 + |z|^2 + small).  The power iteration is the same; the null vector
+// comes back in the caller's column order.  Same accuracy against cv2.triangulatePoints as the functions
+// above (tests/test_dlt_invpower_cpu.py); the bits differ from theirs (another elimination order), so K1 and
+// K3 -- which must agree bit for bit -- both go through prep + finish, K1 with the record read from memory
+// and K3 with the record computed in place by the same function.
 // ---------------------------------------------------------------------------------------
 struct Canon2Rec {
-    double p0, q0, p2, q2;        // camera-2 halves of columns 0 and 2
-    double w0, g10, g12, g13;     // 1/|g0|^2; g1 = (g10, -fy, g12, g13)
-    double w1, g30, g31, g32;     // 1/|g1|^2; g3 = (g30, g31, g32, g33)
-    double g33, w3, r13, r03;     // 1/|g3|^2; R~ entries among the stored columns
-    double r01, B00, B01, B02;    // the stored columns' share of B (B22 = w3)
-    double B11, B12;
+    // f[0..8]: Zm by columns (gx | gy | 1), f[9..20]: Am by columns, f[21..26]: B00 B01 B02 B11 B12 B22, f[27] unused
+    double f[28];
 };
-constexpr int kCanon2RecPlanes = 11;  // double2 planes of the record in memory (structure of arrays)
+constexpr int kCanon2RecPlanes = 14;  // double2 planes of the record in memory
 
 PTK_HD void canon_prep2(const double* __restrict__ cm1, double fx2, const double* __restrict__ Q2, double x2, double y2,
                         Canon2Rec& r)
@@ -550,59 +556,69 @@ PTK_HD void canon_prep2(const double* __restrict__ cm1, double fx2, const double
     const double fx = cm1[0], fy = cm1[1];
     const double p0 = fma(x2, Q2[8], -Q2[0]), q0 = fma(y2, Q2[8], -Q2[4]);
     const double p1 = fma(x2, Q2[9], -Q2[1]), q1 = fma(y2, Q2[9], -Q2[5]);
+    const double p2 = fma(x2, Q2[10], -Q2[2]), q2 = fma(y2, Q2[10], -Q2[6]);
     const double p3 = fma(x2, Q2[11], -Q2[3]), q3 = fma(y2, Q2[11], -Q2[7]);
-    r.p0 = p0; r.q0 = q0;
-    r.p2 = fma(x2, Q2[10], -Q2[2]); r.q2 = fma(y2, Q2[10], -Q2[6]);
     // g0 = a0 = (-fx, 0, p0, q0)
+    const double g0[4] = {-fx, 0.0, p0, q0};
     const double w0 = ptk_rcp(fma(q0, q0, fma(p0, p0, fx2)));
     const double r01 = fma(q0, q1, p0 * p1) * w0;
     const double r03 = fma(q0, q3, p0 * p3) * w0;
     // g1 = a1 - r01 g0,  a3' = a3 - r03 g0
-    const double g10 = r01 * fx, g12 = fma(-r01, p0, p1), g13 = fma(-r01, q0, q1);
+    const double g1[4] = {r01 * fx, -fy, fma(-r01, p0, p1), fma(-r01, q0, q1)};
     const double a30 = r03 * fx, a32 = fma(-r03, p0, p3), a33 = fma(-r03, q0, q3);
-    const double w1 = ptk_rcp(fma(g13, g13, fma(g12, g12, fma(fy, fy, g10 * g10))));
-    const double r13 = fma(g13, a33, fma(g12, a32, g10 * a30)) * w1;
+    const double w1 = ptk_rcp(PTK_DOT(g1, g1));
+    const double r13 = fma(g1[3], a33, fma(g1[2], a32, g1[0] * a30)) * w1;
     // g3 = a3' - r13 g1
-    const double g30 = fma(-r13, g10, a30), g31 = r13 * fy, g32 = fma(-r13, g12, a32), g33 = fma(-r13, g13, a33);
-    const double w3 = ptk_rcp(fma(g33, g33, fma(g32, g32, fma(g31, g31, g30 * g30))));
-    r.w0 = w0; r.g10 = g10; r.g12 = g12; r.g13 = g13;
-    r.w1 = w1; r.g30 = g30; r.g31 = g31; r.g32 = g32;
-    r.g33 = g33; r.w3 = w3; r.r13 = r13; r.r03 = r03;
-    r.r01 = r01;
-    // leading block of T (order 0, 1, 3): t01 = -r01, t13' = -r13, t03' = r01 r13 - r03; B3 = T3 diag(w0, w1, w3) T3^T
+    const double g3[4] = {fma(-r13, g1[0], a30), r13 * fy, fma(-r13, g1[2], a32), fma(-r13, g1[3], a33)};
+    const double w3 = ptk_rcp(PTK_DOT(g3, g3));
+    // the Gram-Schmidt step of the last column, applied to e0, e1 and d = (0, 0, p2, q2): residual and the
+    // column's entries of R~ (r02, r12, r32), from which the last column of T:
+    //   t23 = -r32,  t13 = r13 r32 - r12,  t03 = r03 r32 - (r01 t13 + r02)
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        double b[4] = {c == 0 ? 1.0 : 0.0, c == 1 ? 1.0 : 0.0, c == 2 ? p2 : 0.0, c == 2 ? q2 : 0.0};
+        const double ra = PTK_DOT(g0, b) * w0;
+        PTK_AXPY(b, ra, g0)
+        const double rb = PTK_DOT(g1, b) * w1;
+        PTK_AXPY(b, rb, g1)
+        const double rc = PTK_DOT(g3, b) * w3;
+        PTK_AXPY(b, rc, g3)
+        const double t13 = fma(r13, rc, -rb);
+        r.f[3 * c + 0] = fma(r03, rc, -fma(r01, t13, ra));
+        r.f[3 * c + 1] = t13;
+        r.f[3 * c + 2] = -rc;
+        r.f[9 + 4 * c + 0] = b[0]; r.f[9 + 4 * c + 1] = b[1]; r.f[9 + 4 * c + 2] = b[2]; r.f[9 + 4 * c + 3] = b[3];
+    }
+    // leading block of T (order 0, 1, 3): t01 = -r01, t12' = -r13, t02' = r01 r13 - r03; B3 = T3 diag(w0, w1, w3) T3^T
     const double t02 = fma(r01, r13, -r03);
     const double c01 = -r01 * w1, c02 = t02 * w3, c12 = -r13 * w3;
-    r.B00 = fma(t02, c02, fma(-r01, c01, w0));
-    r.B01 = fma(t02, c12, c01);
-    r.B02 = c02;
-    r.B11 = fma(-r13, c12, w1);
-    r.B12 = c12;
+    r.f[21] = fma(t02, c02, fma(-r01, c01, w0));
+    r.f[22] = fma(t02, c12, c01);
+    r.f[23] = c02;
+    r.f[24] = fma(-r13, c12, w1);
+    r.f[25] = c12;
+    r.f[26] = w3;
+    r.f[27] = 0.0;
 }
 
 // cm1 = (fx, fy, cx, cy); r = canon_prep2 of the camera-2 point; (x1, y1) the camera-1 point.
 PTK_HD bool dlt_null_invpower_canon_rec(const double* __restrict__ cm1, const Canon2Rec& r, double x1, double y1,
                                         double (&v)[4])
 {
-    const double fx = cm1[0], fy = cm1[1];
     const double gx = x1 - cm1[2], gy = y1 - cm1[3];
-    // a2 = (gx, gy, p2, q2) against g0 = (-fx, 0, p0, q0)
-    const double r02 = fma(r.q0, r.q2, fma(r.p0, r.p2, -fx * gx)) * r.w0;
+    const double z0 = fma(r.f[0], gx, fma(r.f[3], gy, r.f[6]));
+    const double z1 = fma(r.f[1], gx, fma(r.f[4], gy, r.f[7]));
+    const double z2 = fma(r.f[2], gx, fma(r.f[5], gy, r.f[8]));
     double a[4];
-    a[0] = fma(r02, fx, gx); a[1] = gy; a[2] = fma(-r02, r.p0, r.p2); a[3] = fma(-r02, r.q0, r.q2);
-    // ... against g1 = (g10, -fy, g12, g13)
-    const double r12 = fma(r.g13, a[3], fma(r.g12, a[2], fma(-fy, a[1], r.g10 * a[0]))) * r.w1;
-    a[0] = fma(-r12, r.g10, a[0]); a[1] = fma(r12, fy, a[1]); a[2] = fma(-r12, r.g12, a[2]); a[3] = fma(-r12, r.g13, a[3]);
-    // ... against g3
-    const double r32 = fma(r.g33, a[3], fma(r.g32, a[2], fma(r.g31, a[1], r.g30 * a[0]))) * r.w3;
-    a[0] = fma(-r32, r.g30, a[0]); a[1] = fma(-r32, r.g31, a[1]); a[2] = fma(-r32, r.g32, a[2]); a[3] = fma(-r32, r.g33, a[3]);
-    const double w2 = ptk_rcp(PTK_DOT(a, a));
-    // last column of T (order 0, 1, 3, 2): t23 = -r32, t13 = r13 r32 - r12, t03 = r03 r32 - (r01 t13 + r02)
-    const double t13 = fma(r.r13, r32, -r12);
-    const double t03 = fma(r.r03, r32, -fma(r.r01, t13, r02));
-    const double c03 = t03 * w2, c13 = t13 * w2, c23 = -r32 * w2;
+    a[0] = fma(r.f[9], gx, fma(r.f[13], gy, r.f[17]));
+    a[1] = fma(r.f[10], gx, fma(r.f[14], gy, r.f[18]));
+    a[2] = fma(r.f[11], gx, fma(r.f[15], gy, r.f[19]));
+    a[3] = fma(r.f[12], gx, fma(r.f[16], gy, r.f[20]));
+    const double n2 = PTK_DOT(a, a);
     double u[4];
-    const bool ok = dlt_invpower_core<3, true>(fma(t03, c03, r.B00), fma(t03, c13, r.B01), fma(t03, c23, r.B02), c03,
-                                         fma(t13, c13, r.B11), fma(t13, c23, r.B12), c13, fma(-r32, c23, r.w3), c23, w2, u);
+    const bool ok = dlt_invpower_core<3, true, false>(fma(z0, z0, n2 * r.f[21]), fma(z0, z1, n2 * r.f[22]),
+                                                      fma(z0, z2, n2 * r.f[23]), z0, fma(z1, z1, n2 * r.f[24]),
+                                                      fma(z1, z2, n2 * r.f[25]), z1, fma(z2, z2, n2 * r.f[26]), z2, 1.0, u);
     v[0] = u[0]; v[1] = u[1]; v[2] = u[3]; v[3] = u[2];
     return ok;
 }

@@ -89,27 +89,17 @@ __host__ __device__ inline size_t rec_index(size_t e) { return (e / kRecBlock) *
 
 __device__ __forceinline__ void rec_store(double2* __restrict__ r, const Canon2Rec& c)
 {
-    r[0 * kRecBlock] = make_double2(c.p0, c.q0);    r[1 * kRecBlock] = make_double2(c.p2, c.q2);
-    r[2 * kRecBlock] = make_double2(c.w0, c.g10);   r[3 * kRecBlock] = make_double2(c.g12, c.g13);
-    r[4 * kRecBlock] = make_double2(c.w1, c.g30);   r[5 * kRecBlock] = make_double2(c.g31, c.g32);
-    r[6 * kRecBlock] = make_double2(c.g33, c.w3);   r[7 * kRecBlock] = make_double2(c.r13, c.r03);
-    r[8 * kRecBlock] = make_double2(c.r01, c.B00);  r[9 * kRecBlock] = make_double2(c.B01, c.B02);
-    r[10 * kRecBlock] = make_double2(c.B11, c.B12);
+#pragma unroll
+    for (int k = 0; k < kCanon2RecPlanes; k++) r[k * kRecBlock] = make_double2(c.f[2 * k], c.f[2 * k + 1]);
 }
 __device__ __forceinline__ void rec_load(const double2* __restrict__ r, Canon2Rec& c)
 {
-    double2 t;
-    t = __ldg(r + 0 * kRecBlock);  c.p0 = t.x;  c.q0 = t.y;
-    t = __ldg(r + 1 * kRecBlock);  c.p2 = t.x;  c.q2 = t.y;
-    t = __ldg(r + 2 * kRecBlock);  c.w0 = t.x;  c.g10 = t.y;
-    t = __ldg(r + 3 * kRecBlock);  c.g12 = t.x; c.g13 = t.y;
-    t = __ldg(r + 4 * kRecBlock);  c.w1 = t.x;  c.g30 = t.y;
-    t = __ldg(r + 5 * kRecBlock);  c.g31 = t.x; c.g32 = t.y;
-    t = __ldg(r + 6 * kRecBlock);  c.g33 = t.x; c.w3 = t.y;
-    t = __ldg(r + 7 * kRecBlock);  c.r13 = t.x; c.r03 = t.y;
-    t = __ldg(r + 8 * kRecBlock);  c.r01 = t.x; c.B00 = t.y;
-    t = __ldg(r + 9 * kRecBlock);  c.B01 = t.x; c.B02 = t.y;
-    t = __ldg(r + 10 * kRecBlock); c.B11 = t.x; c.B12 = t.y;
+#pragma unroll
+    for (int k = 0; k < kCanon2RecPlanes; k++) {
+        const double2 t = __ldg(r + k * kRecBlock);
+        c.f[2 * k] = t.x;
+        c.f[2 * k + 1] = t.y;
+    }
 }
 
 // K0b (canonical rigs): one thread per camera-2 end point, grid = (ceil(2*Nmax/128), P).
@@ -171,12 +161,13 @@ __global__ void __launch_bounds__(128, MINB) k_cost(const __grid_constant__ DevR
     double d1, d2, h[4];
     eval_combo<CANON, SIMPLE>(rig, u1.x, u1.y, a.und2 + off2, rec, o1.x, o1.y, o2.x, o2.y, d1, d2, h);
     // match2D.py:910 np.mean over the two cameras; matchND.py:525 np.sum
-    const double e = rig.agg_sum ? (d1 + d2) : (d1 + d2) / 2.0;
+    const double e = (d1 + d2) * rig.agg_scale;
     // e0+e3 (straight) lives in lanes 0,3 of the quad, e1+e2 (crossed) in lanes 1,2
     const double s_mine = e + __shfl_xor_sync(kFull, e, 3);
     const double s_other = __shfl_xor_sync(kFull, s_mine, 1);
     if (active) {
-        const size_t o = ((size_t)base + i) * a.Nmax + j;
+        // (p, i, j) of one launch stays below 65528 * 256 * 256 < 2^32
+        const unsigned o = (base + (unsigned)i) * (unsigned)a.Nmax + (unsigned)j;
         if (c == 0) {
             a.cost[o] = np_min(s_mine, s_other);          // match2D.py:923-932
             if (a.choice) a.choice[o] = (s_mine <= s_other);  // match2D.py:935-938
@@ -185,12 +176,110 @@ __global__ void __launch_bounds__(128, MINB) k_cost(const __grid_constant__ DevR
             double X, Y, Z, wx, wy, wz;
             dehomogenise(h, X, Y, Z);
             to_world(rig, X, Y, Z, wx, wy, wz);
-            double* w = a.p_world + (o * 4 + c) * 3;
+            double* w = a.p_world + ((size_t)o * 4 + c) * 3;
             w[0] = wx; w[1] = wy; w[2] = wz;
         }
         if (a.rep_errs) {
-            double* r = a.rep_errs + (o * 4 + c) * 2;
+            double* r = a.rep_errs + ((size_t)o * 4 + c) * 2;
             r[0] = d1; r[1] = d2;
+        }
+    }
+}
+
+// K1 for canonical rigs (round 2): a CTA owns a block of the cost matrix -- `rows_per` camera-1 rods x one
+// chunk of WC camera-2 rods of one problem -- instead of one 32-pair tile.  Its prologue stages the chunk's
+// camera-2 records (k_prep2's blocks, copied as they lie), the chunk's original camera-2 points and the rows'
+// camera-1 points in shared memory; the loop then walks the block's pairs 32 at a time (flat index, so ragged
+// rod counts leave no idle lanes) with every per-pair input a shared-memory read.  Against the tile kernel this
+// removes, per 32 pairs, the two dependent global loads at the head of a short-lived thread (22 % of the warp
+// slots were waiting there, ncu) and ~50 instructions of index / address arithmetic.
+constexpr int kRowsMax = 16;  // camera-1 rods per CTA at most
+struct RowsLoopArgs {
+    int rows_per;  // camera-1 rods per CTA (<= kRowsMax); gridDim.x = ceil(Nmax / rows_per)
+};
+__device__ __forceinline__ void rec_load_shared(const double2* r, Canon2Rec& c)
+{
+#pragma unroll
+    for (int k = 0; k < kCanon2RecPlanes; k++) {
+        const double2 t = r[k * kRecBlock];
+        c.f[2 * k] = t.x;
+        c.f[2 * k + 1] = t.y;
+    }
+}
+
+template <bool SIMPLE, int WC, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_cost_rows(const __grid_constant__ DevRig rig, const __grid_constant__ CostArgs a,
+                                                         const __grid_constant__ RowsLoopArgs la)
+{
+    constexpr unsigned kBlk = kRecBlock * kCanon2RecPlanes;  // double2 per record block
+    __shared__ __align__(16) double2 s_rec[(WC * 2 / kRecBlock + 1) * kBlk];
+    __shared__ __align__(16) double2 s_o2[WC * 2];
+    __shared__ __align__(16) double2 s_u1[kRowsMax * 2];
+    __shared__ __align__(16) double2 s_o1[kRowsMax * 2];
+    const int p = blockIdx.y;
+    const int N1 = a.n1[p], N2 = a.n2[p];
+    if (N1 <= 0 || N2 <= 0 || N1 > a.Nmax || N2 > a.Nmax) return;
+    const int j0 = blockIdx.z * WC, i0 = blockIdx.x * la.rows_per;
+    if (j0 >= N2 || i0 >= N1) return;
+    const int W = min(WC, N2 - j0), R = min(la.rows_per, N1 - i0);
+    const unsigned tid = threadIdx.x;
+    const unsigned base = (unsigned)p * (unsigned)a.Nmax;
+    const unsigned e0 = (base + (unsigned)j0) * 2u;  // first camera-2 end point of the chunk
+    const unsigned gb0 = e0 / kRecBlock, gb1 = (e0 + 2u * W - 1u) / kRecBlock + 1u;
+    {
+        const double2* __restrict__ src = a.rec2 + (size_t)gb0 * kBlk;
+        const unsigned n = (gb1 - gb0) * kBlk;
+        for (unsigned t = tid; t < n; t += 128) s_rec[t] = __ldg(src + t);
+        for (unsigned t = tid; t < 2u * W; t += 128) s_o2[t] = ldg2(a.cam2 + (size_t)(e0 + t) * 2);
+        const unsigned r0 = (base + (unsigned)i0) * 2u;
+        if (tid < 2u * R) {
+            s_u1[tid] = ldg2(a.und1 + (size_t)(r0 + tid) * 2);
+            s_o1[tid] = ldg2(a.cam1 + (size_t)(r0 + tid) * 2);
+        }
+    }
+    __syncthreads();
+    const int npairs = R * W;
+    float rW;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rW) : "f"((float)W));
+    const int c = tid & 3;
+    const int e1 = c >> 1, e2 = c & 1;
+    const unsigned eoff = e0 - gb0 * kRecBlock + e2;  // this lane's end of rod 0 of the chunk, within the staged blocks
+#pragma unroll 1
+    for (int q0 = 0; q0 < npairs; q0 += 32) {
+        int q = q0 + (int)(tid >> 2);
+        const bool active = q < npairs;
+        if (!active) q = npairs - 1;  // keep the quad shuffles convergent; results are discarded
+        const int r = __float2int_rz(((float)q + 0.5f) * rW);  // q / W, see pair_row
+        const int jl = q - r * W;
+        if (!PTK_OK_IDX(r, R, 12) || !PTK_OK_IDX(jl, W, 13)) continue;  // (debug build)
+        const unsigned el = eoff + 2u * jl;
+        Canon2Rec rec;
+        rec_load_shared(s_rec + ((el / kRecBlock) * kBlk + (el % kRecBlock)), rec);
+        const double2 u1 = s_u1[2 * r + e1], o1 = s_o1[2 * r + e1], o2 = s_o2[2 * jl + e2];
+        const int j = j0 + jl;
+        double d1, d2, h[4];
+        eval_combo<true, SIMPLE>(rig, u1.x, u1.y, a.und2 + ((base + (unsigned)j) * 4u + 2u * e2), rec, o1.x, o1.y, o2.x, o2.y,
+                                 d1, d2, h);
+        const double e = (d1 + d2) * rig.agg_scale;
+        const double s_mine = e + __shfl_xor_sync(kFull, e, 3);
+        const double s_other = __shfl_xor_sync(kFull, s_mine, 1);
+        if (active) {
+            const unsigned o = (base + (unsigned)(i0 + r)) * (unsigned)a.Nmax + (unsigned)j;
+            if (c == 0) {
+                a.cost[o] = np_min(s_mine, s_other);
+                if (a.choice) a.choice[o] = (s_mine <= s_other);
+            }
+            if (a.p_world) {
+                double X, Y, Z, wx, wy, wz;
+                dehomogenise(h, X, Y, Z);
+                to_world(rig, X, Y, Z, wx, wy, wz);
+                double* w = a.p_world + ((size_t)o * 4 + c) * 3;
+                w[0] = wx; w[1] = wy; w[2] = wz;
+            }
+            if (a.rep_errs) {
+                double* re = a.rep_errs + ((size_t)o * 4 + c) * 2;
+                re[0] = d1; re[1] = d2;
+            }
         }
     }
 }
@@ -542,7 +631,7 @@ __global__ void __launch_bounds__(128) k_rows(const __grid_constant__ DevRig rig
     double d1, d2, h[4], X, Y, Z;
     eval_combo<CANON, SIMPLE>(rig, u1.x, u1.y, u2p, rec, o1.x, o1.y, o2.x, o2.y, d1, d2, h);
     dehomogenise(h, X, Y, Z);
-    const double e = rig.agg_sum ? (d1 + d2) : (d1 + d2) / 2.0;
+    const double e = (d1 + d2) * rig.agg_scale;
     const double s_mine = e + __shfl_xor_sync(kFull, e, 3);
     const double s_other = __shfl_xor_sync(kFull, s_mine, 1);
     // lane 0 of the quad holds (s03, s12); broadcast its verdict

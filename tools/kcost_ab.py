@@ -6,7 +6,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     import numpy as np, torch
     from particletracking_b200 import engine, rig as rigmod, synthetic as syn
     N = int(os.environ.get("KC_N", "32"))
-    data = syn.make_stereo(1000 if N <= 32 else 250, 8, N, seed=2)
+    data = syn.make_stereo(int(os.environ.get("KC_F", 1000 if N <= 32 else 250)), 8, N, seed=2)
     rig = rigmod.rig_from_dicts(data.calibration, data.transformation)
     args = tuple(torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in data.problems())
     for _ in range(3):
