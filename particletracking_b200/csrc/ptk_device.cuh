@@ -370,12 +370,13 @@ static inline double ptk_pow2_inv(double x)
 // The power iteration on B = (A^T A)^-1 (symmetric, given by its upper triangle): scaling by a power of
 // two, NSQ symmetric squarings, the convergence check and the final product with the largest-diagonal
 // column.  Returns whether the iteration has converged.
-// LAST_FIRST: the caller expects the last diagonal entry to be the largest (the record variant, whose last
-// column carries the depth): that column is then taken on a branch without any select.
+// LAST_ONLY: the caller expects the last diagonal entry to be the largest (the record variant, whose last
+// column carries the depth) and has a slow path for everything unusual: the last column is taken
+// unconditionally and "it was not the largest" is reported as not converged (no select, no branch here).
 // SCALE: B is first scaled by a power of two so that its trace is in [1, 2) (the record variant passes
 // B / w2 whose trace is 1 + |z|^2 + small and needs none; absurd magnitudes overflow to Inf / NaN, which the
 // convergence test reports as "not converged").
-template <int NSQ, bool LAST_FIRST = false, bool SCALE = true>
+template <int NSQ, bool LAST_ONLY = false, bool SCALE = true>
 PTK_HD bool dlt_invpower_core(double b00, double b01, double b02, double b03, double b11, double b12, double b13,
                               double b22, double b23, double b33, double (&v)[4])
 {
@@ -414,12 +415,12 @@ PTK_HD bool dlt_invpower_core(double b00, double b01, double b02, double b03, do
     const double tr = (b00 + b11) + (b22 + b33);
     const bool ok = fma(-(1.0 - PTK_INVPOWER_TOL), trh * trh, tr) >= 0.0;
     // v = B^k (column of B^k with the largest diagonal entry: |v_4[j]|^2 >= 1/4 there)
-    if (LAST_FIRST && b33 >= b00 && b33 >= b11 && b33 >= b22) {
+    if (LAST_ONLY) {
         v[0] = fma(b03, b33, fma(b02, b23, fma(b01, b13, b00 * b03)));
         v[1] = fma(b13, b33, fma(b12, b23, fma(b11, b13, b01 * b03)));
         v[2] = fma(b23, b33, fma(b22, b23, fma(b12, b13, b02 * b03)));
         v[3] = fma(b33, b33, fma(b23, b23, fma(b13, b13, b03 * b03)));
-        return ok;
+        return ok && b33 >= b00 && b33 >= b11 && b33 >= b22;
     }
     double u0 = b00, u1 = b01, u2 = b02, u3 = b03, dm = b00;
     if (b11 > dm) { dm = b11; u0 = b01; u1 = b11; u2 = b12; u3 = b13; }
@@ -602,6 +603,9 @@ PTK_HD void canon_prep2(const double* __restrict__ cm1, double fx2, const double
 }
 
 // cm1 = (fx, fy, cx, cy); r = canon_prep2 of the camera-2 point; (x1, y1) the camera-1 point.
+// FAST: straight-line code for the usual case -- true means "converged AND the last diagonal entry of B^8 was the
+// largest"; on false the caller repeats the point with FAST = false (generic column choice; false = not converged).
+template <bool FAST>
 PTK_HD bool dlt_null_invpower_canon_rec(const double* __restrict__ cm1, const Canon2Rec& r, double x1, double y1,
                                         double (&v)[4])
 {
@@ -616,7 +620,7 @@ PTK_HD bool dlt_null_invpower_canon_rec(const double* __restrict__ cm1, const Ca
     a[3] = fma(r.f[12], gx, fma(r.f[16], gy, r.f[20]));
     const double n2 = PTK_DOT(a, a);
     double u[4];
-    const bool ok = dlt_invpower_core<3, true, false>(fma(z0, z0, n2 * r.f[21]), fma(z0, z1, n2 * r.f[22]),
+    const bool ok = dlt_invpower_core<3, FAST, false>(fma(z0, z0, n2 * r.f[21]), fma(z0, z1, n2 * r.f[22]),
                                                       fma(z0, z2, n2 * r.f[23]), z0, fma(z1, z1, n2 * r.f[24]),
                                                       fma(z1, z2, n2 * r.f[25]), z1, fma(z2, z2, n2 * r.f[26]), z2, 1.0, u);
     v[0] = u[0]; v[1] = u[1]; v[2] = u[3]; v[3] = u[2];
@@ -738,11 +742,11 @@ __device__ __forceinline__ void project_point(const double* __restrict__ R, cons
 // depth afterwards; the two divisions cancel -- x / z = (R h[0:3] + t h3)_x / (R h[0:3] + t h3)_z -- so the
 // per-camera path is one reciprocal, not two, and the point itself is only formed where a caller wants it
 // (K3, K1's optional output).  cv2's "z == 0 -> leave x, y undivided" becomes "divide by h3 instead".
-template <bool SIMPLE>
+template <bool SIMPLE, bool FAST>
 __device__ __forceinline__ double reproject_dist_h(const double* __restrict__ R, const double* __restrict__ t,
                                                    const double* __restrict__ cm, const double* __restrict__ k,
                                                    const double (&h)[4], double ou, double ov, bool ext_identity,
-                                                   bool tangential)
+                                                   bool tangential, bool& good)
 {
     double x = h[0], y = h[1], z = h[2];
     if (!ext_identity) {
@@ -759,48 +763,77 @@ __device__ __forceinline__ double reproject_dist_h(const double* __restrict__ R,
     const double q = fma(ex, ex, ey * ey);
     // sqrt as q * rsqrt(q) (seed + one third-order step: an ulp or two, 7 instructions instead of
     // the ~14 of the IEEE sequence); zero, denormal, huge, infinite and NaN arguments take the library
-    // path.  The range test is on the exponent bits (ALU pipe, idle here) instead of two DSETPs on the
-    // FP64 pipe that bounds the kernel: biased exponent in [27, 2019], i.e. 2^-996 <= q < 2^997 (q >= 0).
-    const unsigned ex11 = ((unsigned)__double2hiint(q) >> 20) - 27u;
-    double d = q * rsqrt_refine(q, rsqrt_seed(q));
-    if (__builtin_expect(!(ex11 < 1993u), 0)) d = sqrt(q);
-    return d;
+    // path.  The range test is on the exponent bits (ALU pipe) instead of two DSETPs on the FP64 pipe:
+    // biased exponent in [27, 2019], i.e. 2^-996 <= q < 2^997 (q >= 0).
+    const bool in_range = (((unsigned)__double2hiint(q) >> 20) - 27u) < 1993u;
+    if (FAST) {  // the caller repeats the combination on its slow path if any flag is down
+        good = good && in_range;
+        return q * rsqrt_refine(q, rsqrt_seed(q));
+    }
+    return in_range ? q * rsqrt_refine(q, rsqrt_seed(q)) : sqrt(q);
+}
+
+// The unusual cases of eval_combo, out of line: the power iteration has not converged (extra squaring, then
+// OpenCV's Jacobi), the last diagonal entry of B^8 was not the largest (generic column choice), a squared
+// distance outside the fast square root's range (zero, Inf, NaN).  Everything is recomputed from the inputs;
+// u2 points at the undistorted camera-2 point.
+template <bool CANON, bool SIMPLE>
+__device__ __noinline__ void eval_combo_slow(const DevRig& rig, double u1x, double u1y, const double* __restrict__ u2,
+                                             double o1x, double o1y, double o2x, double o2y, double* __restrict__ out)
+{
+    const double2 q = __ldg(reinterpret_cast<const double2*>(u2));
+    double h[4];
+    bool ok;
+    if (CANON) {
+        Canon2Rec rec;
+        canon_prep2(rig.CM1, rig.fx2, rig.P2o, q.x, q.y, rec);
+        ok = dlt_null_invpower_canon_rec<false>(rig.CM1, rec, u1x, u1y, h);
+    } else {
+        ok = dlt_null_invpower_n<3>(rig.P1o, rig.P2o, u1x, u1y, q.x, q.y, h);
+    }
+    if (!ok) {
+        double xyz[3];
+        dlt_triangulate_fallback(rig, u1x, u1y, q.x, q.y, xyz);
+        h[0] = xyz[0]; h[1] = xyz[1]; h[2] = xyz[2]; h[3] = 1.0;
+    }
+    bool dummy = true;
+    out[0] = reproject_dist_h<SIMPLE, false>(rig.R1, rig.t1, rig.CM1, rig.k1, h, o1x, o1y, CANON || rig.ext_identity[0] != 0,
+                                             rig.tangential[0] != 0, dummy);
+    out[1] = reproject_dist_h<SIMPLE, false>(rig.R2, rig.t2, rig.CM2, rig.k2, h, o2x, o2y, rig.ext_identity[1] != 0,
+                                             rig.tangential[1] != 0, dummy);
+    out[2] = h[0]; out[3] = h[1]; out[4] = h[2]; out[5] = h[3];
 }
 
 // One end-point combination (match2D.py:889-913): triangulate the undistorted pair, reproject into both
 // cameras, per-camera distances d1, d2, and the homogeneous point h (camera-1 coordinates; `dehomogenise`).
 // CANON / SIMPLE: the rig's class (DevRig::canon / ::simple), fixed at compile time so that K1 and K3 -- which
-// must produce the same bits for the same rod pair -- run the same straight-line code.
-// CANON: `rec` is canon_prep2 of the camera-2 point (read from k_prep2's planes by K1, computed in place by K3:
-// the same function, the same bits) and u2 is only read if the power iteration has not converged; otherwise
-// rec is unused and u2 points at the undistorted camera-2 point.
+// must produce the same bits for the same rod pair -- run the same code.
+// CANON: `rec` is canon_prep2 of the camera-2 point (read from k_prep2's records by K1, computed in place by K3:
+// the same function, the same bits); otherwise rec is unused.  u2 points at the undistorted camera-2 point.
+// The main path is straight-line code that only collects "something unusual" flags; ONE branch at the end sends
+// such a combination through eval_combo_slow.
 template <bool CANON, bool SIMPLE>
 __device__ __forceinline__ void eval_combo(const DevRig& rig, double u1x, double u1y, const double* __restrict__ u2,
                                            const Canon2Rec& rec, double o1x, double o1y, double o2x, double o2y,
                                            double& d1, double& d2, double (&h)[4])
 {
-    bool ok;
-    double u2x = 0.0, u2y = 0.0;
+    bool good;
     if (CANON) {
-        ok = dlt_null_invpower_canon_rec(rig.CM1, rec, u1x, u1y, h);
+        good = dlt_null_invpower_canon_rec<true>(rig.CM1, rec, u1x, u1y, h);
     } else {
         const double2 q = __ldg(reinterpret_cast<const double2*>(u2));
-        u2x = q.x; u2y = q.y;
-        ok = dlt_null_invpower_n<3>(rig.P1o, rig.P2o, u1x, u1y, u2x, u2y, h);
+        good = dlt_null_invpower_n<3>(rig.P1o, rig.P2o, u1x, u1y, q.x, q.y, h);
     }
-    if (!ok) {
-        if (CANON) {
-            const double2 q = __ldg(reinterpret_cast<const double2*>(u2));
-            u2x = q.x; u2y = q.y;
-        }
-        double xyz[3];
-        dlt_triangulate_fallback(rig, u1x, u1y, u2x, u2y, xyz);
-        h[0] = xyz[0]; h[1] = xyz[1]; h[2] = xyz[2]; h[3] = 1.0;
+    d1 = reproject_dist_h<SIMPLE, true>(rig.R1, rig.t1, rig.CM1, rig.k1, h, o1x, o1y, CANON || rig.ext_identity[0] != 0,
+                                        rig.tangential[0] != 0, good);
+    d2 = reproject_dist_h<SIMPLE, true>(rig.R2, rig.t2, rig.CM2, rig.k2, h, o2x, o2y, rig.ext_identity[1] != 0,
+                                        rig.tangential[1] != 0, good);
+    if (__builtin_expect(!good, 0)) {
+        double out[6];
+        eval_combo_slow<CANON, SIMPLE>(rig, u1x, u1y, u2, o1x, o1y, o2x, o2y, out);
+        d1 = out[0]; d2 = out[1];
+        h[0] = out[2]; h[1] = out[3]; h[2] = out[4]; h[3] = out[5];
     }
-    d1 = reproject_dist_h<SIMPLE>(rig.R1, rig.t1, rig.CM1, rig.k1, h, o1x, o1y, CANON || rig.ext_identity[0] != 0,
-                                  rig.tangential[0] != 0);
-    d2 = reproject_dist_h<SIMPLE>(rig.R2, rig.t2, rig.CM2, rig.k2, h, o2x, o2y, rig.ext_identity[1] != 0,
-                                  rig.tangential[1] != 0);
 }
 
 // match2D.py:895: p[0:3] / p[3]

@@ -39,7 +39,7 @@ extern "C" void tri_invpower_canon_rec_host(const double* cm1 /*fx fy cx cy*/, c
         ptk::Canon2Rec r;
         ptk::canon_prep2(cm1, fx2, P2, pts[4 * m + 2], pts[4 * m + 3], r);
         double a[4];
-        conv[m] = ptk::dlt_null_invpower_canon_rec(cm1, r, pts[4 * m], pts[4 * m + 1], a) ? 1 : 0;
+        conv[m] = ptk::dlt_null_invpower_canon_rec<false>(cm1, r, pts[4 * m], pts[4 * m + 1], a) ? 1 : 0;
         for (int k = 0; k < 4; k++) v_rec[4 * m + k] = a[k];
     }
 }
