@@ -206,8 +206,7 @@ struct MatchWs {
 
 inline size_t rec2_bytes(long long chunk, int Nmax)
 {
-    const size_t blocks = ((size_t)chunk * Nmax * 2 + kRecBlock - 1) / kRecBlock;  // see rec_index (ptk_kernels.cuh)
-    return blocks * kRecBlock * kCanon2RecPlanes * sizeof(double2);
+    return (size_t)chunk * rec_problem_stride(Nmax) * sizeof(double2);
 }
 
 MatchWs carve_match(void* ws, long long chunk, int Nmax, bool need_cost)
@@ -251,14 +250,13 @@ int launch_cost(const DevRig& rig, long long P, int Nmax, const double* cam1, co
     a.Nmax = Nmax;
     a.tiles = (Nmax * Nmax + 31) / 32;
     if (rig.canon && !rec2) return PTK_ERR_INVALID_ARG;
-    // grid = (tiles, problems): gridDim.y holds 65535; slices start on a multiple of 8 problems so that a
-    // slice's end points start on a record block
+    // grid = (tiles or row blocks, problems): gridDim.y holds 65535
     const long long max_p = 65528;
     for (long long p0 = 0; p0 < P; p0 += max_p) {
         const long long np = (P - p0) < max_p ? (P - p0) : max_p;
         const size_t o4 = (size_t)p0 * Nmax * 4, o2 = (size_t)p0 * Nmax * Nmax;
         a.cam1 = cam1 + o4; a.cam2 = cam2 + o4; a.und1 = und1 + o4; a.und2 = und2 + o4;
-        a.rec2 = rec2 ? rec2 + rec_index((size_t)p0 * Nmax * 2) : nullptr;
+        a.rec2 = rec2 ? rec2 + (size_t)p0 * rec_problem_stride(Nmax) : nullptr;
         a.n1 = n1 + p0; a.n2 = n2 + p0;
         a.cost = cost + o2;
         if (rig.canon) {  // K0b: the camera-2 share of the DLT, once per end point (ptk_device.cuh: canon_prep2)
@@ -277,30 +275,28 @@ int launch_cost(const DevRig& rig, long long P, int Nmax, const double* cam1, co
             LaunchTimer lt(K_COST, st);
             // the rig class picks the instantiation (same bits from every one of them, see eval_combo)
             static const int mb = getenv("PTK_KCOST_CFG") ? atoi(getenv("PTK_KCOST_CFG")) : 0;  // tuning knob
-            static const int rows_env = getenv("PTK_KCOST_ROWS") ? atoi(getenv("PTK_KCOST_ROWS")) : 16;  // 0: tile kernel
-            if (rig.canon && rows_env > 0 && (mb == 0 || mb >= 14)) {
+            static const int rows_env = getenv("PTK_KCOST_ROWS") ? atoi(getenv("PTK_KCOST_ROWS")) : 16;
+            if (rig.canon) {
                 RowsLoopArgs la;
-                la.rows_per = rows_env > kRowsMax ? kRowsMax : rows_env;
+                la.rows_per = rows_env > kRowsMax ? kRowsMax : (rows_env < 1 ? 1 : rows_env);
+                const unsigned gx = (unsigned)((Nmax + la.rows_per - 1) / la.rows_per);
+                // 5 CTAs per SM (96 registers: loop state and constants stay in registers) measured fastest:
+                // 0.600 / 0.580 / 0.586 ms at 6 / 5 / 4 (profiles/README.md)
                 if (Nmax <= 32) {
-                    const dim3 g((unsigned)((Nmax + la.rows_per - 1) / la.rows_per), (unsigned)np, 1);
-                    if (rig.simple && mb == 15) k_cost_rows<true, 32, 5><<<g, 128, 0, st>>>(rig, a, la);
-                    else if (rig.simple && mb == 14) k_cost_rows<true, 32, 4><<<g, 128, 0, st>>>(rig, a, la);
-                    else if (rig.simple) k_cost_rows<true, 32, 6><<<g, 128, 0, st>>>(rig, a, la);
-                    else k_cost_rows<false, 32, 6><<<g, 128, 0, st>>>(rig, a, la);
+                    const dim3 g(gx, (unsigned)np, 1);
+                    if (rig.simple && mb == 6) k_cost_rows<true, 32, 6><<<g, 128, 0, st>>>(rig, a, la);
+                    else if (rig.simple && mb == 4) k_cost_rows<true, 32, 4><<<g, 128, 0, st>>>(rig, a, la);
+                    else if (rig.simple) k_cost_rows<true, 32, 5><<<g, 128, 0, st>>>(rig, a, la);
+                    else k_cost_rows<false, 32, 5><<<g, 128, 0, st>>>(rig, a, la);
                 } else {
-                    const dim3 g((unsigned)((Nmax + la.rows_per - 1) / la.rows_per), (unsigned)np, (unsigned)((Nmax + 63) / 64));
-                    if (rig.simple) k_cost_rows<true, 64, 6><<<g, 128, 0, st>>>(rig, a, la);
-                    else k_cost_rows<false, 64, 6><<<g, 128, 0, st>>>(rig, a, la);
+                    const dim3 g(gx, (unsigned)np, (unsigned)((Nmax + 63) / 64));
+                    if (rig.simple && mb == 6) k_cost_rows<true, 64, 6><<<g, 128, 0, st>>>(rig, a, la);
+                    else if (rig.simple) k_cost_rows<true, 64, 5><<<g, 128, 0, st>>>(rig, a, la);
+                    else k_cost_rows<false, 64, 5><<<g, 128, 0, st>>>(rig, a, la);
                 }
             }
-            else if (rig.canon && rig.simple && mb == 4) k_cost<true, true, 4><<<grid, 128, 0, st>>>(rig, a);
-            else if (rig.canon && rig.simple && mb == 5) k_cost<true, true, 5><<<grid, 128, 0, st>>>(rig, a);
-            else if (rig.canon && rig.simple && mb == 7) k_cost<true, true, 7><<<grid, 128, 0, st>>>(rig, a);
-            else if (rig.canon && rig.simple && mb == 8) k_cost<true, true, 8><<<grid, 128, 0, st>>>(rig, a);
-            else if (rig.canon && rig.simple) k_cost<true, true><<<grid, 128, 0, st>>>(rig, a);
-            else if (rig.canon) k_cost<true, false><<<grid, 128, 0, st>>>(rig, a);
-            else if (rig.simple) k_cost<false, true><<<grid, 128, 0, st>>>(rig, a);
-            else k_cost<false, false><<<grid, 128, 0, st>>>(rig, a);
+            else if (rig.simple) k_cost<true><<<grid, 128, 0, st>>>(rig, a);
+            else k_cost<false><<<grid, 128, 0, st>>>(rig, a);
         }
         LAUNCHED("k_cost");
     }

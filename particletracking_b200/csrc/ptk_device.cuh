@@ -812,28 +812,42 @@ __device__ __noinline__ void eval_combo_slow(const DevRig& rig, double u1x, doub
 // the same function, the same bits); otherwise rec is unused.  u2 points at the undistorted camera-2 point.
 // The main path is straight-line code that only collects "something unusual" flags; ONE branch at the end sends
 // such a combination through eval_combo_slow.
+// (K1 calls the three stages itself so that its shared-memory reads sit right before their use.)
+template <bool CANON>
+__device__ __forceinline__ bool eval_combo_dlt(const DevRig& rig, double u1x, double u1y, const double* __restrict__ u2,
+                                               const Canon2Rec& rec, double (&h)[4])
+{
+    if (CANON) return dlt_null_invpower_canon_rec<true>(rig.CM1, rec, u1x, u1y, h);
+    const double2 q = __ldg(reinterpret_cast<const double2*>(u2));
+    return dlt_null_invpower_n<3>(rig.P1o, rig.P2o, u1x, u1y, q.x, q.y, h);
+}
+template <bool CANON, bool SIMPLE>
+__device__ __forceinline__ void eval_combo_dist(const DevRig& rig, const double (&h)[4], double o1x, double o1y, double o2x,
+                                                double o2y, bool& good, double& d1, double& d2)
+{
+    d1 = reproject_dist_h<SIMPLE, true>(rig.R1, rig.t1, rig.CM1, rig.k1, h, o1x, o1y, CANON || rig.ext_identity[0] != 0,
+                                        rig.tangential[0] != 0, good);
+    d2 = reproject_dist_h<SIMPLE, true>(rig.R2, rig.t2, rig.CM2, rig.k2, h, o2x, o2y, rig.ext_identity[1] != 0,
+                                        rig.tangential[1] != 0, good);
+}
+template <bool CANON, bool SIMPLE>
+__device__ __forceinline__ void eval_combo_redo(const DevRig& rig, double u1x, double u1y, const double* __restrict__ u2,
+                                                double o1x, double o1y, double o2x, double o2y, double& d1, double& d2,
+                                                double (&h)[4])
+{
+    double out[6];
+    eval_combo_slow<CANON, SIMPLE>(rig, u1x, u1y, u2, o1x, o1y, o2x, o2y, out);
+    d1 = out[0]; d2 = out[1];
+    h[0] = out[2]; h[1] = out[3]; h[2] = out[4]; h[3] = out[5];
+}
 template <bool CANON, bool SIMPLE>
 __device__ __forceinline__ void eval_combo(const DevRig& rig, double u1x, double u1y, const double* __restrict__ u2,
                                            const Canon2Rec& rec, double o1x, double o1y, double o2x, double o2y,
                                            double& d1, double& d2, double (&h)[4])
 {
-    bool good;
-    if (CANON) {
-        good = dlt_null_invpower_canon_rec<true>(rig.CM1, rec, u1x, u1y, h);
-    } else {
-        const double2 q = __ldg(reinterpret_cast<const double2*>(u2));
-        good = dlt_null_invpower_n<3>(rig.P1o, rig.P2o, u1x, u1y, q.x, q.y, h);
-    }
-    d1 = reproject_dist_h<SIMPLE, true>(rig.R1, rig.t1, rig.CM1, rig.k1, h, o1x, o1y, CANON || rig.ext_identity[0] != 0,
-                                        rig.tangential[0] != 0, good);
-    d2 = reproject_dist_h<SIMPLE, true>(rig.R2, rig.t2, rig.CM2, rig.k2, h, o2x, o2y, rig.ext_identity[1] != 0,
-                                        rig.tangential[1] != 0, good);
-    if (__builtin_expect(!good, 0)) {
-        double out[6];
-        eval_combo_slow<CANON, SIMPLE>(rig, u1x, u1y, u2, o1x, o1y, o2x, o2y, out);
-        d1 = out[0]; d2 = out[1];
-        h[0] = out[2]; h[1] = out[3]; h[2] = out[4]; h[3] = out[5];
-    }
+    bool good = eval_combo_dlt<CANON>(rig, u1x, u1y, u2, rec, h);
+    eval_combo_dist<CANON, SIMPLE>(rig, h, o1x, o1y, o2x, o2y, good, d1, d2);
+    if (__builtin_expect(!good, 0)) eval_combo_redo<CANON, SIMPLE>(rig, u1x, u1y, u2, o1x, o1y, o2x, o2y, d1, d2, h);
 }
 
 // match2D.py:895: p[0:3] / p[3]

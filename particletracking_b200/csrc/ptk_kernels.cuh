@@ -78,29 +78,11 @@ struct CostArgs {
 
 __device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
 
-// The camera-2 record of the canonical-rig DLT (ptk_device.cuh: canon_prep2) in memory: end points
-// e = (problem * Nmax + rod) * 2 + end are grouped in blocks of 16; a block holds kCanon2RecPlanes planes of
-// 16 double2 (256 bytes each).  A warp of K1 reads 16 consecutive end points, i.e. one or two full 256-byte
-// runs per plane, and a thread's eleven 16-byte loads share ONE address register (the plane is an immediate
-// offset) -- with separate plane arrays every load needed its own 64-bit address (five integer instructions
-// each on the half-rate ALU pipe, which undid half of the gain; profiles/README.md).
-constexpr unsigned kRecBlock = 16;
-__host__ __device__ inline size_t rec_index(size_t e) { return (e / kRecBlock) * (kRecBlock * kCanon2RecPlanes) + (e % kRecBlock); }
-
-__device__ __forceinline__ void rec_store(double2* __restrict__ r, const Canon2Rec& c)
-{
-#pragma unroll
-    for (int k = 0; k < kCanon2RecPlanes; k++) r[k * kRecBlock] = make_double2(c.f[2 * k], c.f[2 * k + 1]);
-}
-__device__ __forceinline__ void rec_load(const double2* __restrict__ r, Canon2Rec& c)
-{
-#pragma unroll
-    for (int k = 0; k < kCanon2RecPlanes; k++) {
-        const double2 t = __ldg(r + k * kRecBlock);
-        c.f[2 * k] = t.x;
-        c.f[2 * k + 1] = t.y;
-    }
-}
+// The camera-2 records of the canonical-rig DLT (ptk_device.cuh: canon_prep2) in memory: per problem,
+// kCanon2RecPlanes planes of 2 * Nmax double2, plane k holding fields (2k, 2k + 1) of end point e = 2 * rod + end.
+// K1's prologue copies a chunk of every plane into shared memory (coalesced runs), where a thread's fourteen
+// 16-byte reads share one address register (the plane is an immediate offset).
+__host__ __device__ inline size_t rec_problem_stride(int Nmax) { return (size_t)kCanon2RecPlanes * 2 * Nmax; }  // double2
 
 // K0b (canonical rigs): one thread per camera-2 end point, grid = (ceil(2*Nmax/128), P).
 __global__ void __launch_bounds__(128) k_prep2(const __grid_constant__ DevRig rig, int Nmax, const double* __restrict__ und2,
@@ -110,11 +92,12 @@ __global__ void __launch_bounds__(128) k_prep2(const __grid_constant__ DevRig ri
     const int e = blockIdx.x * blockDim.x + threadIdx.x;  // 2 * rod + end
     const int n = n2[p];
     if (n <= 0 || n > Nmax || e >= 2 * n) return;
-    const unsigned idx = (unsigned)p * (unsigned)Nmax * 2u + (unsigned)e;
-    const double2 u = ldg2(und2 + (size_t)idx * 2);
+    const double2 u = ldg2(und2 + ((size_t)p * Nmax * 2 + e) * 2);
     Canon2Rec c;
     canon_prep2(rig.CM1, rig.fx2, rig.P2o, u.x, u.y, c);
-    rec_store(rec2 + (idx / kRecBlock) * (kRecBlock * kCanon2RecPlanes) + (idx % kRecBlock), c);
+    double2* __restrict__ r = rec2 + (size_t)p * rec_problem_stride(Nmax) + e;
+#pragma unroll
+    for (int k = 0; k < kCanon2RecPlanes; k++) r[(size_t)k * 2 * Nmax] = make_double2(c.f[2 * k], c.f[2 * k + 1]);
 }
 
 // q / n for 0 <= q < 65536, 1 <= n <= 256 without an integer division: (q + 0.5) / n is at least
@@ -127,12 +110,12 @@ __device__ __forceinline__ int pair_row(int q, int n)
     return __float2int_rz(((float)q + 0.5f) * r);
 }
 
-// 6 CTAs x 4 warps per SM (80 registers) measured fastest: 2.67 / 2.57 / 2.53 / 2.55 / 2.54 ms at
-// 4 / 5 / 6 / 7 / 8 CTAs (Jacobi era, tools/ab_bench.py, profiles/README.md).
+// K1 for general rigs.  6 CTAs x 4 warps per SM (80 registers) measured fastest: 2.67 / 2.57 / 2.53 / 2.55 /
+// 2.54 ms at 4 / 5 / 6 / 7 / 8 CTAs (Jacobi era, tools/ab_bench.py, profiles/README.md).
 #ifndef PTK_KCOST_MINBLOCKS
 #define PTK_KCOST_MINBLOCKS 6
 #endif
-template <bool CANON, bool SIMPLE, int MINB = PTK_KCOST_MINBLOCKS>
+template <bool SIMPLE, int MINB = PTK_KCOST_MINBLOCKS>
 __global__ void __launch_bounds__(128, MINB) k_cost(const __grid_constant__ DevRig rig, const __grid_constant__ CostArgs a)
 {
     const int p = blockIdx.y;
@@ -151,15 +134,11 @@ __global__ void __launch_bounds__(128, MINB) k_cost(const __grid_constant__ DevR
     const unsigned base = (unsigned)p * (unsigned)a.Nmax;
     const unsigned off1 = (base + (unsigned)i) * 4u + 2u * e1, off2 = (base + (unsigned)j) * 4u + 2u * e2;
     const double2 u1 = ldg2(a.und1 + off1);
-    Canon2Rec rec;
-    if (CANON) {
-        const unsigned e = off2 >> 1;  // end point index (problem * Nmax + rod) * 2 + end
-        rec_load(a.rec2 + ((e / kRecBlock) * (kRecBlock * kCanon2RecPlanes) + (e % kRecBlock)), rec);
-    }
     const double2 o1 = ldg2(a.cam1 + off1);
     const double2 o2 = ldg2(a.cam2 + off2);
+    Canon2Rec rec;  // unused by general rigs
     double d1, d2, h[4];
-    eval_combo<CANON, SIMPLE>(rig, u1.x, u1.y, a.und2 + off2, rec, o1.x, o1.y, o2.x, o2.y, d1, d2, h);
+    eval_combo<false, SIMPLE>(rig, u1.x, u1.y, a.und2 + off2, rec, o1.x, o1.y, o2.x, o2.y, d1, d2, h);
     // match2D.py:910 np.mean over the two cameras; matchND.py:525 np.sum
     const double e = (d1 + d2) * rig.agg_scale;
     // e0+e3 (straight) lives in lanes 0,3 of the quad, e1+e2 (crossed) in lanes 1,2
@@ -188,22 +167,33 @@ __global__ void __launch_bounds__(128, MINB) k_cost(const __grid_constant__ DevR
 
 // K1 for canonical rigs (round 2): a CTA owns a block of the cost matrix -- `rows_per` camera-1 rods x one
 // chunk of WC camera-2 rods of one problem -- instead of one 32-pair tile.  Its prologue stages the chunk's
-// camera-2 records (k_prep2's blocks, copied as they lie), the chunk's original camera-2 points and the rows'
-// camera-1 points in shared memory; the loop then walks the block's pairs 32 at a time (flat index, so ragged
-// rod counts leave no idle lanes) with every per-pair input a shared-memory read.  Against the tile kernel this
-// removes, per 32 pairs, the two dependent global loads at the head of a short-lived thread (22 % of the warp
-// slots were waiting there, ncu) and ~50 instructions of index / address arithmetic.
+// camera-2 records (k_prep2's planes), the chunk's original camera-2 points and the rows' camera-1 points in
+// shared memory; the loop then walks the block's pairs 32 at a time (flat index, so ragged rod counts leave no
+// idle lanes) with every per-pair input a shared-memory read off ONE base register.  The kernel is bound by
+// instruction dispatch (FP64 and integer-ALU instructions hold a scheduler's port for two cycles, ncu:
+// profiles/README.md), so what the loop does besides its ~250 FP64 instructions is counted in single
+// instructions: the loop state is four registers (pair index, this lane's shared-memory base, output base,
+// pair count), the shared-memory reads are inline PTX with immediate offsets (the compiler otherwise rebuilds
+// every array's window address per iteration), the distorted points are read after the triangulation.
 constexpr int kRowsMax = 16;  // camera-1 rods per CTA at most
 struct RowsLoopArgs {
     int rows_per;  // camera-1 rods per CTA (<= kRowsMax); gridDim.x = ceil(Nmax / rows_per)
 };
-__device__ __forceinline__ void rec_load_shared(const double2* r, Canon2Rec& c)
+template <int OFF>
+__device__ __forceinline__ double2 lds2(unsigned addr)
 {
-#pragma unroll
-    for (int k = 0; k < kCanon2RecPlanes; k++) {
-        const double2 t = r[k * kRecBlock];
-        c.f[2 * k] = t.x;
-        c.f[2 * k + 1] = t.y;
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v.x), "=d"(v.y) : "r"(addr), "n"(OFF));
+    return v;
+}
+template <int WC, int K>
+__device__ __forceinline__ void rec_load_shared(unsigned addr, Canon2Rec& c)
+{
+    if constexpr (K < kCanon2RecPlanes) {
+        const double2 t = lds2<K * 2 * WC * 16>(addr);
+        c.f[2 * K] = t.x;
+        c.f[2 * K + 1] = t.y;
+        rec_load_shared<WC, K + 1>(addr, c);
     }
 }
 
@@ -211,11 +201,9 @@ template <bool SIMPLE, int WC, int MINB>
 __global__ void __launch_bounds__(128, MINB) k_cost_rows(const __grid_constant__ DevRig rig, const __grid_constant__ CostArgs a,
                                                          const __grid_constant__ RowsLoopArgs la)
 {
-    constexpr unsigned kBlk = kRecBlock * kCanon2RecPlanes;  // double2 per record block
-    __shared__ __align__(16) double2 s_rec[(WC * 2 / kRecBlock + 1) * kBlk];
-    __shared__ __align__(16) double2 s_o2[WC * 2];
-    __shared__ __align__(16) double2 s_u1[kRowsMax * 2];
-    __shared__ __align__(16) double2 s_o1[kRowsMax * 2];
+    // shared memory, in double2: records [planes][2 WC] | o2 [2 WC] | u1 [2 kRowsMax] | o1 [2 kRowsMax]
+    constexpr int kRec = kCanon2RecPlanes * 2 * WC, kO2 = kRec, kU1 = kO2 + 2 * WC, kO1 = kU1 + 2 * kRowsMax;
+    __shared__ __align__(16) double2 sm[kO1 + 2 * kRowsMax];
     const int p = blockIdx.y;
     const int N1 = a.n1[p], N2 = a.n2[p];
     if (N1 <= 0 || N2 <= 0 || N1 > a.Nmax || N2 > a.Nmax) return;
@@ -224,50 +212,59 @@ __global__ void __launch_bounds__(128, MINB) k_cost_rows(const __grid_constant__
     const int W = min(WC, N2 - j0), R = min(la.rows_per, N1 - i0);
     const unsigned tid = threadIdx.x;
     const unsigned base = (unsigned)p * (unsigned)a.Nmax;
-    const unsigned e0 = (base + (unsigned)j0) * 2u;  // first camera-2 end point of the chunk
-    const unsigned gb0 = e0 / kRecBlock, gb1 = (e0 + 2u * W - 1u) / kRecBlock + 1u;
     {
-        const double2* __restrict__ src = a.rec2 + (size_t)gb0 * kBlk;
-        const unsigned n = (gb1 - gb0) * kBlk;
-        for (unsigned t = tid; t < n; t += 128) s_rec[t] = __ldg(src + t);
-        for (unsigned t = tid; t < 2u * W; t += 128) s_o2[t] = ldg2(a.cam2 + (size_t)(e0 + t) * 2);
-        const unsigned r0 = (base + (unsigned)i0) * 2u;
+        const unsigned nE = 2u * W;  // camera-2 end points of the chunk
+        const double2* __restrict__ src = a.rec2 + (size_t)p * rec_problem_stride(a.Nmax) + 2u * j0;
+        for (unsigned e = tid; e < nE; e += 128) {
+#pragma unroll
+            for (int k = 0; k < kCanon2RecPlanes; k++) sm[k * 2 * WC + e] = __ldg(src + (size_t)k * 2 * a.Nmax + e);
+            sm[kO2 + e] = ldg2(a.cam2 + ((size_t)(base + j0) * 2 + e) * 2);
+        }
         if (tid < 2u * R) {
-            s_u1[tid] = ldg2(a.und1 + (size_t)(r0 + tid) * 2);
-            s_o1[tid] = ldg2(a.cam1 + (size_t)(r0 + tid) * 2);
+            sm[kU1 + tid] = ldg2(a.und1 + ((size_t)(base + i0) * 2 + tid) * 2);
+            sm[kO1 + tid] = ldg2(a.cam1 + ((size_t)(base + i0) * 2 + tid) * 2);
         }
     }
     __syncthreads();
     const int npairs = R * W;
     float rW;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rW) : "f"((float)W));
-    const int c = tid & 3;
-    const int e1 = c >> 1, e2 = c & 1;
-    const unsigned eoff = e0 - gb0 * kRecBlock + e2;  // this lane's end of rod 0 of the chunk, within the staged blocks
+    const unsigned c = tid & 3u;
+    // this lane's shared-memory base: byte address of sm[e2] (camera-2 end) -- rod jl is 32 bytes further per rod;
+    // the camera-1 end e1 is folded into the row offset below
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(sm) + (c & 1u) * 16u;
+    const unsigned e1off = (c >> 1) * 16u;
+    const unsigned obase = (base + (unsigned)i0) * (unsigned)a.Nmax + (unsigned)j0;  // < 2^32 per launch
+    const unsigned und2_base = (base + (unsigned)j0) * 4u + 2u * (c & 1u);
 #pragma unroll 1
-    for (int q0 = 0; q0 < npairs; q0 += 32) {
-        int q = q0 + (int)(tid >> 2);
+    for (int q = (int)(tid >> 2); q - (int)(tid >> 2) < npairs; q += 32) {
         const bool active = q < npairs;
-        if (!active) q = npairs - 1;  // keep the quad shuffles convergent; results are discarded
-        const int r = __float2int_rz(((float)q + 0.5f) * rW);  // q / W, see pair_row
-        const int jl = q - r * W;
+        const int qq = active ? q : npairs - 1;  // keep the quad shuffles convergent; results are discarded
+        const int r = __float2int_rz(((float)qq + 0.5f) * rW);  // qq / W, see pair_row
+        const int jl = qq - r * W;
         if (!PTK_OK_IDX(r, R, 12) || !PTK_OK_IDX(jl, W, 13)) continue;  // (debug build)
-        const unsigned el = eoff + 2u * jl;
+        const unsigned s2 = sbase + 32u * (unsigned)jl;                  // record / o2 of (jl, e2)
+        const unsigned s1 = sbase - (c & 1u) * 16u + e1off + 32u * (unsigned)r;  // u1 / o1 of (r, e1)
         Canon2Rec rec;
-        rec_load_shared(s_rec + ((el / kRecBlock) * kBlk + (el % kRecBlock)), rec);
-        const double2 u1 = s_u1[2 * r + e1], o1 = s_o1[2 * r + e1], o2 = s_o2[2 * jl + e2];
-        const int j = j0 + jl;
-        double d1, d2, h[4];
-        eval_combo<true, SIMPLE>(rig, u1.x, u1.y, a.und2 + ((base + (unsigned)j) * 4u + 2u * e2), rec, o1.x, o1.y, o2.x, o2.y,
-                                 d1, d2, h);
-        const double e = (d1 + d2) * rig.agg_scale;
+        rec_load_shared<WC, 0>(s2, rec);
+        const double2 u1 = lds2<kU1 * 16>(s1);
+        double h[4], d1, d2;
+        bool good = eval_combo_dlt<true>(rig, u1.x, u1.y, nullptr, rec, h);
+        const double2 o1 = lds2<kO1 * 16>(s1), o2 = lds2<kO2 * 16>(s2);
+        eval_combo_dist<true, SIMPLE>(rig, h, o1.x, o1.y, o2.x, o2.y, good, d1, d2);
+        if (__builtin_expect(!good, 0)) {
+            const double2 v1 = lds2<kU1 * 16>(s1);
+            eval_combo_redo<true, SIMPLE>(rig, v1.x, v1.y, a.und2 + (und2_base + 4u * (unsigned)jl), o1.x, o1.y, o2.x, o2.y,
+                                          d1, d2, h);
+        }
+        const double e = (d1 + d2) * rig.agg_scale;  // match2D.py:910 np.mean / matchND.py:525 np.sum
         const double s_mine = e + __shfl_xor_sync(kFull, e, 3);
         const double s_other = __shfl_xor_sync(kFull, s_mine, 1);
         if (active) {
-            const unsigned o = (base + (unsigned)(i0 + r)) * (unsigned)a.Nmax + (unsigned)j;
+            const unsigned o = obase + (unsigned)r * (unsigned)a.Nmax + (unsigned)jl;
             if (c == 0) {
-                a.cost[o] = np_min(s_mine, s_other);
-                if (a.choice) a.choice[o] = (s_mine <= s_other);
+                a.cost[o] = np_min(s_mine, s_other);              // match2D.py:923-932
+                if (a.choice) a.choice[o] = (s_mine <= s_other);  // match2D.py:935-938
             }
             if (a.p_world) {
                 double X, Y, Z, wx, wy, wz;
