@@ -282,17 +282,22 @@ int launch_cost(const DevRig& rig, long long P, int Nmax, const double* cam1, co
                 const unsigned gx = (unsigned)((Nmax + la.rows_per - 1) / la.rows_per);
                 // 5 CTAs per SM (96 registers: loop state and constants stay in registers) measured fastest:
                 // 0.600 / 0.580 / 0.586 ms at 6 / 5 / 4 (profiles/README.md)
+                const bool extras = choice || p_world || rep_errs;
                 if (Nmax <= 32) {
                     const dim3 g(gx, (unsigned)np, 1);
-                    if (rig.simple && mb == 6) k_cost_rows<true, 32, 6><<<g, 128, 0, st>>>(rig, a, la);
-                    else if (rig.simple && mb == 4) k_cost_rows<true, 32, 4><<<g, 128, 0, st>>>(rig, a, la);
-                    else if (rig.simple) k_cost_rows<true, 32, 5><<<g, 128, 0, st>>>(rig, a, la);
-                    else k_cost_rows<false, 32, 5><<<g, 128, 0, st>>>(rig, a, la);
+                    if (extras && rig.simple) k_cost_rows<true, 32, 5, true><<<g, 128, 0, st>>>(rig, a, la);
+                    else if (extras) k_cost_rows<false, 32, 5, true><<<g, 128, 0, st>>>(rig, a, la);
+                    else if (rig.simple && mb == 6) k_cost_rows<true, 32, 6, false><<<g, 128, 0, st>>>(rig, a, la);
+                    else if (rig.simple && mb == 4) k_cost_rows<true, 32, 4, false><<<g, 128, 0, st>>>(rig, a, la);
+                    else if (rig.simple) k_cost_rows<true, 32, 5, false><<<g, 128, 0, st>>>(rig, a, la);
+                    else k_cost_rows<false, 32, 5, false><<<g, 128, 0, st>>>(rig, a, la);
                 } else {
                     const dim3 g(gx, (unsigned)np, (unsigned)((Nmax + 63) / 64));
-                    if (rig.simple && mb == 6) k_cost_rows<true, 64, 6><<<g, 128, 0, st>>>(rig, a, la);
-                    else if (rig.simple) k_cost_rows<true, 64, 5><<<g, 128, 0, st>>>(rig, a, la);
-                    else k_cost_rows<false, 64, 5><<<g, 128, 0, st>>>(rig, a, la);
+                    if (extras && rig.simple) k_cost_rows<true, 64, 5, true><<<g, 128, 0, st>>>(rig, a, la);
+                    else if (extras) k_cost_rows<false, 64, 5, true><<<g, 128, 0, st>>>(rig, a, la);
+                    else if (rig.simple && mb == 6) k_cost_rows<true, 64, 6, false><<<g, 128, 0, st>>>(rig, a, la);
+                    else if (rig.simple) k_cost_rows<true, 64, 5, false><<<g, 128, 0, st>>>(rig, a, la);
+                    else k_cost_rows<false, 64, 5, false><<<g, 128, 0, st>>>(rig, a, la);
                 }
             }
             else if (rig.simple) k_cost<true><<<grid, 128, 0, st>>>(rig, a);

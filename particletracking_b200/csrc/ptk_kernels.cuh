@@ -197,7 +197,8 @@ __device__ __forceinline__ void rec_load_shared(unsigned addr, Canon2Rec& c)
     }
 }
 
-template <bool SIMPLE, int WC, int MINB>
+// EXTRAS: the optional outputs (choice, p_world, rep_errs) exist; the reconstruction path wants the cost only.
+template <bool SIMPLE, int WC, int MINB, bool EXTRAS>
 __global__ void __launch_bounds__(128, MINB) k_cost_rows(const __grid_constant__ DevRig rig, const __grid_constant__ CostArgs a,
                                                          const __grid_constant__ RowsLoopArgs la)
 {
@@ -233,7 +234,7 @@ __global__ void __launch_bounds__(128, MINB) k_cost_rows(const __grid_constant__
     // this lane's shared-memory base: byte address of sm[e2] (camera-2 end) -- rod jl is 32 bytes further per rod;
     // the camera-1 end e1 is folded into the row offset below
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(sm) + (c & 1u) * 16u;
-    const unsigned e1off = (c >> 1) * 16u;
+    const unsigned s1base = (unsigned)__cvta_generic_to_shared(sm) + (c >> 1) * 16u;
     const unsigned obase = (base + (unsigned)i0) * (unsigned)a.Nmax + (unsigned)j0;  // < 2^32 per launch
     const unsigned und2_base = (base + (unsigned)j0) * 4u + 2u * (c & 1u);
 #pragma unroll 1
@@ -244,7 +245,7 @@ __global__ void __launch_bounds__(128, MINB) k_cost_rows(const __grid_constant__
         const int jl = qq - r * W;
         if (!PTK_OK_IDX(r, R, 12) || !PTK_OK_IDX(jl, W, 13)) continue;  // (debug build)
         const unsigned s2 = sbase + 32u * (unsigned)jl;                  // record / o2 of (jl, e2)
-        const unsigned s1 = sbase - (c & 1u) * 16u + e1off + 32u * (unsigned)r;  // u1 / o1 of (r, e1)
+        const unsigned s1 = s1base + 32u * (unsigned)r;                  // u1 / o1 of (r, e1)
         Canon2Rec rec;
         rec_load_shared<WC, 0>(s2, rec);
         const double2 u1 = lds2<kU1 * 16>(s1);
@@ -263,17 +264,17 @@ __global__ void __launch_bounds__(128, MINB) k_cost_rows(const __grid_constant__
         if (active) {
             const unsigned o = obase + (unsigned)r * (unsigned)a.Nmax + (unsigned)jl;
             if (c == 0) {
-                a.cost[o] = np_min(s_mine, s_other);              // match2D.py:923-932
-                if (a.choice) a.choice[o] = (s_mine <= s_other);  // match2D.py:935-938
+                a.cost[o] = np_min(s_mine, s_other);                         // match2D.py:923-932
+                if (EXTRAS && a.choice) a.choice[o] = (s_mine <= s_other);  // match2D.py:935-938
             }
-            if (a.p_world) {
+            if (EXTRAS && a.p_world) {
                 double X, Y, Z, wx, wy, wz;
                 dehomogenise(h, X, Y, Z);
                 to_world(rig, X, Y, Z, wx, wy, wz);
                 double* w = a.p_world + ((size_t)o * 4 + c) * 3;
                 w[0] = wx; w[1] = wy; w[2] = wz;
             }
-            if (a.rep_errs) {
+            if (EXTRAS && a.rep_errs) {
                 double* re = a.rep_errs + ((size_t)o * 4 + c) * 2;
                 re[0] = d1; re[1] = d2;
             }
