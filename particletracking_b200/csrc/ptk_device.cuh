@@ -688,25 +688,40 @@ __device__ __forceinline__ void dlt_triangulate(const DevRig& rig, double x1, do
 #endif
 }
 
-// The distortion model and the camera matrix of cv2.projectPoints on a normalised point (x, y)
-// (SURVEY App. B.3).  SIMPLE (compile time): the camera has radial terms k1, k2, k3 only -- the rational,
-// tangential and thin-prism blocks do not exist in the code; otherwise they are warp-uniform branches on
-// rig constants.
+// The distortion model of cv2.projectPoints on a normalised point (x, y): (xd, yd), to be
+// mapped to pixels by the camera matrix.  SIMPLE (compile time): the camera has radial terms k1, k2, k3 only
+// (Horner in r^2) -- the rational, tangential and thin-prism blocks do not exist in the code; otherwise they
+// are warp-uniform branches on rig constants.
 template <bool SIMPLE>
-__device__ __forceinline__ void distort_to_pixel(const double* __restrict__ cm, const double* __restrict__ k, double x,
-                                                 double y, double& u, double& v, bool tangential)
+__device__ __forceinline__ void distort_norm(const double* __restrict__ k, double x, double y, double& xd, double& yd,
+                                             bool tangential)
 {
-    const double r2 = fma(x, x, y * y), r4 = r2 * r2, r6 = r4 * r2;
+    const double r2 = fma(x, x, y * y);
+    if (SIMPLE) {
+        const double cdist = fma(fma(fma(k[4], r2, k[1]), r2, k[0]), r2, 1.0);
+        xd = x * cdist;
+        yd = y * cdist;
+        return;
+    }
+    const double r4 = r2 * r2, r6 = r4 * r2;
     const double cdist = fma(k[4], r6, fma(k[1], r4, fma(k[0], r2, 1.0)));
     double rad = cdist;
-    if (!SIMPLE && (k[5] != 0.0 || k[6] != 0.0 || k[7] != 0.0))  // rational model (k4..k6)
+    if (k[5] != 0.0 || k[6] != 0.0 || k[7] != 0.0)  // rational model (k4..k6)
         rad = cdist * fast_rcp(fma(k[7], r6, fma(k[6], r4, fma(k[5], r2, 1.0))));
-    double xd = x * rad, yd = y * rad;
-    if (!SIMPLE && tangential) {  // p1, p2 and thin-prism s1..s4
+    xd = x * rad;
+    yd = y * rad;
+    if (tangential) {  // p1, p2 and thin-prism s1..s4
         const double a1 = 2 * x * y, a2 = fma(2 * x, x, r2), a3 = fma(2 * y, y, r2);
         xd = fma(k[9], r4, fma(k[8], r2, fma(k[3], a2, fma(k[2], a1, xd))));
         yd = fma(k[11], r4, fma(k[10], r2, fma(k[3], a1, fma(k[2], a3, yd))));
     }
+}
+template <bool SIMPLE>
+__device__ __forceinline__ void distort_to_pixel(const double* __restrict__ cm, const double* __restrict__ k, double x,
+                                                 double y, double& u, double& v, bool tangential)
+{
+    double xd, yd;
+    distort_norm<SIMPLE>(k, x, y, xd, yd, tangential);
     u = fma(xd, cm[0], cm[2]);
     v = fma(yd, cm[1], cm[3]);
 }
@@ -745,7 +760,7 @@ __device__ __forceinline__ void project_point(const double* __restrict__ R, cons
 template <bool SIMPLE, bool FAST>
 __device__ __forceinline__ double reproject_dist_h(const double* __restrict__ R, const double* __restrict__ t,
                                                    const double* __restrict__ cm, const double* __restrict__ k,
-                                                   const double (&h)[4], double ou, double ov, bool ext_identity,
+                                                   const double (&h)[4], double ouc, double ovc, bool ext_identity,
                                                    bool tangential, bool& good)
 {
     double x = h[0], y = h[1], z = h[2];
@@ -754,12 +769,15 @@ __device__ __forceinline__ double reproject_dist_h(const double* __restrict__ R,
         y = fma(R[5], h[2], fma(R[4], h[1], fma(R[3], h[0], t[1] * h[3])));
         z = fma(R[8], h[2], fma(R[7], h[1], fma(R[6], h[0], t[2] * h[3])));
     }
-    const bool znz = ((__double2hiint(z) & 0x7fffffff) | __double2loint(z)) != 0;  // z != 0.0, tested on the ALU pipe
+    // cv2's "z == 0 -> undivided": on the FAST path 1/0 makes the squared distance NaN, which its range test
+    // below reports, and the slow path then takes the select
+    const bool znz = FAST || ((__double2hiint(z) & 0x7fffffff) | __double2loint(z)) != 0;
     const double iz = fast_rcp(znz ? z : h[3]);
-    double u, v;
-    distort_to_pixel<SIMPLE>(cm, k, x * iz, y * iz, u, v, tangential);
-    const double ex = ou - u;
-    const double ey = ov - v;
+    double xd, yd;
+    distort_norm<SIMPLE>(k, x * iz, y * iz, xd, yd, tangential);
+    // (ouc, ovc) = detection - principal point: u - ou = fx xd + cx - ou
+    const double ex = fma(-xd, cm[0], ouc);
+    const double ey = fma(-yd, cm[1], ovc);
     const double q = fma(ex, ex, ey * ey);
     // sqrt as q * rsqrt(q) (seed + one third-order step: an ulp or two, 7 instructions instead of
     // the ~14 of the IEEE sequence); zero, denormal, huge, infinite and NaN arguments take the library
@@ -810,6 +828,7 @@ __device__ __noinline__ void eval_combo_slow(const DevRig& rig, double u1x, doub
 // must produce the same bits for the same rod pair -- run the same code.
 // CANON: `rec` is canon_prep2 of the camera-2 point (read from k_prep2's records by K1, computed in place by K3:
 // the same function, the same bits); otherwise rec is unused.  u2 points at the undistorted camera-2 point.
+// (o1x, o1y), (o2x, o2y): the original (distorted) detections MINUS their camera's principal point (centre_detection).
 // The main path is straight-line code that only collects "something unusual" flags; ONE branch at the end sends
 // such a combination through eval_combo_slow.
 // (K1 calls the three stages itself so that its shared-memory reads sit right before their use.)
@@ -848,6 +867,13 @@ __device__ __forceinline__ void eval_combo(const DevRig& rig, double u1x, double
     bool good = eval_combo_dlt<CANON>(rig, u1x, u1y, u2, rec, h);
     eval_combo_dist<CANON, SIMPLE>(rig, h, o1x, o1y, o2x, o2y, good, d1, d2);
     if (__builtin_expect(!good, 0)) eval_combo_redo<CANON, SIMPLE>(rig, u1x, u1y, u2, o1x, o1y, o2x, o2y, d1, d2, h);
+}
+
+// detection - principal point, the form eval_combo takes the original detections in (the reprojection residual
+// is then one FMA per coordinate: fx xd + cx - u = fx xd - (u - cx))
+__device__ __forceinline__ double2 centre_detection(const double* __restrict__ cm, double2 o)
+{
+    return make_double2(o.x - cm[2], o.y - cm[3]);
 }
 
 // match2D.py:895: p[0:3] / p[3]

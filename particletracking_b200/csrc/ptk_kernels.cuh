@@ -134,8 +134,8 @@ __global__ void __launch_bounds__(128, MINB) k_cost(const __grid_constant__ DevR
     const unsigned base = (unsigned)p * (unsigned)a.Nmax;
     const unsigned off1 = (base + (unsigned)i) * 4u + 2u * e1, off2 = (base + (unsigned)j) * 4u + 2u * e2;
     const double2 u1 = ldg2(a.und1 + off1);
-    const double2 o1 = ldg2(a.cam1 + off1);
-    const double2 o2 = ldg2(a.cam2 + off2);
+    const double2 o1 = centre_detection(rig.CM1, ldg2(a.cam1 + off1));
+    const double2 o2 = centre_detection(rig.CM2, ldg2(a.cam2 + off2));
     Canon2Rec rec;  // unused by general rigs
     double d1, d2, h[4];
     eval_combo<false, SIMPLE>(rig, u1.x, u1.y, a.und2 + off2, rec, o1.x, o1.y, o2.x, o2.y, d1, d2, h);
@@ -203,6 +203,7 @@ __global__ void __launch_bounds__(128, MINB) k_cost_rows(const __grid_constant__
                                                          const __grid_constant__ RowsLoopArgs la)
 {
     // shared memory, in double2: records [planes][2 WC] | o2 [2 WC] | u1 [2 kRowsMax] | o1 [2 kRowsMax]
+    // (o1, o2: the distorted detections minus their camera's principal point, see centre_detection)
     constexpr int kRec = kCanon2RecPlanes * 2 * WC, kO2 = kRec, kU1 = kO2 + 2 * WC, kO1 = kU1 + 2 * kRowsMax;
     __shared__ __align__(16) double2 sm[kO1 + 2 * kRowsMax];
     const int p = blockIdx.y;
@@ -219,11 +220,11 @@ __global__ void __launch_bounds__(128, MINB) k_cost_rows(const __grid_constant__
         for (unsigned e = tid; e < nE; e += 128) {
 #pragma unroll
             for (int k = 0; k < kCanon2RecPlanes; k++) sm[k * 2 * WC + e] = __ldg(src + (size_t)k * 2 * a.Nmax + e);
-            sm[kO2 + e] = ldg2(a.cam2 + ((size_t)(base + j0) * 2 + e) * 2);
+            sm[kO2 + e] = centre_detection(rig.CM2, ldg2(a.cam2 + ((size_t)(base + j0) * 2 + e) * 2));
         }
         if (tid < 2u * R) {
             sm[kU1 + tid] = ldg2(a.und1 + ((size_t)(base + i0) * 2 + tid) * 2);
-            sm[kO1 + tid] = ldg2(a.cam1 + ((size_t)(base + i0) * 2 + tid) * 2);
+            sm[kO1 + tid] = centre_detection(rig.CM1, ldg2(a.cam1 + ((size_t)(base + i0) * 2 + tid) * 2));
         }
     }
     __syncthreads();
@@ -619,8 +620,8 @@ __global__ void __launch_bounds__(128) k_rows(const __grid_constant__ DevRig rig
     const int e1 = c >> 1, e2 = c & 1;
     const double2 u1 = ldg2(a.und1 + (base + mm) * 4 + 2 * e1);
     const double* u2p = a.und2 + (base + i2) * 4 + 2 * e2;
-    const double2 o1 = ldg2(a.cam1 + (base + mm) * 4 + 2 * e1);
-    const double2 o2 = ldg2(a.cam2 + (base + i2) * 4 + 2 * e2);
+    const double2 o1 = centre_detection(rig.CM1, ldg2(a.cam1 + (base + mm) * 4 + 2 * e1));
+    const double2 o2 = centre_detection(rig.CM2, ldg2(a.cam2 + (base + i2) * 4 + 2 * e2));
     Canon2Rec rec;
     if (CANON) {  // the record K1 read from k_prep2's planes, recomputed by the same function: the same bits
         const double2 u2 = ldg2(u2p);
