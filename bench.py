@@ -47,16 +47,18 @@ FRAMES, COLORS, RODS = 1000, 8, 32
 WORKLOAD = "match_csv_complex+tracking_global_assignment: 1000 frames x 8 colours x 32 rods (BASELINE configs[1])"
 METRIC = "stereo frames/sec (match+triangulate+track)"
 # Algorithmic FP64 work of K1 per rod pair (4 end-point combinations), FMA = 2 flop:
-#  * as built (QR + inverse power by squaring, canonical-first-camera instantiation):
-#    222 DFMA + 100 DMUL + 17 DADD executed per combination (ncu source counters,
-#    profiles/r02_k_cost_ncu.txt) = 561 flop -> 2 244 per pair (round 1: 2 400; the kernel got faster
-#    partly by doing less).  This is what roofline.achieved / frac are computed from: the kernel's own
-#    work against the FP64 FMA peak.
+#  * as built (canonical rigs: camera-2 records + operators on the camera-1 point, three squarings of a 4x4
+#    matrix, homogeneous reprojection): 160.5 DFMA + 65.4 DMUL + 14.4 DADD executed per
+#    combination (ncu counters, profiles/r02m_k_cost_ncu.txt) = 400.8 flop -> 1 603 per pair (round 1:
+#    2 400, start of round 2: 2 244 -- the kernel got faster mostly by doing less, which a flop-per-second
+#    fraction only half shows; roofline.fp64_pipe_busy is the pipe's own utilisation).  This is what
+#    roofline.achieved / frac are computed from: the kernel's own work against the FP64 FMA peak.
 #  * SURVEY.md 8d / App. H model of the REFERENCE's algorithm (OpenCV's 4x4 Jacobi SVD per point):
 #    245 + 80*R + 66*S flop per combination with R = 20.5 rotations, S = 4.9 sweeps -> 2 210 per
 #    combination, 8 840 per pair.  Reported beside it as roofline.reference_algorithm (a ratio above
 #    1 there means: faster than the reference's algorithm could run at FP64 peak).
-FLOP_PER_PAIR = 2244.0
+FLOP_PER_PAIR = 1603.0
+FP64_PIPE_INSTR_PER_COMBINATION = 247.0  # 160.5 DFMA + 65.4 DMUL + 14.4 DADD + 7 DSETP (same capture)
 FLOP_PER_PAIR_REFERENCE_ALGORITHM = 8840.0
 N_BATCHES = 4  # distinct synthetic input batches the timed steps rotate over
 
@@ -512,6 +514,8 @@ def run_b200(args):
     k1_avg_ms = k1_ms / k1_n if k1_n else float("nan")
     flops_per_launch = FLOP_PER_PAIR * pairs_per_launch
     achieved_tf = flops_per_launch / (k1_avg_ms * 1e-3) / 1e12
+    sm_clock_hz = (clk.get("sm_mhz") or 0.0) * 1e6  # median SM clock sampled during the timed region
+    n_schedulers = 4 * torch.cuda.get_device_properties(local).multi_processor_count
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -526,13 +530,18 @@ def run_b200(args):
         pass
     ref_tf = FLOP_PER_PAIR_REFERENCE_ALGORITHM * pairs_per_launch / (k1_avg_ms * 1e-3) / 1e12
     roofline = {
-        "kernel": "k_cost<canon, simple> (K1: DLT by QR + inverse power iteration, reprojection; 1 thread per end-point combination)",
+        "kernel": "k_cost_rows<simple> (K1, canonical rig: DLT null vector by inverse power iteration on per-end-point "
+                  "records, reprojection; 1 thread per end-point combination, row-block CTAs)",
         "bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
         "frac": achieved_tf / (fp64_peak / 1e12),
         "peak_source": "measured in this run: dependency-free DFMA loop on all SMs (ptk_measure_fp64_peak); "
                        "MEASURED_PEAKS.json has no FP64 figure",
         "algorithmic_flop_per_pair": FLOP_PER_PAIR, "pairs_per_launch": pairs_per_launch,
-        "flop_model": "as built: 222 DFMA + 100 DMUL + 17 DADD per combination (ncu), FMA = 2",
+        "flop_model": "as built: 160.5 DFMA + 65.4 DMUL + 14.4 DADD per combination (ncu, profiles/r02m_k_cost_ncu.txt), FMA = 2",
+        # utilisation of the FP64 pipe itself: FP64-pipe warp instructions x 2 issue cycles (16 lanes per scheduler) over
+        # the kernel's scheduler-cycles; ncu's sm__pipe_fp64_cycles_active of the same build: 80.3 %
+        "fp64_pipe_busy": FP64_PIPE_INSTR_PER_COMBINATION * 2.0 * (pairs_per_launch * 4 / 32) /
+                          (k1_avg_ms * 1e-3 * sm_clock_hz * n_schedulers) if sm_clock_hz else None,
         "reference_algorithm": {"flop_per_pair": FLOP_PER_PAIR_REFERENCE_ALGORITHM, "achieved": ref_tf,
                                 "frac": ref_tf / (fp64_peak / 1e12),
                                 "note": "SURVEY 8d model of OpenCV's Jacobi SVD; > 1 = algorithmic saving"},
