@@ -177,3 +177,39 @@ def test_canonical_record_variant_flags_near_degenerate_points(harness):
     Xr = vr[:, :3] / vr[:, 3:]
     err = np.abs(Xr - ref).max(axis=1) / np.abs(ref).max(axis=1)
     assert err[ok].max() < 1e-9
+
+
+def test_main_path_flag_of_the_record_variant(harness):
+    """K1's main path takes the last column of B^8 without looking and reports "the last diagonal entry was not the
+    largest" together with "not converged"; the out-of-line path then redoes the point with the generic column
+    choice.  Where the main path says yes, both must give the same bits; detections far off the optical axis
+    (|x - cx| > fx: the depth is no longer the largest component of the null vector) must be flagged, and the
+    generic variant must still agree with cv2 there."""
+    sys.path.insert(0, ROOT)
+    from particletracking_b200 import synthetic as syn
+
+    s = syn.make_stereo(2, 1, 24, 5, sigma_px=0.5)
+    cal = s.calibration
+    P1, P2 = syn.projection_matrices(cal)[:2]
+    CM1 = np.asarray(cal["CM1"], dtype=np.float64)
+    cm1 = np.array([CM1[0, 0], CM1[1, 1], CM1[0, 2], CM1[1, 2]])
+    a = s.cam1[0, 0].copy()
+    a[::3, 0, 0] = cm1[2] + 2.5 * cm1[0]   # every third rod: first end point 68 degrees off axis
+    a[1::3, 1, 1] = cm1[3] - 1.7 * cm1[1]
+    pts = _combos(a, s.cam2[0, 0])
+    M = len(pts)
+    p = lambda x: x.ctypes.data_as(ctypes.c_void_p)
+    vf, vg = np.empty((M, 4)), np.empty((M, 4))
+    fl = np.empty((M, 2), np.int32)
+    harness.tri_invpower_canon_rec_fast_host(p(cm1), p(np.ascontiguousarray(P2)), ctypes.c_longlong(M), p(pts), p(vf), p(vg), p(fl))
+    fast_ok = fl[:, 0] == 1
+    assert 0.2 < fast_ok.mean() < 0.9                      # the off-axis points are flagged ...
+    assert (fl[fast_ok, 1] == 1).all()                      # ... and nothing else is lost
+    assert np.array_equal(vf[fast_ok].view(np.int64), vg[fast_ok].view(np.int64))
+    off = (np.abs(pts[:, 0] - cm1[2]) > 1.2 * cm1[0]) | (np.abs(pts[:, 1] - cm1[3]) > 1.2 * cm1[1])
+    assert not fast_ok[off].any()
+    conv = fl[:, 1] == 1
+    ref = _cv2(P1, P2, pts)
+    X = vg[:, :3] / vg[:, 3:]
+    err = np.abs(X - ref).max(axis=1) / np.abs(ref).max(axis=1)
+    assert err[conv].max() < 1e-11

@@ -647,6 +647,36 @@ def test_near_degenerate_rig_takes_jacobi_fallback(eng, scale):
     np.testing.assert_array_equal(g.col_ind.cpu().numpy(), o["col_ind"])
 
 
+def test_off_axis_detections_take_the_out_of_line_path(eng, crig):
+    """K1's main path assumes the depth is the largest component of the DLT null vector (last column of B^8)
+    and flags everything else -- detections far off the optical axis (|x - cx| > fx), as a wild dummy
+    detection would be -- for its out-of-line path (generic column choice).  Mixed warps must give what the
+    C oracle gives: costs to 1e-9, identical assignments, identical rows."""
+    from oracle import c_oracle as co
+    from particletracking_b200 import synthetic as syn
+
+    data = syn.make_stereo(4, 2, 20, seed=314, sigma_px=0.5)
+    c1, c2, n1, n2 = (np.array(x) for x in data.problems())
+    cal = data.calibration
+    fx, cx = float(np.asarray(cal["CM1"])[0, 0]), float(np.asarray(cal["CM1"])[0, 2])
+    fy, cy = float(np.asarray(cal["CM1"])[1, 1]), float(np.asarray(cal["CM1"])[1, 2])
+    c1[:, ::4, 0, 0] = cx + 2.2 * fx     # every fourth camera-1 rod: one end point 65 degrees off axis
+    c1[:, 1::4, 1, 1] = cy - 1.6 * fy
+    c2[:, 2::5, 0, 0] = float(np.asarray(cal["CM2"])[0, 2]) - 1.9 * float(np.asarray(cal["CM2"])[0, 0])
+    o = co.match_batch(crig, c1, c2, n1, n2, want_cost=True)
+    g = run_match(eng, crig, c1, c2, n1, n2, want_cost=True)
+    np.testing.assert_array_equal(g.status.cpu().numpy(), o["status"])
+    cost = g.cost.cpu().numpy()
+    for p in range(len(n1)):
+        assert rel_err(cost[p, : n1[p], : n2[p]], o["cost"][p, : n1[p], : n2[p]]) < TOL
+    np.testing.assert_array_equal(g.col_ind.cpu().numpy(), o["col_ind"])
+    rows = g.rows.cpu().numpy()
+    for p in range(len(n1)):
+        for k in range(o["n_out"][p]):
+            for sl in (slice(0, 3), slice(3, 6), slice(6, 9)):
+                assert rel_err(rows[p, k, sl], o["rows"][p, k, sl]) < TOL
+
+
 @pytest.mark.parametrize("C,F,N", [(1, 4, 100), (2, 3, 128), (1, 3, 256), (2, 5, 65)])
 def test_tracking_on_the_fly_large_n(eng, C, F, N):
     """N > 64: the tracking LSAP evaluates costs on the fly from the end points (no cost matrix).
