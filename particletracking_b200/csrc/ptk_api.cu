@@ -400,9 +400,18 @@ int launch_lsap_trk(const TrkArgs& a, void* scratch, cudaStream_t st)
     return launch_lsap_trk_t<8, 4, 3>(a, scratch, st);
 }
 
+// Where K3 also writes the tracking layout ends[C,F,N,2,3] (replaces a separate gather kernel): the call's
+// problem 0 is global problem p0 = frame * C + colour.
+struct TrkTarget {
+    double* ends;
+    int F, C, N;
+    long long p0;
+};
+
 int launch_rows(const DevRig& rig, long long P, int Nmax, const double* cam1, const double* cam2, const double* und1,
                 const double* und2, const int32_t* col_ind, const int32_t* n_out, double* rows, cudaStream_t st,
-                double* pair_cost = nullptr, double* ends6 = nullptr, uint8_t* straight = nullptr)
+                double* pair_cost = nullptr, double* ends6 = nullptr, uint8_t* straight = nullptr,
+                const TrkTarget* trk = nullptr)
 {
     for (long long p0 = 0; p0 < P; p0 += 65535) {
         const int np = (int)((P - p0) < 65535 ? (P - p0) : 65535);
@@ -416,6 +425,9 @@ int launch_rows(const DevRig& rig, long long P, int Nmax, const double* cam1, co
         a.pair_cost = pair_cost ? pair_cost + (size_t)p0 * Nmax : nullptr;
         a.ends6 = ends6 ? ends6 + (size_t)p0 * Nmax * 6 : nullptr;
         a.straight = straight ? straight + (size_t)p0 * Nmax : nullptr;
+        a.ends_trk = trk ? trk->ends : nullptr;
+        a.trk_F = trk ? trk->F : 0; a.trk_C = trk ? trk->C : 1; a.trk_N = trk ? trk->N : 0;
+        a.trk_p0 = (trk ? trk->p0 : 0) + p0;
         dim3 grid((Nmax + 31) / 32, np);
         {
             LaunchTimer lt(K_ROWS, st);
@@ -598,7 +610,7 @@ int match_batch_impl(const ptk_rig* rig, int P, int Nmax, const double* cam1, co
                      const int32_t* n1, const int32_t* n2, double* cost, uint8_t* choice, int32_t* row_ind,
                      int32_t* col_ind, int32_t* n_out, int32_t* status, double* rows, double* ends6, uint8_t* straight,
                      double* match_cost, double max_repr_err, uint8_t* keep_mask, void* workspace, size_t workspace_bytes,
-                     void* stream)
+                     void* stream, const TrkTarget* trk = nullptr)
 {
     if (bad_rig(rig) || P < 0 || bad_n(Nmax) || !cam1 || !cam2 || !n1 || !n2 || !row_ind || !col_ind || !n_out || !status ||
         (!rows && !(ends6 && straight)) || !match_cost)
@@ -610,6 +622,7 @@ int match_batch_impl(const ptk_rig* rig, int P, int Nmax, const double* cam1, co
     const long long chunk = match_chunk(P, Nmax);
     MatchWs w = carve_match((void*)align_up((size_t)workspace), chunk, Nmax, true);
     const size_t NN = (size_t)Nmax * Nmax;
+    TrkTarget tchunk{};
     for (long long p0 = 0; p0 < P; p0 += chunk) {
         const long long np = (P - p0) < chunk ? (P - p0) : chunk;
         const size_t o4 = (size_t)p0 * Nmax * 4;
@@ -631,7 +644,8 @@ int match_batch_impl(const ptk_rig* rig, int P, int Nmax, const double* cam1, co
         if (rc) return rc;
         rc = launch_rows(d, np, Nmax, cam1 + o4, cam2 + o4, w.und1, w.und2, col_ind + (size_t)p0 * Nmax, n_out + p0,
                          rows ? rows + (size_t)p0 * Nmax * PTK_ROW_COLS : nullptr, st, nullptr,
-                         ends6 ? ends6 + (size_t)p0 * Nmax * 6 : nullptr, straight ? straight + (size_t)p0 * Nmax : nullptr);
+                         ends6 ? ends6 + (size_t)p0 * Nmax * 6 : nullptr, straight ? straight + (size_t)p0 * Nmax : nullptr,
+                         trk ? &(tchunk = TrkTarget{trk->ends, trk->F, trk->C, trk->N, trk->p0 + p0}) : nullptr);
         if (rc) return rc;
     }
     return PTK_OK;
@@ -841,15 +855,16 @@ PTK_API int ptk_reconstruct_shard(const ptk_rig* rig, int F, int n_halo, int C, 
     int rc;
     {
         NvtxRange nv1("match");
-        rc = ptk_match_batch(rig, (int)P, Nmax, cam1, cam2, n1, n2, nullptr, nullptr, row_ind, col_ind, n_out, status, rows,
-                             match_cost, max_repr_err, keep_mask, base, w.match, stream);
+        if (!rows) return PTK_ERR_INVALID_ARG;
+        // K3 writes the tracking layout beside the rows (no separate gather)
+        const TrkTarget trk{reinterpret_cast<double*>(base + w.match), Ft, C, Nmax, 0};
+        rc = match_batch_impl(rig, (int)P, Nmax, cam1, cam2, n1, n2, nullptr, nullptr, row_ind, col_ind, n_out, status, rows,
+                              nullptr, nullptr, match_cost, max_repr_err, keep_mask, base, w.match, stream, &trk);
         if (rc) return rc;
     }
     double* ends = reinterpret_cast<double*>(base + w.match);
     {
         NvtxRange nv2("track");
-        rc = ptk_rows_to_ends(Ft, C, Nmax, Nmax, rows, ends, stream);
-        if (rc) return rc;
         if (Ft > 1) {
             rc = ptk_track_batch(C, Ft, Nmax, ends, nullptr, track_col, track_total, track_status, base + w.match + w.ends, w.track,
                                  stream);
@@ -879,15 +894,17 @@ PTK_API int ptk_reconstruct_device(const ptk_rig* rig, int F, int C, int Nmax, c
     int rc;
     {
         NvtxRange nv1("match");
-        rc = ptk_match_batch(rig, (int)P, Nmax, cam1, cam2, n1, n2, nullptr, nullptr, row_ind, col_ind, n_out, status, rows,
-                             match_cost, max_repr_err, keep_mask, base, w.match, stream);
+        if (!rows) return PTK_ERR_INVALID_ARG;
+        // with tracking, K3 writes the tracking layout beside the rows (no separate gather)
+        const TrkTarget trk{reinterpret_cast<double*>(base + w.match), F, C, Nmax, 0};
+        rc = match_batch_impl(rig, (int)P, Nmax, cam1, cam2, n1, n2, nullptr, nullptr, row_ind, col_ind, n_out, status, rows,
+                              nullptr, nullptr, match_cost, max_repr_err, keep_mask, base, w.match, stream,
+                              do_track ? &trk : nullptr);
     }
     if (rc || !do_track) return rc;
     double* ends = reinterpret_cast<double*>(base + w.match);
     {
         NvtxRange nv2("track");
-        rc = ptk_rows_to_ends(F, C, Nmax, Nmax, rows, ends, stream);
-        if (rc) return rc;
         if (F > 1) {
             rc = ptk_track_batch(C, F, Nmax, ends, nullptr, track_col, track_total, track_status, base + w.match + w.ends, w.track,
                                  stream);
@@ -1464,6 +1481,7 @@ int reconstruct_host_impl(ptk_ctx* c, const ptk_rig* rig, int F, int C, int Nmax
     // chunk, under the tracking kernels.
     CK(cudaMemcpyAsync(c->n1.as<int32_t>(), n1, P * sizeof(int32_t), cudaMemcpyHostToDevice, c->s_in));
     CK(cudaMemcpyAsync(c->n2.as<int32_t>(), n2, P * sizeof(int32_t), cudaMemcpyHostToDevice, c->s_in));
+    TrkTarget trk{};
     for (int k = 0; k < nchunks; k++) {
         NvtxRange nvc("chunk: H2D + match + D2H");
         const int f0 = chunk_f0[k];
@@ -1483,14 +1501,9 @@ int reconstruct_host_impl(ptk_ctx* c, const ptk_rig* rig, int F, int C, int Nmax
                               c->nout.as<int32_t>() + p0, c->status.as<int32_t>() + p0, compact ? nullptr : drows,
                               compact ? drows : nullptr, compact ? c->straight.as<uint8_t>() + p0 * Nmax : nullptr,
                               c->mc.as<double>() + p0 * Nmax, max_repr_err,
-                              keep_mask ? c->keep.as<uint8_t>() + p0 * Nmax : nullptr, c->ws.p, c->ws.cap, c->s_comp);
+                              keep_mask ? c->keep.as<uint8_t>() + p0 * Nmax : nullptr, c->ws.p, c->ws.cap, c->s_comp,
+                              do_track ? &(trk = TrkTarget{c->ends.as<double>(), F, C, N, p0}) : nullptr);
         if (rc) return rc;
-        if (do_track) {
-            const long long tot = np * N * 6;
-            k_rows_to_ends<<<(unsigned)((tot + 255) / 256), 256, 0, c->s_comp>>>(f0, fn, F, C, N, Nmax, rcols, drows,
-                                                                                   c->ends.as<double>());
-            LAUNCHED("k_rows_to_ends");
-        }
         CK(cudaEventRecord(c->ev_comp[k], c->s_comp));
         // D2H
         CK(cudaStreamWaitEvent(c->s_out, c->ev_comp[k], 0));

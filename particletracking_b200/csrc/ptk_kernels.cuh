@@ -585,6 +585,11 @@ struct RowsArgs {
     // input arrays (ptk_expand_rows_host)
     double* ends6;           // optional [P,Nmax,6]
     uint8_t* straight;       // optional [P,Nmax]
+    // tracking layout (tracking.py:97-98), written here instead of by a separate gather: the six computed
+    // coordinates of row m < trk_N of problem g = trk_p0 + p = frame * C + colour go to ends_trk[colour, frame, m, 2, 3]
+    double* ends_trk;        // optional [C,F,trk_N,6]
+    int trk_F, trk_C, trk_N;
+    long long trk_p0;
 };
 
 template <bool CANON, bool SIMPLE>
@@ -604,6 +609,11 @@ __global__ void __launch_bounds__(128) k_rows(const __grid_constant__ DevRig rig
             }
             if (a.ends6) {
                 double* o = a.ends6 + (base + m) * 6;
+                for (int k = c; k < 6; k += 4) o[k] = qnan;
+            }
+            if (a.ends_trk && m < a.trk_N) {
+                const long long g = a.trk_p0 + p, f = g / a.trk_C, col = g - f * a.trk_C;
+                double* o = a.ends_trk + (((size_t)col * a.trk_F + f) * a.trk_N + m) * 6;
                 for (int k = c; k < 6; k += 4) o[k] = qnan;
             }
             if (c == 0) {
@@ -646,6 +656,12 @@ __global__ void __launch_bounds__(128) k_rows(const __grid_constant__ DevRig rig
     if (c == 0) {
         if (a.pair_cost && m < a.Nmax) a.pair_cost[base + m] = active ? np_min(s_mine, s_other) : qnan;
         if (a.straight && m < a.Nmax) a.straight[base + m] = (active && straight) ? 1 : 0;
+        if (a.ends_trk && m < a.trk_N) {  // rows >= n_out are NaN in every output form
+            const long long g = a.trk_p0 + p, f = g / a.trk_C, col = g - f * a.trk_C;
+            double* o = a.ends_trk + (((size_t)col * a.trk_F + f) * a.trk_N + m) * 6;
+            o[0] = active ? ax : qnan; o[1] = active ? ay : qnan; o[2] = active ? az : qnan;
+            o[3] = active ? bx : qnan; o[4] = active ? by : qnan; o[5] = active ? bz : qnan;
+        }
         if (active) {
             if (a.ends6) {
                 double* o = a.ends6 + (base + m) * 6;
