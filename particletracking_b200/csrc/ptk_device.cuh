@@ -490,42 +490,6 @@ PTK_HD bool dlt_null_invpower_n(const double* __restrict__ Q1, const double* __r
     return dlt_invpower_tail<NSQ>(r01, r02, r03, r12, r13, r23, w0, w1, w2, w3, v);
 }
 
-// The same for a canonical first camera, P1 = CM1 [I|0] with zero skew (what match2D.py:584-586 builds):
-// the DLT columns are a0 = (-fx, 0, p0, q0), a1 = (0, -fy, p1, q1), a2 = (x1-cx, y1-cy, p2, q2),
-// a3 = (0, 0, p3, q3), and the operations on the exact zeros are left out.  Leaving them out does not
-// change a bit (x*0 = 0, fma(x, 0, c) = c on finite data): tests/test_dlt_invpower_cpu.py compares the two
-// functions for bit-identity.  16 FP64 instructions and 12 constant loads fewer per point.
-// cm1 = (fx, fy, cx, cy), fx2 = fx*fx (rounded once, as the device product would be).
-PTK_HD bool dlt_null_invpower_canon(const double* __restrict__ cm1, double fx2, const double* __restrict__ Q2, double x1,
-                                    double y1, double x2, double y2, double (&v)[4])
-{
-    const double fx = cm1[0], fy = cm1[1];
-    const double gx = x1 - cm1[2], gy = y1 - cm1[3];
-    const double p0 = fma(x2, Q2[8], -Q2[0]), q0 = fma(y2, Q2[8], -Q2[4]);
-    const double p1 = fma(x2, Q2[9], -Q2[1]), q1 = fma(y2, Q2[9], -Q2[5]);
-    const double p2 = fma(x2, Q2[10], -Q2[2]), q2 = fma(y2, Q2[10], -Q2[6]);
-    const double p3 = fma(x2, Q2[11], -Q2[3]), q3 = fma(y2, Q2[11], -Q2[7]);
-    // column 0 = (-fx, 0, p0, q0)
-    const double w0 = ptk_rcp(fma(q0, q0, fma(p0, p0, fx2)));
-    const double r01 = fma(q0, q1, p0 * p1) * w0;
-    const double r02 = fma(q0, q2, fma(p0, p2, -fx * gx)) * w0;
-    const double r03 = fma(q0, q3, p0 * p3) * w0;
-    double a1[4], a2[4], a3[4];
-    a1[0] = r01 * fx;              a1[1] = -fy; a1[2] = fma(-r01, p0, p1); a1[3] = fma(-r01, q0, q1);
-    a2[0] = fma(-r02, -fx, gx);    a2[1] = gy;  a2[2] = fma(-r02, p0, p2); a2[3] = fma(-r02, q0, q2);
-    a3[0] = r03 * fx;              /* a3[1] = 0 */ a3[2] = fma(-r03, p0, p3); a3[3] = fma(-r03, q0, q3);
-    const double w1 = ptk_rcp(PTK_DOT(a1, a1));
-    const double r12 = PTK_DOT(a1, a2) * w1;
-    const double r13 = fma(a1[3], a3[3], fma(a1[2], a3[2], a1[0] * a3[0])) * w1;
-    PTK_AXPY(a2, r12, a1)
-    a3[0] = fma(-r13, a1[0], a3[0]); a3[1] = r13 * fy; a3[2] = fma(-r13, a1[2], a3[2]); a3[3] = fma(-r13, a1[3], a3[3]);
-    const double w2 = ptk_rcp(PTK_DOT(a2, a2));
-    const double r23 = PTK_DOT(a2, a3) * w2;
-    PTK_AXPY(a3, r23, a2)
-    const double w3 = ptk_rcp(PTK_DOT(a3, a3));
-    return dlt_invpower_tail<3>(r01, r02, r03, r12, r13, r23, w0, w1, w2, w3, v);
-}
-
 // ---------------------------------------------------------------------------------------
 // Canonical first camera, with the work that depends on the camera-2 point alone taken out of the
 // per-combination path (round 2).  Of the four DLT columns above only a2 = (x1-cx, y1-cy, p2, q2) contains

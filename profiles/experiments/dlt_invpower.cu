@@ -15,22 +15,8 @@ extern "C" void tri_invpower_host(const double* P1, const double* P2, long long 
     }
 }
 
-// The canonical-first-camera variant (P1 = CM1 [I|0]) beside the general one: must give the same bits.
-extern "C" void tri_invpower_canon_host(const double* cm1 /*fx fy cx cy*/, const double* P2, long long M, const double* pts,
-                                        double* v_canon /*[M,4]*/, double* v_general /*[M,4]*/, int* conv /*[M,2]*/)
-{
-    const double P1[12] = {cm1[0], 0, cm1[2], 0, 0, cm1[1], cm1[3], 0, 0, 0, 1, 0};
-    const double fx2 = cm1[0] * cm1[0];
-    for (long long m = 0; m < M; m++) {
-        double a[4], b[4];
-        conv[2 * m] = ptk::dlt_null_invpower_canon(cm1, fx2, P2, pts[4 * m], pts[4 * m + 1], pts[4 * m + 2], pts[4 * m + 3], a) ? 1 : 0;
-        conv[2 * m + 1] = ptk::dlt_null_invpower_n<3>(P1, P2, pts[4 * m], pts[4 * m + 1], pts[4 * m + 2], pts[4 * m + 3], b) ? 1 : 0;
-        for (int k = 0; k < 4; k++) { v_canon[4 * m + k] = a[k]; v_general[4 * m + k] = b[k]; }
-    }
-}
-
-// Round 2: the canonical variant split into a per-camera-2-point record (canon_prep2) and the per-combination
-// finish (dlt_null_invpower_canon_rec): compared with cv2 and with the unsplit function by the CPU tests.
+// K1's canonical-rig path: a per-camera-2-point record (canon_prep2) and the per-combination finish
+// (dlt_null_invpower_canon_rec), compared with cv2 and with the general function by the CPU tests.
 extern "C" void tri_invpower_canon_rec_host(const double* cm1 /*fx fy cx cy*/, const double* P2, long long M, const double* pts,
                                             double* v_rec /*[M,4]*/, int* conv /*[M]*/)
 {
