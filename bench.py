@@ -375,13 +375,14 @@ def run_b200(args):
                   json.dumps({k: round(v / max(sharded._step_idx, 1) * 1e3, 3) for k, v in sharded._prof.items()}), file=sys.stderr)
         sharded._prof.clear()
         prof_step0 = sharded._step_idx
-    # Per-kernel CUDA events inside the timed region only at N = 1 (one library call per step).  At
-    # N > 1 the step is ~25 launches + collectives issued from Python, and event pairs around every
-    # launch together with the NVML sampler made rank 0's host 5x slower in half of the 4-GPU runs
-    # (3 of 6 bad with both on, 0 of 6 with either one off): there the kernel breakdown comes from a
-    # second, untimed pass of K steps right after the timed region.
+    # CUDA events inside the timed region only at N = 1 (one library call per step) and only around the
+    # dominant kernel (K1, the roofline's duration): event pairs around all ten launches of a step cost the
+    # region 4 % (1.083 vs 1.035 ms per step).  The other kernels' breakdown comes from a second, untimed
+    # pass of K steps right after the timed region -- at N > 1 the whole breakdown does (graph replays are
+    # not event-timed, and event pairs around every launch together with the NVML sampler made rank 0's
+    # host 5x slower in half of the 4-GPU runs of round 1).
     timing_in_region = world == 1 and "notiming" not in dbg
-    engine.kernel_timing(timing_in_region)
+    engine.kernel_timing(2 if timing_in_region else False)
     engine.kernel_timing_read(reset=True)
     engine.launch_count(reset=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -401,7 +402,9 @@ def run_b200(args):
     seg_added = torch.cuda.memory_stats(dev).get("segment.all.allocated", 0) - seg0  # cudaMallocs inside the timed region
     launches = engine.launch_count()
     clk = clocks.stop(t_wall0, t_wall1)
-    if not timing_in_region and "notiming" not in dbg:
+    timing_region = engine.kernel_timing_read(reset=True) if timing_in_region else None
+    timing = timing_region
+    if "notiming" not in dbg:
         engine.kernel_timing(True)  # graph replays are not event-timed: this pass launches eagerly
         engine.kernel_timing_read(reset=True)
         for i in range(K):
@@ -409,7 +412,9 @@ def run_b200(args):
         if sharded is not None:
             sharded.finish()
         barrier()
-    timing = engine.kernel_timing_read(reset=True)
+        timing = engine.kernel_timing_read(reset=True)
+    if timing_region is not None:
+        timing = dict(timing, cost=timing_region["cost"])  # K1: the figure measured inside the timed region
     k1_ms, k1_n = timing["cost"]
     engine.kernel_timing(False)
     if world > 1:
@@ -587,7 +592,7 @@ def run_b200(args):
         "wall_s": t_wall1 - t_wall0,
         "host_enqueue_ms_per_step": t_enq / K * 1e3,
         "cuda_mallocs_in_timed_region": int(seg_added),
-        "kernel_timing": "CUDA events around every launch inside the timed region" if timing_in_region
+        "kernel_timing": "K1: CUDA events around its launches inside the timed region; the other kernels: a second pass of K steps right after it" if timing_in_region
                          else "separate untimed pass of K steps after the timed region (eager launches; the timed region replays CUDA graphs)",
         "sustained": sustained,
         "tracking_parity": "col_ind / track ids are bit-exact given identical 3D input (the reference's tracking cost is separable up "

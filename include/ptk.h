@@ -405,7 +405,9 @@ int ptk_measure_fp64_peak(int iters, double* flops, void* stream);
 /* Per-kernel timing for bench.py's roofline: when enabled, CUDA event pairs are recorded on the
  * launching stream around every kernel launch, by kind.  ptk_timing_read sums durations and counts
  * per kind into arrays of PTK_TIMING_KINDS entries (call after synchronising); off by default.
- * kinds: 0 undistort, 1 cost (K1), 2 lsap (matching), 3 rows, 4 rows_to_ends, 5 track_cost,
+ * ptk_timing_enable: 0 off, 1 every launch, 2 the dominant kernel (kind 1) only -- two events per step instead of
+ * twenty, for a timed region whose total is itself a reported figure.
+ * kinds: 0 undistort (+ k_prep2), 1 cost (K1), 2 lsap (matching), 3 rows, 4 rows_to_ends, 5 track_cost,
  *        6 lsap (tracking), 7 chain (3 launches), 8 create_weights, 9 npartite3 */
 #define PTK_TIMING_KINDS 10
 /* Bounds-checked debug build (make -C particletracking_b200/csrc debug -> libptk_dbg.so, selected with

@@ -61,7 +61,8 @@ struct LaunchTimer {
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     LaunchTimer(int k, cudaStream_t s) : kind(k), st(s)
     {
-        if (!g_timing.load(std::memory_order_relaxed)) return;
+        const int mode = g_timing.load(std::memory_order_relaxed);
+        if (!mode || (mode == 2 && k != K_COST)) return;  // mode 2: the dominant kernel (K1) only
         {
             std::lock_guard<std::mutex> lk(g_timing_mu);
             t0 = timing_event();
@@ -515,7 +516,7 @@ PTK_API long long ptk_launch_count(int reset)
     return reset ? g_launches.exchange(0) : g_launches.load();
 }
 
-PTK_API void ptk_timing_enable(int on) { g_timing.store(on ? 1 : 0); }
+PTK_API void ptk_timing_enable(int on) { g_timing.store(on == 2 ? 2 : (on ? 1 : 0)); }
 
 PTK_API int ptk_timing_read(double* ms_by_kind, long long* launches_by_kind, int reset)
 {

@@ -574,12 +574,12 @@ def measure_fp64_peak(iters: int = 20000) -> float:
 _timing_on = False
 
 
-def kernel_timing(enable: bool) -> None:
-    """Switch CUDA-event timing around every kernel launch on or off (graph replays are not timed:
-    ``ShardPipeline.run_graph`` launches eagerly while it is on)."""
+def kernel_timing(enable) -> None:
+    """Switch CUDA-event timing around kernel launches: False / 0 off, True / 1 every launch, 2 the dominant
+    kernel (K1) only (graph replays are not timed: ``ShardPipeline.run_graph`` launches eagerly while it is on)."""
     global _timing_on
     _timing_on = bool(enable)
-    nat.lib().ptk_timing_enable(1 if enable else 0)
+    nat.lib().ptk_timing_enable(2 if enable == 2 else (1 if enable else 0))
 
 
 TIMING_KINDS = ["undistort", "cost", "lsap_match", "rows", "rows_to_ends", "track_cost", "lsap_track", "chain", "weights", "npartite3"]
