@@ -6,7 +6,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     import numpy as np, torch
     from particletracking_b200 import engine
     rng = np.random.default_rng(0)
-    C, F, N = 8, 1000, int(os.environ.get("TRK_N", "32"))
+    C, F, N = 8, int(os.environ.get("TRK_F", "1000")), int(os.environ.get("TRK_N", "32"))
     base = rng.uniform(-40, 40, size=(C, 1, N, 2, 3))
     ends = base + np.cumsum(rng.normal(size=(C, F, N, 2, 3)) * 0.2, axis=1)
     e = torch.from_numpy(ends).cuda()
