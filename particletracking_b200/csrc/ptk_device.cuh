@@ -2,8 +2,9 @@
 //
 // Everything here is plain CUDA-core FP64: the path is ~1300 flop/B, has no
 // dense contraction, so neither tensor cores nor TMA have anything to do; the design rules
-// that matter are (i) keep the 4x4 Jacobi state in registers, (ii) spend FP64-pipe issue
-// slots on FMAs, (iii) keep div/sqrt sequences off the critical loop.
+// that matter are (i) keep the 4x4 state in registers, (ii) count instructions of every kind --
+// FP64 and integer-ALU instructions hold a scheduler's dispatch port for two cycles, and that,
+// not latency, bounds K1 --, (iii) keep div/sqrt sequences and rare cases off the main path.
 //
 // The translation unit is compiled with -fmad=false: the compiler never contracts on its
 // own, every fused multiply-add below is an explicit fma().  That makes the arithmetic a

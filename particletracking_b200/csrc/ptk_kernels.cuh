@@ -1,8 +1,9 @@
 // ptk_kernels.cuh -- the kernels of the stereo hot path (sm_100a), K0..K6.
 //
 //  K0 k_undistort     cam[P,Nmax,2,2] -> und[P,Nmax,2,2]           (match2D.py:846-863, quirk-exact)
-//  K1 k_cost          one thread per end-point combination, 4 lanes per rod pair:
-//                     DLT (register-resident one-sided Jacobi) -> 2x reproject -> quad
+//  K0b k_prep2       canonical rigs: the camera-2 share of every DLT, once per camera-2 end point (records)
+//  K1 k_cost_rows     (canonical rigs) / k_cost (general rigs): one thread per end-point combination, 4 lanes
+//                     per rod pair: DLT null vector by inverse power iteration -> 2x reproject -> quad
 //                     shuffle -> cost[P,Nmax,Nmax] (+choice, +per-combo extras)  (match2D.py:865-939)
 //  K2 k_lsap          one warp per problem, SciPy-exact rectangular LSAP     (match2D.py:933, tracking.py:122)
 //  K3 k_rows          re-evaluates the n matched pairs and writes the 18-column rows (match2D.py:963-983)
@@ -50,16 +51,15 @@ __global__ void __launch_bounds__(128) k_undistort(const __grid_constant__ DevRi
 
 // ------------------------------------------------------------------------------------- K1
 // One thread per end-point combination; lanes 4q..4q+3 of a warp hold combos
-// (e1,e2) = (0,0),(0,1),(1,0),(1,1) of one rod pair.  A block of 128 threads covers 32
-// consecutive pairs (row-major i*N2+j) of one problem; grid = (tiles, problems).
-// Inputs are 16-byte vector loads through the read-only path: 8 consecutive cam2 rods of a
-// warp are one 256-byte segment, the cam1 rod is a broadcast -- no shared-memory staging is
-// needed for coalescing, and bytes are ~0.1 % of the kernel's time (profiles/).
-// The kernel is co-limited by the FP64 pipe and by issue slots (every FP64 instruction blocks
-// the pipe for two cycles; the other instructions have to fit in the cycles between), so the
-// non-FP64 work is kept minimal: the problem index is blockIdx.y (no division), the pair's row
-// comes from one float reciprocal instead of an integer division (exact for q < 2^16,
-// N2 <= 256, see pair_row), the rig class is a template parameter (no rig-constant branches).
+// (e1,e2) = (0,0),(0,1),(1,0),(1,1) of one rod pair.  Two kernels share the arguments below:
+//  * k_cost_rows (canonical rigs, the reference's): a CTA owns a block of the cost matrix, stages its inputs
+//    (k_prep2's records, the points) in shared memory and loops over the block's pairs -- see its comment;
+//  * k_cost (general rigs): a block of 128 threads covers 32 consecutive pairs (row-major i*N2+j) of one
+//    problem, grid = (tiles, problems), inputs are 16-byte loads through the read-only path.
+// Both are bound by instruction dispatch (an FP64 or integer-ALU instruction holds the scheduler's port for
+// two cycles), so the non-FP64 work is counted in single instructions: the problem index is blockIdx.y (no
+// division), the pair's row comes from one float reciprocal instead of an integer division (exact for
+// q < 2^16, N2 <= 256, see pair_row), the rig class is a template parameter (no rig-constant branches).
 struct CostArgs {
     int Nmax;
     int tiles;  // tiles per problem = ceil(Nmax*Nmax/32)
