@@ -336,17 +336,17 @@ __device__ __forceinline__ double ordered_value(unsigned long long k)
     return __longlong_as_double((long long)k);
 }
 
-// value of arr[idx >> 5] held by lane (idx & 31), broadcast to the warp (idx is warp-uniform)
+// value of arr[idx >> 5] held by lane (idx & 31), broadcast to the warp (idx is warp-uniform): every lane first
+// picks its own arr[idx >> 5] (a chain of selects on a warp-uniform predicate), then ONE shuffle fetches the
+// owner's -- instead of one shuffle per slot
 template <int CPL, typename T>
 __device__ __forceinline__ T lane_array_get(const T (&arr)[CPL], int idx)
 {
-    T val = arr[0];
+    T mine = arr[0];
 #pragma unroll
-    for (int t = 0; t < CPL; t++) {
-        const T tmp = __shfl_sync(kFull, arr[t], idx & 31);
-        if (t == (idx >> 5)) val = tmp;
-    }
-    return val;
+    for (int t = 1; t < CPL; t++)
+        if (t == (idx >> 5)) mine = arr[t];
+    return __shfl_sync(kFull, mine, idx & 31);
 }
 
 template <int CPL, typename T>
