@@ -349,12 +349,19 @@ __device__ __forceinline__ T lane_array_get(const T (&arr)[CPL], int idx)
     return __shfl_sync(kFull, mine, idx & 31);
 }
 
-template <int CPL, typename T>
-__device__ __forceinline__ void lane_array_set(T (&arr)[CPL], int idx, T val, int lane)
+// order-preserving map double -> int64 (signed compare), an involution: negative values have their
+// low 63 bits flipped
+__device__ __forceinline__ void skey(double x, int& hi, unsigned& lo)
 {
-#pragma unroll
-    for (int t = 0; t < CPL; t++)
-        if (lane == (idx & 31) && t == (idx >> 5)) arr[t] = val;
+    const int h = __double2hiint(x);
+    const int m = h >> 31;
+    hi = h ^ (m & 0x7fffffff);
+    lo = (unsigned)__double2loint(x) ^ (unsigned)m;
+}
+__device__ __forceinline__ double skey_value(int hi, unsigned lo)
+{
+    const int m = hi >> 31;
+    return __hiloint2double(hi ^ (m & 0x7fffffff), (int)(lo ^ (unsigned)m));
 }
 
 constexpr int kLsapStageBytes = 16 * 1024;  // stage the cost matrix in shared memory up to this size
@@ -400,9 +407,13 @@ __global__ void __launch_bounds__(32) k_lsap(const __grid_constant__ LsapArgs a)
         // validate (SciPy: "matrix contains invalid numeric entries") and stage in solver orientation
         bool bad = false;
         {
+            // one flat sweep (independent loads: the row-by-row form measured 50 % slower); the row index comes
+            // from a float reciprocal instead of an integer division per element (exact here, see pair_row)
             const int tot = nr0 * nc0;
+            float rnc;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rnc) : "f"((float)nc0));
             for (int idx = lane; idx < tot; idx += 32) {
-                const int i = idx / nc0, j = idx - i * nc0;
+                const int i = __float2int_rz(((float)idx + 0.5f) * rnc), j = idx - i * nc0;
                 const double c = C[(size_t)i * ldc + j];
                 bad |= (c != c) || (c == -INFINITY);
                 if (staged) PTK_AT(sm, tr ? (j * nc + i) : (i * nc + j), nr * nc, 20) = c;
@@ -413,70 +424,102 @@ __global__ void __launch_bounds__(32) k_lsap(const __grid_constant__ LsapArgs a)
         __syncwarp();
     }
 
-    double v[CPL], spc[CPL];
-    int path[CPL], r4c[CPL], pos[CPL];
+    // The Dijkstra step is bound by instruction dispatch (integer / select / compare instructions hold the
+    // scheduler's port for two cycles), so it is written like the tracking solver's (ptk_lsap_trk.cuh):
+    //  * keys are the RAW bits of the shortest-path cost -- for non-negative doubles the signed integer order
+    //    of the bits is the value order; one unsigned compare on the first REDUX result catches "every
+    //    remaining column at +inf" and "a negative candidate", and only the latter is redone with the
+    //    order-preserving transform (skey);
+    //  * a visited (or absent) column's high word becomes +NaN's (its real one moves to seen_hi): `r < NaN`,
+    //    `NaN == min` are false and NaN's bits are above +inf's -- no "live" predicate in the loop;
+    //  * the tie-rule candidate is ONE multiply-add from two per-column constants that only change on
+    //    augmentation; it carries row4col + 1 and the column, so the winner needs no further broadcast.
+    const int kDeadHi = 0x7ff80000;
+    double v[CPL];
+    int spc_hi[CPL], spc_lo[CPL], seen_hi[CPL];
+    int path[CPL], r4c[CPL], pos[CPL], jc[CPL];
+    unsigned ka[CPL], kb[CPL];
 #pragma unroll
-    for (int s = 0; s < CPL; s++) { v[s] = 0.0; spc[s] = 0.0; path[s] = -1; r4c[s] = -1; pos[s] = -1; }
-    const unsigned long long kInfKey = 0xfff0000000000000ull;  // ordered_key(+inf)
+    for (int s = 0; s < CPL; s++) {
+        const int j = lane + 32 * s;
+        v[s] = 0.0; spc_hi[s] = kDeadHi; spc_lo[s] = 0; seen_hi[s] = kDeadHi; path[s] = -1; r4c[s] = -1; pos[s] = -1;
+        jc[s] = j < nc ? j : (nc > 0 ? nc - 1 : 0);  // a column index that may be read (absent columns are never used)
+        ka[s] = 0u - (1u << 18);                      // unassigned column: rank = 511 - pos (largest position wins)
+        kb[s] = (511u << 18) | (unsigned)j;
+    }
 
     if (st == PTK_PROBLEM_OK) {
         for (int cur = 0; cur < nr; cur++) {
 #pragma unroll
             for (int s = 0; s < CPL; s++) {
                 const int j = lane + 32 * s;
-                spc[s] = INFINITY;
+                spc_hi[s] = (j < nc) ? 0x7ff00000 : kDeadHi;  // +inf
+                spc_lo[s] = 0;
+                seen_hi[s] = kDeadHi;                 // NaN = not visited in this row
                 pos[s] = (j < nc) ? (nc - 1 - j) : -1;  // remaining[it] = nc-1-it  <=>  pos[j] = nc-1-j
             }
             double minVal = 0.0;
             int i = cur, num_rem = nc, sink = -1;
             while (sink == -1) {
                 const double ui = PTK_AT(u, i, nr, 21);
-                unsigned long long kmin = ~0ull;
-                unsigned long long key[CPL];
+                int mhi;
+                unsigned mlo;
 #pragma unroll
                 for (int s = 0; s < CPL; s++) {
-                    key[s] = ~0ull;
-                    if (pos[s] >= 0) {
-                        const int j = lane + 32 * s;
-                        const double c = staged ? PTK_AT(sm, i * nc + j, nr * nc, 22)
-                                                : (tr ? C[(size_t)j * ldc + i] : C[(size_t)i * ldc + j]);
-                        const double r = ((minVal + c) - ui) - v[s];
-                        if (r < spc[s]) { spc[s] = r; path[s] = i; }
-                        key[s] = ordered_key(spc[s]);
-                        kmin = key[s] < kmin ? key[s] : kmin;
+                    const int j = jc[s];
+                    const double c = staged ? PTK_AT(sm, i * nc + j, nr * nc, 22)
+                                            : (tr ? C[(size_t)j * ldc + i] : C[(size_t)i * ldc + j]);
+                    const double r = ((minVal + c) - ui) - v[s];
+                    if (r < __hiloint2double(spc_hi[s], spc_lo[s])) {  // false for a visited / absent column (NaN)
+                        spc_hi[s] = __double2hiint(r);
+                        spc_lo[s] = __double2loint(r);
+                        path[s] = i;
                     }
+                    const int h = spc_hi[s];
+                    const unsigned l = (unsigned)spc_lo[s];
+                    if (s == 0 || h < mhi || (h == mhi && l < mlo)) { mhi = h; mlo = l; }
                 }
-                // warp argmin with SciPy's tie rule in three REDUX ops: (1) high and (2) low word
-                // of the order-preserving key of the shortest-path cost, then (3) one packed
-                // integer whose order is the tie rule -- unassigned columns first (largest list
-                // position wins), then assigned ones (smallest position wins) -- and whose low
-                // bits carry row4col+1 and the column, so the winner needs no further broadcast.
-                const unsigned mh = __reduce_min_sync(kFull, (unsigned)(kmin >> 32));
-                const unsigned ml = __reduce_min_sync(kFull, (unsigned)(kmin >> 32) == mh ? (unsigned)kmin : 0xffffffffu);
-                const unsigned long long m64 = ((unsigned long long)mh << 32) | ml;
-                if (m64 == kInfKey) { st = PTK_PROBLEM_INFEASIBLE; break; }
+                // warp argmin with SciPy's tie rule in three REDUX ops: (1) high and (2) low word of the cost's
+                // bits, then (3) one packed integer whose order is the tie rule -- unassigned columns first
+                // (largest list position wins), then assigned ones (smallest position wins)
+                const int mh = __reduce_min_sync(kFull, mhi);
+                if ((unsigned)mh >= 0x7ff00000u) {  // rare: +inf everywhere, or a negative candidate
+                    if (mh >= 0) { st = PTK_PROBLEM_INFEASIBLE; break; }
+                    int h2 = 0x7fffffff;
+                    unsigned l2 = 0xffffffffu;
+#pragma unroll
+                    for (int s = 0; s < CPL; s++) {
+                        int h;
+                        unsigned l;
+                        skey(__hiloint2double(spc_hi[s], spc_lo[s]), h, l);
+                        if (h < h2 || (h == h2 && l < l2)) { h2 = h; l2 = l; }
+                    }
+                    const int mh2 = __reduce_min_sync(kFull, h2);
+                    const unsigned ml2 = __reduce_min_sync(kFull, h2 == mh2 ? l2 : 0xffffffffu);
+                    minVal = skey_value(mh2, ml2);
+                } else {
+                    const unsigned ml = __reduce_min_sync(kFull, mhi == mh ? mlo : 0xffffffffu);
+                    minVal = __hiloint2double(mh, (int)ml);
+                }
                 unsigned key3 = 0xffffffffu;
 #pragma unroll
                 for (int s = 0; s < CPL; s++) {
-                    if (key[s] == m64) {  // implies pos[s] >= 0
-                        const unsigned rank = (r4c[s] == -1) ? (unsigned)(511 - pos[s]) : (unsigned)(512 + pos[s]);
-                        const unsigned cand = (rank << 18) | ((unsigned)(r4c[s] + 1) << 9) | (unsigned)(lane + 32 * s);
-                        key3 = min(key3, cand);
-                    }
+                    const unsigned cand = ka[s] * (unsigned)pos[s] + kb[s];
+                    key3 = min(key3, (__hiloint2double(spc_hi[s], spc_lo[s]) == minVal) ? cand : 0xffffffffu);
                 }
                 key3 = __reduce_min_sync(kFull, key3);
                 const int jsel = (int)(key3 & 511u);
                 const int r4 = (int)((key3 >> 9) & 511u) - 1;
                 const unsigned rank = key3 >> 18;
                 const int index = rank < 512u ? (int)(511u - rank) : (int)(rank - 512u);
-                minVal = ordered_value(m64);
                 if (r4 == -1) sink = jsel; else i = r4;
-                // remaining[index] = remaining[--num_remaining]; -2 marks "visited" (SC)
+                // remaining[index] = remaining[--num_remaining]: the column at the last position takes the freed
+                // one; the selected column becomes visited (SC): its high word moves to seen_hi
                 num_rem--;
 #pragma unroll
                 for (int s = 0; s < CPL; s++) {
-                    const int ps = pos[s];
-                    pos[s] = (ps == index) ? -2 : ((ps == num_rem) ? index : ps);
+                    if (lane + 32 * s == jsel) { seen_hi[s] = spc_hi[s]; spc_hi[s] = kDeadHi; }
+                    else if (pos[s] == num_rem) pos[s] = index;
                 }
             }
             if (st != PTK_PROBLEM_OK) break;
@@ -487,8 +530,8 @@ __global__ void __launch_bounds__(32) k_lsap(const __grid_constant__ LsapArgs a)
             if (lane == 0) u[cur] += minVal;
 #pragma unroll
             for (int s = 0; s < CPL; s++) {
-                if (pos[s] == -2) {
-                    const double d = minVal - spc[s];
+                if (seen_hi[s] != kDeadHi) {  // visited in this row
+                    const double d = minVal - __hiloint2double(seen_hi[s], spc_lo[s]);
                     if (r4c[s] >= 0) u[r4c[s]] += d;
                     v[s] -= d;
                 }
@@ -498,8 +541,14 @@ __global__ void __launch_bounds__(32) k_lsap(const __grid_constant__ LsapArgs a)
             int j = sink;
             while (true) {
                 const int r = lane_array_get<CPL>(path, j);
-                lane_array_set<CPL>(r4c, j, r, lane);
                 if (!PTK_OK_IDX(r, nr, 23) || !PTK_OK_IDX(j, nc, 24)) break;  // (debug build) a corrupt augmenting path
+#pragma unroll
+                for (int s = 0; s < CPL; s++)
+                    if (lane + 32 * s == j) {
+                        r4c[s] = r;
+                        ka[s] = 1u << 18;  // assigned column: rank = 512 + pos (smallest position wins)
+                        kb[s] = (512u << 18) | ((unsigned)(r + 1) << 9) | (unsigned)j;
+                    }
                 const int t = c4r[r];
                 __syncwarp();
                 if (lane == 0) c4r[r] = j;

@@ -78,21 +78,6 @@ __device__ __noinline__ double trk_cross_min_q(const TrkArgs& a, long long p, do
     return trk_cross_min(cur, cur + (size_t)a.N * 6, d0, i, j);
 }
 
-// order-preserving map double -> int64 (signed compare), an involution: negative values have their
-// low 63 bits flipped
-__device__ __forceinline__ void skey(double x, int& hi, unsigned& lo)
-{
-    const int h = __double2hiint(x);
-    const int m = h >> 31;
-    hi = h ^ (m & 0x7fffffff);
-    lo = (unsigned)__double2loint(x) ^ (unsigned)m;
-}
-__device__ __forceinline__ double skey_value(int hi, unsigned lo)
-{
-    const int m = hi >> 31;
-    return __hiloint2double(hi ^ (m & 0x7fffffff), (int)(lo ^ (unsigned)m));
-}
-
 // ---- per-problem record written by k_trk_prepare and read by k_lsap_trk (global memory, L2 resident)
 //   double A[N] | double B[N] | double xval[N] | int32 xrow[N] | uint32 xm[N][W] | int32 bad, pad[3]
 // W = mask words per row = ceil(N / 32).
