@@ -429,6 +429,7 @@ int launch_rows(const DevRig& rig, long long P, int Nmax, const double* cam1, co
         a.ends_trk = trk ? trk->ends : nullptr;
         a.trk_F = trk ? trk->F : 0; a.trk_C = trk ? trk->C : 1; a.trk_N = trk ? trk->N : 0;
         a.trk_p0 = (trk ? trk->p0 : 0) + p0;
+        a.trk_rC = 1.0 / (double)a.trk_C;
         dim3 grid((Nmax + 31) / 32, np);
         {
             LaunchTimer lt(K_ROWS, st);

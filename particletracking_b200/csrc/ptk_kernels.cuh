@@ -639,7 +639,11 @@ struct RowsArgs {
     double* ends_trk;        // optional [C,F,trk_N,6]
     int trk_F, trk_C, trk_N;
     long long trk_p0;
+    double trk_rC;           // 1 / trk_C: the frame of a problem from a multiply instead of a 64-bit division
 };
+// frame = g / C for 0 <= g < 2^40: (g + 0.5) / C is at least 0.5 / C away from every integer, far more than the
+// rounding of the product
+__device__ __forceinline__ long long trk_frame(long long g, double rC) { return (long long)(((double)g + 0.5) * rC); }
 
 template <bool CANON, bool SIMPLE>
 __global__ void __launch_bounds__(128) k_rows(const __grid_constant__ DevRig rig, const __grid_constant__ RowsArgs a)
@@ -661,7 +665,7 @@ __global__ void __launch_bounds__(128) k_rows(const __grid_constant__ DevRig rig
                 for (int k = c; k < 6; k += 4) o[k] = qnan;
             }
             if (a.ends_trk && m < a.trk_N) {
-                const long long g = a.trk_p0 + p, f = g / a.trk_C, col = g - f * a.trk_C;
+                const long long g = a.trk_p0 + p, f = trk_frame(g, a.trk_rC), col = g - f * a.trk_C;
                 double* o = a.ends_trk + (((size_t)col * a.trk_F + f) * a.trk_N + m) * 6;
                 for (int k = c; k < 6; k += 4) o[k] = qnan;
             }
@@ -706,7 +710,7 @@ __global__ void __launch_bounds__(128) k_rows(const __grid_constant__ DevRig rig
         if (a.pair_cost && m < a.Nmax) a.pair_cost[base + m] = active ? np_min(s_mine, s_other) : qnan;
         if (a.straight && m < a.Nmax) a.straight[base + m] = (active && straight) ? 1 : 0;
         if (a.ends_trk && m < a.trk_N) {  // rows >= n_out are NaN in every output form
-            const long long g = a.trk_p0 + p, f = g / a.trk_C, col = g - f * a.trk_C;
+            const long long g = a.trk_p0 + p, f = trk_frame(g, a.trk_rC), col = g - f * a.trk_C;
             double* o = a.ends_trk + (((size_t)col * a.trk_F + f) * a.trk_N + m) * 6;
             o[0] = active ? ax : qnan; o[1] = active ? ay : qnan; o[2] = active ? az : qnan;
             o[3] = active ? bx : qnan; o[4] = active ? by : qnan; o[5] = active ? bz : qnan;
