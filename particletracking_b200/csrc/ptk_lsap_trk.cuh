@@ -54,8 +54,18 @@ __device__ __noinline__ double trk_cross_min(const double* __restrict__ cur, con
     return (d0 != d0) ? d0 : ((d1 != d1) ? d1 : (d1 < d0 ? d1 : d0));
 }
 
-// d1 is skipped only where a lower bound on it (largest coordinate difference of each of its two
-// norms) exceeds d0 by more than rounding could bridge: then min(d0, d1) == d0 exactly.
+// d1 is skipped only where a lower bound on it exceeds d0 by more than rounding could bridge: then
+// min(d0, d1) == d0 exactly.  The bound on each of d1's two norms is (|dx| + |dy| + |dz|) / sqrt(3) <= |d|
+// (Cauchy-Schwarz) -- two additions per norm where the largest coordinate difference cost two FP64 maxima
+// (a compare and two selects each); which entries take the exact path changes, their values do not.
+__device__ __forceinline__ bool trk_bound_decides(double p1a0, double p1a1, double p1a2, double q1a0, double q1a1, double q1a2,
+                                                  double p2b0, double p2b1, double p2b2, double q2b0, double q2b1, double q2b2,
+                                                  double d0)
+{
+    const double la = (fabs(p1a0 - q2b0) + fabs(p1a1 - q2b1)) + fabs(p1a2 - q2b2);
+    const double lb = (fabs(p2b0 - q1a0) + fabs(p2b1 - q1a1)) + fabs(p2b2 - q1a2);
+    return (la + lb) * 0.57735026918962 > d0;  // just below 1 / sqrt(3)
+}
 __device__ __forceinline__ double trk_entry(const double* __restrict__ cur, const double* __restrict__ nxt, double d0,
                                             int a, int b)
 {
@@ -63,9 +73,8 @@ __device__ __forceinline__ double trk_entry(const double* __restrict__ cur, cons
     const double* p2b = cur + 6 * b + 3;
     const double* q1a = nxt + 6 * a;
     const double* q2b = nxt + 6 * b + 3;
-    const double la = fmax(fmax(fabs(p1a[0] - q2b[0]), fabs(p1a[1] - q2b[1])), fabs(p1a[2] - q2b[2]));
-    const double lb = fmax(fmax(fabs(p2b[0] - q1a[0]), fabs(p2b[1] - q1a[1])), fabs(p2b[2] - q1a[2]));
-    if ((la + lb) * 0.99999999999999 > d0) return d0;
+    if (trk_bound_decides(p1a[0], p1a[1], p1a[2], q1a[0], q1a[1], q1a[2], p2b[0], p2b[1], p2b[2], q2b[0], q2b[1], q2b[2], d0))
+        return d0;
     return trk_cross_min(cur, nxt, d0, a, b);
 }
 
@@ -142,11 +151,19 @@ __global__ void __launch_bounds__(32 * kTrkPrepWarps) k_trk_prepare(const __grid
         const bool own = j < N;
         const int jj = own ? j : N - 1;
         const double Bj = Bs[jj];
+        // the column's end points stay in registers across the rows
+        const double p2b0 = cur[6 * jj + 3], p2b1 = cur[6 * jj + 4], p2b2 = cur[6 * jj + 5];
+        const double q2b0 = nxt[6 * jj + 3], q2b1 = nxt[6 * jj + 4], q2b2 = nxt[6 * jj + 5];
         int xrow = -1;
         double xval = 0.0;
         for (int i = 0; i < N; i++) {
             const double d0 = As[i] + Bj;
-            const double c = trk_entry(cur, nxt, d0, i, jj);
+            const double* p1a = cur + 6 * i;
+            const double* q1a = nxt + 6 * i;
+            const double c = trk_bound_decides(p1a[0], p1a[1], p1a[2], q1a[0], q1a[1], q1a[2], p2b0, p2b1, p2b2, q2b0, q2b1,
+                                               q2b2, d0)
+                                 ? d0
+                                 : trk_cross_min(cur, nxt, d0, i, jj);
             bool flag = false;
             if (own) {
                 bad |= (c != c) || (c == -INFINITY);  // SciPy: "matrix contains invalid numeric entries"
