@@ -499,10 +499,10 @@ PTK_HD bool dlt_null_invpower_n(const double* __restrict__ Q1, const double* __r
 // block of T = R~^-1 and that block's share B3 of B = T diag(w) T^T functions of (x2, y2) only, and what
 // remains per combination is linear algebra on fixed operators applied to (gx, gy, 1):
 //     z = Zm (gx, gy, 1)      the last column of T (order 0, 1, 3, 2; its fourth entry is 1),
-//     a = Am (gx, gy, 1)      the residual of a2 after the three projections,  n2 = |a|^2,
+//     a = Am (gx, gy, 1)      the residual of a2 after the three projections,  n2 = |a|^2 = a quadratic form in g,
 //     B / w2 = z z^T + n2 [B3 0; 0 0]                          (w2 = 1 / n2, the last pivot)
-// `canon_prep2` computes Zm (3x3), Am (4x3) and B3 (6) ONCE per camera-2 end point (2 N2 per problem, kernel
-// k_prep2) by running the Gram-Schmidt step on e0, e1 and d separately; a combination then costs 32 FP64
+// `canon_prep2` computes Zm (3x3), the six coefficients of n2 and B3 (6) ONCE per camera-2 end point (2 N2 per
+// problem, kernel k_prep2) by running the Gram-Schmidt step on e0, e1 and d separately; a combination then costs 26 FP64
 // instructions up to B instead of 103, needs no reciprocal (B is used divided by w2: same eigenvectors) and no
 // power-of-two scaling (tr(B / w2) = 1 + |z|^2 + small).  The power iteration is the same; the null vector
 // comes back in the caller's column order.  Same accuracy against cv2.triangulatePoints as the functions
@@ -511,10 +511,11 @@ PTK_HD bool dlt_null_invpower_n(const double* __restrict__ Q1, const double* __r
 // and K3 with the record computed in place by the same function.
 // ---------------------------------------------------------------------------------------
 struct Canon2Rec {
-    // f[0..8]: Zm by columns (gx | gy | 1), f[9..20]: Am by columns, f[21..26]: B00 B01 B02 B11 B12 B22, f[27] unused
-    double f[28];
+    // f[0..8]: Zm by columns (gx | gy | 1); f[9..14]: the quadratic form n2 = |Am (gx, gy, 1)|^2 as
+    // Q00, 2 Q01, 2 Q02, Q11, 2 Q12, Q22; f[15..20]: B00 B01 B02 B11 B12 B22; f[21] unused
+    double f[22];
 };
-constexpr int kCanon2RecPlanes = 14;  // double2 planes of the record in memory
+constexpr int kCanon2RecPlanes = 11;  // double2 planes of the record in memory
 
 PTK_HD void canon_prep2(const double* __restrict__ cm1, double fx2, const double* __restrict__ Q2, double x2, double y2,
                         Canon2Rec& r)
@@ -540,6 +541,7 @@ PTK_HD void canon_prep2(const double* __restrict__ cm1, double fx2, const double
     // the Gram-Schmidt step of the last column, applied to e0, e1 and d = (0, 0, p2, q2): residual and the
     // column's entries of R~ (r02, r12, r32), from which the last column of T:
     //   t23 = -r32,  t13 = r13 r32 - r12,  t03 = r03 r32 - (r01 t13 + r02)
+    double am[3][4];  // the residuals: Am by columns
 #pragma unroll
     for (int c = 0; c < 3; c++) {
         double b[4] = {c == 0 ? 1.0 : 0.0, c == 1 ? 1.0 : 0.0, c == 2 ? p2 : 0.0, c == 2 ? q2 : 0.0};
@@ -553,18 +555,28 @@ PTK_HD void canon_prep2(const double* __restrict__ cm1, double fx2, const double
         r.f[3 * c + 0] = fma(r03, rc, -fma(r01, t13, ra));
         r.f[3 * c + 1] = t13;
         r.f[3 * c + 2] = -rc;
-        r.f[9 + 4 * c + 0] = b[0]; r.f[9 + 4 * c + 1] = b[1]; r.f[9 + 4 * c + 2] = b[2]; r.f[9 + 4 * c + 3] = b[3];
+        am[c][0] = b[0]; am[c][1] = b[1]; am[c][2] = b[2]; am[c][3] = b[3];
     }
+    // n2 = |Am g|^2 as a quadratic form in (gx, gy): six coefficients instead of the twelve of Am.  n2 only scales
+    // the SMALL part of B (the eigenvector moves by eps * cond, as with any formation of A^T A), so the
+    // cancellation in the form does not reach the result (tests/test_dlt_invpower_cpu.py: 1.3e-15 against cv2 with
+    // either form, the two forms 2e-16 apart).
+    r.f[9] = PTK_DOT(am[0], am[0]);
+    r.f[10] = 2.0 * PTK_DOT(am[0], am[1]);
+    r.f[11] = 2.0 * PTK_DOT(am[0], am[2]);
+    r.f[12] = PTK_DOT(am[1], am[1]);
+    r.f[13] = 2.0 * PTK_DOT(am[1], am[2]);
+    r.f[14] = PTK_DOT(am[2], am[2]);
     // leading block of T (order 0, 1, 3): t01 = -r01, t12' = -r13, t02' = r01 r13 - r03; B3 = T3 diag(w0, w1, w3) T3^T
     const double t02 = fma(r01, r13, -r03);
     const double c01 = -r01 * w1, c02 = t02 * w3, c12 = -r13 * w3;
-    r.f[21] = fma(t02, c02, fma(-r01, c01, w0));
-    r.f[22] = fma(t02, c12, c01);
-    r.f[23] = c02;
-    r.f[24] = fma(-r13, c12, w1);
-    r.f[25] = c12;
-    r.f[26] = w3;
-    r.f[27] = 0.0;
+    r.f[15] = fma(t02, c02, fma(-r01, c01, w0));
+    r.f[16] = fma(t02, c12, c01);
+    r.f[17] = c02;
+    r.f[18] = fma(-r13, c12, w1);
+    r.f[19] = c12;
+    r.f[20] = w3;
+    r.f[21] = 0.0;
 }
 
 // cm1 = (fx, fy, cx, cy); r = canon_prep2 of the camera-2 point; (x1, y1) the camera-1 point.
@@ -578,16 +590,11 @@ PTK_HD bool dlt_null_invpower_canon_rec(const double* __restrict__ cm1, const Ca
     const double z0 = fma(r.f[0], gx, fma(r.f[3], gy, r.f[6]));
     const double z1 = fma(r.f[1], gx, fma(r.f[4], gy, r.f[7]));
     const double z2 = fma(r.f[2], gx, fma(r.f[5], gy, r.f[8]));
-    double a[4];
-    a[0] = fma(r.f[9], gx, fma(r.f[13], gy, r.f[17]));
-    a[1] = fma(r.f[10], gx, fma(r.f[14], gy, r.f[18]));
-    a[2] = fma(r.f[11], gx, fma(r.f[15], gy, r.f[19]));
-    a[3] = fma(r.f[12], gx, fma(r.f[16], gy, r.f[20]));
-    const double n2 = PTK_DOT(a, a);
+    const double n2 = fma(gx, fma(r.f[9], gx, fma(r.f[10], gy, r.f[11])), fma(gy, fma(r.f[12], gy, r.f[13]), r.f[14]));
     double u[4];
-    const bool ok = dlt_invpower_core<3, FAST, false>(fma(z0, z0, n2 * r.f[21]), fma(z0, z1, n2 * r.f[22]),
-                                                      fma(z0, z2, n2 * r.f[23]), z0, fma(z1, z1, n2 * r.f[24]),
-                                                      fma(z1, z2, n2 * r.f[25]), z1, fma(z2, z2, n2 * r.f[26]), z2, 1.0, u);
+    const bool ok = dlt_invpower_core<3, FAST, false>(fma(z0, z0, n2 * r.f[15]), fma(z0, z1, n2 * r.f[16]),
+                                                      fma(z0, z2, n2 * r.f[17]), z0, fma(z1, z1, n2 * r.f[18]),
+                                                      fma(z1, z2, n2 * r.f[19]), z1, fma(z2, z2, n2 * r.f[20]), z2, 1.0, u);
     v[0] = u[0]; v[1] = u[1]; v[2] = u[3]; v[3] = u[2];
     return ok;
 }
