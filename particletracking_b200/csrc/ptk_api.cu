@@ -231,10 +231,12 @@ int launch_undistort(const DevRig& rig, long long P, int Nmax, const double* cam
     // gridDim.y is limited to 65535: slice the problem axis
     for (long long p0 = 0; p0 < P; p0 += 65535) {
         const int np = (int)((P - p0) < 65535 ? (P - p0) : 65535);
-        dim3 grid((2 * Nmax + 127) / 128, np, 2);
+        // 2 * Nmax pseudo-points per camera and problem: no idle warps in the block for small problems
+        const int thr = 2 * Nmax >= 128 ? 128 : ((2 * Nmax + 31) / 32) * 32;
+        dim3 grid((2 * Nmax + thr - 1) / thr, np, 2);
         {
             LaunchTimer lt(K_UNDISTORT, st);
-            k_undistort<<<grid, 128, 0, st>>>(rig, Nmax, cam1 + (size_t)p0 * Nmax * 4, cam2 + (size_t)p0 * Nmax * 4, n1 + p0,
+            k_undistort<<<grid, thr, 0, st>>>(rig, Nmax, cam1 + (size_t)p0 * Nmax * 4, cam2 + (size_t)p0 * Nmax * 4, n1 + p0,
                                               n2 + p0, und1 + (size_t)p0 * Nmax * 4, und2 + (size_t)p0 * Nmax * 4);
         }
         LAUNCHED("k_undistort");
@@ -261,10 +263,11 @@ int launch_cost(const DevRig& rig, long long P, int Nmax, const double* cam1, co
         a.n1 = n1 + p0; a.n2 = n2 + p0;
         a.cost = cost + o2;
         if (rig.canon) {  // K0b: the camera-2 share of the DLT, once per end point (ptk_device.cuh: canon_prep2)
-            const dim3 pgrid((2 * Nmax + 127) / 128, (unsigned)np);
+            const int pthr = 2 * Nmax >= 128 ? 128 : ((2 * Nmax + 31) / 32) * 32;
+            const dim3 pgrid((2 * Nmax + pthr - 1) / pthr, (unsigned)np);
             {
                 LaunchTimer lt(K_UNDISTORT, st);
-                k_prep2<<<pgrid, 128, 0, st>>>(rig, Nmax, a.und2, a.n2, const_cast<double2*>(a.rec2));
+                k_prep2<<<pgrid, pthr, 0, st>>>(rig, Nmax, a.und2, a.n2, const_cast<double2*>(a.rec2));
             }
             LAUNCHED("k_prep2");
         }
@@ -430,13 +433,14 @@ int launch_rows(const DevRig& rig, long long P, int Nmax, const double* cam1, co
         a.trk_F = trk ? trk->F : 0; a.trk_C = trk ? trk->C : 1; a.trk_N = trk ? trk->N : 0;
         a.trk_p0 = (trk ? trk->p0 : 0) + p0;
         a.trk_rC = 1.0 / (double)a.trk_C;
-        dim3 grid((Nmax + 31) / 32, np);
+        const int thr = Nmax >= 32 ? 128 : ((4 * Nmax + 31) / 32) * 32;  // 4 lanes per row, up to 32 rows per block
+        dim3 grid((4 * Nmax + thr - 1) / thr, np);
         {
             LaunchTimer lt(K_ROWS, st);
-            if (rig.canon && rig.simple) k_rows<true, true><<<grid, 128, 0, st>>>(rig, a);
-            else if (rig.canon) k_rows<true, false><<<grid, 128, 0, st>>>(rig, a);
-            else if (rig.simple) k_rows<false, true><<<grid, 128, 0, st>>>(rig, a);
-            else k_rows<false, false><<<grid, 128, 0, st>>>(rig, a);
+            if (rig.canon && rig.simple) k_rows<true, true><<<grid, thr, 0, st>>>(rig, a);
+            else if (rig.canon) k_rows<true, false><<<grid, thr, 0, st>>>(rig, a);
+            else if (rig.simple) k_rows<false, true><<<grid, thr, 0, st>>>(rig, a);
+            else k_rows<false, false><<<grid, thr, 0, st>>>(rig, a);
         }
         LAUNCHED("k_rows");
     }

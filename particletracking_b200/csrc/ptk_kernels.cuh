@@ -649,12 +649,13 @@ template <bool CANON, bool SIMPLE>
 __global__ void __launch_bounds__(128) k_rows(const __grid_constant__ DevRig rig, const __grid_constant__ RowsArgs a)
 {
     const int p = blockIdx.y;
-    const int m = blockIdx.x * 32 + (threadIdx.x >> 2);
+    const int rpb = blockDim.x >> 2;  // rows per block: 32, fewer for small problems (no idle quads)
+    const int m = blockIdx.x * rpb + (threadIdx.x >> 2);
     const int c = threadIdx.x & 3;
     const int n = a.n_out[p];
     const size_t base = (size_t)p * a.Nmax;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-    if (blockIdx.x * 32 >= n) {  // whole block past the matches: NaN fill
+    if (blockIdx.x * rpb >= n) {  // whole block past the matches: NaN fill
         if (m < a.Nmax) {
             if (a.rows) {
                 double* o = a.rows + (base + m) * PTK_ROW_COLS;
