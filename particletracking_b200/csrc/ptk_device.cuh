@@ -368,24 +368,7 @@ static inline double ptk_pow2_inv(double x)
 #define PTK_HD __host__ __device__ inline
 #endif
 
-// The power iteration on B = (A^T A)^-1 (symmetric, given by its upper triangle): scaling by a power of
-// two, NSQ symmetric squarings, the convergence check and the final product with the largest-diagonal
-// column.  Returns whether the iteration has converged.
-// LAST_ONLY: the caller expects the last diagonal entry to be the largest (the record variant, whose last
-// column carries the depth) and has a slow path for everything unusual: the last column is taken
-// unconditionally and "it was not the largest" is reported as not converged (no select, no branch here).
-// SCALE: B is first scaled by a power of two so that its trace is in [1, 2) (the record variant passes
-// B / w2 whose trace is 1 + |z|^2 + small and needs none; absurd magnitudes overflow to Inf / NaN, which the
-// convergence test reports as "not converged").
-template <int NSQ, bool LAST_ONLY = false, bool SCALE = true>
-PTK_HD bool dlt_invpower_core(double b00, double b01, double b02, double b03, double b11, double b12, double b13,
-                              double b22, double b23, double b33, double (&v)[4])
-{
-    if (SCALE) {
-        const double sc = ptk_pow2_inv((b00 + b11) + (b22 + b33));
-        b00 *= sc; b01 *= sc; b02 *= sc; b03 *= sc; b11 *= sc;
-        b12 *= sc; b13 *= sc; b22 *= sc; b23 *= sc; b33 *= sc;
-    }
+// B <- B B for a symmetric 4x4 matrix given by its upper triangle b00 .. b33 (40 FP64 instructions)
 #define PTK_SQUARE_B                                                                     \
     {                                                                                    \
         const double c00 = fma(b03, b03, fma(b02, b02, fma(b01, b01, b00 * b00)));       \
@@ -401,13 +384,28 @@ PTK_HD bool dlt_invpower_core(double b00, double b01, double b02, double b03, do
         b00 = c00; b01 = c01; b02 = c02; b03 = c03; b11 = c11;                           \
         b12 = c12; b13 = c13; b22 = c22; b23 = c23; b33 = c33;                           \
     }
+
+// The power iteration on B = (A^T A)^-1 (symmetric, given by its upper triangle): scaling by a power of
+// two, NSQ symmetric squarings, the convergence check and the final product with the largest-diagonal
+// column.  Returns whether the iteration has converged.
+// SCALE: B is first scaled by a power of two so that its trace is in [1, 2) (the record variant passes
+// B / w2 whose trace is 1 + |z|^2 + small and needs none; absurd magnitudes overflow to Inf / NaN, which the
+// convergence test reports as "not converged").
+template <int NSQ, bool SCALE = true>
+PTK_HD bool dlt_invpower_core(double b00, double b01, double b02, double b03, double b11, double b12, double b13,
+                              double b22, double b23, double b33, double (&v)[4])
+{
+    if (SCALE) {
+        const double sc = ptk_pow2_inv((b00 + b11) + (b22 + b33));
+        b00 *= sc; b01 *= sc; b02 *= sc; b03 *= sc; b11 *= sc;
+        b12 *= sc; b13 *= sc; b22 *= sc; b23 *= sc; b33 *= sc;
+    }
     PTK_SQUARE_B PTK_SQUARE_B
     // sigma_4/sigma_3 between 0.39 and 0.62 (geometry unlike a rod experiment's): one more squaring, B^16
     // and B^32 e_j below.  tr(B^8) is within 2^-32 .. 2^16, so its square neither overflows nor underflows.
     if (NSQ > 3) PTK_SQUARE_B
     const double trh = (b00 + b11) + (b22 + b33);  // tr(B^(k/2))
     PTK_SQUARE_B
-#undef PTK_SQUARE_B
     // converged?  With k = 2^NSQ: tr(B^k) = |B^(k/2)|_F^2 >= (1 - tol) tr(B^(k/2))^2, i.e. 2 rho^(k/2) <= tol, rho =
     // (sigma_4/sigma_3)^2 -- the trace of the last square against the squared trace before it, six additions
     // instead of a Frobenius norm.  Written as tr - (1 - tol) trh^2 >= 0 so that Inf - Inf (a Gram-Schmidt norm
@@ -416,13 +414,6 @@ PTK_HD bool dlt_invpower_core(double b00, double b01, double b02, double b03, do
     const double tr = (b00 + b11) + (b22 + b33);
     const bool ok = fma(-(1.0 - PTK_INVPOWER_TOL), trh * trh, tr) >= 0.0;
     // v = B^k (column of B^k with the largest diagonal entry: |v_4[j]|^2 >= 1/4 there)
-    if (LAST_ONLY) {
-        v[0] = fma(b03, b33, fma(b02, b23, fma(b01, b13, b00 * b03)));
-        v[1] = fma(b13, b33, fma(b12, b23, fma(b11, b13, b01 * b03)));
-        v[2] = fma(b23, b33, fma(b22, b23, fma(b12, b13, b02 * b03)));
-        v[3] = fma(b33, b33, fma(b23, b23, fma(b13, b13, b03 * b03)));
-        return ok && b33 >= b00 && b33 >= b11 && b33 >= b22;
-    }
     double u0 = b00, u1 = b01, u2 = b02, u3 = b03, dm = b00;
     if (b11 > dm) { dm = b11; u0 = b01; u1 = b11; u2 = b12; u3 = b13; }
     if (b22 > dm) { dm = b22; u0 = b02; u1 = b12; u2 = b22; u3 = b23; }
@@ -580,9 +571,38 @@ PTK_HD void canon_prep2(const double* __restrict__ cm1, double fx2, const double
 }
 
 // cm1 = (fx, fy, cx, cy); r = canon_prep2 of the camera-2 point; (x1, y1) the camera-1 point.
-// FAST: straight-line code for the usual case -- true means "converged AND the last diagonal entry of B^8 was the
-// largest"; on false the caller repeats the point with FAST = false (generic column choice; false = not converged).
-template <bool FAST>
+// The power iteration of the record variant: B = z~ z~^T + E with z~ = (z, 1) and E small, so z~ itself is the
+// dominant eigenvector up to O(rho) -- no column has to be chosen.  B^4 by two squarings, then
+// v = B^4 B^4 B^4 z~: every other direction is down by rho^13 (rho <= 0.15 where the test passes; 0.11 at most on
+// rod data: 1.5e-14 against cv2.triangulatePoints, tests/test_dlt_invpower_cpu.py), 124 FP64 instructions against
+// the 132 + 3 compares of three squarings and a chosen column.  Converged?  tr(B^4) / tr(B^2)^2 ~ 1 - 2 rho^2, same
+// threshold on sigma_4 / sigma_3 (0.39) as the general function's three-squaring test; Inf / NaN (an absurd z)
+// read as "not converged".
+#define PTK_INVPOWER_TOL2 0.0447
+PTK_HD bool dlt_invpower_start(double b00, double b01, double b02, double b11, double b12, double b22, double z0, double z1,
+                               double z2, double (&v)[4])
+{
+    double b03 = z0, b13 = z1, b23 = z2, b33 = 1.0;
+    PTK_SQUARE_B
+    const double trh = (b00 + b11) + (b22 + b33);
+    PTK_SQUARE_B
+    const double tr = (b00 + b11) + (b22 + b33);
+    const bool ok = fma(-(1.0 - PTK_INVPOWER_TOL2), trh * trh, tr) >= 0.0;
+    double x0 = z0, x1 = z1, x2 = z2, x3 = 1.0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const double y0 = fma(b03, x3, fma(b02, x2, fma(b01, x1, b00 * x0)));
+        const double y1 = fma(b13, x3, fma(b12, x2, fma(b11, x1, b01 * x0)));
+        const double y2 = fma(b23, x3, fma(b22, x2, fma(b12, x1, b02 * x0)));
+        const double y3 = fma(b33, x3, fma(b23, x2, fma(b13, x1, b03 * x0)));
+        x0 = y0; x1 = y1; x2 = y2; x3 = y3;
+    }
+    v[0] = x0; v[1] = x1; v[2] = x2; v[3] = x3;
+    return ok;
+}
+
+// cm1 = (fx, fy, cx, cy); r = canon_prep2 of the camera-2 point; (x1, y1) the camera-1 point.  Returns whether
+// the iteration has converged (else: the caller's fallback).
 PTK_HD bool dlt_null_invpower_canon_rec(const double* __restrict__ cm1, const Canon2Rec& r, double x1, double y1,
                                         double (&v)[4])
 {
@@ -592,12 +612,13 @@ PTK_HD bool dlt_null_invpower_canon_rec(const double* __restrict__ cm1, const Ca
     const double z2 = fma(r.f[2], gx, fma(r.f[5], gy, r.f[8]));
     const double n2 = fma(gx, fma(r.f[9], gx, fma(r.f[10], gy, r.f[11])), fma(gy, fma(r.f[12], gy, r.f[13]), r.f[14]));
     double u[4];
-    const bool ok = dlt_invpower_core<3, FAST, false>(fma(z0, z0, n2 * r.f[15]), fma(z0, z1, n2 * r.f[16]),
-                                                      fma(z0, z2, n2 * r.f[17]), z0, fma(z1, z1, n2 * r.f[18]),
-                                                      fma(z1, z2, n2 * r.f[19]), z1, fma(z2, z2, n2 * r.f[20]), z2, 1.0, u);
+    const bool ok = dlt_invpower_start(fma(z0, z0, n2 * r.f[15]), fma(z0, z1, n2 * r.f[16]), fma(z0, z2, n2 * r.f[17]),
+                                       fma(z1, z1, n2 * r.f[18]), fma(z1, z2, n2 * r.f[19]), fma(z2, z2, n2 * r.f[20]), z0, z1,
+                                       z2, u);
     v[0] = u[0]; v[1] = u[1]; v[2] = u[3]; v[3] = u[2];
     return ok;
 }
+#undef PTK_SQUARE_B
 #undef PTK_DOT
 #undef PTK_AXPY
 
@@ -764,9 +785,8 @@ __device__ __forceinline__ double reproject_dist_h(const double* __restrict__ R,
 }
 
 // The unusual cases of eval_combo, out of line: the power iteration has not converged (extra squaring, then
-// OpenCV's Jacobi), the last diagonal entry of B^8 was not the largest (generic column choice), a squared
-// distance outside the fast square root's range (zero, Inf, NaN).  Everything is recomputed from the inputs;
-// u2 points at the undistorted camera-2 point.
+// OpenCV's Jacobi), a squared distance outside the fast square root's range (zero, Inf, NaN -- a zero depth ends
+// up here too).  Everything is recomputed from the inputs; u2 points at the undistorted camera-2 point.
 template <bool CANON, bool SIMPLE>
 __device__ __noinline__ void eval_combo_slow(const DevRig& rig, double u1x, double u1y, const double* __restrict__ u2,
                                              double o1x, double o1y, double o2x, double o2y, double* __restrict__ out)
@@ -777,7 +797,7 @@ __device__ __noinline__ void eval_combo_slow(const DevRig& rig, double u1x, doub
     if (CANON) {
         Canon2Rec rec;
         canon_prep2(rig.CM1, rig.fx2, rig.P2o, q.x, q.y, rec);
-        ok = dlt_null_invpower_canon_rec<false>(rig.CM1, rec, u1x, u1y, h);
+        ok = dlt_null_invpower_canon_rec(rig.CM1, rec, u1x, u1y, h);
     } else {
         ok = dlt_null_invpower_n<3>(rig.P1o, rig.P2o, u1x, u1y, q.x, q.y, h);
     }
@@ -801,14 +821,14 @@ __device__ __noinline__ void eval_combo_slow(const DevRig& rig, double u1x, doub
 // CANON: `rec` is canon_prep2 of the camera-2 point (read from k_prep2's records by K1, computed in place by K3:
 // the same function, the same bits); otherwise rec is unused.  u2 points at the undistorted camera-2 point.
 // (o1x, o1y), (o2x, o2y): the original (distorted) detections MINUS their camera's principal point (centre_detection).
-// The main path is straight-line code that only collects "something unusual" flags; ONE branch at the end sends
-// such a combination through eval_combo_slow.
+// The main path is straight-line code that only collects "something unusual" flags (not converged, a squared
+// distance out of range); ONE branch at the end sends such a combination through eval_combo_slow.
 // (K1 calls the three stages itself so that its shared-memory reads sit right before their use.)
 template <bool CANON>
 __device__ __forceinline__ bool eval_combo_dlt(const DevRig& rig, double u1x, double u1y, const double* __restrict__ u2,
                                                const Canon2Rec& rec, double (&h)[4])
 {
-    if (CANON) return dlt_null_invpower_canon_rec<true>(rig.CM1, rec, u1x, u1y, h);
+    if (CANON) return dlt_null_invpower_canon_rec(rig.CM1, rec, u1x, u1y, h);
     const double2 q = __ldg(reinterpret_cast<const double2*>(u2));
     return dlt_null_invpower_n<3>(rig.P1o, rig.P2o, u1x, u1y, q.x, q.y, h);
 }

@@ -25,23 +25,7 @@ extern "C" void tri_invpower_canon_rec_host(const double* cm1 /*fx fy cx cy*/, c
         ptk::Canon2Rec r;
         ptk::canon_prep2(cm1, fx2, P2, pts[4 * m + 2], pts[4 * m + 3], r);
         double a[4];
-        conv[m] = ptk::dlt_null_invpower_canon_rec<false>(cm1, r, pts[4 * m], pts[4 * m + 1], a) ? 1 : 0;
+        conv[m] = ptk::dlt_null_invpower_canon_rec(cm1, r, pts[4 * m], pts[4 * m + 1], a) ? 1 : 0;
         for (int k = 0; k < 4; k++) v_rec[4 * m + k] = a[k];
-    }
-}
-
-// K1's main-path variant (FAST: last column of B^8 taken unconditionally, "it was not the largest diagonal entry"
-// reported like "not converged") beside the generic one: where FAST says yes the two must give the same bits.
-extern "C" void tri_invpower_canon_rec_fast_host(const double* cm1, const double* P2, long long M, const double* pts,
-                                                 double* v_fast /*[M,4]*/, double* v_generic /*[M,4]*/, int* flags /*[M,2]*/)
-{
-    const double fx2 = cm1[0] * cm1[0];
-    for (long long m = 0; m < M; m++) {
-        ptk::Canon2Rec r;
-        ptk::canon_prep2(cm1, fx2, P2, pts[4 * m + 2], pts[4 * m + 3], r);
-        double a[4], b[4];
-        flags[2 * m] = ptk::dlt_null_invpower_canon_rec<true>(cm1, r, pts[4 * m], pts[4 * m + 1], a) ? 1 : 0;
-        flags[2 * m + 1] = ptk::dlt_null_invpower_canon_rec<false>(cm1, r, pts[4 * m], pts[4 * m + 1], b) ? 1 : 0;
-        for (int k = 0; k < 4; k++) { v_fast[4 * m + k] = a[k]; v_generic[4 * m + k] = b[k]; }
     }
 }

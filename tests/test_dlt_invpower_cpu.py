@@ -120,7 +120,7 @@ def test_canonical_record_variant_matches_cv2_and_the_general_function(harness):
         ref = _cv2(P1, P2, pts)
         Xr = vr[:, :3] / vr[:, 3:]
         scale = np.abs(ref).max(axis=1)
-        assert (np.abs(Xr - ref).max(axis=1) / scale).max() < 1e-13  # measured 1.5e-15
+        assert (np.abs(Xr - ref).max(axis=1) / scale).max() < 1e-13  # measured 1.6e-14 (rho^13 at rho up to 0.11)
         assert (np.abs(Xr - Xg).max(axis=1) / scale).max() < 1e-13
 
 
@@ -156,12 +156,11 @@ def test_canonical_record_variant_flags_near_degenerate_points(harness):
     assert err[ok].max() < 1e-9
 
 
-def test_main_path_flag_of_the_record_variant(harness):
-    """K1's main path takes the last column of B^8 without looking and reports "the last diagonal entry was not the
-    largest" together with "not converged"; the out-of-line path then redoes the point with the generic column
-    choice.  Where the main path says yes, both must give the same bits; detections far off the optical axis
-    (|x - cx| > fx: the depth is no longer the largest component of the null vector) must be flagged, and the
-    generic variant must still agree with cv2 there."""
+def test_record_variant_needs_no_column_choice(harness):
+    """The record variant iterates from the start vector (z, 1) -- the dominant eigenvector of B up to O(rho) --
+    instead of from a chosen column of B^8, so detections far off the optical axis (|x - cx| > fx: the depth is no
+    longer the largest component of the null vector, the case a column choice exists for) take the same path as
+    everything else and must agree with cv2."""
     sys.path.insert(0, ROOT)
     from particletracking_b200 import synthetic as syn
 
@@ -176,17 +175,20 @@ def test_main_path_flag_of_the_record_variant(harness):
     pts = _combos(a, s.cam2[0, 0])
     M = len(pts)
     p = lambda x: x.ctypes.data_as(ctypes.c_void_p)
-    vf, vg = np.empty((M, 4)), np.empty((M, 4))
-    fl = np.empty((M, 2), np.int32)
-    harness.tri_invpower_canon_rec_fast_host(p(cm1), p(np.ascontiguousarray(P2)), ctypes.c_longlong(M), p(pts), p(vf), p(vg), p(fl))
-    fast_ok = fl[:, 0] == 1
-    assert 0.2 < fast_ok.mean() < 0.9                      # the off-axis points are flagged ...
-    assert (fl[fast_ok, 1] == 1).all()                      # ... and nothing else is lost
-    assert np.array_equal(vf[fast_ok].view(np.int64), vg[fast_ok].view(np.int64))
-    off = (np.abs(pts[:, 0] - cm1[2]) > 1.2 * cm1[0]) | (np.abs(pts[:, 1] - cm1[3]) > 1.2 * cm1[1])
-    assert not fast_ok[off].any()
-    conv = fl[:, 1] == 1
+    vr = np.empty((M, 4))
+    conv = np.empty(M, np.int32)
+    harness.tri_invpower_canon_rec_host(p(cm1), p(np.ascontiguousarray(P2)), ctypes.c_longlong(M), p(pts), p(vr), p(conv))
+    ok = conv == 1
+    A = np.stack([pts[:, 0, None] * P1[2] - P1[0], pts[:, 1, None] * P1[2] - P1[1],
+                  pts[:, 2, None] * P2[2] - P2[0], pts[:, 3, None] * P2[2] - P2[1]], axis=1)
+    sv = np.linalg.svd(A, compute_uv=False)
+    ratio = sv[:, 3] / sv[:, 2]
+    # the verdict follows the spectrum alone (the x-displaced points are geometrically inconsistent: sigma_4 / sigma_3
+    # around 0.8, the fallback's), not the direction of the null vector
+    assert ratio[ok].max() < 0.40 and (~ok).sum() > 0 and ratio[~ok].min() > 0.37
+    offy = np.abs(pts[:, 1] - cm1[3]) > 1.2 * cm1[1]
+    assert offy.sum() > 300 and ok[offy].all()
     ref = _cv2(P1, P2, pts)
-    X = vg[:, :3] / vg[:, 3:]
+    X = vr[:, :3] / vr[:, 3:]
     err = np.abs(X - ref).max(axis=1) / np.abs(ref).max(axis=1)
-    assert err[conv].max() < 1e-11
+    assert err[ok].max() < 1e-11
