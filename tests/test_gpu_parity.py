@@ -647,11 +647,12 @@ def test_near_degenerate_rig_takes_jacobi_fallback(eng, scale):
     np.testing.assert_array_equal(g.col_ind.cpu().numpy(), o["col_ind"])
 
 
-def test_off_axis_detections_take_the_out_of_line_path(eng, crig):
-    """K1's main path assumes the depth is the largest component of the DLT null vector (last column of B^8)
-    and flags everything else -- detections far off the optical axis (|x - cx| > fx), as a wild dummy
-    detection would be -- for its out-of-line path (generic column choice).  Mixed warps must give what the
-    C oracle gives: costs to 1e-9, identical assignments, identical rows."""
+def test_off_axis_and_inconsistent_detections(eng, crig):
+    """Detections far off the optical axis (|x - cx| > fx), as a wild dummy detection would be: the depth is no
+    longer the largest component of the DLT null vector (K1 iterates from the start vector (z, 1), no column is
+    chosen), and the x-displaced ones are geometrically inconsistent (sigma_4 / sigma_3 around 0.8): K1's
+    convergence test sends them through the out-of-line path (extra squaring, then OpenCV's Jacobi).  Mixed warps
+    must give what the C oracle gives: costs to 1e-9, identical assignments, identical rows."""
     from oracle import c_oracle as co
     from particletracking_b200 import synthetic as syn
 
