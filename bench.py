@@ -47,9 +47,9 @@ FRAMES, COLORS, RODS = 1000, 8, 32
 WORKLOAD = "match_csv_complex+tracking_global_assignment: 1000 frames x 8 colours x 32 rods (BASELINE configs[1])"
 METRIC = "stereo frames/sec (match+triangulate+track)"
 # Algorithmic FP64 work of K1 per rod pair (4 end-point combinations), FMA = 2 flop:
-#  * as built (canonical rigs: camera-2 records + operators on the camera-1 point, three squarings of a 4x4
-#    matrix, homogeneous reprojection): 152.6 DFMA + 63.7 DMUL + 14.2 DADD executed per
-#    combination (ncu counters, profiles/r02q_k_cost_ncu.txt) = 383.0 flop -> 1 532 per pair (round 1:
+#  * as built (canonical rigs: camera-2 records + operators on the camera-1 point, two squarings of a 4x4
+#    matrix and three products from the start vector, homogeneous reprojection): 141.3 DFMA + 61.2 DMUL + 18.1 DADD executed per
+#    combination (ncu counters, profiles/r02r_k_cost_ncu.txt) = 362.0 flop -> 1 448 per pair (round 1:
 #    2 400, start of round 2: 2 244 -- the kernel got faster mostly by doing less, which a flop-per-second
 #    fraction only half shows; roofline.fp64_pipe_busy is the pipe's own utilisation).  This is what
 #    roofline.achieved / frac are computed from: the kernel's own work against the FP64 FMA peak.
@@ -57,8 +57,8 @@ METRIC = "stereo frames/sec (match+triangulate+track)"
 #    245 + 80*R + 66*S flop per combination with R = 20.5 rotations, S = 4.9 sweeps -> 2 210 per
 #    combination, 8 840 per pair.  Reported beside it as roofline.reference_algorithm (a ratio above
 #    1 there means: faster than the reference's algorithm could run at FP64 peak).
-FLOP_PER_PAIR = 1532.0
-FP64_PIPE_INSTR_PER_COMBINATION = 237.5  # 152.6 DFMA + 63.7 DMUL + 14.2 DADD + 7 DSETP (same capture)
+FLOP_PER_PAIR = 1448.0
+FP64_PIPE_INSTR_PER_COMBINATION = 224.6  # 141.3 DFMA + 61.2 DMUL + 18.1 DADD + 4 DSETP (same capture)
 FLOP_PER_PAIR_REFERENCE_ALGORITHM = 8840.0
 N_BATCHES = 4  # distinct synthetic input batches the timed steps rotate over
 
@@ -542,9 +542,9 @@ def run_b200(args):
         "peak_source": "measured in this run: dependency-free DFMA loop on all SMs (ptk_measure_fp64_peak); "
                        "MEASURED_PEAKS.json has no FP64 figure",
         "algorithmic_flop_per_pair": FLOP_PER_PAIR, "pairs_per_launch": pairs_per_launch,
-        "flop_model": "as built: 152.6 DFMA + 63.7 DMUL + 14.2 DADD per combination (ncu, profiles/r02q_k_cost_ncu.txt), FMA = 2",
+        "flop_model": "as built: 141.3 DFMA + 61.2 DMUL + 18.1 DADD per combination (ncu, profiles/r02r_k_cost_ncu.txt), FMA = 2",
         # utilisation of the FP64 pipe itself: FP64-pipe warp instructions x 2 issue cycles (16 lanes per scheduler) over
-        # the kernel's scheduler-cycles; ncu's sm__pipe_fp64_cycles_active of the same build: 79.4 %
+        # the kernel's scheduler-cycles; ncu's sm__pipe_fp64_cycles_active of the same build: 78.2 %
         "fp64_pipe_busy": FP64_PIPE_INSTR_PER_COMBINATION * 2.0 * (pairs_per_launch * 4 / 32) /
                           (k1_avg_ms * 1e-3 * sm_clock_hz * n_schedulers) if sm_clock_hz else None,
         "reference_algorithm": {"flop_per_pair": FLOP_PER_PAIR_REFERENCE_ALGORITHM, "achieved": ref_tf,

@@ -23,7 +23,7 @@ import torch.distributed as dist
 from particletracking_b200 import distributed as pdist
 from particletracking_b200 import engine, rig as rigmod, synthetic as syn
 
-FLOP_PER_PAIR = 1532.0  # K1 as built (bench.py: 152.6 DFMA + 63.7 DMUL + 14.2 DADD per combination); the reference-algorithm model is 8840
+FLOP_PER_PAIR = 1448.0  # K1 as built (bench.py: 141.3 DFMA + 61.2 DMUL + 18.1 DADD per combination); the reference-algorithm model is 8840
 
 
 def main():
@@ -89,9 +89,9 @@ def main():
                 "k_cost_ms": k1, "k_cost_tflops": flops / (k1 * 1e-3) / 1e12, "fp64_peak_tflops": peak / 1e12,
                 "k_cost_frac": flops / (k1 * 1e-3) / peak,
                 "k_cost_frac_reference_algorithm": flops * (8840.0 / FLOP_PER_PAIR) / (k1 * 1e-3) / peak,
-                # DFMA + DMUL + DADD + DSETP = 237.5 FP64-pipe instructions per combination, two pipe cycles per
+                # DFMA + DMUL + DADD + DSETP = 224.6 FP64-pipe instructions per combination, two pipe cycles per
                 # warp instruction, 16 lanes per scheduler (profiles/r02_k_cost_ncu.txt)
-                "k_cost_fp64_pipe_busy_est": 237.5 * 4 * (F + halo) * C * N * N / 32 * 2 / (148 * 4) / (k1 * 1e-3 * 1.965e9),
+                "k_cost_fp64_pipe_busy_est": 224.6 * 4 * (F + halo) * C * N * N / 32 * 2 / (148 * 4) / (k1 * 1e-3 * 1.965e9),
                 "kernel_ms": {k: v[0] / K for k, v in tm.items() if v[1]},
             }), flush=True)
         del c1, c2, n1, n2, out
