@@ -303,7 +303,8 @@ int ptk_parse_double(const char* s, int len, double* out);
 size_t ptk_workspace_bytes(int kind, long long n_problems, int Nmax);
 
 /* ---- the whole path on DEVICE buffers, one call ----------------------------------------
- * ptk_match_batch -> ptk_rows_to_ends -> ptk_track_batch -> chain pass, enqueued on `stream`
+ * ptk_match_batch (whose row kernel also writes the tracking layout of ptk_rows_to_ends) -> ptk_track_batch ->
+ * chain pass, enqueued on `stream`
  * (replaces the match2D.py:600-625 driver loop + tracking.py:70-138 for F frames x C colours;
  * problem index = f*C + c).  Outputs as in ptk_reconstruct_host but in device memory; tracking
  * (do_track != 0) expects n_out == Nmax for every problem, like tracking.py:97.  Only kernel
