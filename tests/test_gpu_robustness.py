@@ -266,3 +266,44 @@ def test_bounds_log_counts_a_provoked_violation(env):
     assert rep(1) == 0
     assert cnt.value > 0 and site.value == 30 and idx.value == 9 and bnd.value == 6
     assert rep(0) == 0 and cnt.value == 0  # reset: the session-end check sees only real violations
+
+
+def test_cost_matrix_does_not_depend_on_the_block_shape_of_k1(env, tmp_path):
+    """K1 (canonical rigs) gives a CTA `rows_per` camera-1 rods x a chunk of camera-2 rods; the block shape is a
+    tuning knob (PTK_KCOST_ROWS, PTK_KCOST_CFG: read once per process) and must not change a bit of the cost
+    matrix -- ragged counts, partial row blocks (rows_per = 3, 5), several column chunks (80 rods)."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "k1_cost.py"
+    script.write_text(
+        "import sys, numpy as np, torch\n"
+        f"sys.path.insert(0, {root!r})\n"
+        "from particletracking_b200 import engine, rig as rigmod, synthetic as syn\n"
+        "out = []\n"
+        "for n, seed in ((20, 5), (80, 6)):\n"
+        "    d = syn.make_stereo(3, 2, n, seed=seed, p_drop=0.15)\n"
+        "    r = rigmod.rig_from_dicts(d.calibration, d.transformation)\n"
+        "    a = tuple(torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in d.problems())\n"
+        "    c = engine.cost_batch(r, *a, want_choice=True)\n"
+        "    e = engine.cost_batch(r, *a, want_choice=False)\n"
+        "    torch.cuda.synchronize()\n"
+        "    out += [c[0].cpu().numpy(), c[1].cpu().numpy(), e[0].cpu().numpy()]\n"
+        "np.savez(sys.argv[1], *out)\n")
+    res = []
+    for k, (rows, cfg) in enumerate((("16", "0"), ("3", "0"), ("5", "6"), ("1", "4"))):
+        f = tmp_path / f"c{k}.npz"
+        e = dict(os.environ, PTK_KCOST_ROWS=rows, PTK_KCOST_CFG=cfg)
+        subprocess.check_call([sys.executable, str(script), str(f)], env=e)
+        res.append(np.load(f))
+    for other in res[1:]:
+        for key in res[0].files:
+            a, b = res[0][key], other[key]
+            if a.dtype.kind == "f":
+                m = ~np.isnan(a)
+                assert np.array_equal(np.isnan(a), np.isnan(b))
+                assert np.array_equal(a[m].view(np.int64), b[m].view(np.int64))
+            else:
+                assert np.array_equal(a, b)
