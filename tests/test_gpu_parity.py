@@ -128,6 +128,47 @@ def test_lsap_identical_to_scipy(eng):
         assert (row[p, k:] == -1).all() and (col[p, k:] == -1).all()
 
 
+def test_lsap_negative_and_mixed_sign_costs(eng):
+    """The solver's keys are the raw bits of the shortest-path cost (valid for non-negative values); a negative
+    candidate is caught by one compare and redone with the order-preserving transform.  Reprojection errors
+    never take that path, a caller's own matrices may: mixed-sign, all-negative, heavily tied integers around
+    zero, signed zeros -- assignments must equal SciPy's."""
+    from scipy.optimize import linear_sum_assignment
+
+    rng = np.random.default_rng(11)
+    cases = []
+    for _ in range(60):
+        nr, nc = rng.integers(1, 20, size=2)
+        cases.append(rng.normal(size=(nr, nc)))
+        cases.append(-rng.random((nr, nc)))
+        cases.append(rng.integers(-3, 4, size=(nr, nc)).astype(float))
+        m = rng.integers(-1, 2, size=(nr, nc)).astype(float)
+        m[m == 0] = np.where(rng.random((m == 0).sum()) < 0.5, 0.0, -0.0)
+        cases.append(m)
+    for n in (32, 48, 64, 100):
+        cases.append(rng.normal(size=(n, n)) * 1e3)
+        cases.append(rng.integers(-5, 6, size=(n, n + 3)).astype(float))
+        cases.append(rng.normal(size=(n + 4, n)))
+        d1, d2 = rng.normal(size=n), rng.normal(size=n)
+        cases.append(d1[:, None] + d2[None, :])
+    R = max(c.shape[0] for c in cases)
+    Cc = max(c.shape[1] for c in cases)
+    cost = np.full((len(cases), R, Cc), np.nan)
+    nr = np.zeros(len(cases), dtype=np.int32)
+    nc = np.zeros(len(cases), dtype=np.int32)
+    for p, c in enumerate(cases):
+        cost[p, : c.shape[0], : c.shape[1]] = c
+        nr[p], nc[p] = c.shape
+    row, col, n_out, status = (x.cpu().numpy() for x in eng.lsap_batch(dev(cost), dev(nr), dev(nc)))
+    assert (status == 0).all()
+    for p, c in enumerate(cases):
+        er, ec = linear_sum_assignment(c)
+        k = len(er)
+        assert n_out[p] == k
+        np.testing.assert_array_equal(row[p, :k], er, err_msg=f"case {p} {c.shape}")
+        np.testing.assert_array_equal(col[p, :k], ec, err_msg=f"case {p} {c.shape}")
+
+
 def test_lsap_large_and_status_codes(eng):
     import torch
     from scipy.optimize import linear_sum_assignment
