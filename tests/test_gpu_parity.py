@@ -688,6 +688,51 @@ def test_near_degenerate_rig_takes_jacobi_fallback(eng, scale):
     np.testing.assert_array_equal(g.col_ind.cpu().numpy(), o["col_ind"])
 
 
+@pytest.mark.parametrize("tangential", [False, True])
+def test_general_rig_first_camera_not_canonical(eng, rig, tangential):
+    """A rig whose FIRST camera has its own extrinsics (P1 = CM1 [R1|t1], R1 != I): none of the canonical-rig
+    shortcuts apply, K1 / K3 run the general instantiation (tile kernel, QR of all four DLT columns per
+    combination; with tangential terms: the full distortion model as well).  Same detections, the world frame
+    moved by a rigid transform: costs, assignments and rows must equal the C oracle's for that rig."""
+    from scipy.spatial.transform import Rotation
+
+    from oracle import c_oracle as co
+    from particletracking_b200 import rig as rigmod
+    from particletracking_b200 import synthetic as syn
+
+    cal = {k: np.array(v, dtype=np.float64) for k, v in rig["calibration"].items()}
+    if tangential:
+        for key in ("dist1", "dist2"):
+            d = np.zeros(14)
+            d[: cal[key].size] = cal[key].ravel()
+            d[2], d[3] = 3e-4, -2e-4
+            cal[key] = d
+    trf = rig["transformation"]
+    Rg = Rotation.from_rotvec([0.3, -0.2, 0.5]).as_matrix()
+    tg = np.array([[40.0], [-25.0], [300.0]])
+    R, T = cal["R"], cal["T"].reshape(3, 1)
+    r1, t1 = Rg, tg
+    r2, t2 = R @ Rg, R @ tg + T
+    P1 = cal["CM1"] @ np.hstack([r1, t1])
+    P2 = cal["CM2"] @ np.hstack([r2, t2])
+    grig = rigmod.make_rig(cal, P1, P2, Rotation.from_matrix(trf["rotation"]), np.asarray(trf["translation"], dtype=np.float64),
+                           r1, r2, t1, t2)
+    data = syn.make_stereo(3, 2, 22, seed=4242, sigma_px=0.5, p_drop=0.1)
+    c1, c2, n1, n2 = data.problems()
+    o = co.match_batch(grig, c1, c2, n1, n2, want_cost=True)
+    g = run_match(eng, grig, c1, c2, n1, n2, want_cost=True)
+    np.testing.assert_array_equal(g.status.cpu().numpy(), o["status"])
+    cost = g.cost.cpu().numpy()
+    for p in range(len(n1)):
+        assert rel_err(cost[p, : n1[p], : n2[p]], o["cost"][p, : n1[p], : n2[p]]) < TOL
+    np.testing.assert_array_equal(g.col_ind.cpu().numpy(), o["col_ind"])
+    rows = g.rows.cpu().numpy()
+    for p in range(len(n1)):
+        for k in range(o["n_out"][p]):
+            for sl in (slice(0, 3), slice(3, 6), slice(6, 9)):
+                assert rel_err(rows[p, k, sl], o["rows"][p, k, sl]) < TOL
+
+
 def test_off_axis_and_inconsistent_detections(eng, crig):
     """Detections far off the optical axis (|x - cx| > fx), as a wild dummy detection would be: the depth is no
     longer the largest component of the DLT null vector (K1 iterates from the start vector (z, 1), no column is
